@@ -1,0 +1,183 @@
+/*
+ * pathnet_b200.h — C ABI of libpathnet_b200.so (sm_100a).
+ *
+ * The drop-in boundary for PathNet's one hot path: the MERW path sampler and
+ * the PAGG path-aggregation operator (forward + backward).  The reference has
+ * no FFI layer at all — its C++ sampler and its Python model talk through a
+ * text file — so each entry point below cites the reference code it replaces
+ * (paths relative to the reference repo root).  INTEGRATION.md shows the
+ * ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success and a negative pn_status otherwise;
+ *     pn_last_error() returns a thread-local message for the last failure.
+ *   - "device" pointers are CUDA device pointers on the graph's / call's
+ *     current device; "host" pointers are ordinary host memory.
+ *   - no ownership transfer: the caller allocates every output and the
+ *     workspace; the library keeps no global state besides the error TLS.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *     all device work is enqueued on it and nothing synchronises unless said.
+ */
+#ifndef PATHNET_B200_H
+#define PATHNET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PN_VERSION 100 /* 0.1.0 */
+
+typedef enum {
+    PN_OK = 0,
+    PN_ERR_INVALID = -1,   /* bad argument */
+    PN_ERR_CUDA = -2,      /* CUDA runtime failure (message has the detail) */
+    PN_ERR_DEAD_END = -3,  /* a node with no out-rows: gen_merw.cpp:84-87 exit(0)s there */
+    PN_ERR_NOMEM = -4,
+    PN_ERR_UNSUPPORTED = -5
+} pn_status;
+
+int pn_version(void);
+const char *pn_last_error(void);
+
+/* ------------------------------------------------------------------ *
+ *  MERW sampler  (replaces preprocess/gen_merw.cpp, gen_epoch_merw.cpp)
+ * ------------------------------------------------------------------ */
+
+typedef struct pn_graph pn_graph;
+
+/* Replaces the input parse + link() + AliasTable::init loop
+ * (gen_merw.cpp:162-176, :95-99, :23-79).  Rows (u[e], v[e], p[e]) are the
+ * `<name>.in` rows in FILE ORDER (host pointers); duplicates are kept.  Builds,
+ * on the host, the CSR in file-row order and one alias cell per row exactly as
+ * the reference's two-queue construction does in fp64, reduces each cell's
+ * fp64 split S to the int32 threshold thr with  (r/RAND_MAX > S) == (r > thr)
+ * for every rand() output r, and uploads everything to `device`. */
+int pn_graph_from_edges(int32_t n, int64_t m, const int32_t *u, const int32_t *v,
+                        const double *p, int device, pn_graph **out);
+int pn_graph_free(pn_graph *g);
+
+/* n, rows, max out-degree, and the first node without out-rows (-1 if none). */
+int pn_graph_info(const pn_graph *g, int32_t *n, int64_t *m, int32_t *max_deg,
+                  int32_t *dead_end);
+
+/* Host copies of the alias cells, CSR-aligned with the rows: off[n+1],
+ * A[m], B[m], S[m] (fp64 split as the reference stores it) and thr[m].
+ * Any pointer may be NULL.  Used by the parity tests. */
+int pn_graph_cells_host(const pn_graph *g, int64_t *off, int32_t *A, int32_t *B,
+                        double *S, int32_t *thr);
+
+/* Replaces the all-sources bfs() + dis[N][N] table (gen_merw.cpp:101-123,
+ * :10, :178-179) for walks of length L: builds on the device the hop-distance
+ * table the labels are read from (dense u8 [n][n] saturated at L-1; exact for
+ * every distance a walk node can have).  Cached in the graph per L; called
+ * implicitly by pn_merw_sample when labels are requested.  Returns
+ * PN_ERR_UNSUPPORTED if n*n bytes exceed `max_bytes` (0 = default 24 GiB). */
+int pn_graph_prepare_labels(pn_graph *g, int32_t L, size_t max_bytes, void *stream);
+
+typedef enum {
+    PN_RNG_GLIBC = 0 /* bit-exact srand(seed)/rand() stream of the reference */
+} pn_rng_mode;
+
+/* Replaces the walk loop (gen_merw.cpp:182-209 / gen_epoch_merw.cpp:164-206).
+ * Draws, for epochs [epoch_begin, epoch_end) and start nodes
+ * [node_begin, node_end), nw walks of L nodes per start node, reproducing the
+ * reference's output for srand(seed) bit for bit: walk (epoch, st, i) consumes
+ * rand() outputs [2L*g, 2L*(g+1)) with g = (epoch*n + st)*nw + i, obtained by
+ * polynomial jump-ahead of the additive-feedback generator.
+ *   nodes  device int32 [E][n'][nw][L]   walk node at position t
+ *   types  device uint8 [E][n'][nw][L]   hop distance to the start node
+ *                                        (`dis[st][u]-1`, gen_merw.cpp:193,201);
+ *                                        NULL = skip labels
+ * E = epoch_end-epoch_begin, n' = node_end-node_begin. */
+int pn_merw_sample(pn_graph *g, int32_t nw, int32_t L, int64_t epoch_begin,
+                   int64_t epoch_end, int32_t node_begin, int32_t node_end,
+                   int32_t rng_mode, uint64_t seed, int32_t *nodes, uint8_t *types,
+                   void *stream);
+
+/* Text sink / source of the path hand-off format (writer gen_merw.cpp:188-206,
+ * reader PathNet_run.py:325-334, :419-423): "[n0, .., nL-1, o0, .., oL-1]\n".
+ * Host buffers.  format: returns bytes written, or the bytes needed when
+ * out == NULL; < 0 on error.  parse: returns walks parsed, < 0 on error. */
+int64_t pn_paths_format_txt(const int32_t *nodes, const uint8_t *types, int64_t walks,
+                            int32_t L, char *out, int64_t cap);
+int64_t pn_paths_parse_txt(const char *txt, int64_t bytes, int32_t L, int32_t *nodes,
+                           uint8_t *types, int64_t max_walks);
+
+/* ------------------------------------------------------------------ *
+ *  PAGG operator  (replaces PathNet.forward / PathNet_homo.forward and
+ *  their autograd backward, PathNet_run.py:172-211, :239-278, :351)
+ * ------------------------------------------------------------------ */
+
+typedef enum { PN_VARIANT_HETERO = 0, /* class PathNet      (:150) */
+               PN_VARIANT_HOMO = 1    /* class PathNet_homo (:214) */ } pn_variant;
+
+typedef enum { PN_MATH_FP32 = 0, /* CUDA-core fp32 FMA, strict parity         */
+               PN_MATH_TC = 1    /* tcgen05 tensor cores, fp16 operands/fp32 acc */ } pn_math;
+
+typedef struct {
+    int32_t N, F, H, C;      /* nodes, input features, hidden, classes       */
+    int32_t S, nw, L;        /* output rows (sum(indices)), path_num, path_len */
+    int32_t variant;         /* pn_variant                                   */
+    int32_t math_mode;       /* pn_math                                      */
+    int32_t training;        /* F.dropout(training=...) (:194,:209,:264,:276) */
+    float dropout_p;         /* the reference's module-global `dropout` (:71) */
+    uint64_t dropout_seed;   /* counter-based mask stream    */
+} pn_pagg_cfg;
+
+/* Parameter (or gradient) block, fp32 device pointers, PyTorch layouts
+ * (state_dict keys of PathNet_run.py:155-170):
+ *   fc0_w[H,F] fc0_b[H]  nets_w[L,H,H] nets_b[L,H] (nets.{d}.weight/bias stacked)
+ *   w_ih[4H,H] w_hh[4H,H] b_ih[4H] b_hh[4H] (LSTM.*_l0, gate order i,f,g,o)
+ *   attw_w[2H] attw_b[1]  fc2_w[C,2H] fc2_b[C] */
+typedef struct {
+    float *fc0_w, *fc0_b, *nets_w, *nets_b, *w_ih, *w_hh, *b_ih, *b_hh, *attw_w, *attw_b,
+        *fc2_w, *fc2_b;
+} pn_pagg_params;
+
+/* Integer-only canonicalisation of the reference's index tensors into the
+ * form one fused kernel serves for both variants (DESIGN.md §PAGG canonical
+ * form).  neis[S, nw*L] and layer_type[S, nw, L] are the int64 tensors the
+ * reference's forward() receives (device copies); outputs, device:
+ *   seq_node[S][nw][L] int32, seq_type[S][nw][L] uint8 : the L (type,node)
+ *       table entries fed to the LSTM for the w-th sequence pooled into row s
+ *   partner[S][nw] int32 : node whose embedding joins h_n in the attention
+ * hetero reproduces the flip/reshape/view re-interpretations of
+ * PathNet_run.py:179-199 exactly. */
+int pn_pagg_canonicalize(int32_t variant, int32_t S, int32_t nw, int32_t L,
+                         const int64_t *neis, const int64_t *layer_type, int32_t *seq_node,
+                         uint8_t *seq_type, int32_t *partner, void *stream);
+
+/* Bytes of device workspace forward/backward need for this cfg (saved
+ * activations + scratch).  The same workspace must be passed to forward and
+ * to the matching backward, untouched in between. */
+size_t pn_pagg_workspace_bytes(const pn_pagg_cfg *cfg);
+
+/* forward: logits[S,C] = PAGG(X[N,F]; params) for the S rows whose node ids are
+ * rows[S] (= nonzero(indices)).  Replaces Module.forward. */
+int pn_pagg_forward(const pn_pagg_cfg *cfg, const pn_pagg_params *params, const float *X,
+                    const int32_t *seq_node, const uint8_t *seq_type, const int32_t *partner,
+                    const int32_t *rows, void *workspace, float *logits, void *stream);
+
+/* backward: given dlogits[S,C], OVERWRITES every array of `grads` with the
+ * parameter gradients (the reference never needs dX).  Replaces autograd. */
+int pn_pagg_backward(const pn_pagg_cfg *cfg, const pn_pagg_params *params, const float *X,
+                     const int32_t *seq_node, const uint8_t *seq_type, const int32_t *partner,
+                     const int32_t *rows, void *workspace, const float *dlogits,
+                     const pn_pagg_params *grads, void *stream);
+
+/* The dropout keep/scale decision the kernels use for element `idx` of mask
+ * stream `stream_id` (0 = LSTM input [L,P,H], 1 = concat [S,2H]); host
+ * function so tests can feed the oracle the identical masks. */
+uint32_t pn_dropout_hash(uint64_t seed, uint32_t stream_id, uint64_t idx);
+
+/* Number of kernels this library has launched in this process (all entry
+ * points; bench.py reports it as gpu_launches). */
+uint64_t pn_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PATHNET_B200_H */

@@ -1,0 +1,537 @@
+// MERW path sampler for sm_100a — replaces preprocess/gen_merw.cpp and
+// gen_epoch_merw.cpp of the reference (citations are to gen_merw.cpp).
+//
+//   host  : CSR in file-row order + alias cells, exactly the reference's
+//           two-queue fp64 construction (:23-79); each cell's fp64 split S is
+//           reduced to an int32 threshold so the device loop is integer-only.
+//   K_d1/K_relax : dense hop-distance table D[n][n] (u8) — the reference's
+//           `char dis[N][N]` (:10) filled by all-sources bfs() (:101-123),
+//           here by in-place min-plus relaxation sweeps over the CSR.
+//   K_walk: one thread per chunk of WPT consecutive walks.  The thread's
+//           31-word rand() window lives in shared memory; its start offset in
+//           the single sequential srand(seed) stream is reached by polynomial
+//           jump-ahead done cooperatively by the warp (lfg.h).  Each
+//           transition is ONE dependent 32-byte sector: the alias cell carries
+//           the (offset, degree) of both candidate next nodes.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "common.h"
+#include "lfg.h"
+
+namespace pn {
+
+// one alias cell = one 32 B sector
+struct __align__(32) Cell {
+    int32_t A, B;      // next node if r2 > thr / otherwise        (:90)
+    int32_t thr;       // (1.0*r2/RAND_MAX > S) <=> (r2 > thr)
+    uint32_t offA;     // first cell of A's row
+    uint32_t degA;     // cells(A)
+    uint32_t offB, degB;
+    uint32_t pad;
+};
+static_assert(sizeof(Cell) == 32, "cell must be one sector");
+
+}  // namespace pn
+
+struct pn_graph {
+    int device = 0;
+    int32_t n = 0;
+    int64_t m = 0;
+    int32_t max_deg = 0;
+    int32_t dead_end = -1;
+    // host copies (parity tests, text tools)
+    std::vector<int64_t> off;
+    std::vector<int32_t> A, B, thr;
+    std::vector<double> S;
+    // device
+    uint2 *d_noderec = nullptr;   // [n] (off, deg)
+    pn::Cell *d_cells = nullptr;  // [m]
+    uint32_t *d_rowptr = nullptr; // [n+1] for the distance-table build
+    int32_t *d_adj = nullptr;     // [m] E[u] in file-row order
+    uint8_t *d_dist = nullptr;    // [n][n] hop distance, saturated
+    int32_t dist_L = 0;           // walk length the table is valid for
+};
+
+namespace pn {
+
+// largest r in [-1, RAND_MAX] with (double)r / RAND_MAX <= S  (-1: none)
+static int32_t split_to_threshold(double S)
+{
+    const double RM = 2147483647.0;
+    if (std::isnan(S)) return 2147483647;  // p > NaN is false -> always B
+    if (S < 0.0) return -1;
+    if (S >= 1.0) return 2147483647;
+    int64_t g = (int64_t)std::floor(S * RM);
+    if (g < 0) g = 0;
+    if (g > 2147483647) g = 2147483647;
+    while (g < 2147483647 && (double)(g + 1) / RM <= S) g++;
+    while (g >= 0 && (double)g / RM > S) g--;
+    return (int32_t)g;
+}
+
+// AliasTable::init (:23-79) for one node; writes exactly deg cells.
+static void alias_build_node(int deg, const int32_t *ids, const double *p_in, int32_t *A,
+                             int32_t *B, double *S, std::vector<int32_t> &qa_id,
+                             std::vector<double> &qa_p, std::vector<int32_t> &qb_id,
+                             std::vector<double> &qb_p)
+{
+    qa_id.clear(); qa_p.clear(); qb_id.clear(); qb_p.clear();
+    size_t ah = 0, bh = 0;
+    int64_t cells = 0;
+    for (int i = 0; i < deg; i++) {
+        double p = p_in[i] * deg;
+        if (p > 1.0) { qa_id.push_back(ids[i]); qa_p.push_back(p); }
+        else         { qb_id.push_back(ids[i]); qb_p.push_back(p); }
+    }
+    while (ah < qa_id.size() && bh < qb_id.size()) {
+        int32_t idA = qa_id[ah]; double probA = qa_p[ah]; ah++;
+        int32_t idB = qb_id[bh]; double probB = qb_p[bh]; bh++;
+        A[cells] = idA; B[cells] = idB; S[cells] = probB; cells++;
+        double res = probA - (1.0 - probB);
+        if (std::fabs(res - 1.0) < 1e-5) {
+            A[cells] = idA; B[cells] = idA; S[cells] = res; cells++;
+            continue;
+        }
+        if (res > 1.0) { qa_id.push_back(idA); qa_p.push_back(res); }
+        else           { qb_id.push_back(idA); qb_p.push_back(res); }
+    }
+    for (; ah < qa_id.size(); ah++) { A[cells] = B[cells] = qa_id[ah]; S[cells] = 1.0; cells++; }
+    for (; bh < qb_id.size(); bh++) { A[cells] = B[cells] = qb_id[bh]; S[cells] = 1.0; cells++; }
+}
+
+// ----------------------------------------------------------------------------
+// distance table
+// ----------------------------------------------------------------------------
+
+// D[u][u] = 0, D[u][v] = 1 for every row (u,v), v != u; everything else 255.
+__global__ void k_dist_level1(uint8_t *__restrict__ D, const uint32_t *__restrict__ rowptr,
+                              const int32_t *__restrict__ adj, int32_t n)
+{
+    int64_t u = blockIdx.x;
+    uint8_t *row = D + u * (int64_t)n;
+    for (uint32_t e = rowptr[u] + threadIdx.x; e < rowptr[u + 1]; e += blockDim.x) {
+        int32_t v = adj[e];
+        if (v != u) row[v] = 1;
+    }
+    if (threadIdx.x == 0) row[u] = 0;
+}
+
+// One in-place sweep  D[u][x] = min(D[u][x], 1 + min_{v in E[u]} D[v][x]).
+// After level-1 init and k-1 sweeps every entry with true distance <= k is
+// exact and every other entry is >= its true distance (a real path length or
+// 255), which is all the label needs (see pn_graph_prepare_labels).
+// grid: (n, chunks of 16*blockDim bytes)
+__global__ void __launch_bounds__(256)
+k_dist_relax(uint8_t *D, const uint32_t *__restrict__ rowptr, const int32_t *__restrict__ adj,
+             int32_t n, int64_t pitch16 /* n/16 rounded up, in uint4 */)
+{
+    const int64_t u = blockIdx.x;
+    const int64_t c = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;  // uint4 index in row
+    if (c >= pitch16) return;
+    const uint4 *Dv = reinterpret_cast<const uint4 *>(D);
+    uint4 best = make_uint4(~0u, ~0u, ~0u, ~0u);
+    const uint32_t e0 = rowptr[u], e1 = rowptr[u + 1];
+    for (uint32_t e = e0; e < e1; e++) {
+        const int64_t v = adj[e];
+        uint4 d = Dv[v * pitch16 + c];
+        best.x = __vminu4(best.x, d.x); best.y = __vminu4(best.y, d.y);
+        best.z = __vminu4(best.z, d.z); best.w = __vminu4(best.w, d.w);
+    }
+    const uint32_t one = 0x01010101u;
+    uint4 own = Dv[u * pitch16 + c];
+    own.x = __vminu4(own.x, __vaddus4(best.x, one)); own.y = __vminu4(own.y, __vaddus4(best.y, one));
+    own.z = __vminu4(own.z, __vaddus4(best.z, one)); own.w = __vminu4(own.w, __vaddus4(best.w, one));
+    reinterpret_cast<uint4 *>(D)[u * pitch16 + c] = own;
+}
+
+// ----------------------------------------------------------------------------
+// walk kernel
+// ----------------------------------------------------------------------------
+
+constexpr int WALK_THREADS = 256;
+constexpr int NPOLY_BITS = 32;
+
+struct WalkParams {
+    const uint2 *noderec;
+    const Cell *cells;
+    const uint8_t *dist;     // may be null (no labels)
+    int64_t dist_pitch;      // bytes per row of dist
+    int32_t *nodes;
+    uint8_t *types;
+    int32_t n, nw, L, wpt;
+    int32_t node_begin;
+    int64_t wpe;             // walks per epoch in this call = n' * nw
+    int64_t cpe;             // chunks per epoch = ceil(wpe / wpt)
+    int64_t total_chunks;    // E * cpe
+    // jump-ahead tables (host-computed per call)
+    uint32_t base[lfg::DEG];               // window whose first generated word is the
+                                           // first rand() of (epoch_begin, node_begin, walk 0)
+    uint32_t jstep[lfg::DEG];              // x^(2L*wpt)            : next chunk, same epoch
+    uint32_t jwrap[lfg::DEG];              // x^(epoch stride - (cpe-1)*2L*wpt) : first chunk of next epoch
+    uint32_t jchunk[NPOLY_BITS][lfg::DEG]; // x^(2L*wpt * 2^b)
+    uint32_t jepoch[NPOLY_BITS][lfg::DEG]; // x^(2L*n*nw * 2^b)
+};
+
+// warp-cooperative window_apply: w (lane j holds s_j, j < 31) <- window at +k,
+// poly in global/param space.  scratch: 64 words of shared memory per warp.
+__device__ __forceinline__ uint32_t warp_window_apply(const uint32_t *poly, uint32_t w,
+                                                      uint32_t *scratch, int lane)
+{
+    if (lane < lfg::DEG) scratch[lane] = w;
+    __syncwarp();
+    // e_{31+d} = e_d + e_{28+d}, d = 0..29: three independent words per round
+    for (int d0 = 0; d0 < 30; d0 += 3) {
+        if (lane < 3) scratch[31 + d0 + lane] = scratch[d0 + lane] + scratch[28 + d0 + lane];
+        __syncwarp();
+    }
+    uint32_t acc = 0;
+    if (lane < lfg::DEG) {
+#pragma unroll
+        for (int i = 0; i < lfg::DEG; i++) acc += poly[i] * scratch[i + lane];
+    }
+    __syncwarp();
+    return acc;
+}
+
+__global__ void __launch_bounds__(WALK_THREADS)
+k_merw_walk(const __grid_constant__ WalkParams P)
+{
+    __shared__ uint32_t ring[lfg::DEG][WALK_THREADS];  // thread-private windows, bank = tid
+    __shared__ uint32_t scratch[WALK_THREADS / 32][64];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t q_warp = ((int64_t)blockIdx.x * WALK_THREADS + warp * 32);
+    if (q_warp >= P.total_chunks) return;  // whole warp idle
+
+    // ---- warp: window of lane 0's chunk -----------------------------------
+    int64_t e = q_warp / P.cpe, c = q_warp % P.cpe;
+    uint32_t w = lane < lfg::DEG ? P.base[lane] : 0u;
+    {
+        uint64_t cb = (uint64_t)c, eb = (uint64_t)e;
+        for (int b = 0; cb; b++, cb >>= 1)
+            if (cb & 1) w = warp_window_apply(P.jchunk[b], w, scratch[warp], lane);
+        for (int b = 0; eb; b++, eb >>= 1)
+            if (eb & 1) w = warp_window_apply(P.jepoch[b], w, scratch[warp], lane);
+    }
+    // ---- hand each lane its window, stepping chunk by chunk ----------------
+    int64_t my_e = 0, my_c = 0;
+    for (int l = 0; l < 32; l++) {
+        if (lane < lfg::DEG) ring[lane][warp * 32 + l] = w;
+        if (lane == l) { my_e = e; my_c = c; }
+        if (l == 31) break;
+        if (c + 1 < P.cpe) { w = warp_window_apply(P.jstep, w, scratch[warp], lane); c++; }
+        else               { w = warp_window_apply(P.jwrap, w, scratch[warp], lane); c = 0; e++; }
+    }
+    __syncwarp();
+    if (q_warp + lane >= P.total_chunks) return;
+
+    // ---- thread: its chunk of walks ----------------------------------------
+    int head = 0;  // slot of the oldest word
+    auto next_rand = [&]() -> uint32_t {
+        int j28 = head + 28; if (j28 >= lfg::DEG) j28 -= lfg::DEG;
+        uint32_t v = ring[head][tid] + ring[j28][tid];
+        ring[head][tid] = v;
+        head = head + 1 == lfg::DEG ? 0 : head + 1;
+        return v >> 1;
+    };
+    const int L = P.L;
+    int64_t wi = my_c * P.wpt;
+    const int64_t w_end = min(wi + (int64_t)P.wpt, P.wpe);
+    int32_t *out_n = P.nodes + (my_e * P.wpe + wi) * L;
+    uint8_t *out_t = P.types ? P.types + (my_e * P.wpe + wi) * L : nullptr;
+    int32_t st = P.node_begin + (int32_t)(wi / P.nw);
+    int32_t k_in_st = (int32_t)(wi % P.nw);
+    for (; wi < w_end; wi++) {
+        uint2 rec = __ldg(&P.noderec[st]);
+        uint32_t off = rec.x, deg = rec.y;
+        int32_t u = st;
+        const uint8_t *drow = P.dist ? P.dist + (int64_t)st * P.dist_pitch : nullptr;
+        for (int t = 0; t < L; t++) {
+            out_n[t] = u;
+            if (out_t) {
+                uint8_t lab = 0;
+                if (t == 1) lab = (u != st);
+                else if (t >= 2) { uint8_t d = __ldg(drow + u); lab = d < t ? d : (uint8_t)t; }
+                out_t[t] = lab;
+            }
+            uint32_t r1 = next_rand(), r2 = next_rand();  // every roll draws twice (:88-89)
+            if (t + 1 < L) {                                // the L-th roll's result is unused (:190-197)
+                uint32_t x = r1 % deg;
+                const uint4 *cp = reinterpret_cast<const uint4 *>(P.cells + (off + x));
+                uint4 lo = __ldg(cp), hi = __ldg(cp + 1);
+                bool takeA = (int32_t)r2 > (int32_t)lo.z;
+                u = takeA ? (int32_t)lo.x : (int32_t)lo.y;
+                off = takeA ? lo.w : hi.y;
+                deg = takeA ? hi.x : hi.z;
+            }
+        }
+        out_n += L;
+        if (out_t) out_t += L;
+        if (++k_in_st == P.nw) { k_in_st = 0; st++; }
+    }
+}
+
+}  // namespace pn
+
+// ============================================================================
+// C ABI
+// ============================================================================
+using namespace pn;
+
+extern "C" int pn_graph_from_edges(int32_t n, int64_t m, const int32_t *u, const int32_t *v,
+                                   const double *p, int device, pn_graph **out)
+{
+    PN_REQUIRE(out != nullptr, "pn_graph_from_edges: out is NULL");
+    *out = nullptr;
+    PN_REQUIRE(n > 0 && m >= 0, "pn_graph_from_edges: need n > 0, m >= 0 (n=%d m=%lld)", n, (long long)m);
+    PN_REQUIRE(m < (int64_t)0xFFFFFFF0u, "pn_graph_from_edges: more than 2^32 rows");
+    PN_REQUIRE(m == 0 || (u && v && p), "pn_graph_from_edges: NULL edge arrays");
+    for (int64_t e = 0; e < m; e++)
+        PN_REQUIRE(u[e] >= 0 && u[e] < n && v[e] >= 0 && v[e] < n,
+                   "pn_graph_from_edges: row %lld (%d,%d) outside [0,%d)", (long long)e, u[e], v[e], n);
+    pn_graph *g = new pn_graph();
+    g->device = device; g->n = n; g->m = m;
+    g->off.assign((size_t)n + 1, 0);
+    for (int64_t e = 0; e < m; e++) g->off[u[e] + 1]++;
+    for (int32_t i = 0; i < n; i++) {
+        int64_t d = g->off[i + 1];
+        if (d > g->max_deg) g->max_deg = (int32_t)d;
+        if (d == 0 && g->dead_end < 0) g->dead_end = i;
+        g->off[i + 1] += g->off[i];
+    }
+    std::vector<int32_t> adj((size_t)m);
+    std::vector<double> pr((size_t)m);
+    {
+        std::vector<int64_t> cur(g->off.begin(), g->off.end() - 1);
+        for (int64_t e = 0; e < m; e++) {  // stable: file row order per node (:95-99)
+            int64_t k = cur[u[e]]++;
+            adj[k] = v[e]; pr[k] = p[e];
+        }
+    }
+    g->A.resize(m); g->B.resize(m); g->thr.resize(m); g->S.resize(m);
+    // alias build: sequential per node (queue order matters), nodes independent
+    unsigned nthreads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    if (m < 100000) nthreads = 1;
+    auto work = [&](int32_t lo, int32_t hi) {
+        std::vector<int32_t> qa, qb; std::vector<double> pa, pb;
+        for (int32_t i = lo; i < hi; i++) {
+            int64_t o = g->off[i]; int deg = (int)(g->off[i + 1] - o);
+            alias_build_node(deg, adj.data() + o, pr.data() + o, g->A.data() + o, g->B.data() + o,
+                             g->S.data() + o, qa, pa, qb, pb);
+            for (int k = 0; k < deg; k++) g->thr[o + k] = split_to_threshold(g->S[o + k]);
+        }
+    };
+    if (nthreads == 1) work(0, n);
+    else {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nthreads; t++)
+            th.emplace_back(work, (int32_t)((int64_t)n * t / nthreads), (int32_t)((int64_t)n * (t + 1) / nthreads));
+        for (auto &x : th) x.join();
+    }
+    // device upload
+    std::vector<Cell> cells((size_t)m);
+    for (int64_t k = 0; k < m; k++) {
+        Cell c;
+        c.A = g->A[k]; c.B = g->B[k]; c.thr = g->thr[k];
+        c.offA = (uint32_t)g->off[c.A]; c.degA = (uint32_t)(g->off[c.A + 1] - g->off[c.A]);
+        c.offB = (uint32_t)g->off[c.B]; c.degB = (uint32_t)(g->off[c.B + 1] - g->off[c.B]);
+        c.pad = 0;
+        cells[k] = c;
+    }
+    std::vector<uint2> rec((size_t)n);
+    std::vector<uint32_t> rowptr((size_t)n + 1);
+    for (int32_t i = 0; i < n; i++) rec[i] = make_uint2((uint32_t)g->off[i], (uint32_t)(g->off[i + 1] - g->off[i]));
+    for (int32_t i = 0; i <= n; i++) rowptr[i] = (uint32_t)g->off[i];
+    auto fail = [&](int rc) { pn_graph_free(g); return rc; };
+#define PN_G(expr)                                                                    \
+    do {                                                                              \
+        cudaError_t _e = (expr);                                                      \
+        if (_e != cudaSuccess) {                                                      \
+            set_error("%s failed: %s", #expr, cudaGetErrorString(_e));                \
+            return fail(PN_ERR_CUDA);                                                 \
+        }                                                                             \
+    } while (0)
+    if (device < 0) { *out = g; return PN_OK; }  // host-only graph (tests, text tools)
+    PN_G(cudaSetDevice(device));
+    PN_G(cudaMalloc(&g->d_noderec, sizeof(uint2) * (size_t)n));
+    PN_G(cudaMalloc(&g->d_cells, sizeof(Cell) * (size_t)std::max<int64_t>(m, 1)));
+    PN_G(cudaMalloc(&g->d_rowptr, sizeof(uint32_t) * ((size_t)n + 1)));
+    PN_G(cudaMalloc(&g->d_adj, sizeof(int32_t) * (size_t)std::max<int64_t>(m, 1)));
+    PN_G(cudaMemcpy(g->d_noderec, rec.data(), sizeof(uint2) * (size_t)n, cudaMemcpyHostToDevice));
+    PN_G(cudaMemcpy(g->d_cells, cells.data(), sizeof(Cell) * (size_t)m, cudaMemcpyHostToDevice));
+    PN_G(cudaMemcpy(g->d_rowptr, rowptr.data(), sizeof(uint32_t) * ((size_t)n + 1), cudaMemcpyHostToDevice));
+    PN_G(cudaMemcpy(g->d_adj, adj.data(), sizeof(int32_t) * (size_t)m, cudaMemcpyHostToDevice));
+#undef PN_G
+    *out = g;
+    return PN_OK;
+}
+
+extern "C" int pn_graph_free(pn_graph *g)
+{
+    if (!g) return PN_OK;
+    if (g->device < 0) { delete g; return PN_OK; }
+    cudaSetDevice(g->device);
+    cudaFree(g->d_noderec); cudaFree(g->d_cells); cudaFree(g->d_rowptr); cudaFree(g->d_adj);
+    cudaFree(g->d_dist);
+    delete g;
+    return PN_OK;
+}
+
+extern "C" int pn_graph_info(const pn_graph *g, int32_t *n, int64_t *m, int32_t *max_deg,
+                             int32_t *dead_end)
+{
+    PN_REQUIRE(g, "pn_graph_info: NULL graph");
+    if (n) *n = g->n;
+    if (m) *m = g->m;
+    if (max_deg) *max_deg = g->max_deg;
+    if (dead_end) *dead_end = g->dead_end;
+    return PN_OK;
+}
+
+extern "C" int pn_graph_cells_host(const pn_graph *g, int64_t *off, int32_t *A, int32_t *B,
+                                   double *S, int32_t *thr)
+{
+    PN_REQUIRE(g, "pn_graph_cells_host: NULL graph");
+    if (off) memcpy(off, g->off.data(), sizeof(int64_t) * g->off.size());
+    if (A) memcpy(A, g->A.data(), sizeof(int32_t) * g->A.size());
+    if (B) memcpy(B, g->B.data(), sizeof(int32_t) * g->B.size());
+    if (S) memcpy(S, g->S.data(), sizeof(double) * g->S.size());
+    if (thr) memcpy(thr, g->thr.data(), sizeof(int32_t) * g->thr.size());
+    return PN_OK;
+}
+
+extern "C" int pn_graph_prepare_labels(pn_graph *g, int32_t L, size_t max_bytes, void *stream_)
+{
+    PN_REQUIRE(g, "pn_graph_prepare_labels: NULL graph");
+    PN_REQUIRE(L >= 1 && L <= 64, "pn_graph_prepare_labels: L=%d outside [1,64]", L);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    // A table built for L' >= L is also valid for L (more sweeps only make more
+    // entries exact; the rest stay upper bounds).
+    if (g->d_dist && g->dist_L >= L) return PN_OK;
+    if (L <= 2) { g->dist_L = std::max(g->dist_L, L); return PN_OK; }  // labels need no table
+    PN_CUDA(cudaSetDevice(g->device));
+    const int64_t n = g->n;
+    const int64_t pitch16 = ceil_div(n, 16);
+    const size_t bytes = (size_t)pitch16 * 16 * (size_t)n;
+    if (max_bytes == 0) max_bytes = (size_t)24 << 30;
+    if (bytes > max_bytes) {
+        set_error("pn_graph_prepare_labels: dense distance table needs %zu bytes (> %zu); "
+                  "sparse ball tables are not implemented yet", bytes, max_bytes);
+        return PN_ERR_UNSUPPORTED;
+    }
+    if (!g->d_dist) PN_CUDA(cudaMalloc(&g->d_dist, bytes));
+    PN_CUDA(cudaMemsetAsync(g->d_dist, 0xFF, bytes, stream));
+    // level 1 writes bytes; the row pitch is padded to 16
+    k_dist_level1<<<(unsigned)n, 128, 0, stream>>>(g->d_dist, g->d_rowptr, g->d_adj, (int32_t)(pitch16 * 16));
+    PN_LAUNCH_CHECK();
+    // distances up to L-2 must be exact: level 1 + (L-3) sweeps
+    dim3 grid((unsigned)n, (unsigned)ceil_div(pitch16, 256));
+    for (int k = 2; k <= L - 2; k++) {
+        k_dist_relax<<<grid, 256, 0, stream>>>(g->d_dist, g->d_rowptr, g->d_adj, (int32_t)n, pitch16);
+        PN_LAUNCH_CHECK();
+    }
+    g->dist_L = L;
+    return PN_OK;
+}
+
+static void copy_poly(uint32_t dst[lfg::DEG], const lfg::Poly &p) { memcpy(dst, p.c, sizeof(p.c)); }
+
+// Chunking + jump-ahead tables of one pn_merw_sample call (host).
+static int plan_walk(WalkParams &P, int32_t n, int32_t nw, int32_t L, int64_t epoch_begin,
+                     int64_t E, int32_t node_begin, int64_t np, uint64_t seed)
+{
+    memset(&P, 0, sizeof(P));
+    const int64_t wpe = np * nw;
+    P.n = n; P.nw = nw; P.L = L; P.node_begin = node_begin;
+    P.wpe = wpe;
+    // chunk size: enough chunks to fill the machine a few times over, at most
+    // 32 walks per thread (amortises the jump-ahead), at least 4
+    int wpt = 32;
+    const int64_t want_threads = (int64_t)148 * 2048 * 2;
+    while (wpt > 4 && E * ceil_div(wpe, wpt) < want_threads) wpt >>= 1;
+    P.wpt = wpt;
+    P.cpe = ceil_div(wpe, wpt);
+    P.total_chunks = E * P.cpe;
+    PN_REQUIRE(P.cpe < ((int64_t)1 << NPOLY_BITS) && E < ((int64_t)1 << NPOLY_BITS),
+               "pn_merw_sample: too many chunks/epochs in one call");
+    const uint64_t draws_per_walk = 2ull * (uint64_t)L;  // every roll draws twice, L rolls
+    const uint64_t chunk_stride = draws_per_walk * (uint64_t)wpt;
+    const uint64_t epoch_stride = draws_per_walk * (uint64_t)n * (uint64_t)nw;
+    uint32_t s0[lfg::DEG];
+    lfg::seed_window((uint32_t)seed, s0);
+    // the thread's first generated word must be s_{341 + first_draw}: its
+    // window is s_{310 + first_draw .. 340 + first_draw}
+    __uint128_t first = (__uint128_t)((uint64_t)epoch_begin) * epoch_stride +
+                        (__uint128_t)((uint64_t)node_begin * (uint64_t)nw) * draws_per_walk;
+    first += (uint64_t)(lfg::FIRST_OUTPUT - lfg::DEG);
+    PN_REQUIRE((first >> 64) == 0, "pn_merw_sample: stream offset exceeds 2^64");
+    lfg::window_apply(lfg::poly_xpow((uint64_t)first), s0, P.base);
+    lfg::Poly pc = lfg::poly_xpow(chunk_stride), pe = lfg::poly_xpow(epoch_stride);
+    copy_poly(P.jstep, pc);
+    copy_poly(P.jwrap, lfg::poly_xpow(epoch_stride - (uint64_t)(P.cpe - 1) * chunk_stride));
+    for (int b = 0; b < NPOLY_BITS; b++) {
+        copy_poly(P.jchunk[b], pc); copy_poly(P.jepoch[b], pe);
+        pc = lfg::poly_mul(pc, pc); pe = lfg::poly_mul(pe, pe);
+    }
+    return PN_OK;
+}
+
+// Host-only debug view of the plan (tests/test_lfg_jump.py): same tables the
+// kernel receives.  tables = base[31] jstep[31] jwrap[31] jchunk[32][31] jepoch[32][31].
+extern "C" int pn_merw_plan_host(int32_t n, int32_t nw, int32_t L, int64_t epoch_begin,
+                                 int64_t E, int32_t node_begin, int64_t np, uint64_t seed,
+                                 int32_t *wpt, int64_t *cpe, uint32_t *tables)
+{
+    WalkParams P;
+    int rc = plan_walk(P, n, nw, L, epoch_begin, E, node_begin, np, seed);
+    if (rc != PN_OK) return rc;
+    *wpt = P.wpt; *cpe = P.cpe;
+    memcpy(tables, P.base, sizeof(uint32_t) * lfg::DEG * (3 + 2 * NPOLY_BITS));
+    return PN_OK;
+}
+
+extern "C" int pn_merw_sample(pn_graph *g, int32_t nw, int32_t L, int64_t epoch_begin,
+                              int64_t epoch_end, int32_t node_begin, int32_t node_end,
+                              int32_t rng_mode, uint64_t seed, int32_t *nodes, uint8_t *types,
+                              void *stream_)
+{
+    PN_REQUIRE(g, "pn_merw_sample: NULL graph");
+    PN_REQUIRE(nw >= 0 && L >= 1 && L <= 64, "pn_merw_sample: bad nw=%d / L=%d", nw, L);
+    PN_REQUIRE(epoch_begin >= 0 && epoch_end >= epoch_begin, "pn_merw_sample: bad epoch range");
+    PN_REQUIRE(node_begin >= 0 && node_end >= node_begin && node_end <= g->n,
+               "pn_merw_sample: bad node range [%d,%d) for n=%d", node_begin, node_end, g->n);
+    PN_REQUIRE(rng_mode == PN_RNG_GLIBC, "pn_merw_sample: unknown rng_mode %d", rng_mode);
+    if (g->dead_end >= 0) {
+        set_error("pn_merw_sample: node %d has no out-rows (the reference prints "
+                  "'A.size() == 0 in Alias Table' and exits)", g->dead_end);
+        return PN_ERR_DEAD_END;
+    }
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int64_t E = epoch_end - epoch_begin;
+    const int64_t np = node_end - node_begin;
+    const int64_t wpe = np * nw;
+    if (E == 0 || wpe == 0) return PN_OK;
+    PN_REQUIRE(nodes != nullptr, "pn_merw_sample: nodes is NULL");
+    PN_CUDA(cudaSetDevice(g->device));
+    if (types) {
+        int rc = pn_graph_prepare_labels(g, L, 0, stream_);
+        if (rc != PN_OK) return rc;
+    }
+    WalkParams P;
+    {
+        int rc = plan_walk(P, g->n, nw, L, epoch_begin, E, node_begin, np, seed);
+        if (rc != PN_OK) return rc;
+    }
+    P.noderec = g->d_noderec; P.cells = g->d_cells;
+    P.dist = (types && L > 2) ? g->d_dist : nullptr;
+    P.dist_pitch = ceil_div(g->n, 16) * 16;
+    P.nodes = nodes; P.types = types;
+    const int64_t blocks = ceil_div(P.total_chunks, WALK_THREADS);
+    PN_REQUIRE(blocks < ((int64_t)1 << 31), "pn_merw_sample: grid too large; split the epoch range");
+    k_merw_walk<<<(unsigned)blocks, WALK_THREADS, 0, stream>>>(P);
+    PN_LAUNCH_CHECK();
+    return PN_OK;
+}
