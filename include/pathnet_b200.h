@@ -173,6 +173,14 @@ int pn_pagg_backward(const pn_pagg_cfg *cfg, const pn_pagg_params *params, const
  * function so tests can feed the oracle the identical masks. */
 uint32_t pn_dropout_hash(uint64_t seed, uint32_t stream_id, uint64_t idx);
 
+/* In-stream kernel timing for bench.py's roofline: when enabled, the library
+ * brackets its dominant kernels with CUDA events on the launching stream.
+ * pn_profile_read synchronises those events and returns, for slot `name`
+ * ("lstm_fwd", "lstm_bwd", "merw_walk", "wgrad", ...), the summed milliseconds
+ * and the number of launches since the last pn_profile_enable(1). */
+int pn_profile_enable(int on);
+int pn_profile_read(const char *name, double *ms, int64_t *launches);
+
 /* Number of kernels this library has launched in this process (all entry
  * points; bench.py reports it as gpu_launches). */
 uint64_t pn_launch_count(void);

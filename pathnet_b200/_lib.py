@@ -60,6 +60,8 @@ def lib():
     L.pn_paths_format_txt.argtypes = [vp, vp, i64, i32, vp, i64]
     L.pn_paths_parse_txt.restype = i64
     L.pn_paths_parse_txt.argtypes = [vp, i64, i32, vp, vp, i64]
+    L.pn_profile_enable.argtypes = [C.c_int]
+    L.pn_profile_read.argtypes = [C.c_char_p, C.POINTER(C.c_double), C.POINTER(i64)]
     if hasattr(L, "pn_pagg_forward"):
         L.pn_pagg_canonicalize.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]
         L.pn_pagg_workspace_bytes.restype = C.c_size_t
@@ -83,4 +85,14 @@ EXPORTS = ("pn_version", "pn_last_error", "pn_graph_from_edges", "pn_graph_free"
            "pn_graph_cells_host", "pn_graph_prepare_labels", "pn_merw_sample",
            "pn_paths_format_txt", "pn_paths_parse_txt", "pn_pagg_canonicalize",
            "pn_pagg_workspace_bytes", "pn_pagg_forward", "pn_pagg_backward", "pn_dropout_hash",
-           "pn_launch_count")
+           "pn_launch_count", "pn_profile_enable", "pn_profile_read")
+
+
+def profile_enable(on: bool) -> None:
+    lib().pn_profile_enable(1 if on else 0)
+
+
+def profile_read(name: str):
+    ms, n = C.c_double(), C.c_int64()
+    lib().pn_profile_read(name.encode(), C.byref(ms), C.byref(n))
+    return ms.value, n.value

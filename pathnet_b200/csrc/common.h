@@ -42,6 +42,15 @@ inline void count_launch(uint64_t k = 1) { g_launches.fetch_add(k, std::memory_o
         PN_CUDA(cudaGetLastError());          \
     } while (0)
 
+// in-stream timing of named kernels (pn_profile_enable / pn_profile_read)
+void prof_begin(const char *slot, cudaStream_t st);
+void prof_end(const char *slot, cudaStream_t st);
+struct ProfScope {
+    const char *slot; cudaStream_t st;
+    ProfScope(const char *s, cudaStream_t t) : slot(s), st(t) { prof_begin(slot, st); }
+    ~ProfScope() { prof_end(slot, st); }
+};
+
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 }  // namespace pn

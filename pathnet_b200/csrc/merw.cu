@@ -531,6 +531,7 @@ extern "C" int pn_merw_sample(pn_graph *g, int32_t nw, int32_t L, int64_t epoch_
     P.nodes = nodes; P.types = types;
     const int64_t blocks = ceil_div(P.total_chunks, WALK_THREADS);
     PN_REQUIRE(blocks < ((int64_t)1 << 31), "pn_merw_sample: grid too large; split the epoch range");
+    ProfScope prof("merw_walk", stream);
     k_merw_walk<<<(unsigned)blocks, WALK_THREADS, 0, stream>>>(P);
     PN_LAUNCH_CHECK();
     return PN_OK;

@@ -1,0 +1,754 @@
+// PAGG operator (forward + backward) — replaces PathNet.forward /
+// PathNet_homo.forward (PathNet_run.py:172-211, :239-278) and their autograd
+// backward (:351).  fp32 CUDA-core math mode; the tensor-core mode lives in
+// pagg_tc.cu and shares this file's index handling, pooling and parameter-grad
+// plumbing.
+//
+// Canonical form: after pn_pagg_canonicalize both variants are
+//   Z = act0(X W0^T + b0)                       [N,H]
+//   T[n,d] = act1(W_d Z[n] + b_d)               [N,L,H]  (hoisted: the reference
+//            applies all L Linears to every gathered row and then selects one)
+//   x_{s,w,t} = dropout(T[seq_node[s,w,t], seq_type[s,w,t]])
+//   h_{s,w} = LSTM_final_h(x_{s,w,0..L-1})
+//   score = attw . [h ; partner] + b
+//   pooled[s] = 1/nw sum_w weight(score)_w h_{s,w}
+//   logits = fc2(dropout([Z[rows[s]] ; pooled[s]]))
+#include <algorithm>
+
+#include "pagg_common.cuh"
+
+namespace pn {
+
+// ---------------------------------------------------------------------------
+// canonicalisation (integer only)
+// ---------------------------------------------------------------------------
+__global__ void k_canonicalize(int variant, int64_t S, int nw, int L, const int64_t *__restrict__ neis,
+                               const int64_t *__restrict__ ltype, int32_t *__restrict__ seq_node,
+                               uint8_t *__restrict__ seq_type, int32_t *__restrict__ partner)
+{
+    const int64_t P = S * nw;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // over S*nw*L
+    if (i >= P * L) return;
+    const int t = (int)(i % L);
+    const int64_t sw = i / L;  // s*nw + w
+    if (variant == PN_VARIANT_HOMO) {
+        // sequence (s,w) = path p = s*nw+w in natural order (:246-265)
+        seq_node[i] = (int32_t)neis[i];
+        seq_type[i] = (uint8_t)ltype[i];
+        if (t == 0) partner[sw] = (int32_t)neis[sw * L];  // step-0 entry of the same path (:259-260)
+    } else {
+        // output row s pools LSTM batch elements b = w*S + s (:196-197); batch
+        // element b, step t is flat row r = b*L + t of the flipped/reshaped
+        // gather (:182-183,:191): node idx[r mod P][L-1 - r div P], type ltype.flat[r]
+        const int64_t s = sw / nw, w = sw % nw;
+        const int64_t b = w * S + s;
+        const int64_t r = b * L + t;
+        seq_node[i] = (int32_t)neis[(r % P) * L + (L - 1 - r / P)];
+        seq_type[i] = (uint8_t)ltype[r];
+        if (t == 0) partner[sw] = (int32_t)neis[b * L];  // neis[0] row b (:199)
+    }
+}
+
+// ---------------------------------------------------------------------------
+// LSTM weight packing: Wp[k][unit*4+gate] (k < H: W_ih^T, k >= H: W_hh^T)
+// ---------------------------------------------------------------------------
+__global__ void k_pack_lstm(int H, const float *__restrict__ w_ih, const float *__restrict__ w_hh,
+                            const float *__restrict__ b_ih, const float *__restrict__ b_hh,
+                            float *__restrict__ Wp, float *__restrict__ WpT, float *__restrict__ bp)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int G4 = 4 * H, K2 = 2 * H;
+    if (i < K2 * G4) {
+        int k = i / G4, col = i % G4, unit = col >> 2, gate = col & 3;
+        float v = k < H ? w_ih[(gate * H + unit) * H + k] : w_hh[(gate * H + unit) * H + (k - H)];
+        Wp[i] = v;
+        WpT[col * K2 + k] = v;
+    }
+    if (i < G4) {
+        int unit = i >> 2, gate = i & 3;
+        bp[i] = b_ih[gate * H + unit] + b_hh[gate * H + unit];
+    }
+}
+
+__global__ void k_unpack_lstm_grads(int H, const float *__restrict__ dWp, const float *__restrict__ dbp,
+                                    float *__restrict__ dw_ih, float *__restrict__ dw_hh,
+                                    float *__restrict__ db_ih, float *__restrict__ db_hh)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int G4 = 4 * H;
+    if (i < G4 * H) {
+        int row = i / H, k = i % H, gate = row / H, unit = row % H;
+        int col = unit * 4 + gate;
+        dw_ih[i] = dWp[k * G4 + col];
+        dw_hh[i] = dWp[(H + k) * G4 + col];
+    }
+    if (i < G4) {
+        int gate = i / H, unit = i % H;
+        float v = dbp[unit * 4 + gate];
+        db_ih[i] = v;
+        db_hh[i] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// fused gather + dropout + LSTM forward, fp32 FMA
+//   CTA = 64 sequences, all L steps; 256 threads; thread (ty, tx) owns
+//   sequences ty*8..ty*8+7 and hidden units {tx + 32u}, all four gates.
+// ---------------------------------------------------------------------------
+struct LstmArgs {
+    const float *T;          // [N,L,H]
+    const int32_t *seq_node; // [P,L]
+    const uint8_t *seq_type; // [P,L]
+    const float *Wp, *WpT, *bp;
+    float *acts;             // [L][P][5][H]
+    float *hfin;             // [P,H]
+    int64_t P;
+    int L;
+    // dropout of the LSTM input (stream 0, element index (p*L+t)*H + j)
+    uint32_t drop_thr;       // drop iff hash < thr; 0 = no dropout
+    float drop_scale;
+    uint64_t drop_seed;
+    // backward only
+    const float *dhfin;      // [P,H]
+    float *dT;               // [N,L,H]
+    float *dA;               // [L*P,4H]
+    float *XH;               // [L*P,2H]
+};
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+template <int UPT>
+__device__ __forceinline__ void gather_x_tile(const LstmArgs &a, float *As, int apitch, int64_t p0,
+                                              int t, int ty, int tx)
+{
+    constexpr int H = 32 * UPT;
+#pragma unroll
+    for (int pp = 0; pp < 8; pp++) {
+        const int row = ty * 8 + pp;
+        const int64_t p = p0 + row;
+        float *dst = As + row * apitch;
+        if (p < a.P) {
+            const int64_t e = p * a.L + t;
+            const float *src = a.T + ((int64_t)a.seq_node[e] * a.L + a.seq_type[e]) * H;
+            for (int j = tx * 4; j < H; j += 128) {
+                float4 v = __ldg(reinterpret_cast<const float4 *>(src + j));
+                if (a.drop_thr) {
+                    const uint64_t base = (uint64_t)e * H + j;
+                    v.x = dropout_hash(a.drop_seed, 0, base + 0) < a.drop_thr ? 0.f : v.x * a.drop_scale;
+                    v.y = dropout_hash(a.drop_seed, 0, base + 1) < a.drop_thr ? 0.f : v.y * a.drop_scale;
+                    v.z = dropout_hash(a.drop_seed, 0, base + 2) < a.drop_thr ? 0.f : v.z * a.drop_scale;
+                    v.w = dropout_hash(a.drop_seed, 0, base + 3) < a.drop_thr ? 0.f : v.w * a.drop_scale;
+                }
+                *reinterpret_cast<float4 *>(dst + j) = v;
+            }
+        } else {
+            for (int j = tx * 4; j < H; j += 128) *reinterpret_cast<float4 *>(dst + j) = make_float4(0, 0, 0, 0);
+        }
+    }
+}
+
+template <int UPT>
+__global__ void __launch_bounds__(256) k_lstm_fwd_f32(LstmArgs a)
+{
+    constexpr int H = 32 * UPT, K2 = 2 * H, G4 = 4 * H, AP = K2 + 4;
+    extern __shared__ __align__(16) float smem[];
+    float *As = smem;            // [64][AP]   [x_t | h_{t-1}] per sequence
+    float *Bs = As + 64 * AP;    // [16][G4]   k-chunk of Wp
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    const int64_t p0 = (int64_t)blockIdx.x * 64;
+
+    float c[8][UPT];
+#pragma unroll
+    for (int pp = 0; pp < 8; pp++)
+#pragma unroll
+        for (int u = 0; u < UPT; u++) c[pp][u] = 0.f;
+    // h_0 = 0
+    for (int i = tid; i < 64 * H; i += 256) As[(i / H) * AP + H + (i % H)] = 0.f;
+
+    for (int t = 0; t < a.L; t++) {
+        gather_x_tile<UPT>(a, As, AP, p0, t, ty, tx);
+        float acc[8][UPT][4];
+#pragma unroll
+        for (int u = 0; u < UPT; u++) {
+            const float4 b = *reinterpret_cast<const float4 *>(a.bp + (u * 32 + tx) * 4);
+#pragma unroll
+            for (int pp = 0; pp < 8; pp++) { acc[pp][u][0] = b.x; acc[pp][u][1] = b.y; acc[pp][u][2] = b.z; acc[pp][u][3] = b.w; }
+        }
+        for (int k0 = 0; k0 < K2; k0 += 16) {
+            __syncthreads();  // previous chunk consumed (first pass: gather + h visible)
+            for (int i = tid; i < 16 * G4 / 4; i += 256)
+                reinterpret_cast<float4 *>(Bs)[i] = __ldg(reinterpret_cast<const float4 *>(a.Wp + (int64_t)k0 * G4) + i);
+            __syncthreads();
+#pragma unroll
+            for (int k4 = 0; k4 < 16; k4 += 4) {
+                float4 av[8];
+#pragma unroll
+                for (int pp = 0; pp < 8; pp++) av[pp] = *reinterpret_cast<const float4 *>(As + (ty * 8 + pp) * AP + k0 + k4);
+#pragma unroll
+                for (int kk = 0; kk < 4; kk++) {
+#pragma unroll
+                    for (int u = 0; u < UPT; u++) {
+                        const float4 b = *reinterpret_cast<const float4 *>(Bs + (k4 + kk) * G4 + (u * 32 + tx) * 4);
+#pragma unroll
+                        for (int pp = 0; pp < 8; pp++) {
+                            const float x = kk == 0 ? av[pp].x : kk == 1 ? av[pp].y : kk == 2 ? av[pp].z : av[pp].w;
+                            acc[pp][u][0] = fmaf(x, b.x, acc[pp][u][0]);
+                            acc[pp][u][1] = fmaf(x, b.y, acc[pp][u][1]);
+                            acc[pp][u][2] = fmaf(x, b.z, acc[pp][u][2]);
+                            acc[pp][u][3] = fmaf(x, b.w, acc[pp][u][3]);
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();  // everyone is done reading As before h_t / x_{t+1} overwrite it
+#pragma unroll
+        for (int pp = 0; pp < 8; pp++) {
+            const int row = ty * 8 + pp;
+            const int64_t p = p0 + row;
+#pragma unroll
+            for (int u = 0; u < UPT; u++) {
+                const int unit = u * 32 + tx;
+                const float ig = sigmoidf_(acc[pp][u][0]), fg = sigmoidf_(acc[pp][u][1]);
+                const float gg = tanhf(acc[pp][u][2]), og = sigmoidf_(acc[pp][u][3]);
+                const float cn = fg * c[pp][u] + ig * gg;
+                c[pp][u] = cn;
+                const float h = og * tanhf(cn);
+                As[row * AP + H + unit] = h;
+                if (p < a.P) {
+                    float *act = a.acts + (((int64_t)t * a.P + p) * 5) * H + unit;
+                    act[0] = ig; act[H] = fg; act[2 * H] = gg; act[3 * H] = og; act[4 * H] = cn;
+                    if (t == a.L - 1) a.hfin[p * H + unit] = h;
+                }
+            }
+        }
+        // the k0 = 0 barrier of the next step orders these writes before any read
+    }
+}
+
+// ---------------------------------------------------------------------------
+// LSTM backward (BPTT), fp32 FMA.  Same CTA/thread ownership as forward.
+// Per step: da (pre-activation gate grads) -> smem + global dA; XH row
+// [x_t | h_{t-1}] -> global (weight-grad GEMM operand); [dx | dh_{t-1}] =
+// da . Wp^T; dx scattered into dT with red.global.add.
+// ---------------------------------------------------------------------------
+template <int UPT>
+__global__ void __launch_bounds__(256) k_lstm_bwd_f32(LstmArgs a)
+{
+    constexpr int H = 32 * UPT, K2 = 2 * H, G4 = 4 * H, DP = G4 + 4;
+    constexpr int NQ = K2 / 32;  // outputs per thread per sequence
+    extern __shared__ __align__(16) float smem[];
+    float *Ds = smem;            // [64][DP]  da per sequence, packed columns
+    float *Bs = Ds + 64 * DP;    // [16][K2]  chunk of WpT
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    const int64_t p0 = (int64_t)blockIdx.x * 64;
+
+    float dh[8][UPT], dc[8][UPT];
+#pragma unroll
+    for (int pp = 0; pp < 8; pp++) {
+        const int64_t p = p0 + ty * 8 + pp;
+#pragma unroll
+        for (int u = 0; u < UPT; u++) {
+            dh[pp][u] = p < a.P ? a.dhfin[p * H + u * 32 + tx] : 0.f;
+            dc[pp][u] = 0.f;
+        }
+    }
+    for (int t = a.L - 1; t >= 0; t--) {
+        // ---- gate grads from the saved activations ----
+#pragma unroll
+        for (int pp = 0; pp < 8; pp++) {
+            const int row = ty * 8 + pp;
+            const int64_t p = p0 + row;
+#pragma unroll
+            for (int u = 0; u < UPT; u++) {
+                const int unit = u * 32 + tx;
+                float4 da = make_float4(0, 0, 0, 0);
+                if (p < a.P) {
+                    const float *act = a.acts + (((int64_t)t * a.P + p) * 5) * H + unit;
+                    const float ig = act[0], fg = act[H], gg = act[2 * H], og = act[3 * H], cn = act[4 * H];
+                    float cprev = 0.f, hprev = 0.f;
+                    if (t > 0) {
+                        const float *actp = a.acts + (((int64_t)(t - 1) * a.P + p) * 5) * H + unit;
+                        cprev = actp[4 * H];
+                        hprev = actp[3 * H] * tanhf(cprev);
+                    }
+                    const float tc = tanhf(cn);
+                    const float dcn = dc[pp][u] + dh[pp][u] * og * (1.f - tc * tc);
+                    da.x = dcn * gg * ig * (1.f - ig);          // i
+                    da.y = dcn * cprev * fg * (1.f - fg);       // f
+                    da.z = dcn * ig * (1.f - gg * gg);          // g
+                    da.w = dh[pp][u] * tc * og * (1.f - og);    // o
+                    dc[pp][u] = dcn * fg;
+                    const int64_t r = (int64_t)t * a.P + p;
+                    *reinterpret_cast<float4 *>(a.dA + r * G4 + unit * 4) = da;
+                    a.XH[r * K2 + H + unit] = hprev;
+                }
+                *reinterpret_cast<float4 *>(Ds + row * DP + unit * 4) = da;
+            }
+        }
+        // ---- x_t (regathered, same dropout mask) into XH ----
+#pragma unroll
+        for (int pp = 0; pp < 8; pp++) {
+            const int64_t p = p0 + ty * 8 + pp;
+            if (p < a.P) {
+                const int64_t e = p * a.L + t;
+                const float *src = a.T + ((int64_t)a.seq_node[e] * a.L + a.seq_type[e]) * H;
+                float *dst = a.XH + ((int64_t)t * a.P + p) * K2;
+                for (int j = tx; j < H; j += 32) {
+                    float v = __ldg(src + j);
+                    if (a.drop_thr) v = dropout_hash(a.drop_seed, 0, (uint64_t)e * H + j) < a.drop_thr ? 0.f : v * a.drop_scale;
+                    dst[j] = v;
+                }
+            }
+        }
+        // ---- [dx | dh_prev] = da . WpT ----
+        float acc[8][NQ];
+#pragma unroll
+        for (int pp = 0; pp < 8; pp++)
+#pragma unroll
+            for (int q = 0; q < NQ; q++) acc[pp][q] = 0.f;
+        for (int c0 = 0; c0 < G4; c0 += 16) {
+            __syncthreads();
+            for (int i = tid; i < 16 * K2 / 4; i += 256)
+                reinterpret_cast<float4 *>(Bs)[i] = __ldg(reinterpret_cast<const float4 *>(a.WpT + (int64_t)c0 * K2) + i);
+            __syncthreads();
+#pragma unroll
+            for (int c4 = 0; c4 < 16; c4 += 4) {
+                float4 dv[8];
+#pragma unroll
+                for (int pp = 0; pp < 8; pp++) dv[pp] = *reinterpret_cast<const float4 *>(Ds + (ty * 8 + pp) * DP + c0 + c4);
+#pragma unroll
+                for (int cc = 0; cc < 4; cc++) {
+#pragma unroll
+                    for (int q = 0; q < NQ; q++) {
+                        const float b = Bs[(c4 + cc) * K2 + q * 32 + tx];
+#pragma unroll
+                        for (int pp = 0; pp < 8; pp++) {
+                            const float d = cc == 0 ? dv[pp].x : cc == 1 ? dv[pp].y : cc == 2 ? dv[pp].z : dv[pp].w;
+                            acc[pp][q] = fmaf(d, b, acc[pp][q]);
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();  // Ds free for the next step
+        // ---- consume: dh_{t-1} stays in registers, dx goes to dT ----
+#pragma unroll
+        for (int pp = 0; pp < 8; pp++) {
+            const int64_t p = p0 + ty * 8 + pp;
+#pragma unroll
+            for (int u = 0; u < UPT; u++) dh[pp][u] = acc[pp][UPT + u];
+            if (p < a.P) {
+                const int64_t e = p * a.L + t;
+                float *dst = a.dT + ((int64_t)a.seq_node[e] * a.L + a.seq_type[e]) * H;
+#pragma unroll
+                for (int q = 0; q < UPT; q++) {
+                    const int j = q * 32 + tx;
+                    float v = acc[pp][q];
+                    if (a.drop_thr) v = dropout_hash(a.drop_seed, 0, (uint64_t)e * H + j) < a.drop_thr ? 0.f : v * a.drop_scale;
+                    atomicAdd(dst + j, v);
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// attention + pooling + concat (+ dropout): one warp per output row
+// ---------------------------------------------------------------------------
+struct PoolArgs {
+    int variant, H, nw, L;
+    int64_t S;
+    const float *Z, *T, *hfin;
+    const int32_t *seq_node, *partner, *rows;
+    const uint8_t *seq_type;
+    const float *attw_w, *attw_b;
+    float *score, *att, *cat;
+    uint32_t drop_thr; float drop_scale; uint64_t drop_seed;
+    // backward
+    const float *dcat;   // [S,2H] grad wrt the dropped concat
+    float *dhfin, *dZ, *dT, *dattw;
+};
+
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+__device__ __forceinline__ const float *partner_vec(const PoolArgs &a, int64_t p)
+{
+    if (a.variant == PN_VARIANT_HOMO)  // step-0 table entry, before dropout (:259-260)
+        return a.T + ((int64_t)a.seq_node[p * a.L] * a.L + a.seq_type[p * a.L]) * a.H;
+    return a.Z + (int64_t)a.partner[p] * a.H;  // un-projected root embedding (:199)
+}
+
+__global__ void __launch_bounds__(256) k_pool_fwd(PoolArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t s = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (s >= a.S) return;
+    const int H = a.H, nw = a.nw;
+    const float bias = a.attw_b[0];
+    // raw scores
+    float mx = -INFINITY;
+    for (int w = 0; w < nw; w++) {
+        const int64_t p = s * nw + w;
+        const float *h = a.hfin + p * H, *pv = partner_vec(a, p);
+        float d = 0.f;
+        for (int j = lane; j < H; j += 32) d += a.attw_w[j] * h[j] + a.attw_w[H + j] * pv[j];
+        d = warp_sum(d) + bias;
+        if (lane == 0) a.score[p] = d;
+        const float l = d > 0.f ? d : 0.01f * d;
+        mx = fmaxf(mx, l);
+    }
+    __syncwarp();
+    float denom = 0.f;
+    if (a.variant == PN_VARIANT_HETERO) {
+        for (int w = lane; w < nw; w += 32) {
+            const float d = a.score[s * nw + w];
+            denom += expf((d > 0.f ? d : 0.01f * d) - mx);
+        }
+        denom = warp_sum(denom);
+    }
+    for (int w = lane; w < nw; w += 32) {
+        const int64_t p = s * nw + w;
+        const float d = a.score[p];
+        a.att[p] = a.variant == PN_VARIANT_HETERO ? expf((d > 0.f ? d : 0.01f * d) - mx) / denom : 1.f + d;
+    }
+    __syncwarp();
+    const float inv_nw = 1.f / (float)nw;
+    const int64_t node = a.rows[s];
+    for (int j = lane; j < H; j += 32) {
+        float pooled = 0.f;
+        for (int w = 0; w < nw; w++) pooled += a.att[s * nw + w] * a.hfin[(s * nw + w) * H + j];
+        pooled *= inv_nw;
+        float ego = a.Z[node * H + j];
+        if (a.drop_thr) {
+            ego = dropout_hash(a.drop_seed, 1, (uint64_t)s * 2 * H + j) < a.drop_thr ? 0.f : ego * a.drop_scale;
+            pooled = dropout_hash(a.drop_seed, 1, (uint64_t)s * 2 * H + H + j) < a.drop_thr ? 0.f : pooled * a.drop_scale;
+        }
+        a.cat[s * 2 * H + j] = ego;
+        a.cat[s * 2 * H + H + j] = pooled;
+    }
+}
+
+// backward of the above.  dattw is accumulated per CTA in shared memory.
+__global__ void __launch_bounds__(256) k_pool_bwd(PoolArgs a)
+{
+    extern __shared__ float s_dattw[];  // [2H+1]
+    const int H = a.H, nw = a.nw;
+    for (int i = threadIdx.x; i < 2 * H + 1; i += blockDim.x) s_dattw[i] = 0.f;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t s = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (s < a.S) {
+        const float inv_nw = 1.f / (float)nw;
+        const int64_t node = a.rows[s];
+        // grads wrt the un-dropped concat
+        // da_w = inv_nw * <dpooled, h_w>
+        float dot_sum = 0.f;  // sum_v att_v * da_v (softmax backward), hetero only
+        for (int w = 0; w < nw; w++) {
+            const int64_t p = s * nw + w;
+            float d = 0.f;
+            for (int j = lane; j < H; j += 32) {
+                float g = a.dcat[s * 2 * H + H + j];
+                if (a.drop_thr) g = dropout_hash(a.drop_seed, 1, (uint64_t)s * 2 * H + H + j) < a.drop_thr ? 0.f : g * a.drop_scale;
+                d += g * a.hfin[p * H + j];
+            }
+            d = warp_sum(d) * inv_nw;
+            if (lane == 0) a.dhfin[p * H] = d;  // stash da_w in the (not yet written) dhfin row
+            dot_sum += a.att[p] * d;
+        }
+        __syncwarp();
+        for (int j = lane; j < H; j += 32) {  // ego gradient
+            float g = a.dcat[s * 2 * H + j];
+            if (a.drop_thr) g = dropout_hash(a.drop_seed, 1, (uint64_t)s * 2 * H + j) < a.drop_thr ? 0.f : g * a.drop_scale;
+            atomicAdd(a.dZ + node * H + j, g);
+        }
+        float dbias = 0.f;
+        float dw_h[4] = {0.f, 0.f, 0.f, 0.f}, dw_p[4] = {0.f, 0.f, 0.f, 0.f};  // H <= 128: j = lane + 32q
+        for (int w = 0; w < nw; w++) {
+            const int64_t p = s * nw + w;
+            const float da = a.dhfin[p * H];
+            __syncwarp();
+            const float raw = a.score[p], att = a.att[p];
+            float dscore;
+            if (a.variant == PN_VARIANT_HETERO) {
+                const float dl = att * (da - dot_sum);
+                dscore = dl * (raw > 0.f ? 1.f : 0.01f);
+            } else {
+                dscore = da;  // weight = 1 + score
+            }
+            dbias += dscore;
+            const float *h = a.hfin + p * H, *pv = partner_vec(a, p);
+            float *dpv = a.variant == PN_VARIANT_HOMO
+                             ? a.dT + ((int64_t)a.seq_node[p * a.L] * a.L + a.seq_type[p * a.L]) * H
+                             : a.dZ + (int64_t)a.partner[p] * H;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int j = lane + 32 * q;
+                if (j < H) {
+                    float g = a.dcat[s * 2 * H + H + j];
+                    if (a.drop_thr) g = dropout_hash(a.drop_seed, 1, (uint64_t)s * 2 * H + H + j) < a.drop_thr ? 0.f : g * a.drop_scale;
+                    a.dhfin[p * H + j] = inv_nw * att * g + dscore * a.attw_w[j];
+                    dw_h[q] += dscore * h[j];
+                    dw_p[q] += dscore * pv[j];
+                    atomicAdd(dpv + j, dscore * a.attw_w[H + j]);
+                }
+            }
+            __syncwarp();
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int j = lane + 32 * q;
+            if (j < H) { atomicAdd(&s_dattw[j], dw_h[q]); atomicAdd(&s_dattw[H + j], dw_p[q]); }
+        }
+        if (lane == 0) atomicAdd(&s_dattw[2 * H], dbias);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * H + 1; i += blockDim.x) atomicAdd(a.dattw + i, s_dattw[i]);
+}
+
+// ---------------------------------------------------------------------------
+// host orchestration
+// ---------------------------------------------------------------------------
+static int check_cfg(const pn_pagg_cfg *c)
+{
+    PN_REQUIRE(c != nullptr, "pagg: cfg is NULL");
+    PN_REQUIRE(c->N > 0 && c->F > 0 && c->C > 0 && c->S >= 0 && c->nw > 0 && c->L > 0 && c->L <= 255,
+               "pagg: bad sizes N=%d F=%d C=%d S=%d nw=%d L=%d", c->N, c->F, c->C, c->S, c->nw, c->L);
+    PN_REQUIRE(c->H % 32 == 0 && c->H >= 32 && c->H <= 128,
+               "pagg: hidden size %d unsupported (multiples of 32 up to 128)", c->H);
+    PN_REQUIRE(c->variant == PN_VARIANT_HETERO || c->variant == PN_VARIANT_HOMO, "pagg: bad variant %d", c->variant);
+    PN_REQUIRE(c->math_mode == PN_MATH_FP32 || c->math_mode == PN_MATH_TC, "pagg: bad math_mode %d", c->math_mode);
+    PN_REQUIRE(c->dropout_p >= 0.f && c->dropout_p <= 1.f, "pagg: dropout p=%f outside [0,1]", (double)c->dropout_p);
+    return PN_OK;
+}
+
+static void drop_params(const pn_pagg_cfg &c, uint32_t &thr, float &scale)
+{
+    thr = 0; scale = 1.f;
+    if (c.training && c.dropout_p > 0.f) {
+        thr = dropout_threshold(c.dropout_p);
+        scale = c.dropout_p >= 1.f ? 0.f : 1.f / (1.f - c.dropout_p);
+    }
+}
+
+template <int UPT>
+static int launch_lstm_fwd(const LstmArgs &a, cudaStream_t st)
+{
+    constexpr int H = 32 * UPT;
+    const size_t smem = sizeof(float) * (64 * (2 * H + 4) + 16 * 4 * H);
+    PN_CUDA(cudaFuncSetAttribute(k_lstm_fwd_f32<UPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ProfScope prof("lstm_fwd", st);
+    k_lstm_fwd_f32<UPT><<<(unsigned)ceil_div(a.P, 64), 256, smem, st>>>(a);
+    PN_LAUNCH_CHECK();
+    return PN_OK;
+}
+template <int UPT>
+static int launch_lstm_bwd(const LstmArgs &a, cudaStream_t st)
+{
+    constexpr int H = 32 * UPT;
+    const size_t smem = sizeof(float) * (64 * (4 * H + 4) + 16 * 2 * H);
+    PN_CUDA(cudaFuncSetAttribute(k_lstm_bwd_f32<UPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ProfScope prof("lstm_bwd", st);
+    k_lstm_bwd_f32<UPT><<<(unsigned)ceil_div(a.P, 64), 256, smem, st>>>(a);
+    PN_LAUNCH_CHECK();
+    return PN_OK;
+}
+
+int pagg_tc_forward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_params &prm,
+                         const int32_t *seq_node, const uint8_t *seq_type, cudaStream_t st);  // pagg_tc.cu
+
+}  // namespace pn
+
+using namespace pn;
+
+extern "C" int pn_pagg_canonicalize(int32_t variant, int32_t S, int32_t nw, int32_t L,
+                                    const int64_t *neis, const int64_t *layer_type,
+                                    int32_t *seq_node, uint8_t *seq_type, int32_t *partner,
+                                    void *stream)
+{
+    PN_REQUIRE(variant == PN_VARIANT_HETERO || variant == PN_VARIANT_HOMO, "canonicalize: bad variant %d", variant);
+    PN_REQUIRE(S >= 0 && nw > 0 && L > 0, "canonicalize: bad sizes S=%d nw=%d L=%d", S, nw, L);
+    if (S == 0) return PN_OK;
+    PN_REQUIRE(neis && layer_type && seq_node && seq_type && partner, "canonicalize: NULL pointer");
+    const int64_t total = (int64_t)S * nw * L;
+    k_canonicalize<<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        variant, S, nw, L, neis, layer_type, seq_node, seq_type, partner);
+    PN_LAUNCH_CHECK();
+    return PN_OK;
+}
+
+extern "C" size_t pn_pagg_workspace_bytes(const pn_pagg_cfg *cfg)
+{
+    if (check_cfg(cfg) != PN_OK) return 0;
+    return carve_workspace(*cfg, nullptr).bytes + 256;
+}
+
+extern "C" int pn_pagg_forward(const pn_pagg_cfg *cfg, const pn_pagg_params *prm, const float *X,
+                               const int32_t *seq_node, const uint8_t *seq_type,
+                               const int32_t *partner, const int32_t *rows, void *workspace,
+                               float *logits, void *stream)
+{
+    int rc = check_cfg(cfg);
+    if (rc != PN_OK) return rc;
+    const pn_pagg_cfg &c = *cfg;
+    PN_REQUIRE(prm && X && workspace, "pagg_forward: NULL pointer");
+    if (c.S == 0) return PN_OK;
+    PN_REQUIRE(seq_node && seq_type && partner && rows && logits, "pagg_forward: NULL pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const PaggWs w = carve_workspace(c, (void *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255));
+    const int64_t N = c.N, F = c.F, H = c.H, L = c.L, S = c.S, P = (int64_t)c.S * c.nw;
+    const bool homo = c.variant == PN_VARIANT_HOMO;
+    uint32_t thr; float scale;
+    drop_params(c, thr, scale);
+
+    // K0: Z = act(X W0^T + b0)                                     (:175 / :242-243)
+    rc = launch_gemm(st, X, F, 1, prm->fc0_w, 1, F, w.Z, H, N, H, F, prm->fc0_b, homo, false);
+    if (rc) return rc;
+    // K1: T[n, d*H + j] = act(Z nets_w[d]^T + nets_b[d])           (:185-191 / :249-257, hoisted)
+    rc = launch_gemm(st, w.Z, H, 1, prm->nets_w, 1, H, w.T, L * H, N, L * H, H, prm->nets_b, homo, false);
+    if (rc) return rc;
+    k_pack_lstm<<<(unsigned)ceil_div(2 * H * 4 * H, 256), 256, 0, st>>>((int)H, prm->w_ih, prm->w_hh, prm->b_ih,
+                                                                      prm->b_hh, w.Wp, w.WpT, w.bp);
+    PN_LAUNCH_CHECK();
+    // K2: gather + dropout + LSTM                                  (:194-195 / :264-265)
+    LstmArgs la{};
+    la.T = w.T; la.seq_node = seq_node; la.seq_type = seq_type; la.Wp = w.Wp; la.WpT = w.WpT; la.bp = w.bp;
+    la.acts = w.acts; la.hfin = w.hfin; la.P = P; la.L = (int)L;
+    la.drop_thr = thr; la.drop_scale = scale; la.drop_seed = c.dropout_seed;
+    if (c.math_mode == PN_MATH_TC) {
+        rc = pagg_tc_forward_lstm(c, w, *prm, seq_node, seq_type, st);
+    } else {
+        switch (H / 32) {
+            case 1: rc = launch_lstm_fwd<1>(la, st); break;
+            case 2: rc = launch_lstm_fwd<2>(la, st); break;
+            case 3: rc = launch_lstm_fwd<3>(la, st); break;
+            default: rc = launch_lstm_fwd<4>(la, st); break;
+        }
+    }
+    if (rc) return rc;
+    // K3: attention + pool + concat + dropout                      (:196-209 / :266-276)
+    PoolArgs pa{};
+    pa.variant = c.variant; pa.H = (int)H; pa.nw = c.nw; pa.L = (int)L; pa.S = S;
+    pa.Z = w.Z; pa.T = w.T; pa.hfin = w.hfin; pa.seq_node = seq_node; pa.partner = partner; pa.rows = rows;
+    pa.seq_type = seq_type; pa.attw_w = prm->attw_w; pa.attw_b = prm->attw_b;
+    pa.score = w.score; pa.att = w.att; pa.cat = w.cat;
+    pa.drop_thr = thr; pa.drop_scale = scale; pa.drop_seed = c.dropout_seed;
+    k_pool_fwd<<<(unsigned)ceil_div(S, 8), 256, 0, st>>>(pa);
+    PN_LAUNCH_CHECK();
+    // K4: logits = cat fc2_w^T + fc2_b                             (:210 / :277)
+    return launch_gemm(st, w.cat, 2 * H, 1, prm->fc2_w, 1, 2 * H, logits, c.C, S, c.C, 2 * H, prm->fc2_b, false, false);
+}
+
+extern "C" int pn_pagg_backward(const pn_pagg_cfg *cfg, const pn_pagg_params *prm, const float *X,
+                                const int32_t *seq_node, const uint8_t *seq_type,
+                                const int32_t *partner, const int32_t *rows, void *workspace,
+                                const float *dlogits, const pn_pagg_params *grads, void *stream)
+{
+    int rc = check_cfg(cfg);
+    if (rc != PN_OK) return rc;
+    const pn_pagg_cfg &c = *cfg;
+    PN_REQUIRE(prm && X && workspace && grads, "pagg_backward: NULL pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const PaggWs w = carve_workspace(c, (void *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255));
+    const int64_t N = c.N, F = c.F, H = c.H, L = c.L, S = c.S, C = c.C, P = (int64_t)c.S * c.nw;
+    const bool homo = c.variant == PN_VARIANT_HOMO;
+    uint32_t thr; float scale;
+    drop_params(c, thr, scale);
+    const pn_pagg_params &g = *grads;
+#define ZERO(ptr, n) PN_CUDA(cudaMemsetAsync((ptr), 0, sizeof(float) * (size_t)(n), st))
+    if (S == 0) {  // no rows: every gradient is zero
+        ZERO(g.fc0_w, H * F); ZERO(g.fc0_b, H); ZERO(g.nets_w, L * H * H); ZERO(g.nets_b, L * H);
+        ZERO(g.w_ih, 4 * H * H); ZERO(g.w_hh, 4 * H * H); ZERO(g.b_ih, 4 * H); ZERO(g.b_hh, 4 * H);
+        ZERO(g.attw_w, 2 * H); ZERO(g.attw_b, 1); ZERO(g.fc2_w, C * 2 * H); ZERO(g.fc2_b, C);
+        return PN_OK;
+    }
+    PN_REQUIRE(seq_node && seq_type && partner && rows && dlogits, "pagg_backward: NULL pointer");
+    // ---- fc2 ----
+    rc = launch_gemm(st, dlogits, 1, C, w.cat, 2 * H, 1, g.fc2_w, 2 * H, C, 2 * H, S, nullptr, false, false);  // dW2 = dY^T cat
+    if (rc) return rc;
+    rc = launch_colsum(st, dlogits, S, C, C, g.fc2_b);
+    if (rc) return rc;
+    rc = launch_gemm(st, dlogits, C, 1, prm->fc2_w, 2 * H, 1, w.dcat, 2 * H, S, 2 * H, C, nullptr, false, false);  // dcat = dY W2
+    if (rc) return rc;
+    // ---- attention / pooling ----
+    ZERO(w.dZ, N * H); ZERO(w.dT, N * L * H); ZERO(w.dattw, 2 * H + 1);
+    PoolArgs pa{};
+    pa.variant = c.variant; pa.H = (int)H; pa.nw = c.nw; pa.L = (int)L; pa.S = S;
+    pa.Z = w.Z; pa.T = w.T; pa.hfin = w.hfin; pa.seq_node = seq_node; pa.partner = partner; pa.rows = rows;
+    pa.seq_type = seq_type; pa.attw_w = prm->attw_w; pa.attw_b = prm->attw_b;
+    pa.score = w.score; pa.att = w.att; pa.cat = w.cat;
+    pa.drop_thr = thr; pa.drop_scale = scale; pa.drop_seed = c.dropout_seed;
+    pa.dcat = w.dcat; pa.dhfin = w.dhfin; pa.dZ = w.dZ; pa.dT = w.dT; pa.dattw = w.dattw;
+    k_pool_bwd<<<(unsigned)ceil_div(S, 8), 256, sizeof(float) * (2 * H + 1), st>>>(pa);
+    PN_LAUNCH_CHECK();
+    PN_CUDA(cudaMemcpyAsync(g.attw_w, w.dattw, sizeof(float) * 2 * H, cudaMemcpyDeviceToDevice, st));
+    PN_CUDA(cudaMemcpyAsync(g.attw_b, w.dattw + 2 * H, sizeof(float), cudaMemcpyDeviceToDevice, st));
+    // ---- LSTM BPTT ----
+    LstmArgs la{};
+    la.T = w.T; la.seq_node = seq_node; la.seq_type = seq_type; la.Wp = w.Wp; la.WpT = w.WpT; la.bp = w.bp;
+    la.acts = w.acts; la.hfin = w.hfin; la.P = P; la.L = (int)L;
+    la.drop_thr = thr; la.drop_scale = scale; la.drop_seed = c.dropout_seed;
+    la.dhfin = w.dhfin; la.dT = w.dT; la.dA = w.dA; la.XH = w.XH;
+    switch (H / 32) {
+        case 1: rc = launch_lstm_bwd<1>(la, st); break;
+        case 2: rc = launch_lstm_bwd<2>(la, st); break;
+        case 3: rc = launch_lstm_bwd<3>(la, st); break;
+        default: rc = launch_lstm_bwd<4>(la, st); break;
+    }
+    if (rc) return rc;
+    // dWp[k][col] = sum_r XH[r][k] dA[r][col];  dbp = colsum(dA)
+    ZERO(w.dWp, 2 * H * 4 * H);
+    {
+        const int64_t R = L * P;
+        int splitk = (int)std::max<int64_t>(1, std::min<int64_t>(256, R / 2048));
+        {
+            ProfScope prof("wgrad", st);
+            rc = launch_gemm(st, w.XH, 1, 2 * H, w.dA, 4 * H, 1, w.dWp, 4 * H, 2 * H, 4 * H, R, nullptr, false, false, splitk);
+        }
+        if (rc) return rc;
+        rc = launch_colsum(st, w.dA, R, 4 * H, 4 * H, w.dbp);
+        if (rc) return rc;
+    }
+    k_unpack_lstm_grads<<<(unsigned)ceil_div(4 * H * H, 256), 256, 0, st>>>((int)H, w.dWp, w.dbp, g.w_ih, g.w_hh, g.b_ih, g.b_hh);
+    PN_LAUNCH_CHECK();
+    // ---- table projection: T = act(Z Wn^T + bn) ----
+    if (homo) {
+        k_relu_mask<<<(unsigned)ceil_div(N * L * H, 256), 256, 0, st>>>(w.dT, w.T, N * L * H);
+        PN_LAUNCH_CHECK();
+    }
+    {
+        int splitk = (int)std::max<int64_t>(1, std::min<int64_t>(64, N / 1024));
+        if (splitk > 1) ZERO(g.nets_w, L * H * H);
+        rc = launch_gemm(st, w.dT, 1, L * H, w.Z, H, 1, g.nets_w, H, L * H, H, N, nullptr, false, false, splitk);  // dWn = dT^T Z
+        if (rc) return rc;
+    }
+    rc = launch_colsum(st, w.dT, N, L * H, L * H, g.nets_b);
+    if (rc) return rc;
+    rc = launch_gemm(st, w.dT, L * H, 1, prm->nets_w, H, 1, w.dZ, H, N, H, L * H, nullptr, false, true);  // dZ += dT Wn
+    if (rc) return rc;
+    // ---- fc0: Z = act(X W0^T + b0) ----
+    if (homo) {
+        k_relu_mask<<<(unsigned)ceil_div(N * H, 256), 256, 0, st>>>(w.dZ, w.Z, N * H);
+        PN_LAUNCH_CHECK();
+    }
+    {
+        int splitk = (int)std::max<int64_t>(1, std::min<int64_t>(64, N / 1024));
+        if (splitk > 1) ZERO(g.fc0_w, H * F);
+        rc = launch_gemm(st, w.dZ, 1, H, X, F, 1, g.fc0_w, F, H, F, N, nullptr, false, false, splitk);  // dW0 = dZ^T X
+        if (rc) return rc;
+    }
+    rc = launch_colsum(st, w.dZ, N, H, H, g.fc0_b);
+#undef ZERO
+    return rc;
+}

@@ -1,0 +1,246 @@
+"""GPU parity tests of the PAGG operator through the C ABI.
+
+Tolerances (fp32 CUDA-core mode): the reference math is fp32 on CPU (MKL
+summation order); ours is fp32 FMA in a different order, so logits are held to
+rtol 1e-4 / atol 2e-5 and gradients to rtol 2e-3 / atol 2e-5 (gradients reach
+parameters through atomics whose order varies run to run)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pagg_oracle as po
+from pathnet_b200 import _lib, pagg
+from tests.conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+FWD_TOL = dict(rtol=1e-4, atol=2e-5)
+GRAD_TOL = dict(rtol=2e-3, atol=2e-5)
+
+
+def _fixture(path):
+    z = np.load(path)
+    params = {k[6:]: torch.tensor(z[k].astype(np.float32)) for k in z.files if k.startswith("param:")}
+    grads = {k[5:]: torch.tensor(z[k]) for k in z.files if k.startswith("grad:")}
+    return z, params, grads
+
+
+def _module_for(variant, F, H, Cc, L, params, **kw):
+    cls = pagg.PathNet if variant == "hetero" else pagg.PathNet_homo
+    m = cls(F, H, Cc, L, **kw)
+    m.load_state_dict(params)
+    return m.to(DEV)
+
+
+PAGG_FIXTURES = sorted(GOLDEN.glob("pagg_*.npz"))
+
+
+@pytest.mark.parametrize("path", PAGG_FIXTURES, ids=lambda p: p.stem)
+def test_module_matches_reference_fixture(path):
+    """Logits and every parameter gradient against what the reference's own
+    classes produced (tests/golden/make_pagg_golden.py)."""
+    z, params, grads = _fixture(path)
+    variant, nw, L = str(z["variant"]), int(z["nw"]), int(z["L"])
+    m = _module_for(variant, int(z["F"]), int(z["H"]), int(z["C"]), L, params).eval()
+    X = torch.tensor(z["X"].astype(np.float32), device=DEV)
+    neis = torch.tensor(z["neis"].astype(np.int64))            # CPU int64, as the reference passes them
+    lt = torch.tensor(z["layer_type"].astype(np.int64))
+    S = int(z["S"])
+    y = m(X, neis, nw, L, z["mask"], lt, torch.arange(S * nw * L, device=DEV))
+    torch.testing.assert_close(y.cpu(), torch.tensor(z["logits"]), **FWD_TOL)
+    (y * torch.tensor(z["G"].astype(np.float32), device=DEV)).sum().backward()
+    for k, p in m.named_parameters():
+        torch.testing.assert_close(p.grad.cpu(), grads[k], **GRAD_TOL, msg=lambda s: f"{k}: {s}")
+
+
+def test_state_dict_surface_matches_reference_checkpoint_keys():
+    m = pagg.PathNet(1703, 128, 5, 4)
+    want = {"fc0.weight": (128, 1703), "fc0.bias": (128,), "LSTM.weight_ih_l0": (512, 128),
+            "LSTM.weight_hh_l0": (512, 128), "LSTM.bias_ih_l0": (512,), "LSTM.bias_hh_l0": (512,),
+            "fc2.weight": (5, 256), "fc2.bias": (5,), "attw.weight": (1, 256), "attw.bias": (1,)}
+    for d in range(4):
+        want[f"nets.{d}.weight"] = (128, 128)
+        want[f"nets.{d}.bias"] = (128,)
+    got = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert got == want
+
+
+@pytest.mark.parametrize("variant", ["hetero", "homo"])
+@pytest.mark.parametrize("S,nw,L", [(1, 1, 1), (7, 3, 2), (23, 7, 5), (64, 40, 4), (65, 2, 6)])
+def test_canonicalize_matches_oracle(variant, S, nw, L):
+    g = torch.Generator().manual_seed(S * 100 + nw)
+    neis = torch.randint(0, 1000, (S, nw * L), generator=g)
+    lt = torch.randint(0, L, (S, nw, L), generator=g)
+    sn, st, pt = pagg.canonicalize(variant, neis.to(DEV), lt.to(DEV), nw, L)
+    o_sn, o_st, o_pt = po.canonicalize(variant, neis.numpy(), lt.numpy(), nw, L)
+    assert (sn.cpu().numpy() == o_sn).all() and (st.cpu().numpy() == o_st).all()
+    assert (pt.cpu().numpy() == o_pt).all()
+
+
+def _random_case(variant, N, Fd, H, Cc, nw, L, S, seed):
+    g = torch.Generator().manual_seed(seed)
+    torch.manual_seed(seed)
+    cls = pagg.PathNet if variant == "hetero" else pagg.PathNet_homo
+    m = cls(Fd, H, Cc, L)
+    X = torch.randn(N, Fd, generator=g)
+    mask = torch.zeros(N, dtype=torch.bool)
+    mask[torch.randperm(N, generator=g)[:S]] = True
+    neis = torch.randint(0, N, (S, nw * L), generator=g)
+    lt = torch.randint(0, L, (S, nw, L), generator=g)
+    return m, X, mask, neis, lt
+
+
+def _oracle_run(variant, m, X, mask, neis, lt, nw, L, G, mask_seq=None, mask_cat=None, dtype=torch.float64):
+    params = {k: v.detach().clone().to(dtype).requires_grad_(True) for k, v in m.state_dict().items()}
+    y = po.pagg_forward(variant, params, X.to(dtype), neis, nw, L, mask, lt,
+                        mask_seq=mask_seq, mask_cat=mask_cat)
+    (y * G.to(dtype)).sum().backward()
+    return y.detach().float(), {k: p.grad.float() for k, p in params.items()}
+
+
+@pytest.mark.parametrize("variant", ["hetero", "homo"])
+@pytest.mark.parametrize("N,Fd,H,Cc,nw,L,S", [
+    (40, 9, 32, 3, 3, 2, 5),        # tiny
+    (183, 50, 128, 5, 40, 4, 87),   # cornell-shaped train step (S, nw, L, H as configs[0])
+    (300, 33, 64, 7, 5, 6, 129),    # L = 6 (bgp), S not a multiple of the 64-sequence tile
+    (97, 17, 96, 2, 1, 3, 64),      # nw = 1, H = 96
+])
+def test_forward_backward_match_oracle_eval(variant, N, Fd, H, Cc, nw, L, S):
+    m, X, mask, neis, lt = _random_case(variant, N, Fd, H, Cc, nw, L, S, seed=N + S)
+    G = torch.randn(S, Cc)
+    y_ref, g_ref = _oracle_run(variant, m, X, mask, neis, lt, nw, L, G)
+    m = m.to(DEV).eval()
+    y = m(X.to(DEV), neis, nw, L, mask, lt, None)
+    torch.testing.assert_close(y.cpu(), y_ref, **FWD_TOL)
+    (y * G.to(DEV)).sum().backward()
+    for k, p in m.named_parameters():
+        torch.testing.assert_close(p.grad.cpu(), g_ref[k], **GRAD_TOL, msg=lambda s: f"{k}: {s}")
+
+
+def _np_fmix32(h):
+    h = h.astype(np.uint64)
+    h ^= h >> np.uint64(16); h = (h * np.uint64(0x85ebca6b)) & np.uint64(0xFFFFFFFF)
+    h ^= h >> np.uint64(13); h = (h * np.uint64(0xc2b2ae35)) & np.uint64(0xFFFFFFFF)
+    h ^= h >> np.uint64(16)
+    return h
+
+
+def np_dropout_hash(seed, stream_id, idx):
+    """numpy restatement of csrc/dropout_hash.h (checked against pn_dropout_hash below)"""
+    idx = idx.astype(np.uint64)
+    lo, hi = idx & np.uint64(0xFFFFFFFF), idx >> np.uint64(32)
+    h = _np_fmix32(lo ^ np.uint64(seed & 0xFFFFFFFF))
+    h = _np_fmix32(h ^ ((hi * np.uint64(0x9e3779b9)) & np.uint64(0xFFFFFFFF)) ^ np.uint64((seed >> 32) & 0xFFFFFFFF)
+                   ^ np.uint64((stream_id * 0x7f4a7c15) & 0xFFFFFFFF))
+    return _np_fmix32((h + np.uint64(0x6a09e667)) & np.uint64(0xFFFFFFFF))
+
+
+def test_dropout_hash_host_function_matches_numpy():
+    L_ = _lib.lib()
+    idx = np.array([0, 1, 2, 12345, 2 ** 32 - 1, 2 ** 32, 2 ** 40 + 17], dtype=np.uint64)
+    for seed in (0, 1, 0x123456789ABCDEF):
+        for sid in (0, 1):
+            want = [L_.pn_dropout_hash(seed, sid, int(i)) for i in idx]
+            assert np_dropout_hash(seed, sid, idx).tolist() == want
+
+
+@pytest.mark.parametrize("variant", ["hetero", "homo"])
+def test_training_mode_with_identical_dropout_masks(variant):
+    """train(): the kernels' counter-based masks are recomputed on the host and
+    handed to the oracle, so forward and every gradient can be compared exactly
+    as in eval mode (the reference's own Philox masks are not reproducible)."""
+    N, Fd, H, Cc, nw, L, S, p, seed = 120, 21, 64, 4, 6, 4, 37, 0.7, 0x5EED5EED1234
+    m, X, mask, neis, lt = _random_case(variant, N, Fd, H, Cc, nw, L, S, seed=5)
+    thr = int(p * 2 ** 32)
+    scale = 1.0 / (1.0 - p)
+    keep_seq = np_dropout_hash(seed, 0, np.arange(S * nw * L * H, dtype=np.uint64)) >= thr
+    keep_cat = np_dropout_hash(seed, 1, np.arange(S * 2 * H, dtype=np.uint64)) >= thr
+    mask_seq_can = torch.tensor(keep_seq.reshape(S, nw, L, H).astype(np.float64) * scale)
+    mask_cat = torch.tensor(keep_cat.reshape(S, 2 * H).astype(np.float64) * scale)
+    # canonical-order oracle (mask layout [S, nw, L, H])
+    sn, st, pt = po.canonicalize(variant, neis.numpy(), lt.numpy(), nw, L)
+    rows = torch.nonzero(mask).reshape(-1).numpy()
+    params = {k: v.detach().clone().double().requires_grad_(True) for k, v in m.state_dict().items()}
+    y_ref = po.pagg_forward_canonical(variant, params, X.double(), sn, st, pt, rows,
+                                      mask_seq=mask_seq_can, mask_cat=mask_cat)
+    G = torch.randn(S, Cc)
+    (y_ref * G.double()).sum().backward()
+    m = m.to(DEV).train()
+    m.dropout = p
+    dev = lambda a, dt: torch.tensor(a, device=DEV, dtype=dt)
+    sd = dict(m.named_parameters())
+    y = pagg.pagg_forward(variant, X.to(DEV), sd, dev(sn, torch.int32), dev(st, torch.uint8),
+                          dev(pt, torch.int32), dev(rows, torch.int32), dropout=p, training=True, seed=seed)
+    torch.testing.assert_close(y.cpu(), y_ref.detach().float(), **FWD_TOL)
+    (y * G.to(DEV)).sum().backward()
+    for k, pr in m.named_parameters():
+        torch.testing.assert_close(pr.grad.cpu(), params[k].grad.float(), **GRAD_TOL, msg=lambda s: f"{k}: {s}")
+    # and the drop rate is what was asked for
+    assert abs(1.0 - keep_seq.mean() - p) < 0.01
+
+
+def test_module_train_mode_statistics_and_determinism():
+    torch.manual_seed(0)
+    m, X, mask, neis, lt = _random_case("homo", 200, 16, 64, 3, 8, 4, 90, seed=1)
+    m = m.to(DEV)
+    m.dropout = 0.5
+    m.train()
+    torch.manual_seed(11); y1 = m(X.to(DEV), neis, 8, 4, mask, lt, None)
+    torch.manual_seed(11); y2 = m(X.to(DEV), neis, 8, 4, mask, lt, None)
+    torch.manual_seed(12); y3 = m(X.to(DEV), neis, 8, 4, mask, lt, None)
+    assert torch.equal(y1, y2) and not torch.equal(y1, y3)
+    m.eval()
+    ye = m(X.to(DEV), neis, 8, 4, mask, lt, None)
+    assert torch.equal(ye, m(X.to(DEV), neis, 8, 4, mask, lt, None))
+    # E[dropout(x)] = x: averaged train outputs approach eval outputs only for the
+    # linear tail, so just require finite, different, same-shaped results
+    assert torch.isfinite(y1).all() and y1.shape == ye.shape and not torch.equal(y1, ye)
+
+
+def test_rows_are_independent_at_pubmed_scale():
+    """Size-independent property at BASELINE scale (pubmed: N = 19 717, F = 500,
+    H = 128, nw = 40, L = 4, S = 9 463): output rows only depend on their own
+    sequences, so evaluating two halves of the rows separately reproduces the
+    full call (what the multi-GPU row sharding relies on), and parameter
+    gradients of the halves add up to the full gradient."""
+    N, Fd, H, Cc, nw, L, S = 19717, 500, 128, 3, 40, 4, 9463
+    m, X, mask, neis, lt = _random_case("homo", N, Fd, H, Cc, nw, L, S, seed=3)
+    m = m.to(DEV).eval()
+    Xd = X.to(DEV)
+    y = m(Xd, neis, nw, L, mask, lt, None)
+    G = torch.randn(S, Cc, device=DEV)
+    (y * G).sum().backward()
+    full = {k: p.grad.clone() for k, p in m.named_parameters()}
+    m.zero_grad()
+    rows = torch.nonzero(mask).reshape(-1)
+    h = S // 2 + 1
+    parts = []
+    for lo, hi in ((0, h), (h, S)):
+        mk = torch.zeros(N, dtype=torch.bool)
+        mk[rows[lo:hi]] = True
+        yp = m(Xd, neis[lo:hi], nw, L, mk, lt[lo:hi], None)
+        (yp * G[lo:hi]).sum().backward()
+        parts.append(yp)
+    torch.testing.assert_close(torch.cat(parts), y, rtol=1e-5, atol=1e-6)
+    for k, p in m.named_parameters():
+        torch.testing.assert_close(p.grad, full[k], rtol=5e-3, atol=1e-4, msg=lambda s: f"{k}: {s}")
+
+
+def test_empty_and_error_cases():
+    m = pagg.PathNet_homo(8, 32, 3, 2).to(DEV).eval()
+    X = torch.randn(10, 8, device=DEV)
+    y = m(X, torch.zeros((0, 6), dtype=torch.int64), 3, 2, np.zeros(10, dtype=bool),
+          torch.zeros((0, 3, 2), dtype=torch.int64), None)
+    assert y.shape == (0, 3)
+    with pytest.raises(ValueError):
+        m(X, torch.zeros((2, 6), dtype=torch.int64), 3, 2, np.zeros(10, dtype=bool),
+          torch.zeros((2, 3, 2), dtype=torch.int64), None)
+    with pytest.raises(RuntimeError):
+        pagg.PathNet_homo(8, 32, 3, 2)(X.cpu(), torch.zeros((1, 6), dtype=torch.int64), 3, 2,
+                                       np.ones(10, dtype=bool), torch.zeros((1, 3, 2), dtype=torch.int64), None)
+    bad = pagg.PathNet_homo(8, 48, 3, 2).to(DEV)   # H not a multiple of 32
+    mk = np.zeros(10, dtype=bool); mk[0] = True
+    with pytest.raises(_lib.PnError):
+        bad(X, torch.zeros((1, 6), dtype=torch.int64), 3, 2, mk, torch.zeros((1, 3, 2), dtype=torch.int64), None)

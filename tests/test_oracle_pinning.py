@@ -1,0 +1,143 @@
+"""Pins the oracles (test infrastructure) to the reference: committed golden
+fixtures produced by the reference's own code always; the live reference
+binary / classes when /root/reference is mounted (authoring container)."""
+import ctypes
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import merw_oracle as mo
+from oracle import pagg_oracle as po
+from tests.conftest import GOLDEN, REFERENCE
+from tests.helpers import load_graph, messy_graph, ref_hashes, sha256
+
+
+# ------------------------------------------------------------------ sampler --
+def test_glibc_rand_restatement_matches_libc():
+    libc = ctypes.CDLL("libc.so.6")
+    for seed in (12345, 1, 0, 777, 2 ** 31 + 5, 2 ** 32 - 1):
+        libc.srand(ctypes.c_uint(seed))
+        ref = [libc.rand() for _ in range(3000)]
+        assert mo.rand_stream(seed, 3000).tolist() == ref
+        assert mo.rand_stream_at(seed, 1234, 16) == ref[1234:1250]
+    assert mo.rand_stream(12345, 2).tolist() == [383100999, 858300821]  # SURVEY Appendix D anchor
+
+
+@pytest.mark.parametrize("key", [k for k in ref_hashes() if k.split("|")[0] in ("cornell", "cora")])
+def test_sampler_oracle_matches_reference_hashes(key):
+    name, nw, L, seed, epochs = key.split("|")
+    nw, L, seed, epochs = (int(x.split("=")[1]) for x in (nw, L, seed, epochs))
+    g = mo.OracleGraph(*load_graph(name))
+    nodes, types = g.sample(nw, L, seed, 0, epochs)
+    txt = mo.format_txt(nodes, types)
+    want = ref_hashes()[key]
+    assert len(txt) == want["bytes"] and sha256(txt) == want["sha256"]
+
+
+def test_sampler_oracle_matches_parsed_fixture():
+    z = np.load(GOLDEN / "merw_cornell_40_4_s12345_e0.npz")
+    nodes, types = mo.OracleGraph(*load_graph("cornell")).sample(40, 4, 12345, 0, 1)
+    assert (nodes[0] == z["nodes"]).all() and (types[0] == z["types"]).all()
+    assert nodes[0, 0, :3].tolist() == [[0, 48, 70, 70], [0, 0, 146, 89], [0, 52, 48, 77]]
+
+
+def test_sampler_oracle_epoch_skip_is_consistent():
+    g = mo.OracleGraph(*load_graph("cornell"))
+    full, tf = g.sample(7, 3, 99, 0, 3)
+    part, tp = g.sample(7, 3, 99, 2, 3)
+    assert (full[2:] == part).all() and (tf[2:] == tp).all()
+
+
+@pytest.mark.slow
+@pytest.mark.parametrize("name", ["citeseer", "pubmed", "Nba", "Electronics", "bgp"])
+def test_sampler_oracle_matches_reference_hashes_big_graphs(name, have_reference):
+    if not have_reference:
+        pytest.skip("needs /root/reference/edge_input")
+    keys = [k for k in ref_hashes() if k.split("|")[0] == name]
+    if not keys:
+        pytest.skip("no committed hash for " + name)
+    n, u, v, p = mo.read_edge_input(REFERENCE / "edge_input" / f"{name}.in")
+    g = mo.OracleGraph(n, u, v, p)
+    for key in keys:
+        _, nw, L, seed, epochs = key.split("|")
+        nw, L, seed, epochs = (int(x.split("=")[1]) for x in (nw, L, seed, epochs))
+        nodes, types = g.sample(nw, L, seed, 0, epochs)
+        txt = mo.format_txt(nodes, types)
+        assert sha256(txt) == ref_hashes()[key]["sha256"], key
+
+
+def test_sampler_oracle_matches_live_reference_binary_on_messy_graph(tmp_path):
+    """The reference binary travels (oracle/_ref); run it on a synthetic graph
+    with negative/zero p, duplicates, hubs, self loops."""
+    if not mo.have_ref():
+        pytest.skip("oracle/_ref not built")
+    n, u, v, p = messy_graph(400, 6, 11)
+    f = tmp_path / "messy.in"
+    mo.write_edge_input(f, n, u, v, p)
+    n2, u2, v2, p2 = mo.read_edge_input(f)
+    assert (p2 == p).all()
+    txt = mo.run_reference(f, 9, 5, 31337, epochs=1, name="messy")
+    nodes, types = mo.OracleGraph(n, u, v, p).sample(9, 5, 31337, 0, 1)
+    assert mo.format_txt(nodes, types) == txt
+
+
+# --------------------------------------------------------------------- PAGG --
+def _load_pagg(path):
+    z = np.load(path)
+    params = {k[6:]: torch.tensor(z[k].astype(np.float32)) for k in z.files if k.startswith("param:")}
+    grads = {k[5:]: torch.tensor(z[k]) for k in z.files if k.startswith("grad:")}
+    return z, params, grads
+
+
+PAGG_FIXTURES = sorted(GOLDEN.glob("pagg_*.npz"))
+
+
+@pytest.mark.parametrize("path", PAGG_FIXTURES, ids=lambda p: p.stem)
+def test_pagg_oracle_matches_reference_fixture(path):
+    z, params, grads = _load_pagg(path)
+    variant, nw, L = str(z["variant"]), int(z["nw"]), int(z["L"])
+    for p in params.values():
+        p.requires_grad_(True)
+    X = torch.tensor(z["X"].astype(np.float32))
+    neis = torch.tensor(z["neis"].astype(np.int64))
+    lt = torch.tensor(z["layer_type"].astype(np.int64))
+    mask = torch.tensor(z["mask"])
+    y = po.pagg_forward(variant, params, X, neis, nw, L, mask, lt)
+    torch.testing.assert_close(y, torch.tensor(z["logits"]), rtol=1e-5, atol=2e-6)
+    (y * torch.tensor(z["G"].astype(np.float32))).sum().backward()
+    for k, gref in grads.items():
+        torch.testing.assert_close(params[k].grad, gref, rtol=2e-4, atol=2e-6, msg=lambda m: f"{k}: {m}")
+    # the canonical (hoisted table) form is the same function
+    sn, st, pt = po.canonicalize(variant, z["neis"], z["layer_type"], nw, L)
+    rows = np.nonzero(z["mask"])[0]
+    with torch.no_grad():
+        yc = po.pagg_forward_canonical(variant, params, X, sn, st, pt, rows)
+    torch.testing.assert_close(yc, torch.tensor(z["logits"]), rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("variant,cls", [("hetero", "PathNet"), ("homo", "PathNet_homo")])
+def test_pagg_oracle_matches_live_reference_classes(variant, cls, have_reference):
+    if not have_reference:
+        pytest.skip("needs /root/reference/PathNet_run.py")
+    import warnings
+    warnings.filterwarnings("ignore")
+    ns = po.load_reference_classes(dropout=0.0)
+    torch.manual_seed(7)
+    N, Fd, H, C, nw, L, S = 70, 19, 48, 4, 7, 5, 23     # S, nw deliberately awkward
+    model = ns[cls](Fd, H, C, L).eval()
+    X = torch.randn(N, Fd)
+    mask = torch.zeros(N, dtype=torch.bool)
+    mask[torch.randperm(N)[:S]] = True
+    neis = torch.randint(0, N, (S, nw * L))
+    lt = torch.randint(0, L, (S, nw, L))
+    y_ref = model(X, neis, nw, L, mask, lt, torch.arange(S * nw * L))
+    params = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    y = po.pagg_forward(variant, params, X, neis, nw, L, mask, lt)
+    torch.testing.assert_close(y, y_ref, rtol=1e-5, atol=1e-6)
+    G = torch.randn_like(y)
+    (y_ref * G).sum().backward()
+    (y * G).sum().backward()
+    for k, p in model.named_parameters():
+        torch.testing.assert_close(params[k].grad, p.grad, rtol=2e-4, atol=2e-6, msg=lambda m: f"{k}: {m}")
