@@ -168,10 +168,16 @@ int pn_pagg_backward(const pn_pagg_cfg *cfg, const pn_pagg_params *params, const
                      const int32_t *rows, void *workspace, const float *dlogits,
                      const pn_pagg_params *grads, void *stream);
 
-/* The dropout keep/scale decision the kernels use for element `idx` of mask
+/* The 16-bit dropout hash the kernels use for element `idx` (dropped iff
+ * hash < floor(p*65536)) of mask
  * stream `stream_id` (0 = LSTM input [L,P,H], 1 = concat [S,2H]); host
  * function so tests can feed the oracle the identical masks. */
 uint32_t pn_dropout_hash(uint64_t seed, uint32_t stream_id, uint64_t idx);
+
+/* Debug/unit-test entry: C[M,N] = act(A[M,K] B[N,K]^T + bias) on the tcgen05
+ * path (fp16 operands, fp32 accumulate); device pointers, fp32, row-major. */
+int pn_debug_gemm_tc(const float *A, const float *B, float *C, const float *bias, int64_t M,
+                     int64_t N, int64_t K, int relu, void *stream);
 
 /* In-stream kernel timing for bench.py's roofline: when enabled, the library
  * brackets its dominant kernels with CUDA events on the launching stream.

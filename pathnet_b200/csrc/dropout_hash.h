@@ -1,5 +1,5 @@
-// Counter-based dropout mask: one 32-bit hash per element, keep iff
-// hash >= floor(p * 2^32).  Stateless, so forward and backward regenerate the
+// Counter-based dropout mask: 16 hash bits per element, keep iff
+// hash16 >= floor(p * 65536).  Stateless, so forward and backward regenerate the
 // same mask without storing it (F.dropout call sites: PathNet_run.py:194,209,
 // 264,276).  The reference draws its masks from torch's Philox stream, which
 // no other implementation can reproduce; parity tests therefore feed the
@@ -23,19 +23,27 @@ PN_HD uint32_t fmix32(uint32_t h)
     return h;
 }
 
-PN_HD uint32_t dropout_hash(uint64_t seed, uint32_t stream_id, uint64_t idx)
+// one 32-bit hash serves the element PAIR (idx>>1): even idx uses the low 16
+// bits, odd idx the high 16 bits
+PN_HD uint32_t dropout_hash_pair(uint64_t seed, uint32_t stream_id, uint64_t pair)
 {
-    uint32_t h = fmix32((uint32_t)idx ^ (uint32_t)seed);
-    h = fmix32(h ^ ((uint32_t)(idx >> 32) * 0x9e3779b9u) ^ (uint32_t)(seed >> 32) ^ (stream_id * 0x7f4a7c15u));
-    return fmix32(h + 0x6a09e667u);
+    uint32_t h = fmix32((uint32_t)pair ^ (uint32_t)seed);
+    return fmix32(h ^ ((uint32_t)(pair >> 32) * 0x9e3779b9u) ^ (uint32_t)(seed >> 32) ^ (stream_id * 0x7f4a7c15u) ^ 0x6a09e667u);
 }
 
-// threshold for drop probability p: drop iff hash < thr
+// 16-bit value in [0, 65536) for element idx
+PN_HD uint32_t dropout_hash(uint64_t seed, uint32_t stream_id, uint64_t idx)
+{
+    const uint32_t h = dropout_hash_pair(seed, stream_id, idx >> 1);
+    return (idx & 1) ? (h >> 16) : (h & 0xFFFFu);
+}
+
+// threshold for drop probability p: drop iff hash16 < thr  (p resolved to 1/65536)
 PN_HD uint32_t dropout_threshold(float p)
 {
-    double t = (double)p * 4294967296.0;
+    double t = (double)p * 65536.0;
     if (t <= 0.0) return 0u;
-    if (t >= 4294967295.0) return 0xFFFFFFFFu;
+    if (t >= 65536.0) return 65536u;
     return (uint32_t)t;
 }
 

@@ -133,11 +133,12 @@ __device__ __forceinline__ void gather_x_tile(const LstmArgs &a, float *As, int 
             for (int j = tx * 4; j < H; j += 128) {
                 float4 v = __ldg(reinterpret_cast<const float4 *>(src + j));
                 if (a.drop_thr) {
-                    const uint64_t base = (uint64_t)e * H + j;
-                    v.x = dropout_hash(a.drop_seed, 0, base + 0) < a.drop_thr ? 0.f : v.x * a.drop_scale;
-                    v.y = dropout_hash(a.drop_seed, 0, base + 1) < a.drop_thr ? 0.f : v.y * a.drop_scale;
-                    v.z = dropout_hash(a.drop_seed, 0, base + 2) < a.drop_thr ? 0.f : v.z * a.drop_scale;
-                    v.w = dropout_hash(a.drop_seed, 0, base + 3) < a.drop_thr ? 0.f : v.w * a.drop_scale;
+                    const uint64_t pair = ((uint64_t)e * H + j) >> 1;  // (e*H + j) is even
+                    const uint32_t h0 = dropout_hash_pair(a.drop_seed, 0, pair), h1 = dropout_hash_pair(a.drop_seed, 0, pair + 1);
+                    v.x = (h0 & 0xFFFFu) < a.drop_thr ? 0.f : v.x * a.drop_scale;
+                    v.y = (h0 >> 16) < a.drop_thr ? 0.f : v.y * a.drop_scale;
+                    v.z = (h1 & 0xFFFFu) < a.drop_thr ? 0.f : v.z * a.drop_scale;
+                    v.w = (h1 >> 16) < a.drop_thr ? 0.f : v.w * a.drop_scale;
                 }
                 *reinterpret_cast<float4 *>(dst + j) = v;
             }
@@ -567,6 +568,8 @@ static int launch_lstm_bwd(const LstmArgs &a, cudaStream_t st)
 
 int pagg_tc_forward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_params &prm,
                          const int32_t *seq_node, const uint8_t *seq_type, cudaStream_t st);  // pagg_tc.cu
+int launch_gemm_tc(cudaStream_t st, const float *A, int64_t lda, const float *B, int64_t ldb, float *C, int64_t ldc,
+                   int64_t M, int64_t N, int64_t K, const float *bias, bool relu);               // pagg_tc.cu
 
 }  // namespace pn
 
@@ -613,10 +616,13 @@ extern "C" int pn_pagg_forward(const pn_pagg_cfg *cfg, const pn_pagg_params *prm
     drop_params(c, thr, scale);
 
     // K0: Z = act(X W0^T + b0)                                     (:175 / :242-243)
-    rc = launch_gemm(st, X, F, 1, prm->fc0_w, 1, F, w.Z, H, N, H, F, prm->fc0_b, homo, false);
+    const bool tcm = c.math_mode == PN_MATH_TC;
+    rc = tcm ? launch_gemm_tc(st, X, F, prm->fc0_w, F, w.Z, H, N, H, F, prm->fc0_b, homo)
+             : launch_gemm(st, X, F, 1, prm->fc0_w, 1, F, w.Z, H, N, H, F, prm->fc0_b, homo, false);
     if (rc) return rc;
     // K1: T[n, d*H + j] = act(Z nets_w[d]^T + nets_b[d])           (:185-191 / :249-257, hoisted)
-    rc = launch_gemm(st, w.Z, H, 1, prm->nets_w, 1, H, w.T, L * H, N, L * H, H, prm->nets_b, homo, false);
+    rc = tcm ? launch_gemm_tc(st, w.Z, H, prm->nets_w, H, w.T, L * H, N, L * H, H, prm->nets_b, homo)
+             : launch_gemm(st, w.Z, H, 1, prm->nets_w, 1, H, w.T, L * H, N, L * H, H, prm->nets_b, homo, false);
     if (rc) return rc;
     k_pack_lstm<<<(unsigned)ceil_div(2 * H * 4 * H, 256), 256, 0, st>>>((int)H, prm->w_ih, prm->w_hh, prm->b_ih,
                                                                       prm->b_hh, w.Wp, w.WpT, w.bp);

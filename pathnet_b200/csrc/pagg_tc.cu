@@ -1,12 +1,392 @@
-// Tensor-core (tcgen05) math mode of the PAGG LSTM — under construction.
+// Tensor-core (tcgen05 / TMEM) math mode of PAGG: fp16 operands, fp32
+// accumulation in TMEM, fp32 gate math.  See tc_util.cuh for the operand layout.
+//
+//   k_gemm_tc      C = act(A B^T + bias), A/B fp32 in global, converted to fp16
+//                  while staged into the canonical UMMA layout (fc0, table
+//                  projection; also the stand-alone tcgen05 unit test).
+//   k_lstm_fwd_tc  fused gather + dropout + LSTM forward.  One CTA = 128
+//                  sequences (one TMEM lane each), all L steps:
+//                    warps 0-3  gather x_t into the A tile (fp16), then per step
+//                               read the 128x512 fp32 gate pre-activations from
+//                               TMEM, do the gate math (c in registers), write
+//                               h_t back into the A tile as the next step's
+//                               operand, save activations for backward;
+//                    warp 4     one thread issues tcgen05.mma (M128 N256 K16);
+//                    warp 5     one thread streams the packed fp16 weights
+//                               (256 KB, L2-resident) through a 3-stage smem
+//                               ring with cp.async.bulk + mbarriers.
 #include "pagg_common.cuh"
+#include "tc_util.cuh"
 
 namespace pn {
+using namespace tc;
+
+// ---------------------------------------------------------------------------
+// generic tcgen05 GEMM
+// ---------------------------------------------------------------------------
+struct GemmTcArgs {
+    const float *A, *B;  // A [M,K] row-major lda ; B [N,K] row-major ldb
+    float *C;            // [M,N] ldc
+    const float *bias;   // [N] or null
+    int64_t M, N, K, lda, ldb, ldc;
+    int relu;
+};
+
+// stage a [ROWS x 64] fp32 tile as fp16 in the canonical layout (K extent 64)
+template <int ROWS, int NTHREADS>
+__device__ __forceinline__ void stage_tile_f16(unsigned char *dst, const float *src, int64_t ld, int64_t row0,
+                                               int64_t nrows, int64_t k0, int64_t K, int tid)
+{
+    constexpr int CHUNKS = ROWS * 8;  // 16-byte chunks (8 halves)
+    const bool vec_ok = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+    for (int c = tid; c < CHUNKS; c += NTHREADS) {
+        const int r = c % ROWS, k8 = c / ROWS;
+        const int64_t gr = row0 + r, gk = k0 + k8 * 8;
+        float f[8];
+        if (gr < nrows && gk + 8 <= K && vec_ok) {
+            const float4 a = __ldg(reinterpret_cast<const float4 *>(src + gr * ld + gk));
+            const float4 b = __ldg(reinterpret_cast<const float4 *>(src + gr * ld + gk + 4));
+            f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; j++) f[j] = (gr < nrows && gk + j < K) ? __ldg(src + gr * ld + gk + j) : 0.f;
+        }
+        __half2 h0 = __floats2half2_rn(f[0], f[1]), h1 = __floats2half2_rn(f[2], f[3]);
+        __half2 h2 = __floats2half2_rn(f[4], f[5]), h3 = __floats2half2_rn(f[6], f[7]);
+        uint4 pk;
+        pk.x = *reinterpret_cast<uint32_t *>(&h0); pk.y = *reinterpret_cast<uint32_t *>(&h1);
+        pk.z = *reinterpret_cast<uint32_t *>(&h2); pk.w = *reinterpret_cast<uint32_t *>(&h3);
+        *reinterpret_cast<uint4 *>(dst + canon_off(r, k8 * 8, 64)) = pk;
+    }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(128) k_gemm_tc(GemmTcArgs g)
+{
+    constexpr int BM = 128, BK = 64;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char *As = smem_raw;                 // BM x BK fp16 canonical
+    unsigned char *Bs = smem_raw + BM * BK * 2;   // BN x BK
+    __shared__ uint64_t bar;
+    __shared__ uint32_t s_taddr;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN;
+    if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+    if (warp == 0) tmem_alloc<BN>(&s_taddr);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t taddr = s_taddr;
+    constexpr uint32_t idesc = make_idesc_f16(BM, BN);
+    uint32_t phase = 0;
+    for (int64_t k0 = 0; k0 < g.K; k0 += BK) {
+        stage_tile_f16<BM, 128>(As, g.A, g.lda, m0, g.M, k0, g.K, tid);
+        stage_tile_f16<BN, 128>(Bs, g.B, g.ldb, n0, g.N, k0, g.K, tid);
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            const uint64_t ad = make_smem_desc(smem_u32(As), 128, (BK / 8) * 128);
+            const uint64_t bd = make_smem_desc(smem_u32(Bs), 128, (BK / 8) * 128);
+#pragma unroll
+            for (int kk = 0; kk < BK / 16; kk++)
+                mma_f16(taddr, ad + (uint64_t)(kk * 16), bd + (uint64_t)(kk * 16), idesc, (k0 > 0) || (kk > 0));
+            mma_commit(&bar);
+        }
+        mbar_wait(&bar, phase);  // MMAs done reading smem (and, on the last pass, writing TMEM)
+        phase ^= 1;
+    }
+    tc_fence_after();
+    // epilogue: warp w owns TMEM lanes 32w..32w+31 = rows m0+32w+lane
+    const int64_t row = m0 + warp * 32 + lane;
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+        tmem_ld_wait();
+        if (row < g.M) {
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                const int64_t n = n0 + c0 + j;
+                if (n < g.N) {
+                    float x = __uint_as_float(v[j]);
+                    if (g.bias) x += g.bias[n];
+                    if (g.relu) x = fmaxf(x, 0.f);
+                    g.C[row * g.ldc + n] = x;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) { __syncwarp(); tmem_dealloc<BN>(taddr); }
+}
+
+int launch_gemm_tc(cudaStream_t st, const float *A, int64_t lda, const float *B, int64_t ldb, float *C, int64_t ldc,
+                   int64_t M, int64_t N, int64_t K, const float *bias, bool relu)
+{
+    if (M <= 0 || N <= 0) return PN_OK;
+    GemmTcArgs g{A, B, C, bias, M, N, K, lda, ldb, ldc, relu ? 1 : 0};
+    constexpr int BN = 128;
+    const size_t smem = (128 + BN) * 64 * 2;
+    dim3 grid((unsigned)ceil_div(N, BN), (unsigned)ceil_div(M, 128));
+    k_gemm_tc<BN><<<grid, 128, smem, st>>>(g);
+    PN_LAUNCH_CHECK();
+    return PN_OK;
+}
+
+// ---------------------------------------------------------------------------
+// LSTM weights -> fp16, canonical layout, cut into 8 K-chunks of 32 so each
+// chunk ([512 cols][32 k], 32 KB) is one contiguous bulk copy.
+//   column = unit*4 + gate (i,f,g,o), k < H: W_ih, k >= H: W_hh      (H = 128)
+// ---------------------------------------------------------------------------
+constexpr int TC_H = 128, TC_G4 = 512, TC_K2 = 256, TC_KC = 32, TC_NCHUNK = TC_K2 / TC_KC;
+constexpr int TC_CHUNK_BYTES = TC_G4 * TC_KC * 2;  // 32 KB
+
+__global__ void k_pack_lstm_tc(const float *__restrict__ w_ih, const float *__restrict__ w_hh,
+                               const float *__restrict__ b_ih, const float *__restrict__ b_hh,
+                               unsigned char *__restrict__ Wh, float *__restrict__ bp)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < TC_G4 * TC_K2) {
+        const int col = i / TC_K2, k = i % TC_K2, unit = col >> 2, gate = col & 3;
+        const float v = k < TC_H ? w_ih[(gate * TC_H + unit) * TC_H + k] : w_hh[(gate * TC_H + unit) * TC_H + (k - TC_H)];
+        const int chunk = k / TC_KC, kk = k % TC_KC;
+        *reinterpret_cast<__half *>(Wh + (size_t)chunk * TC_CHUNK_BYTES + canon_off(col, kk, TC_KC)) = __float2half_rn(v);
+    }
+    if (i < TC_G4) {
+        const int unit = i >> 2, gate = i & 3;
+        bp[i] = b_ih[gate * TC_H + unit] + b_hh[gate * TC_H + unit];
+    }
+}
+
+struct LstmTcArgs {
+    const float *T;           // [N,L,H] fp32 table
+    const int32_t *seq_node;  // [P,L]
+    const uint8_t *seq_type;  // [P,L]
+    const unsigned char *Wh;  // packed fp16 weights (8 chunks x 32 KB)
+    const float *bp;          // [512]
+    float *acts;              // [L][P][5][H]
+    float *hfin;              // [P,H]
+    int64_t P;
+    int L;
+    uint32_t drop_thr; float drop_scale; uint64_t drop_seed;
+};
+
+constexpr int TC_NSTAGE = 3;
+constexpr int TC_A_BYTES = 128 * TC_K2 * 2;  // 64 KB
+constexpr int TC_SMEM = TC_A_BYTES + TC_NSTAGE * TC_CHUNK_BYTES + 2048 /*bias*/ + 1024 /*align slack*/;
+
+__device__ __forceinline__ float tanh_fast(float x)
+{
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
+
+__global__ void __launch_bounds__(192, 1) k_lstm_fwd_tc(LstmTcArgs a)
+{
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    unsigned char *As = base;                                  // [128][256] fp16 canonical: k<128 x_t, k>=128 h_{t-1}
+    unsigned char *Ws = base + TC_A_BYTES;                     // ring of weight chunks
+    float *bias_s = reinterpret_cast<float *>(Ws + TC_NSTAGE * TC_CHUNK_BYTES);
+    __shared__ uint64_t full_bar[TC_NSTAGE], empty_bar[TC_NSTAGE], a_ready, acc_full;
+    __shared__ uint32_t s_taddr;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t p0 = (int64_t)blockIdx.x * 128;
+    const int L = a.L;
+
+    if (tid == 0) {
+        for (int s = 0; s < TC_NSTAGE; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&a_ready, 128);
+        mbar_init(&acc_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 4) tmem_alloc<512>(&s_taddr);
+    for (int i = tid; i < TC_G4; i += 192) bias_s[i] = a.bp[i];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t taddr = s_taddr;
+
+    if (warp == 5) {
+        // ===== weight producer: chunk sequence per step = (t == 0 ? 0..3 : 0..7) =====
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int t = 0; t < L; t++) {
+                const int nch = t == 0 ? TC_NCHUNK / 2 : TC_NCHUNK;
+                for (int c = 0; c < nch; c++) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);  // slot free (first pass: passes immediately)
+                    mbar_arrive_expect_tx(&full_bar[stage], TC_CHUNK_BYTES);
+                    bulk_g2s(Ws + stage * TC_CHUNK_BYTES, a.Wh + (size_t)c * TC_CHUNK_BYTES, TC_CHUNK_BYTES, &full_bar[stage]);
+                    if (++stage == TC_NSTAGE) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 4) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_f16(128, 256);
+            uint32_t stage = 0, phase = 0;
+            for (int t = 0; t < L; t++) {
+                mbar_wait(&a_ready, t & 1);  // x_t (and h_{t-1}) staged, TMEM drained
+                tc_fence_after();
+                const int nch = t == 0 ? TC_NCHUNK / 2 : TC_NCHUNK;  // h_0 = 0: skip the W_hh half
+                for (int c = 0; c < nch; c++) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t wbase = smem_u32(Ws + stage * TC_CHUNK_BYTES);
+#pragma unroll
+                    for (int ks = 0; ks < TC_KC / 16; ks++) {
+                        const uint64_t ad = make_smem_desc(smem_u32(As) + (uint32_t)(c * (TC_KC / 8) + ks * 2) * 128, 128, (TC_K2 / 8) * 128);
+#pragma unroll
+                        for (int nh = 0; nh < 2; nh++) {
+                            const uint64_t bd = make_smem_desc(wbase + (uint32_t)nh * (256 / 8) * ((TC_KC / 8) * 128) + (uint32_t)ks * 256, 128, (TC_KC / 8) * 128);
+                            mma_f16(taddr + (uint32_t)nh * 256, ad, bd, idesc, (c > 0) || (ks > 0));
+                        }
+                    }
+                    mma_commit(&empty_bar[stage]);  // slot reusable once these MMAs have read it
+                    if (++stage == TC_NSTAGE) { stage = 0; phase ^= 1; }
+                }
+                mma_commit(&acc_full);
+            }
+        }
+    } else {
+        // ===== gather + gate math: thread = sequence p0 + tid = TMEM lane tid =====
+        const int r = tid;
+        const int64_t p = p0 + r;
+        const bool valid = p < a.P;
+        float c[TC_H];
+#pragma unroll
+        for (int j = 0; j < TC_H; j++) c[j] = 0.f;
+        for (int t = 0; t < L; t++) {
+            // ---- stage x_t (fp16) into the A tile ----
+            {
+                const float *src = nullptr;
+                int64_t e = 0;
+                if (valid) {
+                    e = p * L + t;
+                    src = a.T + ((int64_t)a.seq_node[e] * L + a.seq_type[e]) * TC_H;
+                }
+#pragma unroll 4
+                for (int k8 = 0; k8 < TC_H / 8; k8++) {
+                    float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    if (valid) {
+                        const float4 u = __ldg(reinterpret_cast<const float4 *>(src + k8 * 8));
+                        const float4 w = __ldg(reinterpret_cast<const float4 *>(src + k8 * 8 + 4));
+                        f[0] = u.x; f[1] = u.y; f[2] = u.z; f[3] = u.w; f[4] = w.x; f[5] = w.y; f[6] = w.z; f[7] = w.w;
+                        if (a.drop_thr) {
+                            const uint64_t pair = ((uint64_t)e * TC_H + k8 * 8) >> 1;
+#pragma unroll
+                            for (int q = 0; q < 4; q++) {
+                                const uint32_t h = dropout_hash_pair(a.drop_seed, 0, pair + q);
+                                f[2 * q] = (h & 0xFFFFu) < a.drop_thr ? 0.f : f[2 * q] * a.drop_scale;
+                                f[2 * q + 1] = (h >> 16) < a.drop_thr ? 0.f : f[2 * q + 1] * a.drop_scale;
+                            }
+                        }
+                    }
+                    __half2 h0 = __floats2half2_rn(f[0], f[1]), h1 = __floats2half2_rn(f[2], f[3]);
+                    __half2 h2 = __floats2half2_rn(f[4], f[5]), h3 = __floats2half2_rn(f[6], f[7]);
+                    uint4 pk;
+                    pk.x = *reinterpret_cast<uint32_t *>(&h0); pk.y = *reinterpret_cast<uint32_t *>(&h1);
+                    pk.z = *reinterpret_cast<uint32_t *>(&h2); pk.w = *reinterpret_cast<uint32_t *>(&h3);
+                    *reinterpret_cast<uint4 *>(As + canon_off(r, k8 * 8, TC_K2)) = pk;
+                }
+            }
+            fence_proxy_async();   // generic-proxy smem writes -> async proxy (tcgen05.mma)
+            tc_fence_before();     // order this thread's earlier tcgen05.ld before the MMA that overwrites TMEM
+            mbar_arrive(&a_ready);
+            // ---- wait for the gate pre-activations ----
+            mbar_wait(&acc_full, t & 1);
+            tc_fence_after();
+            float *act = valid ? a.acts + (((int64_t)t * a.P + p) * 5) * TC_H : nullptr;
+#pragma unroll
+            for (int c0 = 0; c0 < TC_G4; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(taddr + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+                tmem_ld_wait();
+                float hh[8], gi[8], gf[8], gg[8], go[8], cc[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int unit = c0 / 4 + u;
+                    const float ai = __uint_as_float(v[4 * u + 0]) + bias_s[c0 + 4 * u + 0];
+                    const float af = __uint_as_float(v[4 * u + 1]) + bias_s[c0 + 4 * u + 1];
+                    const float ag = __uint_as_float(v[4 * u + 2]) + bias_s[c0 + 4 * u + 2];
+                    const float ao = __uint_as_float(v[4 * u + 3]) + bias_s[c0 + 4 * u + 3];
+                    gi[u] = sigmoid_fast(ai); gf[u] = sigmoid_fast(af); gg[u] = tanh_fast(ag); go[u] = sigmoid_fast(ao);
+                    const float cn = fmaf(gf[u], c[unit], gi[u] * gg[u]);
+                    c[unit] = cn;
+                    cc[u] = cn;
+                    hh[u] = go[u] * tanh_fast(cn);
+                }
+                // h_t -> A tile (k = 128 + unit) for the next step
+                {
+                    __half2 h0 = __floats2half2_rn(hh[0], hh[1]), h1 = __floats2half2_rn(hh[2], hh[3]);
+                    __half2 h2 = __floats2half2_rn(hh[4], hh[5]), h3 = __floats2half2_rn(hh[6], hh[7]);
+                    uint4 pk;
+                    pk.x = *reinterpret_cast<uint32_t *>(&h0); pk.y = *reinterpret_cast<uint32_t *>(&h1);
+                    pk.z = *reinterpret_cast<uint32_t *>(&h2); pk.w = *reinterpret_cast<uint32_t *>(&h3);
+                    *reinterpret_cast<uint4 *>(As + canon_off(r, TC_H + c0 / 4, TC_K2)) = pk;
+                }
+                if (valid) {
+                    const int u0 = c0 / 4;
+                    *reinterpret_cast<float4 *>(act + 0 * TC_H + u0) = make_float4(gi[0], gi[1], gi[2], gi[3]);
+                    *reinterpret_cast<float4 *>(act + 0 * TC_H + u0 + 4) = make_float4(gi[4], gi[5], gi[6], gi[7]);
+                    *reinterpret_cast<float4 *>(act + 1 * TC_H + u0) = make_float4(gf[0], gf[1], gf[2], gf[3]);
+                    *reinterpret_cast<float4 *>(act + 1 * TC_H + u0 + 4) = make_float4(gf[4], gf[5], gf[6], gf[7]);
+                    *reinterpret_cast<float4 *>(act + 2 * TC_H + u0) = make_float4(gg[0], gg[1], gg[2], gg[3]);
+                    *reinterpret_cast<float4 *>(act + 2 * TC_H + u0 + 4) = make_float4(gg[4], gg[5], gg[6], gg[7]);
+                    *reinterpret_cast<float4 *>(act + 3 * TC_H + u0) = make_float4(go[0], go[1], go[2], go[3]);
+                    *reinterpret_cast<float4 *>(act + 3 * TC_H + u0 + 4) = make_float4(go[4], go[5], go[6], go[7]);
+                    *reinterpret_cast<float4 *>(act + 4 * TC_H + u0) = make_float4(cc[0], cc[1], cc[2], cc[3]);
+                    *reinterpret_cast<float4 *>(act + 4 * TC_H + u0 + 4) = make_float4(cc[4], cc[5], cc[6], cc[7]);
+                    if (t == L - 1) {
+                        *reinterpret_cast<float4 *>(a.hfin + p * TC_H + u0) = make_float4(hh[0], hh[1], hh[2], hh[3]);
+                        *reinterpret_cast<float4 *>(a.hfin + p * TC_H + u0 + 4) = make_float4(hh[4], hh[5], hh[6], hh[7]);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) { __syncwarp(); tmem_dealloc<512>(taddr); }
+}
+
+// Forward LSTM in tensor-core mode (called from pn_pagg_forward).
 int pagg_tc_forward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_params &prm,
                          const int32_t *seq_node, const uint8_t *seq_type, cudaStream_t st)
 {
-    (void)c; (void)w; (void)prm; (void)seq_node; (void)seq_type; (void)st;
-    set_error("PN_MATH_TC: tensor-core LSTM not built in this library");
-    return PN_ERR_UNSUPPORTED;
+    if (c.H != TC_H) {
+        set_error("PN_MATH_TC: the tensor-core LSTM is built for hidden size 128 (got %d)", c.H);
+        return PN_ERR_UNSUPPORTED;
+    }
+    // packed fp16 weights live in the (otherwise unused in this mode) Wp/WpT region: 2 x 256 KB fp32 >= 256 KB fp16
+    unsigned char *Wh = reinterpret_cast<unsigned char *>(w.Wp);
+    k_pack_lstm_tc<<<(unsigned)ceil_div(TC_G4 * TC_K2, 256), 256, 0, st>>>(prm.w_ih, prm.w_hh, prm.b_ih, prm.b_hh, Wh, w.bp);
+    PN_LAUNCH_CHECK();
+    uint32_t thr = 0; float scale = 1.f;
+    if (c.training && c.dropout_p > 0.f) {
+        thr = dropout_threshold(c.dropout_p);
+        scale = c.dropout_p >= 1.f ? 0.f : 1.f / (1.f - c.dropout_p);
+    }
+    const int64_t P = (int64_t)c.S * c.nw;
+    LstmTcArgs a{w.T, seq_node, seq_type, Wh, w.bp, w.acts, w.hfin, P, c.L, thr, scale, c.dropout_seed};
+    PN_CUDA(cudaFuncSetAttribute(k_lstm_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    {
+        ProfScope prof("lstm_fwd", st);
+        k_lstm_fwd_tc<<<(unsigned)ceil_div(P, 128), 192, TC_SMEM, st>>>(a);
+    }
+    PN_LAUNCH_CHECK();
+    return PN_OK;
 }
+
 }  // namespace pn
+
+// stand-alone entry for the tcgen05 GEMM (unit-tested against fp32 math)
+extern "C" int pn_debug_gemm_tc(const float *A, const float *B, float *C, const float *bias, int64_t M, int64_t N,
+                                int64_t K, int relu, void *stream)
+{
+    return pn::launch_gemm_tc((cudaStream_t)stream, A, K, B, K, C, N, M, N, K, bias, relu != 0);
+}

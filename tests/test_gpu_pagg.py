@@ -130,11 +130,12 @@ def _np_fmix32(h):
 def np_dropout_hash(seed, stream_id, idx):
     """numpy restatement of csrc/dropout_hash.h (checked against pn_dropout_hash below)"""
     idx = idx.astype(np.uint64)
-    lo, hi = idx & np.uint64(0xFFFFFFFF), idx >> np.uint64(32)
+    pair = idx >> np.uint64(1)
+    lo, hi = pair & np.uint64(0xFFFFFFFF), pair >> np.uint64(32)
     h = _np_fmix32(lo ^ np.uint64(seed & 0xFFFFFFFF))
     h = _np_fmix32(h ^ ((hi * np.uint64(0x9e3779b9)) & np.uint64(0xFFFFFFFF)) ^ np.uint64((seed >> 32) & 0xFFFFFFFF)
-                   ^ np.uint64((stream_id * 0x7f4a7c15) & 0xFFFFFFFF))
-    return _np_fmix32((h + np.uint64(0x6a09e667)) & np.uint64(0xFFFFFFFF))
+                   ^ np.uint64((stream_id * 0x7f4a7c15) & 0xFFFFFFFF) ^ np.uint64(0x6a09e667))
+    return np.where(idx & np.uint64(1), h >> np.uint64(16), h & np.uint64(0xFFFF))
 
 
 def test_dropout_hash_host_function_matches_numpy():
@@ -153,7 +154,7 @@ def test_training_mode_with_identical_dropout_masks(variant):
     as in eval mode (the reference's own Philox masks are not reproducible)."""
     N, Fd, H, Cc, nw, L, S, p, seed = 120, 21, 64, 4, 6, 4, 37, 0.7, 0x5EED5EED1234
     m, X, mask, neis, lt = _random_case(variant, N, Fd, H, Cc, nw, L, S, seed=5)
-    thr = int(p * 2 ** 32)
+    thr = int(p * 65536)
     scale = 1.0 / (1.0 - p)
     keep_seq = np_dropout_hash(seed, 0, np.arange(S * nw * L * H, dtype=np.uint64)) >= thr
     keep_cat = np_dropout_hash(seed, 1, np.arange(S * 2 * H, dtype=np.uint64)) >= thr
