@@ -568,6 +568,8 @@ static int launch_lstm_bwd(const LstmArgs &a, cudaStream_t st)
 
 int pagg_tc_forward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_params &prm,
                          const int32_t *seq_node, const uint8_t *seq_type, cudaStream_t st);  // pagg_tc.cu
+int pagg_tc_backward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_params &prm,
+                          const int32_t *seq_node, const uint8_t *seq_type, cudaStream_t st);  // pagg_tc.cu
 int launch_gemm_tc(cudaStream_t st, const float *A, int64_t lda, const float *B, int64_t ldb, float *C, int64_t ldc,
                    int64_t M, int64_t N, int64_t K, const float *bias, bool relu);               // pagg_tc.cu
 
@@ -706,16 +708,19 @@ extern "C" int pn_pagg_backward(const pn_pagg_cfg *cfg, const pn_pagg_params *pr
     la.acts = w.acts; la.hfin = w.hfin; la.P = P; la.L = (int)L;
     la.drop_thr = thr; la.drop_scale = scale; la.drop_seed = c.dropout_seed;
     la.dhfin = w.dhfin; la.dT = w.dT; la.dA = w.dA; la.XH = w.XH;
-    switch (H / 32) {
-        case 1: rc = launch_lstm_bwd<1>(la, st); break;
-        case 2: rc = launch_lstm_bwd<2>(la, st); break;
-        case 3: rc = launch_lstm_bwd<3>(la, st); break;
-        default: rc = launch_lstm_bwd<4>(la, st); break;
-    }
-    if (rc) return rc;
-    // dWp[k][col] = sum_r XH[r][k] dA[r][col];  dbp = colsum(dA)
-    ZERO(w.dWp, 2 * H * 4 * H);
-    {
+    if (c.math_mode == PN_MATH_TC) {
+        rc = pagg_tc_backward_lstm(c, w, *prm, seq_node, seq_type, st);
+        if (rc) return rc;
+    } else {
+        switch (H / 32) {
+            case 1: rc = launch_lstm_bwd<1>(la, st); break;
+            case 2: rc = launch_lstm_bwd<2>(la, st); break;
+            case 3: rc = launch_lstm_bwd<3>(la, st); break;
+            default: rc = launch_lstm_bwd<4>(la, st); break;
+        }
+        if (rc) return rc;
+        // dWp[k][col] = sum_r XH[r][k] dA[r][col];  dbp = colsum(dA)
+        ZERO(w.dWp, 2 * H * 4 * H);
         const int64_t R = L * P;
         int splitk = (int)std::max<int64_t>(1, std::min<int64_t>(256, R / 2048));
         {

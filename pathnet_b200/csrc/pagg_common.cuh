@@ -31,6 +31,7 @@ struct PaggWs {
     float *dWp;      // [2H][4H]
     float *dbp;      // [4H]
     float *dattw;    // [2H+1]
+    float *gscale;   // [2] gradient scale of the tensor-core backward (scale, 1/scale)
     size_t bytes;
 };
 
@@ -42,6 +43,7 @@ inline PaggWs carve_workspace(const pn_pagg_cfg &c, void *base)
     char *p = (char *)base;
     size_t off = 0;
     const size_t N = c.N, H = c.H, L = c.L, S = c.S, P = (size_t)c.S * c.nw;
+    const size_t P128 = (P + 127) / 128 * 128;  // the tensor-core kernels work on whole 128-sequence tiles
     auto take = [&](float *&dst, size_t nfloats) {
         dst = (float *)(p + off);
         off += ws_align(nfloats * sizeof(float));
@@ -60,11 +62,12 @@ inline PaggWs carve_workspace(const pn_pagg_cfg &c, void *base)
     take(w.dhfin, P * H);
     take(w.dZ, N * H);
     take(w.dT, N * L * H);
-    take(w.dA, L * P * 4 * H);
-    take(w.XH, L * P * 2 * H);
+    take(w.dA, L * P128 * 4 * H);
+    take(w.XH, L * P128 * 2 * H);
     take(w.dWp, 2 * H * 4 * H);
     take(w.dbp, 4 * H);
     take(w.dattw, 2 * H + 1);
+    take(w.gscale, 2);
     w.bytes = off;
     return w;
 }

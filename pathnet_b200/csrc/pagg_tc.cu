@@ -165,7 +165,7 @@ struct LstmTcArgs {
     const uint8_t *seq_type;  // [P,L]
     const unsigned char *Wh;  // packed fp16 weights (8 chunks x 32 KB)
     const float *bp;          // [512]
-    float *acts;              // [L][P][5][H]
+    __half *acts;             // [L][P][5][H] fp16 (i,f,g,o,c)
     float *hfin;              // [P,H]
     int64_t P;
     int L;
@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(192, 1) k_lstm_fwd_tc(LstmTcArgs a)
             // ---- wait for the gate pre-activations ----
             mbar_wait(&acc_full, t & 1);
             tc_fence_after();
-            float *act = valid ? a.acts + (((int64_t)t * a.P + p) * 5) * TC_H : nullptr;
+            __half *act = valid ? a.acts + (((int64_t)t * a.P + p) * 5) * TC_H : nullptr;
 #pragma unroll
             for (int c0 = 0; c0 < TC_G4; c0 += 32) {
                 uint32_t v[32];
@@ -331,16 +331,11 @@ __global__ void __launch_bounds__(192, 1) k_lstm_fwd_tc(LstmTcArgs a)
                 }
                 if (valid) {
                     const int u0 = c0 / 4;
-                    *reinterpret_cast<float4 *>(act + 0 * TC_H + u0) = make_float4(gi[0], gi[1], gi[2], gi[3]);
-                    *reinterpret_cast<float4 *>(act + 0 * TC_H + u0 + 4) = make_float4(gi[4], gi[5], gi[6], gi[7]);
-                    *reinterpret_cast<float4 *>(act + 1 * TC_H + u0) = make_float4(gf[0], gf[1], gf[2], gf[3]);
-                    *reinterpret_cast<float4 *>(act + 1 * TC_H + u0 + 4) = make_float4(gf[4], gf[5], gf[6], gf[7]);
-                    *reinterpret_cast<float4 *>(act + 2 * TC_H + u0) = make_float4(gg[0], gg[1], gg[2], gg[3]);
-                    *reinterpret_cast<float4 *>(act + 2 * TC_H + u0 + 4) = make_float4(gg[4], gg[5], gg[6], gg[7]);
-                    *reinterpret_cast<float4 *>(act + 3 * TC_H + u0) = make_float4(go[0], go[1], go[2], go[3]);
-                    *reinterpret_cast<float4 *>(act + 3 * TC_H + u0 + 4) = make_float4(go[4], go[5], go[6], go[7]);
-                    *reinterpret_cast<float4 *>(act + 4 * TC_H + u0) = make_float4(cc[0], cc[1], cc[2], cc[3]);
-                    *reinterpret_cast<float4 *>(act + 4 * TC_H + u0 + 4) = make_float4(cc[4], cc[5], cc[6], cc[7]);
+                    *reinterpret_cast<uint4 *>(act + 0 * TC_H + u0) = pack8_f16(gi);
+                    *reinterpret_cast<uint4 *>(act + 1 * TC_H + u0) = pack8_f16(gf);
+                    *reinterpret_cast<uint4 *>(act + 2 * TC_H + u0) = pack8_f16(gg);
+                    *reinterpret_cast<uint4 *>(act + 3 * TC_H + u0) = pack8_f16(go);
+                    *reinterpret_cast<uint4 *>(act + 4 * TC_H + u0) = pack8_f16(cc);
                     if (t == L - 1) {
                         *reinterpret_cast<float4 *>(a.hfin + p * TC_H + u0) = make_float4(hh[0], hh[1], hh[2], hh[3]);
                         *reinterpret_cast<float4 *>(a.hfin + p * TC_H + u0 + 4) = make_float4(hh[4], hh[5], hh[6], hh[7]);
@@ -372,12 +367,439 @@ int pagg_tc_forward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_pa
         scale = c.dropout_p >= 1.f ? 0.f : 1.f / (1.f - c.dropout_p);
     }
     const int64_t P = (int64_t)c.S * c.nw;
-    LstmTcArgs a{w.T, seq_node, seq_type, Wh, w.bp, w.acts, w.hfin, P, c.L, thr, scale, c.dropout_seed};
+    LstmTcArgs a{w.T, seq_node, seq_type, Wh, w.bp, reinterpret_cast<__half *>(w.acts), w.hfin, P, c.L, thr, scale, c.dropout_seed};
     PN_CUDA(cudaFuncSetAttribute(k_lstm_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
     {
         ProfScope prof("lstm_fwd", st);
         k_lstm_fwd_tc<<<(unsigned)ceil_div(P, 128), 192, TC_SMEM, st>>>(a);
     }
+    PN_LAUNCH_CHECK();
+    return PN_OK;
+}
+
+
+// ===========================================================================
+// tensor-core backward
+// ===========================================================================
+// Gradients travel as fp16 multiplied by a power-of-two scale chosen from
+// max|dh_final| (so the largest gate gradient sits near 2^4): the same 11-bit
+// significand as the forward operands, with 2^12 of head-room against growth
+// through the recurrence and 2^-28 relative before flush-to-zero.
+__global__ void k_absmax_bits(const float *__restrict__ x, int64_t n, unsigned int *__restrict__ out)
+{
+    float m = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        m = fmaxf(m, fabsf(x[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
+}
+__global__ void k_make_scale(float *gscale)
+{
+    const float m = __uint_as_float(*reinterpret_cast<unsigned int *>(gscale));
+    float sc = 1.f;
+    if (m > 0.f && isfinite(m)) sc = exp2f(4.f - ceilf(log2f(m)));
+    gscale[0] = sc;
+    gscale[1] = 1.f / sc;
+}
+
+// W' = [W_ih | W_hh] as B operand of the dgrad GEMM: [256 rows = input index k][K = 512 gate columns],
+// fp16 canonical, cut into 16 chunks of 32 columns (16 KB each).
+constexpr int TCB_KC = 32, TCB_NCHUNK = TC_G4 / TCB_KC, TCB_CHUNK_BYTES = TC_K2 * TCB_KC * 2;
+__global__ void k_pack_lstm_tc_bwd(const float *__restrict__ w_ih, const float *__restrict__ w_hh, unsigned char *__restrict__ WhT)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= TC_G4 * TC_K2) return;
+    const int col = i / TC_K2, k = i % TC_K2, unit = col >> 2, gate = col & 3;
+    const float v = k < TC_H ? w_ih[(gate * TC_H + unit) * TC_H + k] : w_hh[(gate * TC_H + unit) * TC_H + (k - TC_H)];
+    const int chunk = col / TCB_KC, kk = col % TCB_KC;
+    *reinterpret_cast<__half *>(WhT + (size_t)chunk * TCB_CHUNK_BYTES + canon_off(k, kk, TCB_KC)) = __float2half_rn(v);
+}
+
+struct LstmBwdTcArgs {
+    const float *T;
+    const int32_t *seq_node;
+    const uint8_t *seq_type;
+    const unsigned char *WhT;  // 16 chunks x 16 KB
+    const __half *acts;        // [L][P][5][H]
+    const float *dhfin;        // [P,H]
+    const float *gscale;       // {scale, 1/scale}
+    float *dT;                 // [N,L,H]
+    unsigned char *da_img;     // block b = t*ntiles + tile: [64 col8][128 r][8] fp16   (128 KB)
+    unsigned char *xh_img;     // block b:                   [32 k8 ][128 r][8] fp16   ( 64 KB)
+    int64_t P, ntiles;
+    int L;
+    uint32_t drop_thr; float drop_scale; uint64_t drop_seed;
+};
+constexpr int TCB_NSTAGE = 3;
+constexpr int TCB_A_BYTES = 128 * TC_G4 * 2;  // 128 KB: da tile [128][512] fp16 canonical
+constexpr int TCB_SMEM = TCB_A_BYTES + TCB_NSTAGE * TCB_CHUNK_BYTES + 1024;
+constexpr int DA_BLOCK_BYTES = 64 * 128 * 16, XH_BLOCK_BYTES = 32 * 128 * 16;
+
+__global__ void __launch_bounds__(192, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
+{
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    unsigned char *As = base;                 // da_t, [128][512] fp16 canonical K-major
+    unsigned char *Ws = base + TCB_A_BYTES;   // ring of W' chunks
+    __shared__ uint64_t full_bar[TCB_NSTAGE], empty_bar[TCB_NSTAGE], a_ready, acc_full;
+    __shared__ uint32_t s_taddr;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t tile = blockIdx.x, p0 = tile * 128;
+    const int L = a.L;
+    if (tid == 0) {
+        for (int s = 0; s < TCB_NSTAGE; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&a_ready, 128);
+        mbar_init(&acc_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 4) tmem_alloc<512>(&s_taddr);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t taddr = s_taddr;  // cols [0,128) dx, [128,256) dh_{t-1}, [256,384) dc
+
+    if (warp == 5) {
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int s = 0; s < L; s++)
+                for (int c = 0; c < TCB_NCHUNK; c++) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[stage], TCB_CHUNK_BYTES);
+                    bulk_g2s(Ws + stage * TCB_CHUNK_BYTES, a.WhT + (size_t)c * TCB_CHUNK_BYTES, TCB_CHUNK_BYTES, &full_bar[stage]);
+                    if (++stage == TCB_NSTAGE) { stage = 0; phase ^= 1; }
+                }
+        }
+    } else if (warp == 4) {
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int s = 0; s < L; s++) {
+                const int t = L - 1 - s;
+                mbar_wait(&a_ready, s & 1);
+                tc_fence_after();
+                const uint32_t idesc = t == 0 ? make_idesc_f16(128, 128) : make_idesc_f16(128, 256);  // t = 0: dh_{-1} unused
+                for (int c = 0; c < TCB_NCHUNK; c++) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t wbase = smem_u32(Ws + stage * TCB_CHUNK_BYTES);
+#pragma unroll
+                    for (int ks = 0; ks < TCB_KC / 16; ks++) {
+                        const uint64_t ad = make_smem_desc(smem_u32(As) + (uint32_t)(c * (TCB_KC / 8) + ks * 2) * 128, 128, (TC_G4 / 8) * 128);
+                        const uint64_t bd = make_smem_desc(wbase + (uint32_t)ks * 256, 128, (TCB_KC / 8) * 128);
+                        mma_f16(taddr, ad, bd, idesc, (c > 0) || (ks > 0));
+                    }
+                    mma_commit(&empty_bar[stage]);
+                    if (++stage == TCB_NSTAGE) { stage = 0; phase ^= 1; }
+                }
+                mma_commit(&acc_full);
+            }
+        }
+    } else {
+        const int r = tid;
+        const int64_t p = p0 + r;
+        const bool valid = p < a.P;
+        const uint32_t lane_base = taddr + ((uint32_t)(warp * 32) << 16);
+        const float scale = a.gscale[0], inv_scale = a.gscale[1];
+        for (int s = 0; s < L; s++) {
+            const int t = L - 1 - s;
+            const int64_t blk = (int64_t)t * a.ntiles + tile;
+            unsigned char *da_blk = a.da_img + blk * DA_BLOCK_BYTES;
+            unsigned char *xh_blk = a.xh_img + blk * XH_BLOCK_BYTES;
+            const __half *act = valid ? a.acts + (((int64_t)t * a.P + p) * 5) * TC_H : nullptr;
+            const __half *actp = (valid && t > 0) ? a.acts + (((int64_t)(t - 1) * a.P + p) * 5) * TC_H : nullptr;
+            // ---- gate gradients ----
+#pragma unroll 1
+            for (int cb = 0; cb < TC_H / 8; cb++) {
+                const int u0 = cb * 8;
+                float dh[8], dc[8];
+                if (s == 0) {
+#pragma unroll
+                    for (int j = 0; j < 8; j++) { dh[j] = 0.f; dc[j] = 0.f; }
+                    if (valid) {
+                        const float4 x0 = __ldg(reinterpret_cast<const float4 *>(a.dhfin + p * TC_H + u0));
+                        const float4 x1 = __ldg(reinterpret_cast<const float4 *>(a.dhfin + p * TC_H + u0 + 4));
+                        dh[0] = x0.x * scale; dh[1] = x0.y * scale; dh[2] = x0.z * scale; dh[3] = x0.w * scale;
+                        dh[4] = x1.x * scale; dh[5] = x1.y * scale; dh[6] = x1.z * scale; dh[7] = x1.w * scale;
+                    }
+                } else {
+                    uint32_t v0[8], v1[8];
+                    tmem_ld8(lane_base + 128 + u0, v0);
+                    tmem_ld8(lane_base + 256 + u0, v1);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 8; j++) { dh[j] = __uint_as_float(v0[j]); dc[j] = __uint_as_float(v1[j]); }
+                }
+                float gi[8], gf[8], gg[8], go[8], cn[8], cp[8], hp[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) { gi[j] = gf[j] = gg[j] = go[j] = cn[j] = cp[j] = hp[j] = 0.f; }
+                if (valid) {
+                    unpack8_f16(__ldg(reinterpret_cast<const uint4 *>(act + 0 * TC_H + u0)), gi);
+                    unpack8_f16(__ldg(reinterpret_cast<const uint4 *>(act + 1 * TC_H + u0)), gf);
+                    unpack8_f16(__ldg(reinterpret_cast<const uint4 *>(act + 2 * TC_H + u0)), gg);
+                    unpack8_f16(__ldg(reinterpret_cast<const uint4 *>(act + 3 * TC_H + u0)), go);
+                    unpack8_f16(__ldg(reinterpret_cast<const uint4 *>(act + 4 * TC_H + u0)), cn);
+                    if (t > 0) {
+                        float op[8];
+                        unpack8_f16(__ldg(reinterpret_cast<const uint4 *>(actp + 3 * TC_H + u0)), op);
+                        unpack8_f16(__ldg(reinterpret_cast<const uint4 *>(actp + 4 * TC_H + u0)), cp);
+#pragma unroll
+                        for (int j = 0; j < 8; j++) hp[j] = op[j] * tanh_fast(cp[j]);
+                    }
+                }
+                float da[4][8];  // [q][.]: packed columns (u0 + 2q + {0,1}) * 4 + gate
+                uint32_t dcn_bits[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const float tcn = tanh_fast(cn[j]);
+                    const float dcn = fmaf(dh[j] * go[j], 1.f - tcn * tcn, dc[j]);
+                    const float d_i = dcn * gg[j] * gi[j] * (1.f - gi[j]);
+                    const float d_f = dcn * cp[j] * gf[j] * (1.f - gf[j]);
+                    const float d_g = dcn * gi[j] * (1.f - gg[j] * gg[j]);
+                    const float d_o = dh[j] * tcn * go[j] * (1.f - go[j]);
+                    dcn_bits[j] = __float_as_uint(dcn * gf[j]);
+                    da[j >> 1][(j & 1) * 4 + 0] = d_i; da[j >> 1][(j & 1) * 4 + 1] = d_f;
+                    da[j >> 1][(j & 1) * 4 + 2] = d_g; da[j >> 1][(j & 1) * 4 + 3] = d_o;
+                }
+                tmem_st8(lane_base + 256 + u0, dcn_bits);
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const uint4 pk = pack8_f16(da[q]);
+                    *reinterpret_cast<uint4 *>(As + canon_off(r, cb * 32 + q * 8, TC_G4)) = pk;          // dgrad operand
+                    *reinterpret_cast<uint4 *>(da_blk + (size_t)(cb * 4 + q) * 2048 + r * 16) = pk;       // wgrad operand image
+                }
+                *reinterpret_cast<uint4 *>(xh_blk + (size_t)(16 + cb) * 2048 + r * 16) = pack8_f16(hp);  // h_{t-1}
+            }
+            // ---- x_t (same dropout mask as forward) into the wgrad image ----
+            {
+                const float *src = nullptr;
+                int64_t e = 0;
+                if (valid) { e = p * L + t; src = a.T + ((int64_t)a.seq_node[e] * L + a.seq_type[e]) * TC_H; }
+#pragma unroll 4
+                for (int k8 = 0; k8 < TC_H / 8; k8++) {
+                    float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    if (valid) {
+                        const float4 u = __ldg(reinterpret_cast<const float4 *>(src + k8 * 8));
+                        const float4 w = __ldg(reinterpret_cast<const float4 *>(src + k8 * 8 + 4));
+                        f[0] = u.x; f[1] = u.y; f[2] = u.z; f[3] = u.w; f[4] = w.x; f[5] = w.y; f[6] = w.z; f[7] = w.w;
+                        if (a.drop_thr) {
+                            const uint64_t pair = ((uint64_t)e * TC_H + k8 * 8) >> 1;
+#pragma unroll
+                            for (int q = 0; q < 4; q++) {
+                                const uint32_t h = dropout_hash_pair(a.drop_seed, 0, pair + q);
+                                f[2 * q] = (h & 0xFFFFu) < a.drop_thr ? 0.f : f[2 * q] * a.drop_scale;
+                                f[2 * q + 1] = (h >> 16) < a.drop_thr ? 0.f : f[2 * q + 1] * a.drop_scale;
+                            }
+                        }
+                    }
+                    *reinterpret_cast<uint4 *>(xh_blk + (size_t)k8 * 2048 + r * 16) = pack8_f16(f);
+                }
+            }
+            tmem_st_wait();
+            fence_proxy_async();
+            tc_fence_before();
+            mbar_arrive(&a_ready);
+            // ---- [dx | dh_{t-1}] = da . W' ----
+            mbar_wait(&acc_full, s & 1);
+            tc_fence_after();
+            if (valid) {
+                const int64_t e = p * L + t;
+                float *dst = a.dT + ((int64_t)a.seq_node[e] * L + a.seq_type[e]) * TC_H;
+#pragma unroll 2
+                for (int cb = 0; cb < TC_H / 8; cb++) {
+                    uint32_t v[8];
+                    tmem_ld8(lane_base + cb * 8, v);
+                    tmem_ld_wait();
+                    float f[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) f[j] = __uint_as_float(v[j]) * inv_scale;
+                    if (a.drop_thr) {
+                        const uint64_t pair = ((uint64_t)e * TC_H + cb * 8) >> 1;
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const uint32_t h = dropout_hash_pair(a.drop_seed, 0, pair + q);
+                            f[2 * q] = (h & 0xFFFFu) < a.drop_thr ? 0.f : f[2 * q] * a.drop_scale;
+                            f[2 * q + 1] = (h >> 16) < a.drop_thr ? 0.f : f[2 * q + 1] * a.drop_scale;
+                        }
+                    }
+                    atomicAdd(reinterpret_cast<float4 *>(dst + cb * 8), make_float4(f[0], f[1], f[2], f[3]));
+                    atomicAdd(reinterpret_cast<float4 *>(dst + cb * 8 + 4), make_float4(f[4], f[5], f[6], f[7]));
+                }
+            }
+            tc_fence_before();  // the TMEM reads above precede the next step's MMA (ordered through a_ready)
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) { __syncwarp(); tmem_dealloc<512>(taddr); }
+}
+
+// ---------------------------------------------------------------------------
+// weight gradients: dWp[k][col] (+)= sum over blocks  XH_blk^T . dA_blk
+// CTA = one 128 (k) x 256 (col) output tile (blockIdx.y) x one split of the
+// block list (blockIdx.x); operands are bulk-copied images (MN-major UMMA).
+// ---------------------------------------------------------------------------
+struct WgradTcArgs {
+    const unsigned char *xh_img, *da_img;
+    int64_t nblocks;
+    const float *gscale;
+    float *dWp;  // [256][512] fp32, atomically accumulated
+};
+constexpr int WG_STAGE_BYTES = 32768 + 65536;
+constexpr int WG_SMEM = 2 * WG_STAGE_BYTES + 1024;
+
+__global__ void __launch_bounds__(192, 1) k_wgrad_tc(WgradTcArgs a)
+{
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t full_bar[2], empty_bar[2], acc_full;
+    __shared__ uint32_t s_taddr;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int mt = blockIdx.y >> 1, nt = blockIdx.y & 1;
+    if (tid == 0) {
+        for (int s = 0; s < 2; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&acc_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 4) tmem_alloc<256>(&s_taddr);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t taddr = s_taddr;
+    const int64_t first = blockIdx.x, step = gridDim.x;
+    if (warp == 5) {
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int64_t b = first; b < a.nblocks; b += step) {
+                unsigned char *dst = base + stage * WG_STAGE_BYTES;
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                mbar_arrive_expect_tx(&full_bar[stage], WG_STAGE_BYTES);
+                bulk_g2s(dst, a.xh_img + b * XH_BLOCK_BYTES + (size_t)mt * 32768, 32768, &full_bar[stage]);
+                bulk_g2s(dst + 32768, a.da_img + b * DA_BLOCK_BYTES + (size_t)nt * 65536, 32768, &full_bar[stage]);
+                bulk_g2s(dst + 65536, a.da_img + b * DA_BLOCK_BYTES + (size_t)nt * 65536 + 32768, 32768, &full_bar[stage]);
+                if (++stage == 2) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 4) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_f16_mn(128, 256);
+            uint32_t stage = 0, phase = 0;
+            bool first_blk = true;
+            for (int64_t b = first; b < a.nblocks; b += step) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                const uint32_t abase = smem_u32(base + stage * WG_STAGE_BYTES), bbase = abase + 32768;
+#pragma unroll
+                for (int ks = 0; ks < 8; ks++) {  // 128 rows of the block = 8 K-steps of 16
+                    const uint64_t ad = make_smem_desc(abase + ks * 256, 128, 2048);
+                    const uint64_t bd = make_smem_desc(bbase + ks * 256, 128, 2048);
+                    mma_f16(taddr, ad, bd, idesc, !first_blk || ks > 0);
+                }
+                first_blk = false;
+                mma_commit(&empty_bar[stage]);
+                if (++stage == 2) { stage = 0; phase ^= 1; }
+            }
+            mma_commit(&acc_full);
+        }
+    } else {
+        mbar_wait(&acc_full, 0);
+        tc_fence_after();
+        if (first < a.nblocks) {
+            const float inv_scale = a.gscale[1];
+            float *dst = a.dWp + (int64_t)(mt * 128 + tid) * TC_G4 + nt * 256;
+            for (int c0 = 0; c0 < 256; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(taddr + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    atomicAdd(reinterpret_cast<float4 *>(dst + c0 + j),
+                              make_float4(__uint_as_float(v[j]) * inv_scale, __uint_as_float(v[j + 1]) * inv_scale,
+                                          __uint_as_float(v[j + 2]) * inv_scale, __uint_as_float(v[j + 3]) * inv_scale));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) { __syncwarp(); tmem_dealloc<256>(taddr); }
+}
+
+// bias gradient: dbp[col] = (1/scale) * sum over all rows of all da blocks
+__global__ void __launch_bounds__(256) k_colsum_da_img(const unsigned char *__restrict__ da_img, int64_t nblocks,
+                                                        const float *__restrict__ gscale, float *__restrict__ dbp)
+{
+    __shared__ float acc[TC_G4];
+    for (int i = threadIdx.x; i < TC_G4; i += 256) acc[i] = 0.f;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int64_t b = blockIdx.x; b < nblocks; b += gridDim.x) {
+        const unsigned char *blk = da_img + b * DA_BLOCK_BYTES;
+        for (int col8 = warp; col8 < 64; col8 += 8) {
+            float s8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int rr = 0; rr < 4; rr++) {
+                float f[8];
+                unpack8_f16(__ldg(reinterpret_cast<const uint4 *>(blk + (size_t)col8 * 2048 + (rr * 32 + lane) * 16)), f);
+#pragma unroll
+                for (int j = 0; j < 8; j++) s8[j] += f[j];
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s8[j] += __shfl_xor_sync(0xffffffffu, s8[j], o);
+            }
+            if (lane == 0)
+#pragma unroll
+                for (int j = 0; j < 8; j++) acc[col8 * 8 + j] += s8[j];
+        }
+    }
+    __syncthreads();
+    const float inv_scale = gscale[1];
+    for (int i = threadIdx.x; i < TC_G4; i += 256) atomicAdd(dbp + i, acc[i] * inv_scale);
+}
+
+// LSTM backward in tensor-core mode: fills w.dWp [2H][4H] and w.dbp [4H] (packed
+// layouts, same as the fp32 path) and scatters dx into w.dT.
+int pagg_tc_backward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_params &prm,
+                          const int32_t *seq_node, const uint8_t *seq_type, cudaStream_t st)
+{
+    if (c.H != TC_H) {
+        set_error("PN_MATH_TC: the tensor-core LSTM is built for hidden size 128 (got %d)", c.H);
+        return PN_ERR_UNSUPPORTED;
+    }
+    const int64_t P = (int64_t)c.S * c.nw, ntiles = ceil_div(P, 128), nblocks = ntiles * c.L;
+    PN_CUDA(cudaMemsetAsync(w.gscale, 0, 2 * sizeof(float), st));
+    k_absmax_bits<<<(unsigned)std::min<int64_t>(1024, ceil_div(P * TC_H, 256)), 256, 0, st>>>(w.dhfin, P * TC_H, reinterpret_cast<unsigned int *>(w.gscale));
+    PN_LAUNCH_CHECK();
+    k_make_scale<<<1, 1, 0, st>>>(w.gscale);
+    PN_LAUNCH_CHECK();
+    unsigned char *WhT = reinterpret_cast<unsigned char *>(w.WpT);  // 256 KB of the 512 KB fp32 region
+    k_pack_lstm_tc_bwd<<<(unsigned)ceil_div(TC_G4 * TC_K2, 256), 256, 0, st>>>(prm.w_ih, prm.w_hh, WhT);
+    PN_LAUNCH_CHECK();
+    uint32_t thr = 0; float scale = 1.f;
+    if (c.training && c.dropout_p > 0.f) {
+        thr = dropout_threshold(c.dropout_p);
+        scale = c.dropout_p >= 1.f ? 0.f : 1.f / (1.f - c.dropout_p);
+    }
+    unsigned char *da_img = reinterpret_cast<unsigned char *>(w.dA), *xh_img = reinterpret_cast<unsigned char *>(w.XH);
+    LstmBwdTcArgs a{w.T, seq_node, seq_type, WhT, reinterpret_cast<const __half *>(w.acts), w.dhfin, w.gscale, w.dT,
+                    da_img, xh_img, P, ntiles, c.L, thr, scale, c.dropout_seed};
+    PN_CUDA(cudaFuncSetAttribute(k_lstm_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TCB_SMEM));
+    {
+        ProfScope prof("lstm_bwd", st);
+        k_lstm_bwd_tc<<<(unsigned)ntiles, 192, TCB_SMEM, st>>>(a);
+    }
+    PN_LAUNCH_CHECK();
+    PN_CUDA(cudaMemsetAsync(w.dWp, 0, sizeof(float) * TC_K2 * TC_G4, st));
+    PN_CUDA(cudaMemsetAsync(w.dbp, 0, sizeof(float) * TC_G4, st));
+    WgradTcArgs wa{xh_img, da_img, nblocks, w.gscale, w.dWp};
+    PN_CUDA(cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
+    {
+        ProfScope prof("wgrad", st);
+        const unsigned nsplit = (unsigned)std::max<int64_t>(1, std::min<int64_t>(37, nblocks));
+        k_wgrad_tc<<<dim3(nsplit, 4), 192, WG_SMEM, st>>>(wa);
+    }
+    PN_LAUNCH_CHECK();
+    k_colsum_da_img<<<(unsigned)std::min<int64_t>(296, nblocks), 256, 0, st>>>(da_img, nblocks, w.gscale, w.dbp);
     PN_LAUNCH_CHECK();
     return PN_OK;
 }

@@ -94,6 +94,13 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N)
            | ((uint32_t)(M >> 4) << 24);  // m_dim
 }
 
+// same, operands MN-major (M/N contiguous in 16-byte groups, K strided): used by the
+// weight-gradient GEMM whose reduction dimension is the row index of both operands
+__host__ __device__ constexpr uint32_t make_idesc_f16_mn(int M, int N)
+{
+    return make_idesc_f16(M, N) | (1u << 15) | (1u << 16);
+}
+
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread
 __device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate)
 {
@@ -122,7 +129,37 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
           "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr) : "memory");
+}
+// registers -> TMEM (thread i writes its lane's 8 consecutive columns)
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+                 "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// pack 8 floats into 8 halves (16 bytes)
+__device__ __forceinline__ uint4 pack8_f16(const float (&f)[8])
+{
+    __half2 h0 = __floats2half2_rn(f[0], f[1]), h1 = __floats2half2_rn(f[2], f[3]);
+    __half2 h2 = __floats2half2_rn(f[4], f[5]), h3 = __floats2half2_rn(f[6], f[7]);
+    uint4 pk;
+    pk.x = *reinterpret_cast<uint32_t *>(&h0); pk.y = *reinterpret_cast<uint32_t *>(&h1);
+    pk.z = *reinterpret_cast<uint32_t *>(&h2); pk.w = *reinterpret_cast<uint32_t *>(&h3);
+    return pk;
+}
+__device__ __forceinline__ void unpack8_f16(const uint4 &pk, float (&f)[8])
+{
+    const __half2 *h = reinterpret_cast<const __half2 *>(&pk);
+#pragma unroll
+    for (int i = 0; i < 4; i++) { const float2 t = __half22float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
 
 // byte offset of element (r, k) in the canonical layout of a [rows][K] fp16 operand
 __host__ __device__ constexpr uint32_t canon_off(int r, int k, int K)

@@ -2,10 +2,12 @@
 
 Tolerance: operands are rounded to fp16 (11-bit significand, the same width
 as TF32), products accumulate in fp32 in TMEM, gate non-linearities use
-tanh.approx (2^-11 relative).  Against the fp64 oracle the logits are held to
-rtol 1e-2 / atol 3e-3 and gradients to rtol 3e-2 / atol 3e-3 — the 'stated
-fp32 tolerance' of BASELINE.json's north_star for this mode (the strict fp32
-mode is tested in test_gpu_pagg.py at 1e-4)."""
+tanh.approx (2^-11 relative).  In the backward pass gradients
+travel as scaled fp16 too.  Against the fp64 oracle the logits are held to
+rtol 1e-2 / atol 3e-3, and every parameter gradient to a max-norm error of
+2 % of that gradient's largest entry — the 'stated fp32 tolerance' of
+BASELINE.json's north_star for this mode (the strict fp32 mode is tested in
+test_gpu_pagg.py at 1e-4)."""
 import numpy as np
 import pytest
 import torch
@@ -16,7 +18,14 @@ from tests.test_gpu_pagg import _oracle_run, _random_case
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 TC_FWD = dict(rtol=1e-2, atol=3e-3)
-TC_GRAD = dict(rtol=3e-2, atol=3e-3)
+TC_GRAD_REL_MAXNORM = 2e-2
+
+
+def assert_grad_close(got, want, name):
+    scale = want.abs().max().item()
+    err = (got - want).abs().max().item()
+    assert err <= TC_GRAD_REL_MAXNORM * scale + 1e-7, f"{name}: max err {err:.3e} vs max |g| {scale:.3e}"
+    return err / max(scale, 1e-30)
 
 
 @pytest.mark.parametrize("M,N,K,relu", [(128, 128, 64, False), (128, 128, 256, False), (300, 200, 500, True),
@@ -51,8 +60,8 @@ def test_tc_mode_forward_backward_match_oracle(variant, N, Fd, Cc, nw, L, S):
     print(f"tc fwd max abs err {err:.3e} (ref max {y_ref.abs().max().item():.3f})")
     torch.testing.assert_close(y.cpu(), y_ref, **TC_FWD)
     (y * G.to(DEV)).sum().backward()
-    for k, p in m.named_parameters():
-        torch.testing.assert_close(p.grad.cpu(), g_ref[k], **TC_GRAD, msg=lambda s: f"{k}: {s}")
+    worst = max(assert_grad_close(p.grad.cpu(), g_ref[k], k) for k, p in m.named_parameters())
+    print(f"tc grad worst relative max-norm err {worst:.3e}")
 
 
 def test_tc_mode_matches_fp32_mode_at_pubmed_scale():
@@ -66,3 +75,39 @@ def test_tc_mode_matches_fp32_mode_at_pubmed_scale():
     ytc = m(Xd, neis, nw, L, mask, lt, None)
     print("tc vs fp32 max abs diff", (ytc - y32).abs().max().item())
     torch.testing.assert_close(ytc, y32, **TC_FWD)
+    G = torch.randn(S, Cc, device=DEV) / S
+    (ytc * G).sum().backward()
+    gtc = {k: p.grad.clone() for k, p in m.named_parameters()}
+    m.zero_grad()
+    m.math_mode = "fp32"
+    (m(Xd, neis, nw, L, mask, lt, None) * G).sum().backward()
+    worst = max(assert_grad_close(gtc[k], p.grad, k) for k, p in m.named_parameters())
+    print(f"tc vs fp32 grad worst relative max-norm err {worst:.3e}")
+
+
+@pytest.mark.parametrize("variant", ["homo", "hetero"])
+def test_tc_mode_training_dropout_matches_oracle_with_same_masks(variant):
+    from oracle import pagg_oracle as po
+    from tests.test_gpu_pagg import np_dropout_hash
+    N, Fd, H, Cc, nw, L, S, p, seed = 150, 21, 128, 4, 6, 4, 70, 0.7, 0xABCDEF0123
+    m, X, mask, neis, lt = _random_case(variant, N, Fd, H, Cc, nw, L, S, seed=8)
+    thr, scale = int(p * 65536), 1.0 / (1.0 - p)
+    keep_seq = np_dropout_hash(seed, 0, np.arange(S * nw * L * H, dtype=np.uint64)) >= thr
+    keep_cat = np_dropout_hash(seed, 1, np.arange(S * 2 * H, dtype=np.uint64)) >= thr
+    ms = torch.tensor(keep_seq.reshape(S, nw, L, H).astype(np.float64) * scale)
+    mc = torch.tensor(keep_cat.reshape(S, 2 * H).astype(np.float64) * scale)
+    sn, st, pt = po.canonicalize(variant, neis.numpy(), lt.numpy(), nw, L)
+    rows = torch.nonzero(mask).reshape(-1).numpy()
+    params = {k: v.detach().clone().double().requires_grad_(True) for k, v in m.state_dict().items()}
+    y_ref = po.pagg_forward_canonical(variant, params, X.double(), sn, st, pt, rows, mask_seq=ms, mask_cat=mc)
+    G = torch.randn(S, Cc)
+    (y_ref * G.double()).sum().backward()
+    m = m.to(DEV).train()
+    dev = lambda a, dt: torch.tensor(a, device=DEV, dtype=dt)
+    y = pagg.pagg_forward(variant, X.to(DEV), dict(m.named_parameters()), dev(sn, torch.int32), dev(st, torch.uint8),
+                          dev(pt, torch.int32), dev(rows, torch.int32), dropout=p, training=True, seed=seed,
+                          math_mode="tc")
+    torch.testing.assert_close(y.cpu(), y_ref.detach().float(), **TC_FWD)
+    (y * G.to(DEV)).sum().backward()
+    for k, pr in m.named_parameters():
+        assert_grad_close(pr.grad.cpu(), params[k].grad.float(), k)
