@@ -154,6 +154,7 @@ k_dist_relax(uint8_t *D, const uint32_t *__restrict__ rowptr, const int32_t *__r
 
 constexpr int WALK_THREADS = 256;
 constexpr int NPOLY_BITS = 32;
+constexpr int NDIGITS = 8;  // radix-16 digits of the chunk index
 
 struct WalkParams {
     const uint2 *noderec;
@@ -167,12 +168,13 @@ struct WalkParams {
     int64_t wpe;             // walks per epoch in this call = n' * nw
     int64_t cpe;             // chunks per epoch = ceil(wpe / wpt)
     int64_t total_chunks;    // E * cpe
-    // jump-ahead tables (host-computed per call)
+    // jump-ahead tables (host-computed per call); chunk stride = 2L*wpt draws
     uint32_t base[lfg::DEG];               // window whose first generated word is the
                                            // first rand() of (epoch_begin, node_begin, walk 0)
-    uint32_t jstep[lfg::DEG];              // x^(2L*wpt)            : next chunk, same epoch
-    uint32_t jwrap[lfg::DEG];              // x^(epoch stride - (cpe-1)*2L*wpt) : first chunk of next epoch
-    uint32_t jchunk[NPOLY_BITS][lfg::DEG]; // x^(2L*wpt * 2^b)
+    uint32_t jstep[lfg::DEG];              // x^(chunk stride)      : next chunk, same epoch
+    uint32_t jwrap[lfg::DEG];              // x^(epoch stride - (cpe-1)*chunk stride) : first chunk of next epoch
+    uint32_t jlane[32][lfg::DEG];          // x^(chunk stride * l), l = 0..31 : lane l's chunk from the warp's base
+    uint32_t jchunk16[NDIGITS][15][lfg::DEG];  // x^(chunk stride * d * 16^i), d = 1..15
     uint32_t jepoch[NPOLY_BITS][lfg::DEG]; // x^(2L*n*nw * 2^b)
 };
 
@@ -197,33 +199,63 @@ __device__ __forceinline__ uint32_t warp_window_apply(const uint32_t *poly, uint
     return acc;
 }
 
-__global__ void __launch_bounds__(WALK_THREADS)
+__global__ void __launch_bounds__(WALK_THREADS, 4)
 k_merw_walk(const __grid_constant__ WalkParams P)
 {
     __shared__ uint32_t ring[lfg::DEG][WALK_THREADS];  // thread-private windows, bank = tid
     __shared__ uint32_t scratch[WALK_THREADS / 32][64];
+    __shared__ uint32_t lane_poly[32][lfg::DEG];       // stride 31 words: conflict-free across lanes
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < 32 * lfg::DEG; i += WALK_THREADS) lane_poly[i / lfg::DEG][i % lfg::DEG] = P.jlane[i / lfg::DEG][i % lfg::DEG];
+    __syncthreads();
     const int64_t q_warp = ((int64_t)blockIdx.x * WALK_THREADS + warp * 32);
     if (q_warp >= P.total_chunks) return;  // whole warp idle
 
-    // ---- warp: window of lane 0's chunk -----------------------------------
+    // ---- warp: window of lane 0's chunk (radix-16 digits of c, bits of e) ----
     int64_t e = q_warp / P.cpe, c = q_warp % P.cpe;
     uint32_t w = lane < lfg::DEG ? P.base[lane] : 0u;
     {
         uint64_t cb = (uint64_t)c, eb = (uint64_t)e;
-        for (int b = 0; cb; b++, cb >>= 1)
-            if (cb & 1) w = warp_window_apply(P.jchunk[b], w, scratch[warp], lane);
+        for (int i = 0; cb; i++, cb >>= 4)
+            if (cb & 15) w = warp_window_apply(P.jchunk16[i][(cb & 15) - 1], w, scratch[warp], lane);
         for (int b = 0; eb; b++, eb >>= 1)
             if (eb & 1) w = warp_window_apply(P.jepoch[b], w, scratch[warp], lane);
     }
-    // ---- hand each lane its window, stepping chunk by chunk ----------------
-    int64_t my_e = 0, my_c = 0;
-    for (int l = 0; l < 32; l++) {
-        if (lane < lfg::DEG) ring[lane][warp * 32 + l] = w;
-        if (lane == l) { my_e = e; my_c = c; }
-        if (l == 31) break;
-        if (c + 1 < P.cpe) { w = warp_window_apply(P.jstep, w, scratch[warp], lane); c++; }
-        else               { w = warp_window_apply(P.jwrap, w, scratch[warp], lane); c = 0; e++; }
+    int64_t my_e = e, my_c = c + lane;
+    if (c + 31 < P.cpe) {
+        // ---- fast path: the warp's 32 chunks lie in one epoch; every lane applies its
+        //      own polynomial x^(lane * chunk stride) to the warp's window, in parallel ----
+        uint32_t *ext = scratch[warp];
+        if (lane < lfg::DEG) ext[lane] = w;
+        __syncwarp();
+        for (int d0 = 0; d0 < 30; d0 += 3) {
+            if (lane < 3) ext[31 + d0 + lane] = ext[d0 + lane] + ext[28 + d0 + lane];
+            __syncwarp();
+        }
+        // two passes of 16 / 15 coefficients keep the register footprint small
+#pragma unroll 1
+        for (int half = 0; half < 2; half++) {
+            const int i0 = half * 16;
+            uint32_t cf[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) cf[i] = (i0 + i < lfg::DEG) ? lane_poly[lane][i0 + i] : 0u;
+#pragma unroll 1
+            for (int j = 0; j < lfg::DEG; j++) {
+                uint32_t acc = half ? ring[j][tid] : 0u;
+#pragma unroll
+                for (int i = 0; i < 16; i++) acc += cf[i] * ext[(i0 + i + j) & 63];  // warp-broadcast reads
+                ring[j][tid] = acc;
+            }
+        }
+    } else {
+        // ---- slow path (warp straddles an epoch boundary or the end): step lane by lane ----
+        for (int l = 0; l < 32; l++) {
+            if (lane < lfg::DEG) ring[lane][warp * 32 + l] = w;
+            if (lane == l) { my_e = e; my_c = c; }
+            if (l == 31) break;
+            if (c + 1 < P.cpe) { w = warp_window_apply(P.jstep, w, scratch[warp], lane); c++; }
+            else               { w = warp_window_apply(P.jwrap, w, scratch[warp], lane); c = 0; e++; }
+        }
     }
     __syncwarp();
     if (q_warp + lane >= P.total_chunks) return;
@@ -450,12 +482,12 @@ static int plan_walk(WalkParams &P, int32_t n, int32_t nw, int32_t L, int64_t ep
     // chunk size: enough chunks to fill the machine a few times over, at most
     // 32 walks per thread (amortises the jump-ahead), at least 4
     int wpt = 32;
-    const int64_t want_threads = (int64_t)148 * 2048 * 2;
+    const int64_t want_threads = (int64_t)148 * 2048;
     while (wpt > 4 && E * ceil_div(wpe, wpt) < want_threads) wpt >>= 1;
     P.wpt = wpt;
     P.cpe = ceil_div(wpe, wpt);
     P.total_chunks = E * P.cpe;
-    PN_REQUIRE(P.cpe < ((int64_t)1 << NPOLY_BITS) && E < ((int64_t)1 << NPOLY_BITS),
+    PN_REQUIRE(P.cpe < ((int64_t)1 << (4 * NDIGITS)) && E < ((int64_t)1 << NPOLY_BITS),
                "pn_merw_sample: too many chunks/epochs in one call");
     const uint64_t draws_per_walk = 2ull * (uint64_t)L;  // every roll draws twice, L rolls
     const uint64_t chunk_stride = draws_per_walk * (uint64_t)wpt;
@@ -472,15 +504,24 @@ static int plan_walk(WalkParams &P, int32_t n, int32_t nw, int32_t L, int64_t ep
     lfg::Poly pc = lfg::poly_xpow(chunk_stride), pe = lfg::poly_xpow(epoch_stride);
     copy_poly(P.jstep, pc);
     copy_poly(P.jwrap, lfg::poly_xpow(epoch_stride - (uint64_t)(P.cpe - 1) * chunk_stride));
-    for (int b = 0; b < NPOLY_BITS; b++) {
-        copy_poly(P.jchunk[b], pc); copy_poly(P.jepoch[b], pe);
-        pc = lfg::poly_mul(pc, pc); pe = lfg::poly_mul(pe, pe);
+    {
+        lfg::Poly acc = lfg::poly_one();
+        for (int l = 0; l < 32; l++) { copy_poly(P.jlane[l], acc); acc = lfg::poly_mul(acc, pc); }
     }
+    {
+        lfg::Poly digit = pc;  // x^(chunk stride * 16^i)
+        for (int i = 0; i < NDIGITS; i++) {
+            lfg::Poly acc = digit;
+            for (int d = 1; d <= 15; d++) { copy_poly(P.jchunk16[i][d - 1], acc); acc = lfg::poly_mul(acc, digit); }
+            digit = acc;  // digit^16
+        }
+    }
+    for (int b = 0; b < NPOLY_BITS; b++) { copy_poly(P.jepoch[b], pe); pe = lfg::poly_mul(pe, pe); }
     return PN_OK;
 }
 
-// Host-only debug view of the plan (tests/test_lfg_jump.py): same tables the
-// kernel receives.  tables = base[31] jstep[31] jwrap[31] jchunk[32][31] jepoch[32][31].
+// Host-only debug view of the plan (tests/test_sampler_host.py): the tables the kernel
+// receives: base[31] jstep[31] jwrap[31] jlane[32][31] jchunk16[8][15][31] jepoch[32][31].
 extern "C" int pn_merw_plan_host(int32_t n, int32_t nw, int32_t L, int64_t epoch_begin,
                                  int64_t E, int32_t node_begin, int64_t np, uint64_t seed,
                                  int32_t *wpt, int64_t *cpe, uint32_t *tables)
@@ -489,7 +530,7 @@ extern "C" int pn_merw_plan_host(int32_t n, int32_t nw, int32_t L, int64_t epoch
     int rc = plan_walk(P, n, nw, L, epoch_begin, E, node_begin, np, seed);
     if (rc != PN_OK) return rc;
     *wpt = P.wpt; *cpe = P.cpe;
-    memcpy(tables, P.base, sizeof(uint32_t) * lfg::DEG * (3 + 2 * NPOLY_BITS));
+    memcpy(tables, P.base, sizeof(uint32_t) * lfg::DEG * (3 + 32 + NDIGITS * 15 + NPOLY_BITS));
     return PN_OK;
 }
 

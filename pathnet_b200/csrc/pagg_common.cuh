@@ -53,7 +53,7 @@ inline PaggWs carve_workspace(const pn_pagg_cfg &c, void *base)
     take(w.Wp, 2 * H * 4 * H);
     take(w.WpT, 4 * H * 2 * H);
     take(w.bp, 4 * H);
-    take(w.acts, L * P * 5 * H);
+    take(w.acts, L * P128 * 5 * H);
     take(w.hfin, P * H);
     take(w.score, P);
     take(w.att, P);

@@ -165,13 +165,14 @@ struct LstmTcArgs {
     const uint8_t *seq_type;  // [P,L]
     const unsigned char *Wh;  // packed fp16 weights (8 chunks x 32 KB)
     const float *bp;          // [512]
-    __half *acts;             // [L][P][5][H] fp16 (i,f,g,o,c)
+    __half *acts;             // tile images: block (tile, t) = [5 (i,f,g,o,c)][16 unit8][128 rows][8] fp16
     float *hfin;              // [P,H]
     int64_t P;
     int L;
     uint32_t drop_thr; float drop_scale; uint64_t drop_seed;
 };
 
+constexpr int ACT_BLOCK_HALFS = 5 * 16 * 128 * 8;  // 160 KB per (tile, step)
 constexpr int TC_NSTAGE = 3;
 constexpr int TC_A_BYTES = 128 * TC_K2 * 2;  // 64 KB
 constexpr int TC_SMEM = TC_A_BYTES + TC_NSTAGE * TC_CHUNK_BYTES + 2048 /*bias*/ + 1024 /*align slack*/;
@@ -300,7 +301,8 @@ __global__ void __launch_bounds__(192, 1) k_lstm_fwd_tc(LstmTcArgs a)
             // ---- wait for the gate pre-activations ----
             mbar_wait(&acc_full, t & 1);
             tc_fence_after();
-            __half *act = valid ? a.acts + (((int64_t)t * a.P + p) * 5) * TC_H : nullptr;
+            // activations of (tile, t): chunk (q, unit8, row) -> consecutive rows are consecutive 16-byte chunks
+            __half *act = a.acts + ((int64_t)blockIdx.x * L + t) * ACT_BLOCK_HALFS + r * 8;
 #pragma unroll
             for (int c0 = 0; c0 < TC_G4; c0 += 32) {
                 uint32_t v[32];
@@ -331,11 +333,12 @@ __global__ void __launch_bounds__(192, 1) k_lstm_fwd_tc(LstmTcArgs a)
                 }
                 if (valid) {
                     const int u0 = c0 / 4;
-                    *reinterpret_cast<uint4 *>(act + 0 * TC_H + u0) = pack8_f16(gi);
-                    *reinterpret_cast<uint4 *>(act + 1 * TC_H + u0) = pack8_f16(gf);
-                    *reinterpret_cast<uint4 *>(act + 2 * TC_H + u0) = pack8_f16(gg);
-                    *reinterpret_cast<uint4 *>(act + 3 * TC_H + u0) = pack8_f16(go);
-                    *reinterpret_cast<uint4 *>(act + 4 * TC_H + u0) = pack8_f16(cc);
+                    const int ub = (c0 / 32) * 1024;  // unit8 block of 128 rows x 8 halves
+                    *reinterpret_cast<uint4 *>(act + 0 * 16384 + ub) = pack8_f16(gi);
+                    *reinterpret_cast<uint4 *>(act + 1 * 16384 + ub) = pack8_f16(gf);
+                    *reinterpret_cast<uint4 *>(act + 2 * 16384 + ub) = pack8_f16(gg);
+                    *reinterpret_cast<uint4 *>(act + 3 * 16384 + ub) = pack8_f16(go);
+                    *reinterpret_cast<uint4 *>(act + 4 * 16384 + ub) = pack8_f16(cc);
                     if (t == L - 1) {
                         *reinterpret_cast<float4 *>(a.hfin + p * TC_H + u0) = make_float4(hh[0], hh[1], hh[2], hh[3]);
                         *reinterpret_cast<float4 *>(a.hfin + p * TC_H + u0 + 4) = make_float4(hh[4], hh[5], hh[6], hh[7]);
@@ -421,7 +424,7 @@ struct LstmBwdTcArgs {
     const int32_t *seq_node;
     const uint8_t *seq_type;
     const unsigned char *WhT;  // 16 chunks x 16 KB
-    const __half *acts;        // [L][P][5][H]
+    const __half *acts;        // tile images (see LstmTcArgs)
     const float *dhfin;        // [P,H]
     const float *gscale;       // {scale, 1/scale}
     float *dT;                 // [N,L,H]
@@ -505,8 +508,8 @@ __global__ void __launch_bounds__(192, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
             const int64_t blk = (int64_t)t * a.ntiles + tile;
             unsigned char *da_blk = a.da_img + blk * DA_BLOCK_BYTES;
             unsigned char *xh_blk = a.xh_img + blk * XH_BLOCK_BYTES;
-            const __half *act = valid ? a.acts + (((int64_t)t * a.P + p) * 5) * TC_H : nullptr;
-            const __half *actp = (valid && t > 0) ? a.acts + (((int64_t)(t - 1) * a.P + p) * 5) * TC_H : nullptr;
+            const __half *act = a.acts + ((int64_t)tile * L + t) * ACT_BLOCK_HALFS + r * 8;
+            const __half *actp = act - ACT_BLOCK_HALFS;  // step t-1 (only read when t > 0)
             // ---- gate gradients ----
 #pragma unroll 1
             for (int cb = 0; cb < TC_H / 8; cb++) {
@@ -533,15 +536,16 @@ __global__ void __launch_bounds__(192, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
 #pragma unroll
                 for (int j = 0; j < 8; j++) { gi[j] = gf[j] = gg[j] = go[j] = cn[j] = cp[j] = hp[j] = 0.f; }
                 if (valid) {
-                    unpack8_f16(__ldg(reinterpret_cast<const uint4 *>(act + 0 * TC_H + u0)), gi);
-                    unpack8_f16(__ldg(reinterpret_cast<const uint4 *>(act + 1 * TC_H + u0)), gf);
-                    unpack8_f16(__ldg(reinterpret_cast<const uint4 *>(act + 2 * TC_H + u0)), gg);
-                    unpack8_f16(__ldg(reinterpret_cast<const uint4 *>(act + 3 * TC_H + u0)), go);
-                    unpack8_f16(__ldg(reinterpret_cast<const uint4 *>(act + 4 * TC_H + u0)), cn);
+                    const int ub = cb * 1024;
+                    unpack8_f16(__ldg(reinterpret_cast<const uint4 *>(act + 0 * 16384 + ub)), gi);
+                    unpack8_f16(__ldg(reinterpret_cast<const uint4 *>(act + 1 * 16384 + ub)), gf);
+                    unpack8_f16(__ldg(reinterpret_cast<const uint4 *>(act + 2 * 16384 + ub)), gg);
+                    unpack8_f16(__ldg(reinterpret_cast<const uint4 *>(act + 3 * 16384 + ub)), go);
+                    unpack8_f16(__ldg(reinterpret_cast<const uint4 *>(act + 4 * 16384 + ub)), cn);
                     if (t > 0) {
                         float op[8];
-                        unpack8_f16(__ldg(reinterpret_cast<const uint4 *>(actp + 3 * TC_H + u0)), op);
-                        unpack8_f16(__ldg(reinterpret_cast<const uint4 *>(actp + 4 * TC_H + u0)), cp);
+                        unpack8_f16(__ldg(reinterpret_cast<const uint4 *>(actp + 3 * 16384 + ub)), op);
+                        unpack8_f16(__ldg(reinterpret_cast<const uint4 *>(actp + 4 * 16384 + ub)), cp);
 #pragma unroll
                         for (int j = 0; j < 8; j++) hp[j] = op[j] * tanh_fast(cp[j]);
                     }
@@ -601,28 +605,32 @@ __global__ void __launch_bounds__(192, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
             // ---- [dx | dh_{t-1}] = da . W' ----
             mbar_wait(&acc_full, s & 1);
             tc_fence_after();
-            if (valid) {
-                const int64_t e = p * L + t;
-                float *dst = a.dT + ((int64_t)a.seq_node[e] * L + a.seq_type[e]) * TC_H;
+            {
+                // tcgen05.ld is warp-collective (.sync.aligned): every lane loads, only valid rows scatter
+                const int64_t e = valid ? p * L + t : 0;
+                float *dst = valid ? a.dT + ((int64_t)a.seq_node[e] * L + a.seq_type[e]) * TC_H : nullptr;
 #pragma unroll 2
                 for (int cb = 0; cb < TC_H / 8; cb++) {
                     uint32_t v[8];
                     tmem_ld8(lane_base + cb * 8, v);
                     tmem_ld_wait();
-                    float f[8];
+                    if (valid) {
+                        float f[8];
 #pragma unroll
-                    for (int j = 0; j < 8; j++) f[j] = __uint_as_float(v[j]) * inv_scale;
-                    if (a.drop_thr) {
-                        const uint64_t pair = ((uint64_t)e * TC_H + cb * 8) >> 1;
+                        for (int j = 0; j < 8; j++) f[j] = __uint_as_float(v[j]) * inv_scale;
+                        if (a.drop_thr) {
+                            const uint64_t pair = ((uint64_t)e * TC_H + cb * 8) >> 1;
 #pragma unroll
-                        for (int q = 0; q < 4; q++) {
-                            const uint32_t h = dropout_hash_pair(a.drop_seed, 0, pair + q);
-                            f[2 * q] = (h & 0xFFFFu) < a.drop_thr ? 0.f : f[2 * q] * a.drop_scale;
-                            f[2 * q + 1] = (h >> 16) < a.drop_thr ? 0.f : f[2 * q + 1] * a.drop_scale;
+                            for (int q = 0; q < 4; q++) {
+                                const uint32_t h = dropout_hash_pair(a.drop_seed, 0, pair + q);
+                                f[2 * q] = (h & 0xFFFFu) < a.drop_thr ? 0.f : f[2 * q] * a.drop_scale;
+                                f[2 * q + 1] = (h >> 16) < a.drop_thr ? 0.f : f[2 * q + 1] * a.drop_scale;
+                            }
                         }
+                        atomicAdd(reinterpret_cast<float4 *>(dst + cb * 8), make_float4(f[0], f[1], f[2], f[3]));
+                        atomicAdd(reinterpret_cast<float4 *>(dst + cb * 8 + 4), make_float4(f[4], f[5], f[6], f[7]));
                     }
-                    atomicAdd(reinterpret_cast<float4 *>(dst + cb * 8), make_float4(f[0], f[1], f[2], f[3]));
-                    atomicAdd(reinterpret_cast<float4 *>(dst + cb * 8 + 4), make_float4(f[4], f[5], f[6], f[7]));
+                    __syncwarp();
                 }
             }
             tc_fence_before();  // the TMEM reads above precede the next step's MMA (ordered through a_ready)

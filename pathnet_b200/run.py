@@ -96,8 +96,8 @@ def install_stubs():
     except Exception:
         from scipy.sparse.linalg import eigsh
         mod("scipy.sparse.linalg.eigen"); mod("scipy.sparse.linalg.eigen.arpack", eigsh=eigsh)
-    for alias, typ in (("bool", bool), ("int", int), ("float", float), ("object", object)):
-        if not hasattr(np, alias):
+    for alias, typ in (("bool", bool), ("int", int), ("float", float)):
+        if alias not in np.__dict__:
             setattr(np, alias, typ)
 
 

@@ -88,12 +88,13 @@ def test_jump_ahead_tables(cfg):
     n, nw, L, eb, E, nb, npr = cfg
     seed = 4242
     wpt, cpe = C.c_int32(), C.c_int64()
-    tables = np.zeros((3 + 64, 31), dtype=np.uint32)
+    tables = np.zeros((3 + 32 + 120 + 32, 31), dtype=np.uint32)
     _lib.check(_lib.lib().pn_merw_plan_host(n, nw, L, eb, E, nb, npr, seed, C.byref(wpt),
                                             C.byref(cpe), tables.ctypes.data))
     wpt, cpe = wpt.value, cpe.value
     assert cpe == -(-npr * nw // wpt)
-    base, jstep, jwrap, jchunk, jepoch = tables[0], tables[1], tables[2], tables[3:35], tables[35:67]
+    base, jstep, jwrap = tables[0], tables[1], tables[2]
+    jlane, jchunk16, jepoch = tables[3:35], tables[35:155].reshape(8, 15, 31), tables[155:187]
     total = E * cpe
     draws = 2 * L
     last_off = draws * (((eb + E - 1) * n + nb) * nw + npr * nw)
@@ -103,15 +104,23 @@ def test_jump_ahead_tables(cfg):
     for q0 in starts:
         e, c = divmod(q0, cpe)
         w = list(base)
-        for b in range(32):
-            if (c >> b) & 1:
-                w = _apply(jchunk[b], w)
+        cb, i = c, 0
+        while cb:
+            if cb & 15:
+                w = _apply(jchunk16[i][(cb & 15) - 1], w)
+            cb >>= 4
+            i += 1
         for b in range(32):
             if (e >> b) & 1:
                 w = _apply(jepoch[b], w)
+        fast = c + 31 < cpe
         for lane in range(32):
             if q0 + lane >= total:
                 break
+            if fast:   # every lane applies its own polynomial to the warp's window
+                off = draws * (((eb + e) * n + nb) * nw + (c + lane) * wpt)
+                assert _window_rands(_apply(jlane[lane], w), 6) == mo.rand_stream_at(seed, off, 6), (q0, lane)
+                continue
             off = draws * (((eb + e) * n + nb) * nw + c * wpt)
             want = mo.rand_stream_at(seed, off, 6)
             assert _window_rands(w, 6) == want, (q0, lane, e, c)
