@@ -225,22 +225,31 @@ static long bfs_row(const merw_graph *g, int S, int seq_len, unsigned char *dis,
  * exactly dis[st][u] without the 10 GB table.  Returns 0, or -1 if a
  * dead-end node was rolled (reference would exit(0)).
  */
-int merw_oracle_sample(const merw_graph *g, int nw, int L, unsigned int seed,
-                       long epoch_begin, long epoch_end, int32_t *nodes,
-                       uint8_t *types)
+int merw_oracle_sample_range(const merw_graph *g, int nw, int L, unsigned int seed,
+                             long epoch_begin, long epoch_end, int node_begin, int node_end,
+                             int32_t *nodes, uint8_t *types)
 {
+    /* Same as the reference loop, but only start nodes [node_begin, node_end)
+     * are materialised: nodes[e][st - node_begin][i][t].  Walks of other start
+     * nodes only advance the RNG (2 draws per roll, L rolls, whatever happens). */
     glibc_rng rng;
     glibc_srand(&rng, seed);
     const int n = g->n;
+    const long np = node_end - node_begin;
     for (long epoch = 0; epoch < epoch_end; epoch++) {
-        if (epoch < epoch_begin) { /* fixed consumption: 2 draws per roll */
+        if (epoch < epoch_begin) {
             long draws = (long)n * nw * L * 2;
             for (long k = 0; k < draws; k++) (void)glibc_rand(&rng);
             continue;
         }
-        for (int st = 0; st < n; st++)
+        for (int st = 0; st < n; st++) {
+            if (st < node_begin || st >= node_end) {
+                long draws = (long)nw * L * 2;
+                for (long k = 0; k < draws; k++) (void)glibc_rand(&rng);
+                continue;
+            }
             for (int i = 0; i < nw; i++) {
-                int32_t *o = nodes + ((((epoch - epoch_begin) * n + st) * nw + i) * L);
+                int32_t *o = nodes + ((((epoch - epoch_begin) * np + (st - node_begin)) * nw + i) * L);
                 int u = st;
                 for (int t = 0; t < L; t++) {
                     o[t] = u;
@@ -248,16 +257,17 @@ int merw_oracle_sample(const merw_graph *g, int nw, int L, unsigned int seed,
                     if (u < 0) return -1;
                 }
             }
+        }
     }
     if (!types) return 0;
     unsigned char *dis = (unsigned char *)calloc((size_t)(n ? n : 1), 1);
     int *queue = (int *)malloc(sizeof(int) * (size_t)(n ? n : 1));
     long E = epoch_end - epoch_begin;
-    for (int st = 0; st < n; st++) {
+    for (int st = node_begin; st < node_end; st++) {
         long touched = bfs_row(g, st, L, dis, queue);
         for (long e = 0; e < E; e++)
             for (int i = 0; i < nw; i++) {
-                long base = ((e * n + st) * nw + i) * L;
+                long base = ((e * np + (st - node_begin)) * nw + i) * L;
                 for (int t = 0; t < L; t++)
                     types[base + t] = (uint8_t)(dis[nodes[base + t]] - 1);
             }
@@ -265,6 +275,13 @@ int merw_oracle_sample(const merw_graph *g, int nw, int L, unsigned int seed,
     }
     free(dis); free(queue);
     return 0;
+}
+
+int merw_oracle_sample(const merw_graph *g, int nw, int L, unsigned int seed,
+                       long epoch_begin, long epoch_end, int32_t *nodes,
+                       uint8_t *types)
+{
+    return merw_oracle_sample_range(g, nw, L, seed, epoch_begin, epoch_end, 0, g->n, nodes, types);
 }
 
 /* Text sink, gen_merw.cpp:188-206: "[n0, n1, ..., o0, o1, ...]\n" per walk.

@@ -52,6 +52,9 @@ def lib():
         L.merw_oracle_sample.restype = C.c_int
         L.merw_oracle_sample.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_long,
                                          C.c_long, C.c_void_p, C.c_void_p]
+        L.merw_oracle_sample_range.restype = C.c_int
+        L.merw_oracle_sample_range.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_long, C.c_long,
+                                               C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.merw_oracle_format.restype = C.c_long
         L.merw_oracle_format.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_void_p]
         L.merw_oracle_rand_stream.argtypes = [C.c_uint, C.c_long, C.c_void_p]
@@ -98,12 +101,13 @@ class OracleGraph:
                                       S.ctypes.data)
         return off, A, B, S
 
-    def sample(self, nw, L, seed, epoch_begin=0, epoch_end=1, labels=True):
+    def sample(self, nw, L, seed, epoch_begin=0, epoch_end=1, labels=True, node_begin=0, node_end=None):
+        node_end = self.n if node_end is None else node_end
         E = epoch_end - epoch_begin
-        nodes = np.zeros((E, self.n, nw, L), dtype=np.int32)
-        types = np.zeros((E, self.n, nw, L), dtype=np.uint8) if labels else None
-        rc = lib().merw_oracle_sample(self._h, nw, L, seed, epoch_begin, epoch_end,
-                                      nodes.ctypes.data, types.ctypes.data if labels else None)
+        nodes = np.zeros((E, node_end - node_begin, nw, L), dtype=np.int32)
+        types = np.zeros((E, node_end - node_begin, nw, L), dtype=np.uint8) if labels else None
+        rc = lib().merw_oracle_sample_range(self._h, nw, L, seed, epoch_begin, epoch_end, node_begin, node_end,
+                                            nodes.ctypes.data, types.ctypes.data if labels else None)
         if rc != 0:
             raise RuntimeError("dead-end node rolled (reference would exit(0))")
         return nodes, types

@@ -61,6 +61,7 @@ def lib():
     L.pn_paths_parse_txt.restype = i64
     L.pn_paths_parse_txt.argtypes = [vp, i64, i32, vp, vp, i64]
     L.pn_debug_gemm_tc.argtypes = [vp, vp, vp, vp, i64, i64, i64, C.c_int, vp]
+    L.pn_debug_gemm_tc2.argtypes = [vp, vp, vp, i64, i64, i64, C.c_int, C.c_int, vp]
     L.pn_profile_enable.argtypes = [C.c_int]
     L.pn_profile_read.argtypes = [C.c_char_p, C.POINTER(C.c_double), C.POINTER(i64)]
     if hasattr(L, "pn_pagg_forward"):

@@ -571,7 +571,8 @@ int pagg_tc_forward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_pa
 int pagg_tc_backward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_params &prm,
                           const int32_t *seq_node, const uint8_t *seq_type, cudaStream_t st);  // pagg_tc.cu
 int launch_gemm_tc(cudaStream_t st, const float *A, int64_t lda, const float *B, int64_t ldb, float *C, int64_t ldc,
-                   int64_t M, int64_t N, int64_t K, const float *bias, bool relu);               // pagg_tc.cu
+                   int64_t M, int64_t N, int64_t K, const float *bias, bool relu, bool a_mn = false, bool b_mn = false,
+                   bool bf16 = false, bool accumulate = false, int splitk = 1);                  // pagg_tc.cu
 
 }  // namespace pn
 
@@ -738,15 +739,20 @@ extern "C" int pn_pagg_backward(const pn_pagg_cfg *cfg, const pn_pagg_params *pr
         k_relu_mask<<<(unsigned)ceil_div(N * L * H, 256), 256, 0, st>>>(w.dT, w.T, N * L * H);
         PN_LAUNCH_CHECK();
     }
+    const bool tcm = c.math_mode == PN_MATH_TC;
     {
         int splitk = (int)std::max<int64_t>(1, std::min<int64_t>(64, N / 1024));
         if (splitk > 1) ZERO(g.nets_w, L * H * H);
-        rc = launch_gemm(st, w.dT, 1, L * H, w.Z, H, 1, g.nets_w, H, L * H, H, N, nullptr, false, false, splitk);  // dWn = dT^T Z
+        // dWn[m][i] = sum_n dT[n][m] Z[n][i]: both operands have the reduction index as their row (MN-major);
+        // raw gradients go through bf16 (fp16 would underflow), fp32 accumulate
+        rc = tcm ? launch_gemm_tc(st, w.dT, L * H, w.Z, H, g.nets_w, H, L * H, H, N, nullptr, false, true, true, true, false, splitk)
+                 : launch_gemm(st, w.dT, 1, L * H, w.Z, H, 1, g.nets_w, H, L * H, H, N, nullptr, false, false, splitk);
         if (rc) return rc;
     }
     rc = launch_colsum(st, w.dT, N, L * H, L * H, g.nets_b);
     if (rc) return rc;
-    rc = launch_gemm(st, w.dT, L * H, 1, prm->nets_w, H, 1, w.dZ, H, N, H, L * H, nullptr, false, true);  // dZ += dT Wn
+    rc = tcm ? launch_gemm_tc(st, w.dT, L * H, prm->nets_w, H, w.dZ, H, N, H, L * H, nullptr, false, false, true, true, true, 1)
+             : launch_gemm(st, w.dT, L * H, 1, prm->nets_w, H, 1, w.dZ, H, N, H, L * H, nullptr, false, true);  // dZ += dT Wn
     if (rc) return rc;
     // ---- fc0: Z = act(X W0^T + b0) ----
     if (homo) {
@@ -756,7 +762,8 @@ extern "C" int pn_pagg_backward(const pn_pagg_cfg *cfg, const pn_pagg_params *pr
     {
         int splitk = (int)std::max<int64_t>(1, std::min<int64_t>(64, N / 1024));
         if (splitk > 1) ZERO(g.fc0_w, H * F);
-        rc = launch_gemm(st, w.dZ, 1, H, X, F, 1, g.fc0_w, F, H, F, N, nullptr, false, false, splitk);  // dW0 = dZ^T X
+        rc = tcm ? launch_gemm_tc(st, w.dZ, H, X, F, g.fc0_w, F, H, F, N, nullptr, false, true, true, true, false, splitk)
+                 : launch_gemm(st, w.dZ, 1, H, X, F, 1, g.fc0_w, F, H, F, N, nullptr, false, false, splitk);  // dW0 = dZ^T X
         if (rc) return rc;
     }
     rc = launch_colsum(st, w.dZ, N, H, H, g.fc0_b);

@@ -16,72 +16,108 @@
 //                               (256 KB, L2-resident) through a 3-stage smem
 //                               ring with cp.async.bulk + mbarriers.
 #include "pagg_common.cuh"
+#include <cuda_bf16.h>
+
 #include "tc_util.cuh"
 
 namespace pn {
 using namespace tc;
 
 // ---------------------------------------------------------------------------
-// generic tcgen05 GEMM
+// generic tcgen05 GEMM:  C[M,N] (+)= act( op(A) op(B)^T + bias )
+//   A_MN = false: A is [M][K] row-major (K contiguous)  -> K-major operand
+//   A_MN = true : A is [K][M] row-major (M contiguous)  -> MN-major operand
+//   likewise B ([N][K] or [K][N]).  fp32 sources are converted to fp16 (or bf16,
+//   for raw gradients whose magnitude would underflow fp16) while being staged.
+//   gridDim.z > 1 splits K; split or `accumulate` results are added atomically.
+// Both layouts use 16-byte chunks of 8 elements, LBO = 128, SBO = 1024 for a
+// 64-deep K tile, and advance 256 bytes per K = 16 step.
 // ---------------------------------------------------------------------------
 struct GemmTcArgs {
-    const float *A, *B;  // A [M,K] row-major lda ; B [N,K] row-major ldb
+    const float *A, *B;
     float *C;            // [M,N] ldc
     const float *bias;   // [N] or null
     int64_t M, N, K, lda, ldb, ldc;
-    int relu;
+    int relu, accumulate;
 };
 
-// stage a [ROWS x 64] fp32 tile as fp16 in the canonical layout (K extent 64)
-template <int ROWS, int NTHREADS>
-__device__ __forceinline__ void stage_tile_f16(unsigned char *dst, const float *src, int64_t ld, int64_t row0,
-                                               int64_t nrows, int64_t k0, int64_t K, int tid)
+template <bool BF16>
+__device__ __forceinline__ uint4 pack8_half_or_bf16(const float (&f)[8])
 {
-    constexpr int CHUNKS = ROWS * 8;  // 16-byte chunks (8 halves)
+    if (!BF16) return pack8_f16(f);
+    uint4 pk;
+    __nv_bfloat162 b0 = __floats2bfloat162_rn(f[0], f[1]), b1 = __floats2bfloat162_rn(f[2], f[3]);
+    __nv_bfloat162 b2 = __floats2bfloat162_rn(f[4], f[5]), b3 = __floats2bfloat162_rn(f[6], f[7]);
+    pk.x = *reinterpret_cast<uint32_t *>(&b0); pk.y = *reinterpret_cast<uint32_t *>(&b1);
+    pk.z = *reinterpret_cast<uint32_t *>(&b2); pk.w = *reinterpret_cast<uint32_t *>(&b3);
+    return pk;
+}
+
+// stage a [ROWS x 64] operand tile.  MN = false: src[row][k]; MN = true: src[k][row].
+template <int ROWS, int NTHREADS, bool MN, bool BF16>
+__device__ __forceinline__ void stage_tile(unsigned char *dst, const float *src, int64_t ld, int64_t row0,
+                                           int64_t nrows, int64_t k0, int64_t kend, int tid)
+{
+    constexpr int CHUNKS = ROWS * 8;  // 16-byte chunks (8 elements)
     const bool vec_ok = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
     for (int c = tid; c < CHUNKS; c += NTHREADS) {
-        const int r = c % ROWS, k8 = c / ROWS;
-        const int64_t gr = row0 + r, gk = k0 + k8 * 8;
         float f[8];
-        if (gr < nrows && gk + 8 <= K && vec_ok) {
-            const float4 a = __ldg(reinterpret_cast<const float4 *>(src + gr * ld + gk));
-            const float4 b = __ldg(reinterpret_cast<const float4 *>(src + gr * ld + gk + 4));
-            f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
-        } else {
+        uint32_t off;
+        if (!MN) {
+            const int r = c % ROWS, k8 = c / ROWS;
+            const int64_t gr = row0 + r, gk = k0 + k8 * 8;
+            if (gr < nrows && gk + 8 <= kend && vec_ok) {
+                const float4 a = __ldg(reinterpret_cast<const float4 *>(src + gr * ld + gk));
+                const float4 b = __ldg(reinterpret_cast<const float4 *>(src + gr * ld + gk + 4));
+                f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+            } else {
 #pragma unroll
-            for (int j = 0; j < 8; j++) f[j] = (gr < nrows && gk + j < K) ? __ldg(src + gr * ld + gk + j) : 0.f;
+                for (int j = 0; j < 8; j++) f[j] = (gr < nrows && gk + j < kend) ? __ldg(src + gr * ld + gk + j) : 0.f;
+            }
+            off = canon_off(r, k8 * 8, 64);
+        } else {
+            const int k = c % 64, r8 = c / 64;
+            const int64_t gk = k0 + k, gr = row0 + r8 * 8;
+            if (gk < kend && gr + 8 <= nrows && vec_ok) {
+                const float4 a = __ldg(reinterpret_cast<const float4 *>(src + gk * ld + gr));
+                const float4 b = __ldg(reinterpret_cast<const float4 *>(src + gk * ld + gr + 4));
+                f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; j++) f[j] = (gk < kend && gr + j < nrows) ? __ldg(src + gk * ld + gr + j) : 0.f;
+            }
+            off = (uint32_t)(r8 * 1024 + (k >> 3) * 128 + (k & 7) * 16);
         }
-        __half2 h0 = __floats2half2_rn(f[0], f[1]), h1 = __floats2half2_rn(f[2], f[3]);
-        __half2 h2 = __floats2half2_rn(f[4], f[5]), h3 = __floats2half2_rn(f[6], f[7]);
-        uint4 pk;
-        pk.x = *reinterpret_cast<uint32_t *>(&h0); pk.y = *reinterpret_cast<uint32_t *>(&h1);
-        pk.z = *reinterpret_cast<uint32_t *>(&h2); pk.w = *reinterpret_cast<uint32_t *>(&h3);
-        *reinterpret_cast<uint4 *>(dst + canon_off(r, k8 * 8, 64)) = pk;
+        *reinterpret_cast<uint4 *>(dst + off) = pack8_half_or_bf16<BF16>(f);
     }
 }
 
-template <int BN>
+template <int BN, bool A_MN, bool B_MN, bool BF16>
 __global__ void __launch_bounds__(128) k_gemm_tc(GemmTcArgs g)
 {
     constexpr int BM = 128, BK = 64;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    unsigned char *As = smem_raw;                 // BM x BK fp16 canonical
+    unsigned char *As = smem_raw;                 // BM x BK, 16-bit
     unsigned char *Bs = smem_raw + BM * BK * 2;   // BN x BK
     __shared__ uint64_t bar;
     __shared__ uint32_t s_taddr;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN;
+    // split-K range (multiples of BK)
+    const int64_t kt = (g.K + BK - 1) / BK, per = (kt + gridDim.z - 1) / gridDim.z;
+    const int64_t kbeg = (int64_t)blockIdx.z * per * BK, kend = min(g.K, kbeg + per * BK);
     if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
     if (warp == 0) tmem_alloc<BN>(&s_taddr);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t taddr = s_taddr;
-    constexpr uint32_t idesc = make_idesc_f16(BM, BN);
+    constexpr uint32_t idesc = make_idesc_f16(BM, BN) | (BF16 ? ((1u << 7) | (1u << 10)) : 0u) |
+                               (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u);
     uint32_t phase = 0;
-    for (int64_t k0 = 0; k0 < g.K; k0 += BK) {
-        stage_tile_f16<BM, 128>(As, g.A, g.lda, m0, g.M, k0, g.K, tid);
-        stage_tile_f16<BN, 128>(Bs, g.B, g.ldb, n0, g.N, k0, g.K, tid);
+    for (int64_t k0 = kbeg; k0 < kend; k0 += BK) {
+        stage_tile<BM, 128, A_MN, BF16>(As, g.A, g.lda, m0, g.M, k0, kend, tid);
+        stage_tile<BN, 128, B_MN, BF16>(Bs, g.B, g.ldb, n0, g.N, k0, kend, tid);
         fence_proxy_async();
         __syncthreads();
         if (tid == 0) {
@@ -90,7 +126,7 @@ __global__ void __launch_bounds__(128) k_gemm_tc(GemmTcArgs g)
             const uint64_t bd = make_smem_desc(smem_u32(Bs), 128, (BK / 8) * 128);
 #pragma unroll
             for (int kk = 0; kk < BK / 16; kk++)
-                mma_f16(taddr, ad + (uint64_t)(kk * 16), bd + (uint64_t)(kk * 16), idesc, (k0 > 0) || (kk > 0));
+                mma_f16(taddr, ad + (uint64_t)(kk * 16), bd + (uint64_t)(kk * 16), idesc, (k0 > kbeg) || (kk > 0));
             mma_commit(&bar);
         }
         mbar_wait(&bar, phase);  // MMAs done reading smem (and, on the last pass, writing TMEM)
@@ -99,19 +135,22 @@ __global__ void __launch_bounds__(128) k_gemm_tc(GemmTcArgs g)
     tc_fence_after();
     // epilogue: warp w owns TMEM lanes 32w..32w+31 = rows m0+32w+lane
     const int64_t row = m0 + warp * 32 + lane;
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(taddr + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
-        tmem_ld_wait();
-        if (row < g.M) {
+    const bool atomic = gridDim.z > 1 || g.accumulate;
+    if (kbeg < kend) {
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(taddr + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+            tmem_ld_wait();
+            if (row < g.M) {
 #pragma unroll
-            for (int j = 0; j < 32; j++) {
-                const int64_t n = n0 + c0 + j;
-                if (n < g.N) {
-                    float x = __uint_as_float(v[j]);
-                    if (g.bias) x += g.bias[n];
-                    if (g.relu) x = fmaxf(x, 0.f);
-                    g.C[row * g.ldc + n] = x;
+                for (int j = 0; j < 32; j++) {
+                    const int64_t n = n0 + c0 + j;
+                    if (n < g.N) {
+                        float x = __uint_as_float(v[j]);
+                        if (g.bias && blockIdx.z == 0) x += g.bias[n];
+                        if (atomic) atomicAdd(g.C + row * g.ldc + n, x);
+                        else g.C[row * g.ldc + n] = g.relu ? fmaxf(x, 0.f) : x;
+                    }
                 }
             }
         }
@@ -121,15 +160,27 @@ __global__ void __launch_bounds__(128) k_gemm_tc(GemmTcArgs g)
     if (warp == 0) { __syncwarp(); tmem_dealloc<BN>(taddr); }
 }
 
+// a_mn / b_mn: operand given as [K][M] / [K][N]; bf16: 16-bit format of the operands;
+// splitk > 1 or accumulate: results are atomically added to C (no ReLU then).
 int launch_gemm_tc(cudaStream_t st, const float *A, int64_t lda, const float *B, int64_t ldb, float *C, int64_t ldc,
-                   int64_t M, int64_t N, int64_t K, const float *bias, bool relu)
+                   int64_t M, int64_t N, int64_t K, const float *bias, bool relu, bool a_mn, bool b_mn, bool bf16,
+                   bool accumulate, int splitk)
 {
     if (M <= 0 || N <= 0) return PN_OK;
-    GemmTcArgs g{A, B, C, bias, M, N, K, lda, ldb, ldc, relu ? 1 : 0};
+    if ((splitk > 1 || accumulate) && relu) { set_error("launch_gemm_tc: ReLU with atomic accumulation"); return PN_ERR_INVALID; }
+    GemmTcArgs g{A, B, C, bias, M, N, K, lda, ldb, ldc, relu ? 1 : 0, accumulate ? 1 : 0};
     constexpr int BN = 128;
     const size_t smem = (128 + BN) * 64 * 2;
-    dim3 grid((unsigned)ceil_div(N, BN), (unsigned)ceil_div(M, 128));
-    k_gemm_tc<BN><<<grid, 128, smem, st>>>(g);
+    dim3 grid((unsigned)ceil_div(N, BN), (unsigned)ceil_div(M, 128), (unsigned)std::max(1, splitk));
+#define PN_GEMM_CASE(AM, BM_, BF) k_gemm_tc<BN, AM, BM_, BF><<<grid, 128, smem, st>>>(g)
+    if (!a_mn && !b_mn && !bf16) PN_GEMM_CASE(false, false, false);
+    else if (!a_mn && b_mn && bf16) PN_GEMM_CASE(false, true, true);
+    else if (a_mn && b_mn && bf16) PN_GEMM_CASE(true, true, true);
+    else if (a_mn && b_mn && !bf16) PN_GEMM_CASE(true, true, false);
+    else if (!a_mn && b_mn && !bf16) PN_GEMM_CASE(false, true, false);
+    else if (!a_mn && !b_mn && bf16) PN_GEMM_CASE(false, false, true);
+    else { set_error("launch_gemm_tc: operand layout combination not instantiated"); return PN_ERR_UNSUPPORTED; }
+#undef PN_GEMM_CASE
     PN_LAUNCH_CHECK();
     return PN_OK;
 }
@@ -814,9 +865,17 @@ int pagg_tc_backward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_p
 
 }  // namespace pn
 
-// stand-alone entry for the tcgen05 GEMM (unit-tested against fp32 math)
+// stand-alone entry for the tcgen05 GEMM (unit-tested against fp64 math).  flags: bit0 A given as [K][M],
+// bit1 B given as [K][N], bit2 bf16 operands, bit3 accumulate into C; splitk >= 1.
 extern "C" int pn_debug_gemm_tc(const float *A, const float *B, float *C, const float *bias, int64_t M, int64_t N,
                                 int64_t K, int relu, void *stream)
 {
-    return pn::launch_gemm_tc((cudaStream_t)stream, A, K, B, K, C, N, M, N, K, bias, relu != 0);
+    return pn::launch_gemm_tc((cudaStream_t)stream, A, K, B, K, C, N, M, N, K, bias, relu != 0, false, false, false, false, 1);
+}
+extern "C" int pn_debug_gemm_tc2(const float *A, const float *B, float *C, int64_t M, int64_t N, int64_t K, int flags,
+                                 int splitk, void *stream)
+{
+    const bool a_mn = flags & 1, b_mn = flags & 2, bf16 = flags & 4, acc = flags & 8;
+    return pn::launch_gemm_tc((cudaStream_t)stream, A, a_mn ? M : K, B, b_mn ? N : K, C, N, M, N, K, nullptr, false, a_mn,
+                              b_mn, bf16, acc, splitk);
 }

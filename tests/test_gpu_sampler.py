@@ -101,6 +101,21 @@ def test_invariants_at_pubmed_scale():
     assert (o_n[0] == nodes[0]).all() and (o_t[0] == types[0]).all()
 
 
+def test_bgp_scale_hub_graph_L6_slice_matches_oracle():
+    """bgp-shaped: n = 63 977, ~700 k rows, hubs with thousands of rows, negative and
+    zero p, L = 6 (dense 4.1 GB distance table, 3 relaxation sweeps).  The oracle
+    labels a slice of start nodes (its per-root BFS over a hub graph is what costs
+    the reference 253 s of setup); the GPU output for that slice must match bit for bit."""
+    n = 63977
+    gr = messy_graph(n, 10, 13, hubs=3, neg_frac=0.2, zero_frac=0.4, dup_frac=0.03, self_loops=False)
+    g = sampler.MerwGraph(*gr)
+    nodes, types = _gpu_sample(g, 40, 6, 4242, epochs=1, node_begin=31000, node_end=31400)
+    o_n, o_t = mo.OracleGraph(*gr).sample(40, 6, 4242, 0, 1, node_begin=31000, node_end=31400)
+    assert (nodes == o_n).all()
+    assert (types == o_t).all()
+    assert types.max() <= 5
+
+
 def test_gen_merw_returns_the_tensors_pathnet_run_builds(tmp_path):
     n, u, v, p = load_graph("cornell")
     f = tmp_path / "cornell.in"

@@ -46,6 +46,26 @@ def test_tcgen05_gemm_matches_fp32(M, N, K, relu):
     torch.testing.assert_close(C.cpu().double(), want, rtol=1e-4, atol=1e-4)
 
 
+@pytest.mark.parametrize("flags,splitk", [(3, 1), (3, 7), (2, 1), (7, 5), (6, 1), (14, 1), (4, 3)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (512, 128, 1000), (300, 77, 130)])
+def test_tcgen05_gemm_operand_layouts(M, N, K, flags, splitk):
+    """MN-major operands, bf16 operands, split-K and accumulate variants of the GEMM."""
+    g = torch.Generator().manual_seed(M + N + K + flags)
+    a_mn, b_mn, bf16, acc = bool(flags & 1), bool(flags & 2), bool(flags & 4), bool(flags & 8)
+    q = (lambda t: t.bfloat16().float()) if bf16 else (lambda t: t.half().float())
+    A = q(torch.randn(M, K, generator=g))
+    B = q(torch.randn(N, K, generator=g) * 0.1)
+    C0 = torch.randn(M, N, generator=g) if acc else torch.zeros(M, N)
+    want = A.double() @ B.double().t() + C0.double()
+    Ad = (A.t().contiguous() if a_mn else A).to(DEV)
+    Bd = (B.t().contiguous() if b_mn else B).to(DEV)
+    C = C0.clone().to(DEV)
+    _lib.check(_lib.lib().pn_debug_gemm_tc2(Ad.data_ptr(), Bd.data_ptr(), C.data_ptr(), M, N, K, flags, splitk,
+                                            torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    torch.testing.assert_close(C.cpu().double(), want, rtol=1e-4, atol=2e-4)
+
+
 @pytest.mark.parametrize("variant", ["homo", "hetero"])
 @pytest.mark.parametrize("N,Fd,Cc,nw,L,S", [(183, 50, 5, 40, 4, 87), (300, 33, 7, 5, 6, 129), (64, 16, 3, 1, 1, 64)])
 def test_tc_mode_forward_backward_match_oracle(variant, N, Fd, Cc, nw, L, S):

@@ -48,6 +48,8 @@ def test_sampler_oracle_epoch_skip_is_consistent():
     full, tf = g.sample(7, 3, 99, 0, 3)
     part, tp = g.sample(7, 3, 99, 2, 3)
     assert (full[2:] == part).all() and (tf[2:] == tp).all()
+    rng_n, rng_t = g.sample(7, 3, 99, 0, 3, node_begin=50, node_end=120)
+    assert (full[:, 50:120] == rng_n).all() and (tf[:, 50:120] == rng_t).all()
 
 
 @pytest.mark.slow
