@@ -236,7 +236,10 @@ __device__ __forceinline__ float tanh_fast(float x)
 }
 __device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
 
-__global__ void __launch_bounds__(192, 1) k_lstm_fwd_tc(LstmTcArgs a)
+constexpr int TC_CWARPS = 16;                    // compute warps: 4 TMEM lane quarters x 4 column quarters
+constexpr int TC_THREADS = (TC_CWARPS + 2) * 32;  // + MMA warp + weight-producer warp
+
+__global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_fwd_tc(LstmTcArgs a)
 {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
@@ -251,18 +254,18 @@ __global__ void __launch_bounds__(192, 1) k_lstm_fwd_tc(LstmTcArgs a)
 
     if (tid == 0) {
         for (int s = 0; s < TC_NSTAGE; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(&a_ready, 128);
+        mbar_init(&a_ready, TC_CWARPS * 32);
         mbar_init(&acc_full, 1);
         fence_mbar_init();
     }
-    if (warp == 4) tmem_alloc<512>(&s_taddr);
-    for (int i = tid; i < TC_G4; i += 192) bias_s[i] = a.bp[i];
+    if (warp == TC_CWARPS) tmem_alloc<512>(&s_taddr);
+    for (int i = tid; i < TC_G4; i += TC_THREADS) bias_s[i] = a.bp[i];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t taddr = s_taddr;
 
-    if (warp == 5) {
+    if (warp == TC_CWARPS + 1) {
         // ===== weight producer: chunk sequence per step = (t == 0 ? 0..3 : 0..7) =====
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
@@ -276,7 +279,7 @@ __global__ void __launch_bounds__(192, 1) k_lstm_fwd_tc(LstmTcArgs a)
                 }
             }
         }
-    } else if (warp == 4) {
+    } else if (warp == TC_CWARPS) {
         // ===== MMA issuer =====
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc_f16(128, 256);
@@ -305,13 +308,15 @@ __global__ void __launch_bounds__(192, 1) k_lstm_fwd_tc(LstmTcArgs a)
             }
         }
     } else {
-        // ===== gather + gate math: thread = sequence p0 + tid = TMEM lane tid =====
-        const int r = tid;
+        // ===== gather + gate math: warp = (TMEM lane quarter lq, column quarter cq); the thread owns
+        //       sequence p0 + 32 lq + lane (= its TMEM lane) and hidden units [32 cq, 32 cq + 32) =====
+        const int lq = warp & 3, cq = warp >> 2;
+        const int r = lq * 32 + lane;
         const int64_t p = p0 + r;
         const bool valid = p < a.P;
-        float c[TC_H];
+        float c[32];
 #pragma unroll
-        for (int j = 0; j < TC_H; j++) c[j] = 0.f;
+        for (int j = 0; j < 32; j++) c[j] = 0.f;
         for (int t = 0; t < L; t++) {
             // ---- stage x_t (fp16) into the A tile ----
             {
@@ -321,8 +326,8 @@ __global__ void __launch_bounds__(192, 1) k_lstm_fwd_tc(LstmTcArgs a)
                     e = p * L + t;
                     src = a.T + ((int64_t)a.seq_node[e] * L + a.seq_type[e]) * TC_H;
                 }
-#pragma unroll 4
-                for (int k8 = 0; k8 < TC_H / 8; k8++) {
+#pragma unroll 2
+                for (int k8 = cq * 4; k8 < cq * 4 + 4; k8++) {   // this thread's quarter of the row
                     float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                     if (valid) {
                         const float4 u = __ldg(reinterpret_cast<const float4 *>(src + k8 * 8));
@@ -354,53 +359,59 @@ __global__ void __launch_bounds__(192, 1) k_lstm_fwd_tc(LstmTcArgs a)
             tc_fence_after();
             // activations of (tile, t): chunk (q, unit8, row) -> consecutive rows are consecutive 16-byte chunks
             __half *act = a.acts + ((int64_t)blockIdx.x * L + t) * ACT_BLOCK_HALFS + r * 8;
+            const bool t_is_last = t == L - 1;
 #pragma unroll
-            for (int c0 = 0; c0 < TC_G4; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(taddr + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
-                tmem_ld_wait();
-                float hh[8], gi[8], gf[8], gg[8], go[8], cc[8];
+            for (int jj = 0; jj < 4; jj++) {
+                const int c0 = cq * 128 + jj * 32;   // packed gate columns of units [c0/4, c0/4 + 8)
+                // outputs are packed to fp16 pairs as they are produced (keeps the register footprint small)
+                uint32_t pi[4], pf[4], pg[4], po[4], pc[4], ph[4];
+                uint32_t v[16];
 #pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const int unit = c0 / 4 + u;
-                    const float ai = __uint_as_float(v[4 * u + 0]) + bias_s[c0 + 4 * u + 0];
-                    const float af = __uint_as_float(v[4 * u + 1]) + bias_s[c0 + 4 * u + 1];
-                    const float ag = __uint_as_float(v[4 * u + 2]) + bias_s[c0 + 4 * u + 2];
-                    const float ao = __uint_as_float(v[4 * u + 3]) + bias_s[c0 + 4 * u + 3];
-                    gi[u] = sigmoid_fast(ai); gf[u] = sigmoid_fast(af); gg[u] = tanh_fast(ag); go[u] = sigmoid_fast(ao);
-                    const float cn = fmaf(gf[u], c[unit], gi[u] * gg[u]);
-                    c[unit] = cn;
-                    cc[u] = cn;
-                    hh[u] = go[u] * tanh_fast(cn);
+                for (int u2 = 0; u2 < 4; u2++) {
+                    if ((u2 & 1) == 0) {   // 16 columns = 4 units per TMEM load
+                        tmem_ld16(taddr + ((uint32_t)(lq * 32) << 16) + (uint32_t)(c0 + u2 * 8), v);
+                        tmem_ld_wait();
+                    }
+                    float gi2[2], gf2[2], gg2[2], go2[2], cn2[2], hh2[2];
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        const int u = 2 * u2 + e, unit = jj * 8 + u;   // index into this thread's 32 cell states
+                        const int vi = 4 * (u & 3);
+                        const float ai = __uint_as_float(v[vi + 0]) + bias_s[c0 + 4 * u + 0];
+                        const float af = __uint_as_float(v[vi + 1]) + bias_s[c0 + 4 * u + 1];
+                        const float ag = __uint_as_float(v[vi + 2]) + bias_s[c0 + 4 * u + 2];
+                        const float ao = __uint_as_float(v[vi + 3]) + bias_s[c0 + 4 * u + 3];
+                        gi2[e] = sigmoid_fast(ai); gf2[e] = sigmoid_fast(af); gg2[e] = tanh_fast(ag); go2[e] = sigmoid_fast(ao);
+                        const float cn = fmaf(gf2[e], c[unit], gi2[e] * gg2[e]);
+                        c[unit] = cn;
+                        cn2[e] = cn;
+                        hh2[e] = go2[e] * tanh_fast(cn);
+                    }
+                    __half2 t;
+                    t = __floats2half2_rn(gi2[0], gi2[1]); pi[u2] = *reinterpret_cast<uint32_t *>(&t);
+                    t = __floats2half2_rn(gf2[0], gf2[1]); pf[u2] = *reinterpret_cast<uint32_t *>(&t);
+                    t = __floats2half2_rn(gg2[0], gg2[1]); pg[u2] = *reinterpret_cast<uint32_t *>(&t);
+                    t = __floats2half2_rn(go2[0], go2[1]); po[u2] = *reinterpret_cast<uint32_t *>(&t);
+                    t = __floats2half2_rn(cn2[0], cn2[1]); pc[u2] = *reinterpret_cast<uint32_t *>(&t);
+                    t = __floats2half2_rn(hh2[0], hh2[1]); ph[u2] = *reinterpret_cast<uint32_t *>(&t);
+                    if (valid && t_is_last) *reinterpret_cast<float2 *>(a.hfin + p * TC_H + c0 / 4 + 2 * u2) = make_float2(hh2[0], hh2[1]);
                 }
                 // h_t -> A tile (k = 128 + unit) for the next step
-                {
-                    __half2 h0 = __floats2half2_rn(hh[0], hh[1]), h1 = __floats2half2_rn(hh[2], hh[3]);
-                    __half2 h2 = __floats2half2_rn(hh[4], hh[5]), h3 = __floats2half2_rn(hh[6], hh[7]);
-                    uint4 pk;
-                    pk.x = *reinterpret_cast<uint32_t *>(&h0); pk.y = *reinterpret_cast<uint32_t *>(&h1);
-                    pk.z = *reinterpret_cast<uint32_t *>(&h2); pk.w = *reinterpret_cast<uint32_t *>(&h3);
-                    *reinterpret_cast<uint4 *>(As + canon_off(r, TC_H + c0 / 4, TC_K2)) = pk;
-                }
+                *reinterpret_cast<uint4 *>(As + canon_off(r, TC_H + c0 / 4, TC_K2)) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
                 if (valid) {
-                    const int u0 = c0 / 4;
                     const int ub = (c0 / 32) * 1024;  // unit8 block of 128 rows x 8 halves
-                    *reinterpret_cast<uint4 *>(act + 0 * 16384 + ub) = pack8_f16(gi);
-                    *reinterpret_cast<uint4 *>(act + 1 * 16384 + ub) = pack8_f16(gf);
-                    *reinterpret_cast<uint4 *>(act + 2 * 16384 + ub) = pack8_f16(gg);
-                    *reinterpret_cast<uint4 *>(act + 3 * 16384 + ub) = pack8_f16(go);
-                    *reinterpret_cast<uint4 *>(act + 4 * 16384 + ub) = pack8_f16(cc);
-                    if (t == L - 1) {
-                        *reinterpret_cast<float4 *>(a.hfin + p * TC_H + u0) = make_float4(hh[0], hh[1], hh[2], hh[3]);
-                        *reinterpret_cast<float4 *>(a.hfin + p * TC_H + u0 + 4) = make_float4(hh[4], hh[5], hh[6], hh[7]);
-                    }
+                    *reinterpret_cast<uint4 *>(act + 0 * 16384 + ub) = make_uint4(pi[0], pi[1], pi[2], pi[3]);
+                    *reinterpret_cast<uint4 *>(act + 1 * 16384 + ub) = make_uint4(pf[0], pf[1], pf[2], pf[3]);
+                    *reinterpret_cast<uint4 *>(act + 2 * 16384 + ub) = make_uint4(pg[0], pg[1], pg[2], pg[3]);
+                    *reinterpret_cast<uint4 *>(act + 3 * 16384 + ub) = make_uint4(po[0], po[1], po[2], po[3]);
+                    *reinterpret_cast<uint4 *>(act + 4 * 16384 + ub) = make_uint4(pc[0], pc[1], pc[2], pc[3]);
                 }
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) { __syncwarp(); tmem_dealloc<512>(taddr); }
+    if (warp == TC_CWARPS) { __syncwarp(); tmem_dealloc<512>(taddr); }
 }
 
 // Forward LSTM in tensor-core mode (called from pn_pagg_forward).
@@ -425,7 +436,7 @@ int pagg_tc_forward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_pa
     PN_CUDA(cudaFuncSetAttribute(k_lstm_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
     {
         ProfScope prof("lstm_fwd", st);
-        k_lstm_fwd_tc<<<(unsigned)ceil_div(P, 128), 192, TC_SMEM, st>>>(a);
+        k_lstm_fwd_tc<<<(unsigned)ceil_div(P, 128), TC_THREADS, TC_SMEM, st>>>(a);
     }
     PN_LAUNCH_CHECK();
     return PN_OK;
@@ -490,7 +501,7 @@ constexpr int TCB_A_BYTES = 128 * TC_G4 * 2;  // 128 KB: da tile [128][512] fp16
 constexpr int TCB_SMEM = TCB_A_BYTES + TCB_NSTAGE * TCB_CHUNK_BYTES + 1024;
 constexpr int DA_BLOCK_BYTES = 64 * 128 * 16, XH_BLOCK_BYTES = 32 * 128 * 16;
 
-__global__ void __launch_bounds__(192, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
+__global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
 {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
@@ -503,17 +514,17 @@ __global__ void __launch_bounds__(192, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
     const int L = a.L;
     if (tid == 0) {
         for (int s = 0; s < TCB_NSTAGE; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(&a_ready, 128);
+        mbar_init(&a_ready, TC_CWARPS * 32);
         mbar_init(&acc_full, 1);
         fence_mbar_init();
     }
-    if (warp == 4) tmem_alloc<512>(&s_taddr);
+    if (warp == TC_CWARPS) tmem_alloc<512>(&s_taddr);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t taddr = s_taddr;  // cols [0,128) dx, [128,256) dh_{t-1}, [256,384) dc
 
-    if (warp == 5) {
+    if (warp == TC_CWARPS + 1) {
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
             for (int s = 0; s < L; s++)
@@ -524,7 +535,7 @@ __global__ void __launch_bounds__(192, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
                     if (++stage == TCB_NSTAGE) { stage = 0; phase ^= 1; }
                 }
         }
-    } else if (warp == 4) {
+    } else if (warp == TC_CWARPS) {
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
             for (int s = 0; s < L; s++) {
@@ -549,10 +560,12 @@ __global__ void __launch_bounds__(192, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
             }
         }
     } else {
-        const int r = tid;
+        // warp = (TMEM lane quarter lq, column quarter cq): sequence p0 + 32 lq + lane, units [32 cq, 32 cq + 32)
+        const int lq = warp & 3, cq = warp >> 2;
+        const int r = lq * 32 + lane;
         const int64_t p = p0 + r;
         const bool valid = p < a.P;
-        const uint32_t lane_base = taddr + ((uint32_t)(warp * 32) << 16);
+        const uint32_t lane_base = taddr + ((uint32_t)(lq * 32) << 16);
         const float scale = a.gscale[0], inv_scale = a.gscale[1];
         for (int s = 0; s < L; s++) {
             const int t = L - 1 - s;
@@ -563,7 +576,7 @@ __global__ void __launch_bounds__(192, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
             const __half *actp = act - ACT_BLOCK_HALFS;  // step t-1 (only read when t > 0)
             // ---- gate gradients ----
 #pragma unroll 1
-            for (int cb = 0; cb < TC_H / 8; cb++) {
+            for (int cb = cq * 4; cb < cq * 4 + 4; cb++) {
                 const int u0 = cb * 8;
                 float dh[8], dc[8];
                 if (s == 0) {
@@ -629,8 +642,8 @@ __global__ void __launch_bounds__(192, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
                 const float *src = nullptr;
                 int64_t e = 0;
                 if (valid) { e = p * L + t; src = a.T + ((int64_t)a.seq_node[e] * L + a.seq_type[e]) * TC_H; }
-#pragma unroll 4
-                for (int k8 = 0; k8 < TC_H / 8; k8++) {
+#pragma unroll
+                for (int k8 = cq * 4; k8 < cq * 4 + 4; k8++) {
                     float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                     if (valid) {
                         const float4 u = __ldg(reinterpret_cast<const float4 *>(src + k8 * 8));
@@ -660,8 +673,8 @@ __global__ void __launch_bounds__(192, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
                 // tcgen05.ld is warp-collective (.sync.aligned): every lane loads, only valid rows scatter
                 const int64_t e = valid ? p * L + t : 0;
                 float *dst = valid ? a.dT + ((int64_t)a.seq_node[e] * L + a.seq_type[e]) * TC_H : nullptr;
-#pragma unroll 2
-                for (int cb = 0; cb < TC_H / 8; cb++) {
+#pragma unroll
+                for (int cb = cq * 4; cb < cq * 4 + 4; cb++) {
                     uint32_t v[8];
                     tmem_ld8(lane_base + cb * 8, v);
                     tmem_ld_wait();
@@ -689,7 +702,7 @@ __global__ void __launch_bounds__(192, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) { __syncwarp(); tmem_dealloc<512>(taddr); }
+    if (warp == TC_CWARPS) { __syncwarp(); tmem_dealloc<512>(taddr); }
 }
 
 // ---------------------------------------------------------------------------
@@ -845,7 +858,7 @@ int pagg_tc_backward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_p
     PN_CUDA(cudaFuncSetAttribute(k_lstm_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TCB_SMEM));
     {
         ProfScope prof("lstm_bwd", st);
-        k_lstm_bwd_tc<<<(unsigned)ntiles, 192, TCB_SMEM, st>>>(a);
+        k_lstm_bwd_tc<<<(unsigned)ntiles, TC_THREADS, TCB_SMEM, st>>>(a);
     }
     PN_LAUNCH_CHECK();
     PN_CUDA(cudaMemsetAsync(w.dWp, 0, sizeof(float) * TC_K2 * TC_G4, st));
