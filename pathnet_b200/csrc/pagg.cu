@@ -684,8 +684,12 @@ extern "C" int pn_pagg_backward(const pn_pagg_cfg *cfg, const pn_pagg_params *pr
     }
     PN_REQUIRE(seq_node && seq_type && partner && rows && dlogits, "pagg_backward: NULL pointer");
     // ---- fc2 ----
-    rc = launch_gemm(st, dlogits, 1, C, w.cat, 2 * H, 1, g.fc2_w, 2 * H, C, 2 * H, S, nullptr, false, false);  // dW2 = dY^T cat
-    if (rc) return rc;
+    {
+        const int splitk = (int)std::max<int64_t>(1, std::min<int64_t>(128, S / 128));  // K = S on very few output tiles
+        if (splitk > 1) ZERO(g.fc2_w, C * 2 * H);
+        rc = launch_gemm(st, dlogits, 1, C, w.cat, 2 * H, 1, g.fc2_w, 2 * H, C, 2 * H, S, nullptr, false, false, splitk);  // dW2 = dY^T cat
+        if (rc) return rc;
+    }
     rc = launch_colsum(st, dlogits, S, C, C, g.fc2_b);
     if (rc) return rc;
     rc = launch_gemm(st, dlogits, C, 1, prm->fc2_w, 2 * H, 1, w.dcat, 2 * H, S, 2 * H, C, nullptr, false, false);  // dcat = dY W2

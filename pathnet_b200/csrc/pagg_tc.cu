@@ -13,7 +13,7 @@
 //                               operand, save activations for backward;
 //                    warp 4     one thread issues tcgen05.mma (M128 N256 K16);
 //                    warp 5     one thread streams the packed fp16 weights
-//                               (256 KB, L2-resident) through a 3-stage smem
+//                               (256 KB, L2-resident) through a 9-stage smem
 //                               ring with cp.async.bulk + mbarriers.
 #include "pagg_common.cuh"
 #include <cuda_bf16.h>
@@ -186,12 +186,12 @@ int launch_gemm_tc(cudaStream_t st, const float *A, int64_t lda, const float *B,
 }
 
 // ---------------------------------------------------------------------------
-// LSTM weights -> fp16, canonical layout, cut into 8 K-chunks of 32 so each
-// chunk ([512 cols][32 k], 32 KB) is one contiguous bulk copy.
+// LSTM weights -> fp16, canonical layout, cut into 16 K-chunks of 16 so each
+// chunk ([512 cols][16 k], 16 KB) is one contiguous bulk copy.
 //   column = unit*4 + gate (i,f,g,o), k < H: W_ih, k >= H: W_hh      (H = 128)
 // ---------------------------------------------------------------------------
-constexpr int TC_H = 128, TC_G4 = 512, TC_K2 = 256, TC_KC = 32, TC_NCHUNK = TC_K2 / TC_KC;
-constexpr int TC_CHUNK_BYTES = TC_G4 * TC_KC * 2;  // 32 KB
+constexpr int TC_H = 128, TC_G4 = 512, TC_K2 = 256, TC_KC = 16, TC_NCHUNK = TC_K2 / TC_KC;
+constexpr int TC_CHUNK_BYTES = TC_G4 * TC_KC * 2;  // 16 KB
 
 __global__ void k_pack_lstm_tc(const float *__restrict__ w_ih, const float *__restrict__ w_hh,
                                const float *__restrict__ b_ih, const float *__restrict__ b_hh,
@@ -214,7 +214,7 @@ struct LstmTcArgs {
     const float *T;           // [N,L,H] fp32 table
     const int32_t *seq_node;  // [P,L]
     const uint8_t *seq_type;  // [P,L]
-    const unsigned char *Wh;  // packed fp16 weights (8 chunks x 32 KB)
+    const unsigned char *Wh;  // packed fp16 weights (16 chunks x 16 KB)
     const float *bp;          // [512]
     __half *acts;             // tile images: block (tile, t) = [5 (i,f,g,o,c)][16 unit8][128 rows][8] fp16
     float *hfin;              // [P,H]
@@ -224,7 +224,7 @@ struct LstmTcArgs {
 };
 
 constexpr int ACT_BLOCK_HALFS = 5 * 16 * 128 * 8;  // 160 KB per (tile, step)
-constexpr int TC_NSTAGE = 3;
+constexpr int TC_NSTAGE = 9;   // 144 KB ring: most of a step's 256 KB of weights is prefetched during the previous epilogue
 constexpr int TC_A_BYTES = 128 * TC_K2 * 2;  // 64 KB
 constexpr int TC_SMEM = TC_A_BYTES + TC_NSTAGE * TC_CHUNK_BYTES + 2048 /*bias*/ + 1024 /*align slack*/;
 
@@ -496,7 +496,7 @@ struct LstmBwdTcArgs {
     int L;
     uint32_t drop_thr; float drop_scale; uint64_t drop_seed;
 };
-constexpr int TCB_NSTAGE = 3;
+constexpr int TCB_NSTAGE = 5;
 constexpr int TCB_A_BYTES = 128 * TC_G4 * 2;  // 128 KB: da tile [128][512] fp16 canonical
 constexpr int TCB_SMEM = TCB_A_BYTES + TCB_NSTAGE * TCB_CHUNK_BYTES + 1024;
 constexpr int DA_BLOCK_BYTES = 64 * 128 * 16, XH_BLOCK_BYTES = 32 * 128 * 16;
@@ -795,7 +795,8 @@ __global__ void __launch_bounds__(192, 1) k_wgrad_tc(WgradTcArgs a)
     if (warp == 4) { __syncwarp(); tmem_dealloc<256>(taddr); }
 }
 
-// bias gradient: dbp[col] = (1/scale) * sum over all rows of all da blocks
+// bias gradient: dbp[col] = (1/scale) * sum over all rows of all da blocks.
+// One warp per (block, col8 group of 4): 16 independent 16-byte loads in flight per lane.
 __global__ void __launch_bounds__(256) k_colsum_da_img(const unsigned char *__restrict__ da_img, int64_t nblocks,
                                                         const float *__restrict__ gscale, float *__restrict__ dbp)
 {
@@ -803,14 +804,25 @@ __global__ void __launch_bounds__(256) k_colsum_da_img(const unsigned char *__re
     for (int i = threadIdx.x; i < TC_G4; i += 256) acc[i] = 0.f;
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int64_t b = blockIdx.x; b < nblocks; b += gridDim.x) {
-        const unsigned char *blk = da_img + b * DA_BLOCK_BYTES;
-        for (int col8 = warp; col8 < 64; col8 += 8) {
+    // work item = (block b, group g of 4 col8): 16 groups per block
+    const int64_t nitems = nblocks * 16;
+    for (int64_t it = (int64_t)blockIdx.x * 8 + warp; it < nitems; it += (int64_t)gridDim.x * 8) {
+        const int64_t b = it >> 4;
+        const int g = (int)(it & 15);
+        const unsigned char *blk = da_img + b * DA_BLOCK_BYTES + (size_t)g * 4 * 2048;
+        uint4 ld[4][4];
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+#pragma unroll
+            for (int rr = 0; rr < 4; rr++)
+                ld[c][rr] = __ldg(reinterpret_cast<const uint4 *>(blk + (size_t)c * 2048 + (rr * 32 + lane) * 16));
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
             float s8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int rr = 0; rr < 4; rr++) {
                 float f[8];
-                unpack8_f16(__ldg(reinterpret_cast<const uint4 *>(blk + (size_t)col8 * 2048 + (rr * 32 + lane) * 16)), f);
+                unpack8_f16(ld[c][rr], f);
 #pragma unroll
                 for (int j = 0; j < 8; j++) s8[j] += f[j];
             }
@@ -819,9 +831,12 @@ __global__ void __launch_bounds__(256) k_colsum_da_img(const unsigned char *__re
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) s8[j] += __shfl_xor_sync(0xffffffffu, s8[j], o);
             }
-            if (lane == 0)
+            if (lane < 8) {
+                float v = s8[0];
 #pragma unroll
-                for (int j = 0; j < 8; j++) acc[col8 * 8 + j] += s8[j];
+                for (int j = 1; j < 8; j++) v = lane == j ? s8[j] : v;
+                atomicAdd(&acc[(g * 4 + c) * 8 + lane], v);
+            }
         }
     }
     __syncthreads();
@@ -871,7 +886,7 @@ int pagg_tc_backward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_p
         k_wgrad_tc<<<dim3(nsplit, 4), 192, WG_SMEM, st>>>(wa);
     }
     PN_LAUNCH_CHECK();
-    k_colsum_da_img<<<(unsigned)std::min<int64_t>(296, nblocks), 256, 0, st>>>(da_img, nblocks, w.gscale, w.dbp);
+    k_colsum_da_img<<<(unsigned)std::min<int64_t>(148 * 4, nblocks * 2), 256, 0, st>>>(da_img, nblocks, w.gscale, w.dbp);
     PN_LAUNCH_CHECK();
     return PN_OK;
 }
