@@ -400,6 +400,7 @@ __global__ void __launch_bounds__(256) k_pool_fwd(PoolArgs a)
     const float bias = a.attw_b[0];
     // raw scores
     float mx = -INFINITY;
+#pragma unroll 4
     for (int w = 0; w < nw; w++) {
         const int64_t p = s * nw + w;
         const float *h = a.hfin + p * H, *pv = partner_vec(a, p);
@@ -429,6 +430,7 @@ __global__ void __launch_bounds__(256) k_pool_fwd(PoolArgs a)
     const int64_t node = a.rows[s];
     for (int j = lane; j < H; j += 32) {
         float pooled = 0.f;
+#pragma unroll 8
         for (int w = 0; w < nw; w++) pooled += a.att[s * nw + w] * a.hfin[(s * nw + w) * H + j];
         pooled *= inv_nw;
         float ego = a.Z[node * H + j];
@@ -456,6 +458,7 @@ __global__ void __launch_bounds__(256) k_pool_bwd(PoolArgs a)
         // grads wrt the un-dropped concat
         // da_w = inv_nw * <dpooled, h_w>
         float dot_sum = 0.f;  // sum_v att_v * da_v (softmax backward), hetero only
+#pragma unroll 4
         for (int w = 0; w < nw; w++) {
             const int64_t p = s * nw + w;
             float d = 0.f;

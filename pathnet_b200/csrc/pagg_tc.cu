@@ -18,6 +18,8 @@
 #include "pagg_common.cuh"
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "tc_util.cuh"
 
 namespace pn {
@@ -97,16 +99,15 @@ __global__ void __launch_bounds__(128) k_gemm_tc(GemmTcArgs g)
 {
     constexpr int BM = 128, BK = 64;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    unsigned char *As = smem_raw;                 // BM x BK, 16-bit
-    unsigned char *Bs = smem_raw + BM * BK * 2;   // BN x BK
-    __shared__ uint64_t bar;
+    constexpr int STAGE = (BM + BN) * BK * 2;     // A tile then B tile, 16-bit; two stages (double buffer)
+    __shared__ uint64_t bar[2];
     __shared__ uint32_t s_taddr;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN;
     // split-K range (multiples of BK)
     const int64_t kt = (g.K + BK - 1) / BK, per = (kt + gridDim.z - 1) / gridDim.z;
     const int64_t kbeg = (int64_t)blockIdx.z * per * BK, kend = min(g.K, kbeg + per * BK);
-    if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+    if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); fence_mbar_init(); }
     if (warp == 0) tmem_alloc<BN>(&s_taddr);
     tc_fence_before();
     __syncthreads();
@@ -114,8 +115,14 @@ __global__ void __launch_bounds__(128) k_gemm_tc(GemmTcArgs g)
     const uint32_t taddr = s_taddr;
     constexpr uint32_t idesc = make_idesc_f16(BM, BN) | (BF16 ? ((1u << 7) | (1u << 10)) : 0u) |
                                (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u);
-    uint32_t phase = 0;
-    for (int64_t k0 = kbeg; k0 < kend; k0 += BK) {
+    // staging of tile i+1 overlaps the MMAs of tile i; a buffer is reused once the MMAs that
+    // read it (two tiles earlier) have committed
+    uint32_t phase[2] = {0, 0};
+    int it = 0;
+    for (int64_t k0 = kbeg; k0 < kend; k0 += BK, it++) {
+        const int b = it & 1;
+        unsigned char *As = smem_raw + b * STAGE, *Bs = As + BM * BK * 2;
+        if (it >= 2) { mbar_wait(&bar[b], phase[b]); phase[b] ^= 1; }
         stage_tile<BM, 128, A_MN, BF16>(As, g.A, g.lda, m0, g.M, k0, kend, tid);
         stage_tile<BN, 128, B_MN, BF16>(Bs, g.B, g.ldb, n0, g.N, k0, kend, tid);
         fence_proxy_async();
@@ -127,11 +134,12 @@ __global__ void __launch_bounds__(128) k_gemm_tc(GemmTcArgs g)
 #pragma unroll
             for (int kk = 0; kk < BK / 16; kk++)
                 mma_f16(taddr, ad + (uint64_t)(kk * 16), bd + (uint64_t)(kk * 16), idesc, (k0 > kbeg) || (kk > 0));
-            mma_commit(&bar);
+            mma_commit(&bar[b]);
         }
-        mbar_wait(&bar, phase);  // MMAs done reading smem (and, on the last pass, writing TMEM)
-        phase ^= 1;
     }
+    // drain: the last (up to two) commits
+    if (it >= 2) { const int b = it & 1; mbar_wait(&bar[b], phase[b]); }
+    if (it >= 1) { const int b = (it - 1) & 1; mbar_wait(&bar[b], phase[b]); }
     tc_fence_after();
     // epilogue: warp w owns TMEM lanes 32w..32w+31 = rows m0+32w+lane
     const int64_t row = m0 + warp * 32 + lane;
@@ -170,9 +178,13 @@ int launch_gemm_tc(cudaStream_t st, const float *A, int64_t lda, const float *B,
     if ((splitk > 1 || accumulate) && relu) { set_error("launch_gemm_tc: ReLU with atomic accumulation"); return PN_ERR_INVALID; }
     GemmTcArgs g{A, B, C, bias, M, N, K, lda, ldb, ldc, relu ? 1 : 0, accumulate ? 1 : 0};
     constexpr int BN = 128;
-    const size_t smem = (128 + BN) * 64 * 2;
+    const size_t smem = 2 * (128 + BN) * 64 * 2;
     dim3 grid((unsigned)ceil_div(N, BN), (unsigned)ceil_div(M, 128), (unsigned)std::max(1, splitk));
-#define PN_GEMM_CASE(AM, BM_, BF) k_gemm_tc<BN, AM, BM_, BF><<<grid, 128, smem, st>>>(g)
+#define PN_GEMM_CASE(AM, BM_, BF)                                                                              \
+    do {                                                                                                       \
+        PN_CUDA(cudaFuncSetAttribute(k_gemm_tc<BN, AM, BM_, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_gemm_tc<BN, AM, BM_, BF><<<grid, 128, smem, st>>>(g);                                                \
+    } while (0)
     if (!a_mn && !b_mn && !bf16) PN_GEMM_CASE(false, false, false);
     else if (!a_mn && b_mn && bf16) PN_GEMM_CASE(false, true, true);
     else if (a_mn && b_mn && bf16) PN_GEMM_CASE(true, true, true);
@@ -221,12 +233,15 @@ struct LstmTcArgs {
     int64_t P;
     int L;
     uint32_t drop_thr; float drop_scale; uint64_t drop_seed;
+    long long *trace;         // optional clock64() trace of CTA `trace_block` (debug)
+    int trace_block;
 };
 
 constexpr int ACT_BLOCK_HALFS = 5 * 16 * 128 * 8;  // 160 KB per (tile, step)
-constexpr int TC_NSTAGE = 9;   // 144 KB ring: most of a step's 256 KB of weights is prefetched during the previous epilogue
-constexpr int TC_A_BYTES = 128 * TC_K2 * 2;  // 64 KB
-constexpr int TC_SMEM = TC_A_BYTES + TC_NSTAGE * TC_CHUNK_BYTES + 2048 /*bias*/ + 1024 /*align slack*/;
+constexpr int TC_NSTAGE = 6;                        // 96 KB weight ring
+constexpr int TC_XBYTES = 128 * TC_H * 2;           // 32 KB: one [128][128] fp16 operand half (x_t or h_{t-1})
+constexpr int TC_SMEM = 3 * TC_XBYTES + TC_NSTAGE * TC_CHUNK_BYTES + 2048 /*bias*/ + 128 * 8 * 4 /*row offsets*/ + 1024 /*align*/;
+constexpr int TC_MAX_L = 8;
 
 __device__ __forceinline__ float tanh_fast(float x)
 {
@@ -239,13 +254,42 @@ __device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_
 constexpr int TC_CWARPS = 16;                    // compute warps: 4 TMEM lane quarters x 4 column quarters
 constexpr int TC_THREADS = (TC_CWARPS + 2) * 32;  // + MMA warp + weight-producer warp
 
+// this thread's quarter (32 floats) of table row `row_off` -> dropout -> fp16 -> x tile (canonical, K extent 128)
+__device__ __forceinline__ void tc_gather_quarter(const LstmTcArgs &a, unsigned char *Xs, int r, int cq, int32_t row_off,
+                                                   uint64_t elem0 /* (p*L + t) * H */)
+{
+    const bool valid = row_off >= 0;
+    const float *src = a.T + (int64_t)(valid ? row_off : 0) * TC_H;
+#pragma unroll 2
+    for (int k8 = cq * 4; k8 < cq * 4 + 4; k8++) {
+        float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (valid) {
+            const float4 u = __ldg(reinterpret_cast<const float4 *>(src + k8 * 8));
+            const float4 w = __ldg(reinterpret_cast<const float4 *>(src + k8 * 8 + 4));
+            f[0] = u.x; f[1] = u.y; f[2] = u.z; f[3] = u.w; f[4] = w.x; f[5] = w.y; f[6] = w.z; f[7] = w.w;
+            if (a.drop_thr) {
+                const uint64_t pair = (elem0 + k8 * 8) >> 1;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const uint32_t h = dropout_hash_pair(a.drop_seed, 0, pair + q);
+                    f[2 * q] = (h & 0xFFFFu) < a.drop_thr ? 0.f : f[2 * q] * a.drop_scale;
+                    f[2 * q + 1] = (h >> 16) < a.drop_thr ? 0.f : f[2 * q + 1] * a.drop_scale;
+                }
+            }
+        }
+        *reinterpret_cast<uint4 *>(Xs + canon_off(r, k8 * 8, TC_H)) = pack8_f16(f);
+    }
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_fwd_tc(LstmTcArgs a)
 {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
-    unsigned char *As = base;                                  // [128][256] fp16 canonical: k<128 x_t, k>=128 h_{t-1}
-    unsigned char *Ws = base + TC_A_BYTES;                     // ring of weight chunks
+    unsigned char *Xs = base;                       // two x_t buffers (double buffer), [128][128] fp16 canonical each
+    unsigned char *Hs = base + 2 * TC_XBYTES;       // h_{t-1}
+    unsigned char *Ws = base + 3 * TC_XBYTES;       // ring of weight chunks
     float *bias_s = reinterpret_cast<float *>(Ws + TC_NSTAGE * TC_CHUNK_BYTES);
+    int32_t *rowoff_s = reinterpret_cast<int32_t *>(bias_s + TC_G4);   // [128][TC_MAX_L]: table row of (sequence, step), -1 = padding
     __shared__ uint64_t full_bar[TC_NSTAGE], empty_bar[TC_NSTAGE], a_ready, acc_full;
     __shared__ uint32_t s_taddr;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -260,13 +304,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_fwd_tc(LstmTcArgs a)
     }
     if (warp == TC_CWARPS) tmem_alloc<512>(&s_taddr);
     for (int i = tid; i < TC_G4; i += TC_THREADS) bias_s[i] = a.bp[i];
+    for (int i = tid; i < 128 * L; i += TC_THREADS) {
+        const int r = i / L, t = i % L;
+        const int64_t p = p0 + r;
+        int32_t off = -1;
+        if (p < a.P) { const int64_t e = p * L + t; off = a.seq_node[e] * L + a.seq_type[e]; }
+        rowoff_s[r * TC_MAX_L + t] = off;
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t taddr = s_taddr;
 
     if (warp == TC_CWARPS + 1) {
-        // ===== weight producer: chunk sequence per step = (t == 0 ? 0..3 : 0..7) =====
+        // ===== weight producer: chunk sequence per step = (t == 0 ? x half : x half + h half) =====
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
             for (int t = 0; t < L; t++) {
@@ -287,24 +338,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_fwd_tc(LstmTcArgs a)
             for (int t = 0; t < L; t++) {
                 mbar_wait(&a_ready, t & 1);  // x_t (and h_{t-1}) staged, TMEM drained
                 tc_fence_after();
+                if (a.trace && blockIdx.x == a.trace_block) a.trace[t * 8 + 4] = clock64();
                 const int nch = t == 0 ? TC_NCHUNK / 2 : TC_NCHUNK;  // h_0 = 0: skip the W_hh half
+                const uint32_t xbase = smem_u32(Xs + (t & 1) * TC_XBYTES), hbase = smem_u32(Hs);
                 for (int c = 0; c < nch; c++) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t wbase = smem_u32(Ws + stage * TC_CHUNK_BYTES);
+                    // chunk c = 16 consecutive k: two core matrices (256 B) of the x half (c < 8) or the h half
+                    const uint32_t abase = (c < TC_NCHUNK / 2 ? xbase + (uint32_t)c * 256 : hbase + (uint32_t)(c - TC_NCHUNK / 2) * 256);
+                    const uint64_t ad = make_smem_desc(abase, 128, (TC_H / 8) * 128);
 #pragma unroll
-                    for (int ks = 0; ks < TC_KC / 16; ks++) {
-                        const uint64_t ad = make_smem_desc(smem_u32(As) + (uint32_t)(c * (TC_KC / 8) + ks * 2) * 128, 128, (TC_K2 / 8) * 128);
-#pragma unroll
-                        for (int nh = 0; nh < 2; nh++) {
-                            const uint64_t bd = make_smem_desc(wbase + (uint32_t)nh * (256 / 8) * ((TC_KC / 8) * 128) + (uint32_t)ks * 256, 128, (TC_KC / 8) * 128);
-                            mma_f16(taddr + (uint32_t)nh * 256, ad, bd, idesc, (c > 0) || (ks > 0));
-                        }
+                    for (int nh = 0; nh < 2; nh++) {
+                        const uint64_t bd = make_smem_desc(wbase + (uint32_t)nh * (256 / 8) * ((TC_KC / 8) * 128), 128, (TC_KC / 8) * 128);
+                        mma_f16(taddr + (uint32_t)nh * 256, ad, bd, idesc, c > 0);
                     }
                     mma_commit(&empty_bar[stage]);  // slot reusable once these MMAs have read it
                     if (++stage == TC_NSTAGE) { stage = 0; phase ^= 1; }
                 }
                 mma_commit(&acc_full);
+                if (a.trace && blockIdx.x == a.trace_block) a.trace[t * 8 + 5] = clock64();
             }
         }
     } else {
@@ -317,46 +370,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_fwd_tc(LstmTcArgs a)
         float c[32];
 #pragma unroll
         for (int j = 0; j < 32; j++) c[j] = 0.f;
+        const bool tr = a.trace && blockIdx.x == a.trace_block && tid == 0;
+        if (tr) a.trace[6] = clock64();
+        tc_gather_quarter(a, Xs, r, cq, rowoff_s[r * TC_MAX_L + 0], (uint64_t)(p * L + 0) * TC_H);
         for (int t = 0; t < L; t++) {
-            // ---- stage x_t (fp16) into the A tile ----
-            {
-                const float *src = nullptr;
-                int64_t e = 0;
-                if (valid) {
-                    e = p * L + t;
-                    src = a.T + ((int64_t)a.seq_node[e] * L + a.seq_type[e]) * TC_H;
-                }
-#pragma unroll 2
-                for (int k8 = cq * 4; k8 < cq * 4 + 4; k8++) {   // this thread's quarter of the row
-                    float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                    if (valid) {
-                        const float4 u = __ldg(reinterpret_cast<const float4 *>(src + k8 * 8));
-                        const float4 w = __ldg(reinterpret_cast<const float4 *>(src + k8 * 8 + 4));
-                        f[0] = u.x; f[1] = u.y; f[2] = u.z; f[3] = u.w; f[4] = w.x; f[5] = w.y; f[6] = w.z; f[7] = w.w;
-                        if (a.drop_thr) {
-                            const uint64_t pair = ((uint64_t)e * TC_H + k8 * 8) >> 1;
-#pragma unroll
-                            for (int q = 0; q < 4; q++) {
-                                const uint32_t h = dropout_hash_pair(a.drop_seed, 0, pair + q);
-                                f[2 * q] = (h & 0xFFFFu) < a.drop_thr ? 0.f : f[2 * q] * a.drop_scale;
-                                f[2 * q + 1] = (h >> 16) < a.drop_thr ? 0.f : f[2 * q + 1] * a.drop_scale;
-                            }
-                        }
-                    }
-                    __half2 h0 = __floats2half2_rn(f[0], f[1]), h1 = __floats2half2_rn(f[2], f[3]);
-                    __half2 h2 = __floats2half2_rn(f[4], f[5]), h3 = __floats2half2_rn(f[6], f[7]);
-                    uint4 pk;
-                    pk.x = *reinterpret_cast<uint32_t *>(&h0); pk.y = *reinterpret_cast<uint32_t *>(&h1);
-                    pk.z = *reinterpret_cast<uint32_t *>(&h2); pk.w = *reinterpret_cast<uint32_t *>(&h3);
-                    *reinterpret_cast<uint4 *>(As + canon_off(r, k8 * 8, TC_K2)) = pk;
-                }
-            }
-            fence_proxy_async();   // generic-proxy smem writes -> async proxy (tcgen05.mma)
+            if (tr) a.trace[t * 8 + 0] = clock64();
+            fence_proxy_async();   // generic-proxy smem writes (x_t, h_{t-1}) -> async proxy (tcgen05.mma)
             tc_fence_before();     // order this thread's earlier tcgen05.ld before the MMA that overwrites TMEM
             mbar_arrive(&a_ready);
+            // x_{t+1} into the other x buffer while the tensor core works on step t (MMA(t-1), the last
+            // reader of that buffer, completed before acc_full(t-1) was observed)
+            if (t + 1 < L)
+                tc_gather_quarter(a, Xs + ((t + 1) & 1) * TC_XBYTES, r, cq, rowoff_s[r * TC_MAX_L + t + 1],
+                                  (uint64_t)(p * L + t + 1) * TC_H);
+            if (tr) a.trace[t * 8 + 1] = clock64();
             // ---- wait for the gate pre-activations ----
             mbar_wait(&acc_full, t & 1);
             tc_fence_after();
+            if (tr) a.trace[t * 8 + 2] = clock64();
             // activations of (tile, t): chunk (q, unit8, row) -> consecutive rows are consecutive 16-byte chunks
             __half *act = a.acts + ((int64_t)blockIdx.x * L + t) * ACT_BLOCK_HALFS + r * 8;
             const bool t_is_last = t == L - 1;
@@ -365,6 +396,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_fwd_tc(LstmTcArgs a)
                 const int c0 = cq * 128 + jj * 32;   // packed gate columns of units [c0/4, c0/4 + 8)
                 // outputs are packed to fp16 pairs as they are produced (keeps the register footprint small)
                 uint32_t pi[4], pf[4], pg[4], po[4], pc[4], ph[4];
+                float hq[4];
                 uint32_t v[16];
 #pragma unroll
                 for (int u2 = 0; u2 < 4; u2++) {
@@ -387,17 +419,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_fwd_tc(LstmTcArgs a)
                         cn2[e] = cn;
                         hh2[e] = go2[e] * tanh_fast(cn);
                     }
-                    __half2 t;
-                    t = __floats2half2_rn(gi2[0], gi2[1]); pi[u2] = *reinterpret_cast<uint32_t *>(&t);
-                    t = __floats2half2_rn(gf2[0], gf2[1]); pf[u2] = *reinterpret_cast<uint32_t *>(&t);
-                    t = __floats2half2_rn(gg2[0], gg2[1]); pg[u2] = *reinterpret_cast<uint32_t *>(&t);
-                    t = __floats2half2_rn(go2[0], go2[1]); po[u2] = *reinterpret_cast<uint32_t *>(&t);
-                    t = __floats2half2_rn(cn2[0], cn2[1]); pc[u2] = *reinterpret_cast<uint32_t *>(&t);
-                    t = __floats2half2_rn(hh2[0], hh2[1]); ph[u2] = *reinterpret_cast<uint32_t *>(&t);
-                    if (valid && t_is_last) *reinterpret_cast<float2 *>(a.hfin + p * TC_H + c0 / 4 + 2 * u2) = make_float2(hh2[0], hh2[1]);
+                    __half2 t2;
+                    t2 = __floats2half2_rn(gi2[0], gi2[1]); pi[u2] = *reinterpret_cast<uint32_t *>(&t2);
+                    t2 = __floats2half2_rn(gf2[0], gf2[1]); pf[u2] = *reinterpret_cast<uint32_t *>(&t2);
+                    t2 = __floats2half2_rn(gg2[0], gg2[1]); pg[u2] = *reinterpret_cast<uint32_t *>(&t2);
+                    t2 = __floats2half2_rn(go2[0], go2[1]); po[u2] = *reinterpret_cast<uint32_t *>(&t2);
+                    t2 = __floats2half2_rn(cn2[0], cn2[1]); pc[u2] = *reinterpret_cast<uint32_t *>(&t2);
+                    t2 = __floats2half2_rn(hh2[0], hh2[1]); ph[u2] = *reinterpret_cast<uint32_t *>(&t2);
+                    hq[(u2 & 1) * 2] = hh2[0]; hq[(u2 & 1) * 2 + 1] = hh2[1];
+                    if (t_is_last && (u2 & 1)) {
+                        // final h (fp32) -> staging tile in the (now idle) x buffers, 16-byte slots XOR-swizzled by
+                        // the row so that 8 consecutive rows hit 8 different bank groups
+                        const int j4 = c0 / 16 + (u2 >> 1);   // float4 slot of units [4 j4, 4 j4 + 4)
+                        *reinterpret_cast<float4 *>(Xs + r * 512 + ((j4 ^ (r & 7)) << 4)) = make_float4(hq[0], hq[1], hq[2], hq[3]);
+                    }
                 }
-                // h_t -> A tile (k = 128 + unit) for the next step
-                *reinterpret_cast<uint4 *>(As + canon_off(r, TC_H + c0 / 4, TC_K2)) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                // h_t -> operand tile for the next step
+                if (!t_is_last) *reinterpret_cast<uint4 *>(Hs + canon_off(r, c0 / 4, TC_H)) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
                 if (valid) {
                     const int ub = (c0 / 32) * 1024;  // unit8 block of 128 rows x 8 halves
                     *reinterpret_cast<uint4 *>(act + 0 * 16384 + ub) = make_uint4(pi[0], pi[1], pi[2], pi[3]);
@@ -407,7 +445,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_fwd_tc(LstmTcArgs a)
                     *reinterpret_cast<uint4 *>(act + 4 * 16384 + ub) = make_uint4(pc[0], pc[1], pc[2], pc[3]);
                 }
             }
+            if (tr) a.trace[t * 8 + 3] = clock64();
         }
+        // ---- final h: staging tile -> hfin[P][H], whole 512-byte rows per warp ----
+        asm volatile("bar.sync 1, %0;" ::"n"(TC_CWARPS * 32) : "memory");
+        for (int rr = warp * 8; rr < warp * 8 + 8; rr++) {
+            const int64_t pr = p0 + rr;
+            if (pr < a.P) {
+                const float4 hv = *reinterpret_cast<const float4 *>(Xs + rr * 512 + ((lane ^ (rr & 7)) << 4));
+                *reinterpret_cast<float4 *>(a.hfin + pr * TC_H + lane * 4) = hv;
+            }
+        }
+        if (tr) a.trace[7] = clock64();
     }
     tc_fence_before();
     __syncthreads();
@@ -418,8 +467,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_fwd_tc(LstmTcArgs a)
 int pagg_tc_forward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_params &prm,
                          const int32_t *seq_node, const uint8_t *seq_type, cudaStream_t st)
 {
-    if (c.H != TC_H) {
-        set_error("PN_MATH_TC: the tensor-core LSTM is built for hidden size 128 (got %d)", c.H);
+    if (c.H != TC_H || c.L > TC_MAX_L) {
+        set_error("PN_MATH_TC: the tensor-core LSTM is built for hidden size 128 and path_len <= %d (got H=%d L=%d)", TC_MAX_L, c.H, c.L);
         return PN_ERR_UNSUPPORTED;
     }
     // packed fp16 weights live in the (otherwise unused in this mode) Wp/WpT region: 2 x 256 KB fp32 >= 256 KB fp16
@@ -432,13 +481,33 @@ int pagg_tc_forward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_pa
         scale = c.dropout_p >= 1.f ? 0.f : 1.f / (1.f - c.dropout_p);
     }
     const int64_t P = (int64_t)c.S * c.nw;
-    LstmTcArgs a{w.T, seq_node, seq_type, Wh, w.bp, reinterpret_cast<__half *>(w.acts), w.hfin, P, c.L, thr, scale, c.dropout_seed};
+    LstmTcArgs a{w.T, seq_node, seq_type, Wh, w.bp, reinterpret_cast<__half *>(w.acts), w.hfin, P, c.L, thr, scale, c.dropout_seed,
+                 nullptr, 0};
+    long long *d_trace = nullptr;
+    const char *trace_env = getenv("PN_TRACE_FWD");
+    if (trace_env) {
+        PN_CUDA(cudaMalloc(&d_trace, sizeof(long long) * 8 * 64));
+        PN_CUDA(cudaMemsetAsync(d_trace, 0, sizeof(long long) * 8 * 64, st));
+        a.trace = d_trace;
+        a.trace_block = atoi(trace_env);
+    }
     PN_CUDA(cudaFuncSetAttribute(k_lstm_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
     {
         ProfScope prof("lstm_fwd", st);
         k_lstm_fwd_tc<<<(unsigned)ceil_div(P, 128), TC_THREADS, TC_SMEM, st>>>(a);
     }
     PN_LAUNCH_CHECK();
+    if (d_trace) {  // debug only: synchronous dump of the phase timestamps of one CTA
+        long long h[8 * 64];
+        PN_CUDA(cudaStreamSynchronize(st));
+        PN_CUDA(cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost));
+        cudaFree(d_trace);
+        const long long t00 = h[0];
+        for (int t = 0; t < c.L && t < 64; t++)
+            fprintf(stderr, "[trace fwd cta %d] t=%d  begin %lld | arrive+prefetch done %lld | mma-thread saw a_ready %lld | mma issued %lld | acc_full seen %lld | epilogue done %lld\n",
+                    a.trace_block, t, h[t * 8 + 0] - t00, h[t * 8 + 1] - t00, h[t * 8 + 4] - t00, h[t * 8 + 5] - t00, h[t * 8 + 2] - t00, h[t * 8 + 3] - t00);
+        fprintf(stderr, "[trace fwd cta %d] first gather started %lld, hfin written %lld\n", a.trace_block, h[6] - t00, h[7] - t00);
+    }
     return PN_OK;
 }
 
@@ -495,11 +564,15 @@ struct LstmBwdTcArgs {
     int64_t P, ntiles;
     int L;
     uint32_t drop_thr; float drop_scale; uint64_t drop_seed;
+    long long *trace;
+    int trace_block;
 };
-constexpr int TCB_NSTAGE = 5;
+constexpr int TCB_NSTAGE = 3;
 constexpr int TCB_A_BYTES = 128 * TC_G4 * 2;  // 128 KB: da tile [128][512] fp16 canonical
 constexpr int TCB_SMEM = TCB_A_BYTES + TCB_NSTAGE * TCB_CHUNK_BYTES + 1024;
 constexpr int DA_BLOCK_BYTES = 64 * 128 * 16, XH_BLOCK_BYTES = 32 * 128 * 16;
+
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
 {
@@ -567,8 +640,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
         const bool valid = p < a.P;
         const uint32_t lane_base = taddr + ((uint32_t)(lq * 32) << 16);
         const float scale = a.gscale[0], inv_scale = a.gscale[1];
+        const bool tr = a.trace && blockIdx.x == a.trace_block && tid == 0;
         for (int s = 0; s < L; s++) {
             const int t = L - 1 - s;
+            if (tr) a.trace[s * 8 + 0] = clock64();
             const int64_t blk = (int64_t)t * a.ntiles + tile;
             unsigned char *da_blk = a.da_img + blk * DA_BLOCK_BYTES;
             unsigned char *xh_blk = a.xh_img + blk * XH_BLOCK_BYTES;
@@ -637,7 +712,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
                 }
                 *reinterpret_cast<uint4 *>(xh_blk + (size_t)(16 + cb) * 2048 + r * 16) = pack8_f16(hp);  // h_{t-1}
             }
-            // ---- x_t (same dropout mask as forward) into the wgrad image ----
+            tmem_st_wait();
+            fence_proxy_async();
+            tc_fence_before();
+            mbar_arrive(&a_ready);
+            if (tr) a.trace[s * 8 + 1] = clock64();
+            // ---- while the tensor core works: pull the next step's activations towards L2 ... ----
+            if (valid && t > 0) {
+#pragma unroll
+                for (int cb = cq * 4; cb < cq * 4 + 4; cb++) {
+#pragma unroll
+                    for (int q = 0; q < 5; q++) prefetch_l2(actp + q * 16384 + cb * 1024);
+                    if (t > 1) { prefetch_l2(actp - ACT_BLOCK_HALFS + 3 * 16384 + cb * 1024); prefetch_l2(actp - ACT_BLOCK_HALFS + 4 * 16384 + cb * 1024); }
+                }
+            }
+            // ---- ... and write x_t (same dropout mask as forward) into the wgrad image ----
             {
                 const float *src = nullptr;
                 int64_t e = 0;
@@ -662,13 +751,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
                     *reinterpret_cast<uint4 *>(xh_blk + (size_t)k8 * 2048 + r * 16) = pack8_f16(f);
                 }
             }
-            tmem_st_wait();
-            fence_proxy_async();
-            tc_fence_before();
-            mbar_arrive(&a_ready);
+            if (tr) a.trace[s * 8 + 2] = clock64();
             // ---- [dx | dh_{t-1}] = da . W' ----
             mbar_wait(&acc_full, s & 1);
             tc_fence_after();
+            if (tr) a.trace[s * 8 + 3] = clock64();
             {
                 // tcgen05.ld is warp-collective (.sync.aligned): every lane loads, only valid rows scatter
                 const int64_t e = valid ? p * L + t : 0;
@@ -698,6 +785,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
                 }
             }
             tc_fence_before();  // the TMEM reads above precede the next step's MMA (ordered through a_ready)
+            if (tr) a.trace[s * 8 + 4] = clock64();
         }
     }
     tc_fence_before();
@@ -869,13 +957,31 @@ int pagg_tc_backward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_p
     }
     unsigned char *da_img = reinterpret_cast<unsigned char *>(w.dA), *xh_img = reinterpret_cast<unsigned char *>(w.XH);
     LstmBwdTcArgs a{w.T, seq_node, seq_type, WhT, reinterpret_cast<const __half *>(w.acts), w.dhfin, w.gscale, w.dT,
-                    da_img, xh_img, P, ntiles, c.L, thr, scale, c.dropout_seed};
+                    da_img, xh_img, P, ntiles, c.L, thr, scale, c.dropout_seed, nullptr, 0};
+    long long *d_trace = nullptr;
+    const char *trace_env = getenv("PN_TRACE_BWD");
+    if (trace_env) {
+        PN_CUDA(cudaMalloc(&d_trace, sizeof(long long) * 8 * 64));
+        PN_CUDA(cudaMemsetAsync(d_trace, 0, sizeof(long long) * 8 * 64, st));
+        a.trace = d_trace;
+        a.trace_block = atoi(trace_env);
+    }
     PN_CUDA(cudaFuncSetAttribute(k_lstm_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TCB_SMEM));
     {
         ProfScope prof("lstm_bwd", st);
         k_lstm_bwd_tc<<<(unsigned)ntiles, TC_THREADS, TCB_SMEM, st>>>(a);
     }
     PN_LAUNCH_CHECK();
+    if (d_trace) {  // debug only
+        long long h[8 * 64];
+        PN_CUDA(cudaStreamSynchronize(st));
+        PN_CUDA(cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost));
+        cudaFree(d_trace);
+        const long long t00 = h[0];
+        for (int q = 0; q < c.L && q < 64; q++)
+            fprintf(stderr, "[trace bwd cta %d] s=%d  begin %lld | da staged+arrive %lld | regather/prefetch done %lld | acc_full seen %lld | dx scattered %lld\n",
+                    a.trace_block, q, h[q * 8 + 0] - t00, h[q * 8 + 1] - t00, h[q * 8 + 2] - t00, h[q * 8 + 3] - t00, h[q * 8 + 4] - t00);
+    }
     PN_CUDA(cudaMemsetAsync(w.dWp, 0, sizeof(float) * TC_K2 * TC_G4, st));
     PN_CUDA(cudaMemsetAsync(w.dbp, 0, sizeof(float) * TC_G4, st));
     WgradTcArgs wa{xh_img, da_img, nblocks, w.gscale, w.dWp};
