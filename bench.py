@@ -114,6 +114,17 @@ class ClockSampler:
                 "power_w_max": max(float(r[2]) for r in self.rows), "samples": len(self.rows)}
 
 
+def ncu_traffic(slot):
+    """DRAM bytes per launch of a kernel from the committed `ncu --set full` capture
+    (profiles/r01/ncu_traffic.json, written by tools/ncu_summary.py), or None."""
+    f = ROOT / "profiles" / "r01" / "ncu_traffic.json"
+    if f.exists():
+        d = json.loads(f.read_text()).get(slot)
+        if d:
+            return d["dram_bytes_per_launch"]
+    return None
+
+
 def measured_peaks():
     f = ROOT / "MEASURED_PEAKS.json"
     if f.exists():
@@ -337,7 +348,8 @@ def main():
     roofline = None
     if dom:
         roofline = {"kernel": dom, "bound": "tensor", "achieved": kern[dom]["tflops"], "peak": peak,
-                    "unit": "TFLOP/s", "frac": kern[dom]["tflops"] / peak, "traffic": None,
+                    "unit": "TFLOP/s", "frac": kern[dom]["tflops"] / peak, "traffic": ncu_traffic(dom),
+                    "traffic_note": "DRAM read+write bytes per launch from the committed ncu --set full capture (profiles/r01)",
                     "peak_source": f"{peaks['src']} bf16 sustained (MEASURED_PEAKS.json)",
                     "math_mode": args.math, "kernels": kern,
                     "note": "algorithmic FLOPs = 16*L*H^2 per path per LSTM GEMM pass (SURVEY 8d): forward gates, "
@@ -377,7 +389,7 @@ def main():
                          "achieved": walks * bytes_per_walk / ((kms / max(kn, 1)) * 1e-3) / 1e9 if kn else None,
                          "peak": peaks["hbm"], "unit": "GB/s",
                          "frac": (walks * bytes_per_walk / ((kms / kn) * 1e-3) / 1e9 / peaks["hbm"]) if kn else None,
-                         "traffic": None, "bytes_per_walk": bytes_per_walk,
+                         "traffic": ncu_traffic("merw_walk"), "bytes_per_walk": bytes_per_walk,
                          "peak_source": f"{peaks['src']} HBM copy bandwidth"}}
 
     line = {

@@ -214,11 +214,14 @@ __global__ void k_pack_lstm_tc(const float *__restrict__ w_ih, const float *__re
         const int col = i / TC_K2, k = i % TC_K2, unit = col >> 2, gate = col & 3;
         const float v = k < TC_H ? w_ih[(gate * TC_H + unit) * TC_H + k] : w_hh[(gate * TC_H + unit) * TC_H + (k - TC_H)];
         const int chunk = k / TC_KC, kk = k % TC_KC;
-        *reinterpret_cast<__half *>(Wh + (size_t)chunk * TC_CHUNK_BYTES + canon_off(col, kk, TC_KC)) = __float2half_rn(v);
+        // sigmoid(a) = 0.5 tanh(a/2) + 0.5: the 1/2 of the i, f, o gates is folded into weights and bias
+        // (exact in fp16), so the epilogue issues one tanh.approx per gate and no pre-scale
+        const float sc = gate == 2 ? 1.f : 0.5f;
+        *reinterpret_cast<__half *>(Wh + (size_t)chunk * TC_CHUNK_BYTES + canon_off(col, kk, TC_KC)) = __float2half_rn(sc * v);
     }
     if (i < TC_G4) {
         const int unit = i >> 2, gate = i & 3;
-        bp[i] = b_ih[gate * TC_H + unit] + b_hh[gate * TC_H + unit];
+        bp[i] = (gate == 2 ? 1.f : 0.5f) * (b_ih[gate * TC_H + unit] + b_hh[gate * TC_H + unit]);
     }
 }
 
@@ -233,11 +236,13 @@ struct LstmTcArgs {
     int64_t P;
     int L;
     uint32_t drop_thr; float drop_scale; uint64_t drop_seed;
+    unsigned char *xh_img;    // wgrad operand images [x_t | h_{t-1}] (see LstmBwdTcArgs), written here
     long long *trace;         // optional clock64() trace of CTA `trace_block` (debug)
     int trace_block;
 };
 
 constexpr int ACT_BLOCK_HALFS = 5 * 16 * 128 * 8;  // 160 KB per (tile, step)
+constexpr int DA_BLOCK_BYTES = 64 * 128 * 16, XH_BLOCK_BYTES = 32 * 128 * 16;  // wgrad operand images per (tile, step)
 constexpr int TC_NSTAGE = 6;                        // 96 KB weight ring
 constexpr int TC_XBYTES = 128 * TC_H * 2;           // 32 KB: one [128][128] fp16 operand half (x_t or h_{t-1})
 constexpr int TC_SMEM = 3 * TC_XBYTES + TC_NSTAGE * TC_CHUNK_BYTES + 2048 /*bias*/ + 128 * 8 * 4 /*row offsets*/ + 1024 /*align*/;
@@ -256,7 +261,7 @@ constexpr int TC_THREADS = (TC_CWARPS + 2) * 32;  // + MMA warp + weight-produce
 
 // this thread's quarter (32 floats) of table row `row_off` -> dropout -> fp16 -> x tile (canonical, K extent 128)
 __device__ __forceinline__ void tc_gather_quarter(const LstmTcArgs &a, unsigned char *Xs, int r, int cq, int32_t row_off,
-                                                   uint64_t elem0 /* (p*L + t) * H */)
+                                                   uint64_t elem0 /* (p*L + t) * H */, unsigned char *xh_blk)
 {
     const bool valid = row_off >= 0;
     const float *src = a.T + (int64_t)(valid ? row_off : 0) * TC_H;
@@ -277,7 +282,9 @@ __device__ __forceinline__ void tc_gather_quarter(const LstmTcArgs &a, unsigned 
                 }
             }
         }
-        *reinterpret_cast<uint4 *>(Xs + canon_off(r, k8 * 8, TC_H)) = pack8_f16(f);
+        const uint4 pk = pack8_f16(f);
+        *reinterpret_cast<uint4 *>(Xs + canon_off(r, k8 * 8, TC_H)) = pk;
+        *reinterpret_cast<uint4 *>(xh_blk + (size_t)k8 * 2048 + r * 16) = pk;   // x half of the wgrad operand image
     }
 }
 
@@ -372,7 +379,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_fwd_tc(LstmTcArgs a)
         for (int j = 0; j < 32; j++) c[j] = 0.f;
         const bool tr = a.trace && blockIdx.x == a.trace_block && tid == 0;
         if (tr) a.trace[6] = clock64();
-        tc_gather_quarter(a, Xs, r, cq, rowoff_s[r * TC_MAX_L + 0], (uint64_t)(p * L + 0) * TC_H);
+        const int64_t ntiles = gridDim.x;
+        tc_gather_quarter(a, Xs, r, cq, rowoff_s[r * TC_MAX_L + 0], (uint64_t)(p * L + 0) * TC_H,
+                          a.xh_img + ((int64_t)0 * ntiles + blockIdx.x) * XH_BLOCK_BYTES);
+        // h_{-1} = 0: h half of step 0's image
+#pragma unroll
+        for (int k8 = 16 + cq * 4; k8 < 16 + cq * 4 + 4; k8++)
+            *reinterpret_cast<uint4 *>(a.xh_img + (int64_t)blockIdx.x * XH_BLOCK_BYTES + (size_t)k8 * 2048 + r * 16) = make_uint4(0, 0, 0, 0);
         for (int t = 0; t < L; t++) {
             if (tr) a.trace[t * 8 + 0] = clock64();
             fence_proxy_async();   // generic-proxy smem writes (x_t, h_{t-1}) -> async proxy (tcgen05.mma)
@@ -382,7 +395,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_fwd_tc(LstmTcArgs a)
             // reader of that buffer, completed before acc_full(t-1) was observed)
             if (t + 1 < L)
                 tc_gather_quarter(a, Xs + ((t + 1) & 1) * TC_XBYTES, r, cq, rowoff_s[r * TC_MAX_L + t + 1],
-                                  (uint64_t)(p * L + t + 1) * TC_H);
+                                  (uint64_t)(p * L + t + 1) * TC_H, a.xh_img + ((int64_t)(t + 1) * ntiles + blockIdx.x) * XH_BLOCK_BYTES);
             if (tr) a.trace[t * 8 + 1] = clock64();
             // ---- wait for the gate pre-activations ----
             mbar_wait(&acc_full, t & 1);
@@ -409,11 +422,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_fwd_tc(LstmTcArgs a)
                     for (int e = 0; e < 2; e++) {
                         const int u = 2 * u2 + e, unit = jj * 8 + u;   // index into this thread's 32 cell states
                         const int vi = 4 * (u & 3);
-                        const float ai = __uint_as_float(v[vi + 0]) + bias_s[c0 + 4 * u + 0];
-                        const float af = __uint_as_float(v[vi + 1]) + bias_s[c0 + 4 * u + 1];
-                        const float ag = __uint_as_float(v[vi + 2]) + bias_s[c0 + 4 * u + 2];
-                        const float ao = __uint_as_float(v[vi + 3]) + bias_s[c0 + 4 * u + 3];
-                        gi2[e] = sigmoid_fast(ai); gf2[e] = sigmoid_fast(af); gg2[e] = tanh_fast(ag); go2[e] = sigmoid_fast(ao);
+                        const float4 b4 = *reinterpret_cast<const float4 *>(bias_s + c0 + 4 * u);
+                        gi2[e] = fmaf(0.5f, tanh_fast(__uint_as_float(v[vi + 0]) + b4.x), 0.5f);   // pre-activation already halved
+                        gf2[e] = fmaf(0.5f, tanh_fast(__uint_as_float(v[vi + 1]) + b4.y), 0.5f);
+                        gg2[e] = tanh_fast(__uint_as_float(v[vi + 2]) + b4.z);
+                        go2[e] = fmaf(0.5f, tanh_fast(__uint_as_float(v[vi + 3]) + b4.w), 0.5f);
                         const float cn = fmaf(gf2[e], c[unit], gi2[e] * gg2[e]);
                         c[unit] = cn;
                         cn2[e] = cn;
@@ -434,8 +447,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_fwd_tc(LstmTcArgs a)
                         *reinterpret_cast<float4 *>(Xs + r * 512 + ((j4 ^ (r & 7)) << 4)) = make_float4(hq[0], hq[1], hq[2], hq[3]);
                     }
                 }
-                // h_t -> operand tile for the next step
-                if (!t_is_last) *reinterpret_cast<uint4 *>(Hs + canon_off(r, c0 / 4, TC_H)) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                // h_t -> operand tile for the next step, and h half of the next step's wgrad operand image
+                if (!t_is_last) {
+                    const uint4 hpk = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                    *reinterpret_cast<uint4 *>(Hs + canon_off(r, c0 / 4, TC_H)) = hpk;
+                    *reinterpret_cast<uint4 *>(a.xh_img + ((int64_t)(t + 1) * ntiles + blockIdx.x) * XH_BLOCK_BYTES + (size_t)(16 + c0 / 32) * 2048 + r * 16) = hpk;
+                }
                 if (valid) {
                     const int ub = (c0 / 32) * 1024;  // unit8 block of 128 rows x 8 halves
                     *reinterpret_cast<uint4 *>(act + 0 * 16384 + ub) = make_uint4(pi[0], pi[1], pi[2], pi[3]);
@@ -482,7 +499,7 @@ int pagg_tc_forward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_pa
     }
     const int64_t P = (int64_t)c.S * c.nw;
     LstmTcArgs a{w.T, seq_node, seq_type, Wh, w.bp, reinterpret_cast<__half *>(w.acts), w.hfin, P, c.L, thr, scale, c.dropout_seed,
-                 nullptr, 0};
+                 reinterpret_cast<unsigned char *>(w.XH), nullptr, 0};
     long long *d_trace = nullptr;
     const char *trace_env = getenv("PN_TRACE_FWD");
     if (trace_env) {
@@ -560,7 +577,7 @@ struct LstmBwdTcArgs {
     const float *gscale;       // {scale, 1/scale}
     float *dT;                 // [N,L,H]
     unsigned char *da_img;     // block b = t*ntiles + tile: [64 col8][128 r][8] fp16   (128 KB)
-    unsigned char *xh_img;     // block b:                   [32 k8 ][128 r][8] fp16   ( 64 KB)
+    const unsigned char *xh_img;  // block b: [32 k8][128 r][8] fp16 (64 KB): k8 < 16 x_t, k8 >= 16 h_{t-1}; written by the FORWARD kernel
     int64_t P, ntiles;
     int L;
     uint32_t drop_thr; float drop_scale; uint64_t drop_seed;
@@ -570,7 +587,6 @@ struct LstmBwdTcArgs {
 constexpr int TCB_NSTAGE = 3;
 constexpr int TCB_A_BYTES = 128 * TC_G4 * 2;  // 128 KB: da tile [128][512] fp16 canonical
 constexpr int TCB_SMEM = TCB_A_BYTES + TCB_NSTAGE * TCB_CHUNK_BYTES + 1024;
-constexpr int DA_BLOCK_BYTES = 64 * 128 * 16, XH_BLOCK_BYTES = 32 * 128 * 16;
 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
@@ -646,7 +662,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
             if (tr) a.trace[s * 8 + 0] = clock64();
             const int64_t blk = (int64_t)t * a.ntiles + tile;
             unsigned char *da_blk = a.da_img + blk * DA_BLOCK_BYTES;
-            unsigned char *xh_blk = a.xh_img + blk * XH_BLOCK_BYTES;
             const __half *act = a.acts + ((int64_t)tile * L + t) * ACT_BLOCK_HALFS + r * 8;
             const __half *actp = act - ACT_BLOCK_HALFS;  // step t-1 (only read when t > 0)
             // ---- gate gradients ----
@@ -671,9 +686,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
 #pragma unroll
                     for (int j = 0; j < 8; j++) { dh[j] = __uint_as_float(v0[j]); dc[j] = __uint_as_float(v1[j]); }
                 }
-                float gi[8], gf[8], gg[8], go[8], cn[8], cp[8], hp[8];
+                float gi[8], gf[8], gg[8], go[8], cn[8], cp[8];
 #pragma unroll
-                for (int j = 0; j < 8; j++) { gi[j] = gf[j] = gg[j] = go[j] = cn[j] = cp[j] = hp[j] = 0.f; }
+                for (int j = 0; j < 8; j++) { gi[j] = gf[j] = gg[j] = go[j] = cn[j] = cp[j] = 0.f; }
                 if (valid) {
                     const int ub = cb * 1024;
                     unpack8_f16(__ldg(reinterpret_cast<const uint4 *>(act + 0 * 16384 + ub)), gi);
@@ -681,13 +696,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
                     unpack8_f16(__ldg(reinterpret_cast<const uint4 *>(act + 2 * 16384 + ub)), gg);
                     unpack8_f16(__ldg(reinterpret_cast<const uint4 *>(act + 3 * 16384 + ub)), go);
                     unpack8_f16(__ldg(reinterpret_cast<const uint4 *>(act + 4 * 16384 + ub)), cn);
-                    if (t > 0) {
-                        float op[8];
-                        unpack8_f16(__ldg(reinterpret_cast<const uint4 *>(actp + 3 * 16384 + ub)), op);
-                        unpack8_f16(__ldg(reinterpret_cast<const uint4 *>(actp + 4 * 16384 + ub)), cp);
-#pragma unroll
-                        for (int j = 0; j < 8; j++) hp[j] = op[j] * tanh_fast(cp[j]);
-                    }
+                    if (t > 0) unpack8_f16(__ldg(reinterpret_cast<const uint4 *>(actp + 4 * 16384 + ub)), cp);
                 }
                 float da[4][8];  // [q][.]: packed columns (u0 + 2q + {0,1}) * 4 + gate
                 uint32_t dcn_bits[8];
@@ -710,7 +719,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
                     *reinterpret_cast<uint4 *>(As + canon_off(r, cb * 32 + q * 8, TC_G4)) = pk;          // dgrad operand
                     *reinterpret_cast<uint4 *>(da_blk + (size_t)(cb * 4 + q) * 2048 + r * 16) = pk;       // wgrad operand image
                 }
-                *reinterpret_cast<uint4 *>(xh_blk + (size_t)(16 + cb) * 2048 + r * 16) = pack8_f16(hp);  // h_{t-1}
             }
             tmem_st_wait();
             fence_proxy_async();
@@ -723,32 +731,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
                 for (int cb = cq * 4; cb < cq * 4 + 4; cb++) {
 #pragma unroll
                     for (int q = 0; q < 5; q++) prefetch_l2(actp + q * 16384 + cb * 1024);
-                    if (t > 1) { prefetch_l2(actp - ACT_BLOCK_HALFS + 3 * 16384 + cb * 1024); prefetch_l2(actp - ACT_BLOCK_HALFS + 4 * 16384 + cb * 1024); }
-                }
-            }
-            // ---- ... and write x_t (same dropout mask as forward) into the wgrad image ----
-            {
-                const float *src = nullptr;
-                int64_t e = 0;
-                if (valid) { e = p * L + t; src = a.T + ((int64_t)a.seq_node[e] * L + a.seq_type[e]) * TC_H; }
-#pragma unroll
-                for (int k8 = cq * 4; k8 < cq * 4 + 4; k8++) {
-                    float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                    if (valid) {
-                        const float4 u = __ldg(reinterpret_cast<const float4 *>(src + k8 * 8));
-                        const float4 w = __ldg(reinterpret_cast<const float4 *>(src + k8 * 8 + 4));
-                        f[0] = u.x; f[1] = u.y; f[2] = u.z; f[3] = u.w; f[4] = w.x; f[5] = w.y; f[6] = w.z; f[7] = w.w;
-                        if (a.drop_thr) {
-                            const uint64_t pair = ((uint64_t)e * TC_H + k8 * 8) >> 1;
-#pragma unroll
-                            for (int q = 0; q < 4; q++) {
-                                const uint32_t h = dropout_hash_pair(a.drop_seed, 0, pair + q);
-                                f[2 * q] = (h & 0xFFFFu) < a.drop_thr ? 0.f : f[2 * q] * a.drop_scale;
-                                f[2 * q + 1] = (h >> 16) < a.drop_thr ? 0.f : f[2 * q + 1] * a.drop_scale;
-                            }
-                        }
-                    }
-                    *reinterpret_cast<uint4 *>(xh_blk + (size_t)k8 * 2048 + r * 16) = pack8_f16(f);
+                    if (t > 1) prefetch_l2(actp - ACT_BLOCK_HALFS + 4 * 16384 + cb * 1024);
                 }
             }
             if (tr) a.trace[s * 8 + 2] = clock64();

@@ -39,6 +39,19 @@ def main(rep, out):
             pass
     open(out, "w").write("\n".join(lines) + "\n")
     print("\n".join(lines[:80]))
+    # per-kernel DRAM traffic (bytes per launch, last launch of each kernel) for bench.py's roofline.traffic
+    import json, os
+    mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    slot = {"k_lstm_fwd_tc": "lstm_fwd", "k_lstm_bwd_tc": "lstm_bwd", "k_wgrad_tc": "wgrad", "k_merw_walk": "merw_walk"}
+    tpath = os.path.join(os.path.dirname(out), "ncu_traffic.json")
+    traffic = json.load(open(tpath)) if os.path.exists(tpath) else {}
+    for r in rows[2:]:
+        name = re.sub(r"\(.*", "", r[idx["Kernel Name"]]).split("::")[-1]
+        if name in slot:
+            rd = float(r[idx["dram__bytes_read.sum"]].replace(",", "")) * mult.get(units[idx["dram__bytes_read.sum"]], 1)
+            wr = float(r[idx["dram__bytes_write.sum"]].replace(",", "")) * mult.get(units[idx["dram__bytes_write.sum"]], 1)
+            traffic[slot[name]] = {"dram_bytes_per_launch": rd + wr, "read": rd, "write": wr, "source": os.path.basename(rep)}
+    json.dump(traffic, open(tpath, "w"), indent=1)
 
 
 if __name__ == "__main__":
