@@ -369,6 +369,7 @@ struct PoolArgs {
     // backward
     const float *dcat;   // [S,2H] grad wrt the dropped concat
     float *dhfin, *dZ, *dT, *dattw;
+    unsigned int *absmax_bits;  // max |dhfin| as float bits (tensor-core backward's gradient scale), may be null
 };
 
 __device__ __forceinline__ float warp_sum(float v)
@@ -477,8 +478,12 @@ __global__ void __launch_bounds__(256) k_pool_bwd(PoolArgs a)
             if (a.drop_thr) g = dropout_hash(a.drop_seed, 1, (uint64_t)s * 2 * H + j) < a.drop_thr ? 0.f : g * a.drop_scale;
             atomicAdd(a.dZ + node * H + j, g);
         }
-        float dbias = 0.f;
+        float dbias = 0.f, amax = 0.f;
         float dw_h[4] = {0.f, 0.f, 0.f, 0.f}, dw_p[4] = {0.f, 0.f, 0.f, 0.f};  // H <= 128: j = lane + 32q
+        // partner gradient: consecutive sequences often share the partner row (homo: always the row's own
+        // step-0 entry), so accumulate in registers and flush with atomics only when the target changes
+        float dp_acc[4] = {0.f, 0.f, 0.f, 0.f};
+        float *dp_cur = nullptr;
         for (int w = 0; w < nw; w++) {
             const int64_t p = s * nw + w;
             const float da = a.dhfin[p * H];
@@ -496,16 +501,29 @@ __global__ void __launch_bounds__(256) k_pool_bwd(PoolArgs a)
             float *dpv = a.variant == PN_VARIANT_HOMO
                              ? a.dT + ((int64_t)a.seq_node[p * a.L] * a.L + a.seq_type[p * a.L]) * H
                              : a.dZ + (int64_t)a.partner[p] * H;
+            if (dpv != dp_cur) {
+                if (dp_cur) {
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const int j = lane + 32 * q;
+                        if (j < H) atomicAdd(dp_cur + j, dp_acc[q]);
+                        dp_acc[q] = 0.f;
+                    }
+                }
+                dp_cur = dpv;
+            }
 #pragma unroll
             for (int q = 0; q < 4; q++) {
                 const int j = lane + 32 * q;
                 if (j < H) {
                     float g = a.dcat[s * 2 * H + H + j];
                     if (a.drop_thr) g = dropout_hash(a.drop_seed, 1, (uint64_t)s * 2 * H + H + j) < a.drop_thr ? 0.f : g * a.drop_scale;
-                    a.dhfin[p * H + j] = inv_nw * att * g + dscore * a.attw_w[j];
+                    const float dhv = inv_nw * att * g + dscore * a.attw_w[j];
+                    a.dhfin[p * H + j] = dhv;
+                    amax = fmaxf(amax, fabsf(dhv));
                     dw_h[q] += dscore * h[j];
                     dw_p[q] += dscore * pv[j];
-                    atomicAdd(dpv + j, dscore * a.attw_w[H + j]);
+                    dp_acc[q] += dscore * a.attw_w[H + j];
                 }
             }
             __syncwarp();
@@ -513,9 +531,16 @@ __global__ void __launch_bounds__(256) k_pool_bwd(PoolArgs a)
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             const int j = lane + 32 * q;
-            if (j < H) { atomicAdd(&s_dattw[j], dw_h[q]); atomicAdd(&s_dattw[H + j], dw_p[q]); }
+            if (j < H) {
+                atomicAdd(&s_dattw[j], dw_h[q]); atomicAdd(&s_dattw[H + j], dw_p[q]);
+                if (dp_cur) atomicAdd(dp_cur + j, dp_acc[q]);
+            }
         }
         if (lane == 0) atomicAdd(&s_dattw[2 * H], dbias);
+        if (a.absmax_bits) {
+            amax = warp_max(amax);
+            if (lane == 0 && amax > 0.f) atomicMax(a.absmax_bits, __float_as_uint(amax));
+        }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 2 * H + 1; i += blockDim.x) atomicAdd(a.dattw + i, s_dattw[i]);
@@ -706,6 +731,11 @@ extern "C" int pn_pagg_backward(const pn_pagg_cfg *cfg, const pn_pagg_params *pr
     pa.score = w.score; pa.att = w.att; pa.cat = w.cat;
     pa.drop_thr = thr; pa.drop_scale = scale; pa.drop_seed = c.dropout_seed;
     pa.dcat = w.dcat; pa.dhfin = w.dhfin; pa.dZ = w.dZ; pa.dT = w.dT; pa.dattw = w.dattw;
+    pa.absmax_bits = nullptr;
+    if (c.math_mode == PN_MATH_TC) {
+        ZERO(w.gscale, 2);
+        pa.absmax_bits = reinterpret_cast<unsigned int *>(w.gscale);
+    }
     k_pool_bwd<<<(unsigned)ceil_div(S, 8), 256, sizeof(float) * (2 * H + 1), st>>>(pa);
     PN_LAUNCH_CHECK();
     PN_CUDA(cudaMemcpyAsync(g.attw_w, w.dattw, sizeof(float) * 2 * H, cudaMemcpyDeviceToDevice, st));

@@ -786,28 +786,39 @@ struct WgradTcArgs {
     int64_t nblocks;
     const float *gscale;
     float *dWp;  // [256][512] fp32, atomically accumulated
+    float *dbp;  // [512]      fp32, atomically accumulated (bias gradient = column sums of da)
 };
 constexpr int WG_STAGE_BYTES = 32768 + 65536;
-constexpr int WG_SMEM = 2 * WG_STAGE_BYTES + 1024;
+constexpr int WG_ONES_BYTES = 32768;   // constant A operand [128 (m)][128 (r)] with row m = 0 all ones
+constexpr int WG_SMEM = 2 * WG_STAGE_BYTES + WG_ONES_BYTES + 1024;
 
 __global__ void __launch_bounds__(192, 1) k_wgrad_tc(WgradTcArgs a)
 {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    unsigned char *ones = base + 2 * WG_STAGE_BYTES;
     __shared__ uint64_t full_bar[2], empty_bar[2], acc_full;
     __shared__ uint32_t s_taddr;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int mt = blockIdx.y >> 1, nt = blockIdx.y & 1;
+    const bool do_bias = mt == 0;   // the mt = 0 CTAs also produce the column sums of their 256 da columns
     if (tid == 0) {
         for (int s = 0; s < 2; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(&acc_full, 1);
         fence_mbar_init();
     }
-    if (warp == 4) tmem_alloc<256>(&s_taddr);
+    if (warp == 4) tmem_alloc<512>(&s_taddr);
+    // ones operand, MN-major image like the XH blocks: chunk (m8, r) at m8*2048 + r*16 holds m = 8 m8 .. 8 m8 + 7
+    for (int i = tid; i < WG_ONES_BYTES / 16; i += 192) {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (i < 128) v.x = 0x00003C00u;   // m8 = 0: element m = 0 is fp16 1.0, m = 1..7 are 0
+        reinterpret_cast<uint4 *>(ones)[i] = v;
+    }
+    fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t taddr = s_taddr;
+    const uint32_t taddr = s_taddr;   // cols [0,256): dWp tile, cols [256,512): bias rows (lane 0 = column sums)
     const int64_t first = blockIdx.x, step = gridDim.x;
     if (warp == 5) {
         if (lane == 0) {
@@ -830,12 +841,13 @@ __global__ void __launch_bounds__(192, 1) k_wgrad_tc(WgradTcArgs a)
             for (int64_t b = first; b < a.nblocks; b += step) {
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                const uint32_t abase = smem_u32(base + stage * WG_STAGE_BYTES), bbase = abase + 32768;
+                const uint32_t abase = smem_u32(base + stage * WG_STAGE_BYTES), bbase = abase + 32768, obase = smem_u32(ones);
 #pragma unroll
                 for (int ks = 0; ks < 8; ks++) {  // 128 rows of the block = 8 K-steps of 16
                     const uint64_t ad = make_smem_desc(abase + ks * 256, 128, 2048);
                     const uint64_t bd = make_smem_desc(bbase + ks * 256, 128, 2048);
                     mma_f16(taddr, ad, bd, idesc, !first_blk || ks > 0);
+                    if (do_bias) mma_f16(taddr + 256, make_smem_desc(obase + ks * 256, 128, 2048), bd, idesc, !first_blk || ks > 0);
                 }
                 first_blk = false;
                 mma_commit(&empty_bar[stage]);
@@ -859,11 +871,21 @@ __global__ void __launch_bounds__(192, 1) k_wgrad_tc(WgradTcArgs a)
                               make_float4(__uint_as_float(v[j]) * inv_scale, __uint_as_float(v[j + 1]) * inv_scale,
                                           __uint_as_float(v[j + 2]) * inv_scale, __uint_as_float(v[j + 3]) * inv_scale));
             }
+            if (do_bias && warp == 0) {   // TMEM lane 0 of the second accumulator = sum over rows of da[:, col]
+                for (int c0 = 0; c0 < 256; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + 256 + (uint32_t)c0, v);
+                    tmem_ld_wait();
+                    if (lane == 0)
+#pragma unroll
+                        for (int j = 0; j < 32; j++) atomicAdd(a.dbp + nt * 256 + c0 + j, __uint_as_float(v[j]) * inv_scale);
+                }
+            }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) { __syncwarp(); tmem_dealloc<256>(taddr); }
+    if (warp == 4) { __syncwarp(); tmem_dealloc<512>(taddr); }
 }
 
 // bias gradient: dbp[col] = (1/scale) * sum over all rows of all da blocks.
@@ -925,9 +947,7 @@ int pagg_tc_backward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_p
         return PN_ERR_UNSUPPORTED;
     }
     const int64_t P = (int64_t)c.S * c.nw, ntiles = ceil_div(P, 128), nblocks = ntiles * c.L;
-    PN_CUDA(cudaMemsetAsync(w.gscale, 0, 2 * sizeof(float), st));
-    k_absmax_bits<<<(unsigned)std::min<int64_t>(1024, ceil_div(P * TC_H, 256)), 256, 0, st>>>(w.dhfin, P * TC_H, reinterpret_cast<unsigned int *>(w.gscale));
-    PN_LAUNCH_CHECK();
+    // max |dh_final| was accumulated into gscale[0] (as float bits) by k_pool_bwd
     k_make_scale<<<1, 1, 0, st>>>(w.gscale);
     PN_LAUNCH_CHECK();
     unsigned char *WhT = reinterpret_cast<unsigned char *>(w.WpT);  // 256 KB of the 512 KB fp32 region
@@ -967,15 +987,13 @@ int pagg_tc_backward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_p
     }
     PN_CUDA(cudaMemsetAsync(w.dWp, 0, sizeof(float) * TC_K2 * TC_G4, st));
     PN_CUDA(cudaMemsetAsync(w.dbp, 0, sizeof(float) * TC_G4, st));
-    WgradTcArgs wa{xh_img, da_img, nblocks, w.gscale, w.dWp};
+    WgradTcArgs wa{xh_img, da_img, nblocks, w.gscale, w.dWp, w.dbp};
     PN_CUDA(cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
     {
         ProfScope prof("wgrad", st);
         const unsigned nsplit = (unsigned)std::max<int64_t>(1, std::min<int64_t>(37, nblocks));
         k_wgrad_tc<<<dim3(nsplit, 4), 192, WG_SMEM, st>>>(wa);
     }
-    PN_LAUNCH_CHECK();
-    k_colsum_da_img<<<(unsigned)std::min<int64_t>(148 * 4, nblocks * 2), 256, 0, st>>>(da_img, nblocks, w.gscale, w.dbp);
     PN_LAUNCH_CHECK();
     return PN_OK;
 }
