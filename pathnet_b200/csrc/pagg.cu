@@ -456,38 +456,60 @@ __global__ void __launch_bounds__(256) k_pool_bwd(PoolArgs a)
     if (s < a.S) {
         const float inv_nw = 1.f / (float)nw;
         const int64_t node = a.rows[s];
-        // grads wrt the un-dropped concat
-        // da_w = inv_nw * <dpooled, h_w>
+        // gradient wrt the pooled half of the concat, dropout applied once (H <= 128: j = lane + 32 q)
+        float gq[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int j = lane + 32 * q;
+            float g = 0.f;
+            if (j < H) {
+                g = a.dcat[s * 2 * H + H + j];
+                if (a.drop_thr) g = dropout_hash(a.drop_seed, 1, (uint64_t)s * 2 * H + H + j) < a.drop_thr ? 0.f : g * a.drop_scale;
+            }
+            gq[q] = g;
+        }
+        // da_w = inv_nw * <dpooled, h_w>, kept by lane (w mod 32) for w < 64, else recomputed
+        float da_keep0 = 0.f, da_keep1 = 0.f;
         float dot_sum = 0.f;  // sum_v att_v * da_v (softmax backward), hetero only
 #pragma unroll 4
         for (int w = 0; w < nw; w++) {
             const int64_t p = s * nw + w;
             float d = 0.f;
-            for (int j = lane; j < H; j += 32) {
-                float g = a.dcat[s * 2 * H + H + j];
-                if (a.drop_thr) g = dropout_hash(a.drop_seed, 1, (uint64_t)s * 2 * H + H + j) < a.drop_thr ? 0.f : g * a.drop_scale;
-                d += g * a.hfin[p * H + j];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int j = lane + 32 * q;
+                if (j < H) d += gq[q] * a.hfin[p * H + j];
             }
             d = warp_sum(d) * inv_nw;
-            if (lane == 0) a.dhfin[p * H] = d;  // stash da_w in the (not yet written) dhfin row
+            if ((w & 31) == lane) { if (w < 32) da_keep0 = d; else if (w < 64) da_keep1 = d; }
             dot_sum += a.att[p] * d;
         }
-        __syncwarp();
         for (int j = lane; j < H; j += 32) {  // ego gradient
             float g = a.dcat[s * 2 * H + j];
             if (a.drop_thr) g = dropout_hash(a.drop_seed, 1, (uint64_t)s * 2 * H + j) < a.drop_thr ? 0.f : g * a.drop_scale;
             atomicAdd(a.dZ + node * H + j, g);
         }
         float dbias = 0.f, amax = 0.f;
-        float dw_h[4] = {0.f, 0.f, 0.f, 0.f}, dw_p[4] = {0.f, 0.f, 0.f, 0.f};  // H <= 128: j = lane + 32q
+        float dw_h[4] = {0.f, 0.f, 0.f, 0.f}, dw_p[4] = {0.f, 0.f, 0.f, 0.f};
         // partner gradient: consecutive sequences often share the partner row (homo: always the row's own
         // step-0 entry), so accumulate in registers and flush with atomics only when the target changes
         float dp_acc[4] = {0.f, 0.f, 0.f, 0.f};
         float *dp_cur = nullptr;
+#pragma unroll 2
         for (int w = 0; w < nw; w++) {
             const int64_t p = s * nw + w;
-            const float da = a.dhfin[p * H];
-            __syncwarp();
+            const float *h = a.hfin + p * H, *pv = partner_vec(a, p);
+            float hq[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) hq[q] = (lane + 32 * q < H) ? h[lane + 32 * q] : 0.f;
+            float da;
+            if (w < 64) da = __shfl_sync(0xffffffffu, w < 32 ? da_keep0 : da_keep1, w & 31);
+            else {
+                float d = 0.f;
+#pragma unroll
+                for (int q = 0; q < 4; q++) d += gq[q] * hq[q];
+                da = warp_sum(d) * inv_nw;
+            }
             const float raw = a.score[p], att = a.att[p];
             float dscore;
             if (a.variant == PN_VARIANT_HETERO) {
@@ -497,7 +519,6 @@ __global__ void __launch_bounds__(256) k_pool_bwd(PoolArgs a)
                 dscore = da;  // weight = 1 + score
             }
             dbias += dscore;
-            const float *h = a.hfin + p * H, *pv = partner_vec(a, p);
             float *dpv = a.variant == PN_VARIANT_HOMO
                              ? a.dT + ((int64_t)a.seq_node[p * a.L] * a.L + a.seq_type[p * a.L]) * H
                              : a.dZ + (int64_t)a.partner[p] * H;
@@ -516,17 +537,14 @@ __global__ void __launch_bounds__(256) k_pool_bwd(PoolArgs a)
             for (int q = 0; q < 4; q++) {
                 const int j = lane + 32 * q;
                 if (j < H) {
-                    float g = a.dcat[s * 2 * H + H + j];
-                    if (a.drop_thr) g = dropout_hash(a.drop_seed, 1, (uint64_t)s * 2 * H + H + j) < a.drop_thr ? 0.f : g * a.drop_scale;
-                    const float dhv = inv_nw * att * g + dscore * a.attw_w[j];
+                    const float dhv = inv_nw * att * gq[q] + dscore * a.attw_w[j];
                     a.dhfin[p * H + j] = dhv;
                     amax = fmaxf(amax, fabsf(dhv));
-                    dw_h[q] += dscore * h[j];
+                    dw_h[q] += dscore * hq[q];
                     dw_p[q] += dscore * pv[j];
                     dp_acc[q] += dscore * a.attw_w[H + j];
                 }
             }
-            __syncwarp();
         }
 #pragma unroll
         for (int q = 0; q < 4; q++) {
