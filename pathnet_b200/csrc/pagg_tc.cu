@@ -198,13 +198,12 @@ int launch_gemm_tc(cudaStream_t st, const float *A, int64_t lda, const float *B,
 }
 
 // ---------------------------------------------------------------------------
-// LSTM weights -> fp16, canonical layout, cut into 2 column halves x 16 K-chunks of 16 so each
-// chunk ([256 cols][16 k], 8 KB; index nh*16 + kchunk) is one contiguous bulk copy.
+// LSTM weights -> fp16, canonical layout, cut into 16 K-chunks of 16 so each
+// chunk ([512 cols][16 k], 16 KB) is one contiguous bulk copy.
 //   column = unit*4 + gate (i,f,g,o), k < H: W_ih, k >= H: W_hh      (H = 128)
 // ---------------------------------------------------------------------------
 constexpr int TC_H = 128, TC_G4 = 512, TC_K2 = 256, TC_KC = 16, TC_NCHUNK = TC_K2 / TC_KC;
-constexpr int TC_NHALF = TC_G4 / 2;                    // gate columns per half (units [0,64) | [64,128))
-constexpr int TC_CHUNK_BYTES = TC_NHALF * TC_KC * 2;   // 8 KB: [256 cols][16 k]
+constexpr int TC_CHUNK_BYTES = TC_G4 * TC_KC * 2;  // 16 KB
 
 __global__ void k_pack_lstm_tc(const float *__restrict__ w_ih, const float *__restrict__ w_hh,
                                const float *__restrict__ b_ih, const float *__restrict__ b_hh,
@@ -218,8 +217,7 @@ __global__ void k_pack_lstm_tc(const float *__restrict__ w_ih, const float *__re
         // sigmoid(a) = 0.5 tanh(a/2) + 0.5: the 1/2 of the i, f, o gates is folded into weights and bias
         // (exact in fp16), so the epilogue issues one tanh.approx per gate and no pre-scale
         const float sc = gate == 2 ? 1.f : 0.5f;
-        const int nh = col / TC_NHALF, cl = col % TC_NHALF;
-        *reinterpret_cast<__half *>(Wh + (size_t)(nh * TC_NCHUNK + chunk) * TC_CHUNK_BYTES + canon_off(cl, kk, TC_KC)) = __float2half_rn(sc * v);
+        *reinterpret_cast<__half *>(Wh + (size_t)chunk * TC_CHUNK_BYTES + canon_off(col, kk, TC_KC)) = __float2half_rn(sc * v);
     }
     if (i < TC_G4) {
         const int unit = i >> 2, gate = i & 3;
@@ -245,7 +243,7 @@ struct LstmTcArgs {
 
 constexpr int ACT_BLOCK_HALFS = 5 * 16 * 128 * 8;  // 160 KB per (tile, step)
 constexpr int DA_BLOCK_BYTES = 64 * 128 * 16, XH_BLOCK_BYTES = 32 * 128 * 16;  // wgrad operand images per (tile, step)
-constexpr int TC_NSTAGE = 8;                        // 64 KB weight ring
+constexpr int TC_NSTAGE = 7;                        // 112 KB weight ring (largest that fits beside the operand tiles)
 constexpr int TC_XBYTES = 128 * TC_H * 2;           // 32 KB: one [128][128] fp16 operand half (x_t or h_{t-1})
 constexpr int TC_SMEM = 3 * TC_XBYTES + TC_NSTAGE * TC_CHUNK_BYTES + 2048 /*bias*/ + 128 * 8 * 4 /*row offsets*/ + 1024 /*align*/;
 constexpr int TC_MAX_L = 8;
@@ -299,7 +297,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_fwd_tc(LstmTcArgs a)
     unsigned char *Ws = base + 3 * TC_XBYTES;       // ring of weight chunks
     float *bias_s = reinterpret_cast<float *>(Ws + TC_NSTAGE * TC_CHUNK_BYTES);
     int32_t *rowoff_s = reinterpret_cast<int32_t *>(bias_s + TC_G4);   // [128][TC_MAX_L]: table row of (sequence, step), -1 = padding
-    __shared__ uint64_t full_bar[TC_NSTAGE], empty_bar[TC_NSTAGE], a_ready, acc_full[2];
+    __shared__ uint64_t full_bar[TC_NSTAGE], empty_bar[TC_NSTAGE], a_ready, acc_full;
     __shared__ uint32_t s_taddr;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t p0 = (int64_t)blockIdx.x * 128;
@@ -308,8 +306,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_fwd_tc(LstmTcArgs a)
     if (tid == 0) {
         for (int s = 0; s < TC_NSTAGE; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(&a_ready, TC_CWARPS * 32);
-        mbar_init(&acc_full[0], 1);
-        mbar_init(&acc_full[1], 1);
+        mbar_init(&acc_full, 1);
         fence_mbar_init();
     }
     if (warp == TC_CWARPS) tmem_alloc<512>(&s_taddr);
@@ -332,13 +329,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_fwd_tc(LstmTcArgs a)
             uint32_t stage = 0, phase = 0;
             for (int t = 0; t < L; t++) {
                 const int nch = t == 0 ? TC_NCHUNK / 2 : TC_NCHUNK;
-                for (int nh = 0; nh < 2; nh++)
-                    for (int c = 0; c < nch; c++) {
-                        mbar_wait(&empty_bar[stage], phase ^ 1);  // slot free (first pass: passes immediately)
-                        mbar_arrive_expect_tx(&full_bar[stage], TC_CHUNK_BYTES);
-                        bulk_g2s(Ws + stage * TC_CHUNK_BYTES, a.Wh + (size_t)(nh * TC_NCHUNK + c) * TC_CHUNK_BYTES, TC_CHUNK_BYTES, &full_bar[stage]);
-                        if (++stage == TC_NSTAGE) { stage = 0; phase ^= 1; }
-                    }
+                for (int c = 0; c < nch; c++) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);  // slot free (first pass: passes immediately)
+                    mbar_arrive_expect_tx(&full_bar[stage], TC_CHUNK_BYTES);
+                    bulk_g2s(Ws + stage * TC_CHUNK_BYTES, a.Wh + (size_t)c * TC_CHUNK_BYTES, TC_CHUNK_BYTES, &full_bar[stage]);
+                    if (++stage == TC_NSTAGE) { stage = 0; phase ^= 1; }
+                }
             }
         }
     } else if (warp == TC_CWARPS) {
@@ -352,28 +348,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_fwd_tc(LstmTcArgs a)
                 if (a.trace && blockIdx.x == a.trace_block) a.trace[t * 8 + 4] = clock64();
                 const int nch = t == 0 ? TC_NCHUNK / 2 : TC_NCHUNK;  // h_0 = 0: skip the W_hh half
                 const uint32_t xbase = smem_u32(Xs + (t & 1) * TC_XBYTES), hbase = smem_u32(Hs);
-                // half 0 (units 0..63) completes first: its epilogue overlaps the MMAs of half 1
-                for (int nh = 0; nh < 2; nh++) {
-                    for (int c = 0; c < nch; c++) {
-                        mbar_wait(&full_bar[stage], phase);
-                        tc_fence_after();
-                        const uint32_t wbase = smem_u32(Ws + stage * TC_CHUNK_BYTES);
-                        // chunk c = 16 consecutive k: two core matrices (256 B) of the x half (c < 8) or the h half
-                        const uint32_t abase = (c < TC_NCHUNK / 2 ? xbase + (uint32_t)c * 256 : hbase + (uint32_t)(c - TC_NCHUNK / 2) * 256);
-                        const uint64_t ad = make_smem_desc(abase, 128, (TC_H / 8) * 128);
-                        const uint64_t bd = make_smem_desc(wbase, 128, (TC_KC / 8) * 128);
+                for (int c = 0; c < nch; c++) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t wbase = smem_u32(Ws + stage * TC_CHUNK_BYTES);
+                    // chunk c = 16 consecutive k: two core matrices (256 B) of the x half (c < 8) or the h half
+                    const uint32_t abase = (c < TC_NCHUNK / 2 ? xbase + (uint32_t)c * 256 : hbase + (uint32_t)(c - TC_NCHUNK / 2) * 256);
+                    const uint64_t ad = make_smem_desc(abase, 128, (TC_H / 8) * 128);
+#pragma unroll
+                    for (int nh = 0; nh < 2; nh++) {
+                        const uint64_t bd = make_smem_desc(wbase + (uint32_t)nh * (256 / 8) * ((TC_KC / 8) * 128), 128, (TC_KC / 8) * 128);
                         mma_f16(taddr + (uint32_t)nh * 256, ad, bd, idesc, c > 0);
-                        mma_commit(&empty_bar[stage]);  // slot reusable once this MMA has read it
-                        if (++stage == TC_NSTAGE) { stage = 0; phase ^= 1; }
                     }
-                    mma_commit(&acc_full[nh]);
+                    mma_commit(&empty_bar[stage]);  // slot reusable once these MMAs have read it
+                    if (++stage == TC_NSTAGE) { stage = 0; phase ^= 1; }
                 }
+                mma_commit(&acc_full);
                 if (a.trace && blockIdx.x == a.trace_block) a.trace[t * 8 + 5] = clock64();
             }
         }
     } else {
-        // ===== gather + gate math: warp = (TMEM lane quarter lq, column group cq); the thread owns sequence
-        //       p0 + 32 lq + lane (= its TMEM lane) and hidden units [64 nh + 16 cq, +16) of both halves nh =====
+        // ===== gather + gate math: warp = (TMEM lane quarter lq, column quarter cq); the thread owns
+        //       sequence p0 + 32 lq + lane (= its TMEM lane) and hidden units [32 cq, 32 cq + 32) =====
         const int lq = warp & 3, cq = warp >> 2;
         const int r = lq * 32 + lane;
         const int64_t p = p0 + r;
@@ -401,19 +397,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_fwd_tc(LstmTcArgs a)
                 tc_gather_quarter(a, Xs + ((t + 1) & 1) * TC_XBYTES, r, cq, rowoff_s[r * TC_MAX_L + t + 1],
                                   (uint64_t)(p * L + t + 1) * TC_H, a.xh_img + ((int64_t)(t + 1) * ntiles + blockIdx.x) * XH_BLOCK_BYTES);
             if (tr) a.trace[t * 8 + 1] = clock64();
-            if (tr) a.trace[t * 8 + 2] = 0;
+            // ---- wait for the gate pre-activations ----
+            mbar_wait(&acc_full, t & 1);
+            tc_fence_after();
+            if (tr) a.trace[t * 8 + 2] = clock64();
             // activations of (tile, t): chunk (q, unit8, row) -> consecutive rows are consecutive 16-byte chunks
             __half *act = a.acts + ((int64_t)blockIdx.x * L + t) * ACT_BLOCK_HALFS + r * 8;
             const bool t_is_last = t == L - 1;
 #pragma unroll
             for (int jj = 0; jj < 4; jj++) {
-                const int nh = jj >> 1;
-                if ((jj & 1) == 0) {   // wait for this half's gate pre-activations
-                    mbar_wait(&acc_full[nh], t & 1);
-                    tc_fence_after();
-                    if (tr && nh == 0) a.trace[t * 8 + 2] = clock64();
-                }
-                const int c0 = nh * 256 + cq * 64 + (jj & 1) * 32;   // packed gate columns of units [c0/4, c0/4 + 8)
+                const int c0 = cq * 128 + jj * 32;   // packed gate columns of units [c0/4, c0/4 + 8)
                 // outputs are packed to fp16 pairs as they are produced (keeps the register footprint small)
                 uint32_t pi[4], pf[4], pg[4], po[4], pc[4], ph[4];
                 float hq[4];
