@@ -56,40 +56,52 @@ __device__ __forceinline__ uint4 pack8_half_or_bf16(const float (&f)[8])
 }
 
 // stage a [ROWS x 64] operand tile.  MN = false: src[row][k]; MN = true: src[k][row].
+// Two phases so that all of a thread's global loads are in flight together.
 template <int ROWS, int NTHREADS, bool MN, bool BF16>
-__device__ __forceinline__ void stage_tile(unsigned char *dst, const float *src, int64_t ld, int64_t row0,
+__device__ __forceinline__ void stage_tile(unsigned char *dst, const float *__restrict__ src, int64_t ld, int64_t row0,
                                            int64_t nrows, int64_t k0, int64_t kend, int tid)
 {
     constexpr int CHUNKS = ROWS * 8;  // 16-byte chunks (8 elements)
+    constexpr int PER = CHUNKS / NTHREADS;
+    static_assert(CHUNKS % NTHREADS == 0, "tile must divide evenly among the threads");
     const bool vec_ok = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
-    for (int c = tid; c < CHUNKS; c += NTHREADS) {
-        float f[8];
-        uint32_t off;
+    float4 lo[PER], hi[PER];
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+        const int c = tid + i * NTHREADS;
+        int64_t base;   // element offset of the chunk's first value; its 8 values are contiguous in src
+        bool full, any;
         if (!MN) {
             const int r = c % ROWS, k8 = c / ROWS;
             const int64_t gr = row0 + r, gk = k0 + k8 * 8;
-            if (gr < nrows && gk + 8 <= kend && vec_ok) {
-                const float4 a = __ldg(reinterpret_cast<const float4 *>(src + gr * ld + gk));
-                const float4 b = __ldg(reinterpret_cast<const float4 *>(src + gr * ld + gk + 4));
-                f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
-            } else {
-#pragma unroll
-                for (int j = 0; j < 8; j++) f[j] = (gr < nrows && gk + j < kend) ? __ldg(src + gr * ld + gk + j) : 0.f;
-            }
-            off = canon_off(r, k8 * 8, 64);
+            base = gr * ld + gk;
+            any = gr < nrows && gk < kend;
+            full = gr < nrows && gk + 8 <= kend;
         } else {
             const int k = c % 64, r8 = c / 64;
             const int64_t gk = k0 + k, gr = row0 + r8 * 8;
-            if (gk < kend && gr + 8 <= nrows && vec_ok) {
-                const float4 a = __ldg(reinterpret_cast<const float4 *>(src + gk * ld + gr));
-                const float4 b = __ldg(reinterpret_cast<const float4 *>(src + gk * ld + gr + 4));
-                f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
-            } else {
-#pragma unroll
-                for (int j = 0; j < 8; j++) f[j] = (gk < kend && gr + j < nrows) ? __ldg(src + gk * ld + gr + j) : 0.f;
-            }
-            off = (uint32_t)(r8 * 1024 + (k >> 3) * 128 + (k & 7) * 16);
+            base = gk * ld + gr;
+            any = gk < kend && gr < nrows;
+            full = gk < kend && gr + 8 <= nrows;
         }
+        if (full && vec_ok) {
+            lo[i] = __ldg(reinterpret_cast<const float4 *>(src + base));
+            hi[i] = __ldg(reinterpret_cast<const float4 *>(src + base + 4));
+        } else {
+            float f[8];
+            const int64_t lim = !MN ? (kend - (k0 + (c / ROWS) * 8)) : (nrows - (row0 + (c / 64) * 8));
+#pragma unroll
+            for (int j = 0; j < 8; j++) f[j] = (any && j < lim) ? __ldg(src + base + j) : 0.f;
+            lo[i] = make_float4(f[0], f[1], f[2], f[3]);
+            hi[i] = make_float4(f[4], f[5], f[6], f[7]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+        const int c = tid + i * NTHREADS;
+        const uint32_t off = !MN ? canon_off(c % ROWS, (c / ROWS) * 8, 64)
+                                 : (uint32_t)((c / 64) * 1024 + ((c % 64) >> 3) * 128 + ((c % 64) & 7) * 16);
+        const float f[8] = {lo[i].x, lo[i].y, lo[i].z, lo[i].w, hi[i].x, hi[i].y, hi[i].z, hi[i].w};
         *reinterpret_cast<uint4 *>(dst + off) = pack8_half_or_bf16<BF16>(f);
     }
 }
