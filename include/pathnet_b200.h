@@ -97,6 +97,18 @@ int pn_merw_sample(pn_graph *g, int32_t nw, int32_t L, int64_t epoch_begin,
                    int32_t rng_mode, uint64_t seed, int32_t *nodes, uint8_t *types,
                    void *stream);
 
+/* Replaces compute_merw() (preprocess/compute_merw.py:109-121) whose output init_rw.py:81-86 writes
+ * as the p column of `<name>.in`: MERW transition probabilities p[e] = w[e] psi[col[e]] / (lambda psi[row])
+ * from the dominant eigenpair of the symmetric adjacency A given in CSR (device pointers; w = NULL means
+ * all-ones).  Shifted power iteration in fp64, run per connected component (on a connected graph this
+ * is the reference's P; on a disconnected one every component gets a proper stochastic P instead of the
+ * reference's negative / zero entries).  Outputs (device): p[m], psi[n] (unit norm per component),
+ * lambda[n] (valid at the component's label node), component[n] (smallest node id of the component).
+ * Stops when max |psi_new - psi_old| < tol or after max_iter iterations (*iters_out = iterations run). */
+int pn_merw_probabilities(int32_t n, const int64_t *rowptr, const int32_t *col, const double *w, double *p,
+                          double *psi, double *lambda, int32_t *component, double tol, int32_t max_iter,
+                          int32_t *iters_out, void *stream);
+
 /* Text sink / source of the path hand-off format (writer gen_merw.cpp:188-206,
  * reader PathNet_run.py:325-334, :419-423): "[n0, .., nL-1, o0, .., oL-1]\n".
  * Host buffers.  format: returns bytes written, or the bytes needed when

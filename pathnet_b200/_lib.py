@@ -56,6 +56,7 @@ def lib():
     L.pn_merw_sample.argtypes = [vp, i32, i32, i64, i64, i32, i32, i32, u64, vp, vp, vp]
     L.pn_merw_plan_host.argtypes = [i32, i32, i32, i64, i64, i32, i64, u64, C.POINTER(i32),
                                     C.POINTER(i64), vp]
+    L.pn_merw_probabilities.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, C.c_double, i32, C.POINTER(i32), vp]
     L.pn_paths_format_txt.restype = i64
     L.pn_paths_format_txt.argtypes = [vp, vp, i64, i32, vp, i64]
     L.pn_paths_parse_txt.restype = i64
@@ -84,7 +85,7 @@ def check(rc: int) -> int:
 
 # symbols include/pathnet_b200.h declares (tests assert the .so exports each)
 EXPORTS = ("pn_version", "pn_last_error", "pn_graph_from_edges", "pn_graph_free", "pn_graph_info",
-           "pn_graph_cells_host", "pn_graph_prepare_labels", "pn_merw_sample",
+           "pn_graph_cells_host", "pn_graph_prepare_labels", "pn_merw_sample", "pn_merw_probabilities",
            "pn_paths_format_txt", "pn_paths_parse_txt", "pn_pagg_canonicalize",
            "pn_pagg_workspace_bytes", "pn_pagg_forward", "pn_pagg_backward", "pn_dropout_hash",
            "pn_launch_count", "pn_profile_enable", "pn_profile_read")

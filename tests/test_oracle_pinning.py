@@ -143,3 +143,28 @@ def test_pagg_oracle_matches_live_reference_classes(variant, cls, have_reference
     (y * G).sum().backward()
     for k, p in model.named_parameters():
         torch.testing.assert_close(params[k].grad, p.grad, rtol=2e-4, atol=2e-6, msg=lambda m: f"{k}: {m}")
+
+
+# ------------------------------------------------- MERW probability builder --
+def test_merw_prob_oracle_matches_reference_function_golden():
+    """oracle/merw_prob_oracle.py against values produced by the reference's own compute_merw()
+    (tests/golden/make_merw_prob_golden.py)."""
+    from oracle import merw_prob_oracle as mpo
+    z = np.load(GOLDEN / "merw_prob_reference.npz")
+    for name in ("cornell", "small"):
+        n = int(z[f"{name}_n"])
+        p, psi, lam = mpo.compute_merw(n, z[f"{name}_u"].astype(np.int64), z[f"{name}_v"].astype(np.int64))
+        assert abs(lam - float(z[f"{name}_lambda"])) < 1e-10
+        assert np.abs(p - z[f"{name}_p"]).max() < 1e-11
+        assert (psi > 0).all()
+
+
+def test_shipped_edge_inputs_are_not_a_golden_for_the_builder():
+    """Documented caveat: the p column of the shipped cornell.in is NOT the MERW of the adjacency in
+    that same file (it was generated from another graph version), so it cannot pin the builder."""
+    from oracle import merw_prob_oracle as mpo
+    n, u, v, p = load_graph("cornell")
+    key = u.astype(np.int64) * n + v
+    uk, idx = np.unique(key, return_index=True)
+    pp, _, lam = mpo.compute_merw(n, uk // n, uk % n)
+    assert np.abs(pp - p[idx]).max() > 1e-2 and abs(lam - 11.0787866794) < 1e-8
