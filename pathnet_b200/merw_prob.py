@@ -52,4 +52,4 @@ def write_edge_input(path, edge_index, p, n):
     with open(path, "w") as f:
         f.write(f"{n} {2 * M}\n")
         for i in range(M):
-            f.write(f"{ei[0, i]} {ei[1, i]} {pk[i]!r}\n{ei[1, i]} {ei[0, i]} {rev[i]!r}\n")
+            f.write(f"{ei[0, i]} {ei[1, i]} {float(pk[i])!r}\n{ei[1, i]} {ei[0, i]} {float(rev[i])!r}\n")
