@@ -261,48 +261,79 @@ k_merw_walk(const __grid_constant__ WalkParams P)
     if (q_warp + lane >= P.total_chunks) return;
 
     // ---- thread: its chunk of walks ----------------------------------------
-    int head = 0;  // slot of the oldest word
-    auto next_rand = [&]() -> uint32_t {
-        int j28 = head + 28; if (j28 >= lfg::DEG) j28 -= lfg::DEG;
-        uint32_t v = ring[head][tid] + ring[j28][tid];
-        ring[head][tid] = v;
-        head = head + 1 == lfg::DEG ? 0 : head + 1;
-        return v >> 1;
-    };
+    // The 31-word window moves to registers.  All lanes consume draws in lockstep (2L per walk,
+    // whatever the walk does), so a refill of 31 draws is fully unrolled with static register
+    // indices and every draw is handed to a warp-uniform stepper: even draws are r1 of a roll
+    // (the cell index), odd draws are r2 (the alias decision) and perform the roll.
+    uint32_t s[lfg::DEG];
+#pragma unroll
+    for (int j = 0; j < lfg::DEG; j++) s[j] = ring[j][tid];
     const int L = P.L;
     int64_t wi = my_c * P.wpt;
     const int64_t w_end = min(wi + (int64_t)P.wpt, P.wpe);
+    const int nwalks = (int)(w_end - wi);                  // this lane's walks (the last chunk of an epoch may be short)
     int32_t *out_n = P.nodes + (my_e * P.wpe + wi) * L;
     uint8_t *out_t = P.types ? P.types + (my_e * P.wpe + wi) * L : nullptr;
     int32_t st = P.node_begin + (int32_t)(wi / P.nw);
     int32_t k_in_st = (int32_t)(wi % P.nw);
-    for (; wi < w_end; wi++) {
-        uint2 rec = __ldg(&P.noderec[st]);
-        uint32_t off = rec.x, deg = rec.y;
-        int32_t u = st;
-        const uint8_t *drow = P.dist ? P.dist + (int64_t)st * P.dist_pitch : nullptr;
-        for (int t = 0; t < L; t++) {
-            out_n[t] = u;
-            if (out_t) {
-                uint8_t lab = 0;
-                if (t == 1) lab = (u != st);
-                else if (t >= 2) { uint8_t d = __ldg(drow + u); lab = d < t ? d : (uint8_t)t; }
-                out_t[t] = lab;
-            }
-            uint32_t r1 = next_rand(), r2 = next_rand();  // every roll draws twice (:88-89)
-            if (t + 1 < L) {                                // the L-th roll's result is unused (:190-197)
-                uint32_t x = r1 % deg;
-                const uint4 *cp = reinterpret_cast<const uint4 *>(P.cells + (off + x));
-                uint4 lo = __ldg(cp), hi = __ldg(cp + 1);
-                bool takeA = (int32_t)r2 > (int32_t)lo.z;
-                u = takeA ? (int32_t)lo.x : (int32_t)lo.y;
-                off = takeA ? lo.w : hi.y;
-                deg = takeA ? hi.x : hi.z;
+    // walk state
+    int walk = 0, t = 0;          // walk index within the chunk, position within the walk
+    uint32_t r1 = 0, off = 0, deg = 1;
+    int32_t u = st;
+    {
+        const uint2 rec = __ldg(&P.noderec[st]);
+        off = rec.x; deg = rec.y;
+    }
+    const int total_draws = P.wpt * 2 * L;                 // uniform across the warp
+    int drawn = 0;
+    bool second = false;                                   // false: next draw is r1, true: r2
+    while (drawn < total_draws) {
+#pragma unroll
+        for (int j = 0; j < lfg::DEG; j++) {
+            s[j] += s[(j + 28) % lfg::DEG];                // s_{k+31} = s_k + s_{k+28}
+            if (drawn < total_draws) {                     // uniform
+                const uint32_t o = s[j] >> 1;
+                drawn++;
+                if (!second) { r1 = o; second = true; }
+                else {
+                    second = false;
+                    const bool active = walk < nwalks;
+                    if (active) {
+                        out_n[t] = u;
+                        if (out_t) {
+                            uint8_t lab = 0;
+                            if (t == 1) lab = (u != st);
+                            else if (t >= 2) {
+                                const uint8_t d = __ldg(P.dist + (int64_t)st * P.dist_pitch + u);
+                                lab = d < t ? d : (uint8_t)t;
+                            }
+                            out_t[t] = lab;
+                        }
+                        if (t + 1 < L) {                   // the L-th roll's result is unused (:190-197)
+                            const uint32_t x = r1 % deg;
+                            const uint4 *cp = reinterpret_cast<const uint4 *>(P.cells + (off + x));
+                            const uint4 lo = __ldg(cp), hi = __ldg(cp + 1);
+                            const bool takeA = (int32_t)o > (int32_t)lo.z;     // (1.0*r2/RAND_MAX > S) (:88-90)
+                            u = takeA ? (int32_t)lo.x : (int32_t)lo.y;
+                            off = takeA ? lo.w : hi.y;
+                            deg = takeA ? hi.x : hi.z;
+                        }
+                    }
+                    if (++t == L) {                        // next walk (uniform)
+                        t = 0;
+                        walk++;
+                        out_n += L;
+                        if (out_t) out_t += L;
+                        if (++k_in_st == P.nw) { k_in_st = 0; st++; }
+                        if (walk < nwalks) {
+                            const uint2 rec = __ldg(&P.noderec[st]);
+                            off = rec.x; deg = rec.y;
+                            u = st;
+                        }
+                    }
+                }
             }
         }
-        out_n += L;
-        if (out_t) out_t += L;
-        if (++k_in_st == P.nw) { k_in_st = 0; st++; }
     }
 }
 
