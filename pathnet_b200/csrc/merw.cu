@@ -232,18 +232,21 @@ k_merw_walk(const __grid_constant__ WalkParams P)
             if (lane < 3) ext[31 + d0 + lane] = ext[d0 + lane] + ext[28 + d0 + lane];
             __syncwarp();
         }
-        // two passes of 16 / 15 coefficients keep the register footprint small
+        // four passes of 8 coefficients: the 38-word slice of the extended window a pass needs is read
+        // once (warp-broadcast) into registers, so each multiply-add runs on registers only
 #pragma unroll 1
-        for (int half = 0; half < 2; half++) {
-            const int i0 = half * 16;
-            uint32_t cf[16];
+        for (int pass = 0; pass < 4; pass++) {
+            const int i0 = pass * 8;
+            uint32_t cf[8], win[38];
 #pragma unroll
-            for (int i = 0; i < 16; i++) cf[i] = (i0 + i < lfg::DEG) ? lane_poly[lane][i0 + i] : 0u;
-#pragma unroll 1
+            for (int i = 0; i < 8; i++) cf[i] = (i0 + i < lfg::DEG) ? lane_poly[lane][i0 + i] : 0u;
+#pragma unroll
+            for (int k = 0; k < 38; k++) win[k] = ext[(i0 + k) & 63];   // ext[61..63] only meet zero coefficients
+#pragma unroll
             for (int j = 0; j < lfg::DEG; j++) {
-                uint32_t acc = half ? ring[j][tid] : 0u;
+                uint32_t acc = pass ? ring[j][tid] : 0u;
 #pragma unroll
-                for (int i = 0; i < 16; i++) acc += cf[i] * ext[(i0 + i + j) & 63];  // warp-broadcast reads
+                for (int i = 0; i < 8; i++) acc += cf[i] * win[i + j];
                 ring[j][tid] = acc;
             }
         }
@@ -510,9 +513,9 @@ static int plan_walk(WalkParams &P, int32_t n, int32_t nw, int32_t L, int64_t ep
     const int64_t wpe = np * nw;
     P.n = n; P.nw = nw; P.L = L; P.node_begin = node_begin;
     P.wpe = wpe;
-    // chunk size: enough chunks to fill the machine a few times over, at most
-    // 32 walks per thread (amortises the jump-ahead), at least 4
-    int wpt = 32;
+    // chunk size: enough chunks to fill the machine, at most 64 walks per thread
+    // (amortises the jump-ahead, ~45 % of a warp's instructions at 16), at least 4
+    int wpt = 64;
     const int64_t want_threads = (int64_t)148 * 2048;
     while (wpt > 4 && E * ceil_div(wpe, wpt) < want_threads) wpt >>= 1;
     P.wpt = wpt;
