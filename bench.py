@@ -35,7 +35,7 @@ sys.path.insert(0, str(ROOT))
 
 WORKLOAD = dict(name="pubmed-shaped", n=19717, undirected_edges=44324, F=500, C=3, H=128, nw=40, L=4,
                 S=9463, variant="homo", dropout=0.7)
-MERW_EPOCHS_PER_STEP = 32
+MERW_EPOCHS_PER_STEP = 16
 
 
 # --------------------------------------------------------------------------- data

@@ -281,12 +281,13 @@ k_merw_walk(const __grid_constant__ WalkParams P)
     int32_t k_in_st = (int32_t)(wi % P.nw);
     // walk state
     int walk = 0, t = 0;          // walk index within the chunk, position within the walk
-    uint32_t r1 = 0, off = 0, deg = 1;
+    uint32_t r1 = 0;
     int32_t u = st;
-    {
-        const uint2 rec = __ldg(&P.noderec[st]);
-        off = rec.x; deg = rec.y;
-    }
+    uint2 rec = __ldg(&P.noderec[st]);                     // (off, deg) of the start node, kept while st is unchanged
+    uint32_t off = rec.x, deg = rec.y;
+    const bool vec4 = (L & 3) == 0;                        // walk outputs are 16-byte (ids) / 4-byte (labels) aligned groups
+    int32_t pk_n[4] = {0, 0, 0, 0};
+    uint32_t pk_t = 0;
     const int total_draws = P.wpt * 2 * L;                 // uniform across the warp
     int drawn = 0;
     bool second = false;                                   // false: next draw is r1, true: r2
@@ -302,24 +303,37 @@ k_merw_walk(const __grid_constant__ WalkParams P)
                     second = false;
                     const bool active = walk < nwalks;
                     if (active) {
-                        out_n[t] = u;
+                        uint32_t lab = 0;
                         if (out_t) {
-                            uint8_t lab = 0;
                             if (t == 1) lab = (u != st);
                             else if (t >= 2) {
-                                const uint8_t d = __ldg(P.dist + (int64_t)st * P.dist_pitch + u);
-                                lab = d < t ? d : (uint8_t)t;
+                                const uint32_t d = __ldg(P.dist + (int64_t)st * P.dist_pitch + u);
+                                lab = d < (uint32_t)t ? d : (uint32_t)t;
                             }
-                            out_t[t] = lab;
+                        }
+                        if (vec4) {                        // four positions per 16-byte / 4-byte store
+                            const int q = t & 3;
+                            pk_n[0] = q == 0 ? u : pk_n[0]; pk_n[1] = q == 1 ? u : pk_n[1];
+                            pk_n[2] = q == 2 ? u : pk_n[2]; pk_n[3] = q == 3 ? u : pk_n[3];
+                            pk_t = q == 0 ? lab : (pk_t | (lab << (8 * q)));
+                            if (q == 3) {
+                                *reinterpret_cast<int4 *>(out_n + t - 3) = make_int4(pk_n[0], pk_n[1], pk_n[2], pk_n[3]);
+                                if (out_t) *reinterpret_cast<uint32_t *>(out_t + t - 3) = pk_t;
+                            }
+                        } else {
+                            out_n[t] = u;
+                            if (out_t) out_t[t] = (uint8_t)lab;
                         }
                         if (t + 1 < L) {                   // the L-th roll's result is unused (:190-197)
                             const uint32_t x = r1 % deg;
-                            const uint4 *cp = reinterpret_cast<const uint4 *>(P.cells + (off + x));
-                            const uint4 lo = __ldg(cp), hi = __ldg(cp + 1);
-                            const bool takeA = (int32_t)o > (int32_t)lo.z;     // (1.0*r2/RAND_MAX > S) (:88-90)
-                            u = takeA ? (int32_t)lo.x : (int32_t)lo.y;
-                            off = takeA ? lo.w : hi.y;
-                            deg = takeA ? hi.x : hi.z;
+                            uint32_t c0, c1, c2, c3, c4, c5, c6, c7;   // one 32-byte sector = one 256-bit load
+                            asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                                         : "=r"(c0), "=r"(c1), "=r"(c2), "=r"(c3), "=r"(c4), "=r"(c5), "=r"(c6), "=r"(c7)
+                                         : "l"(P.cells + (off + x)));
+                            const bool takeA = (int32_t)o > (int32_t)c2;       // (1.0*r2/RAND_MAX > S) (:88-90)
+                            u = takeA ? (int32_t)c0 : (int32_t)c1;
+                            off = takeA ? c3 : c5;
+                            deg = takeA ? c4 : c6;
                         }
                     }
                     if (++t == L) {                        // next walk (uniform)
@@ -327,12 +341,12 @@ k_merw_walk(const __grid_constant__ WalkParams P)
                         walk++;
                         out_n += L;
                         if (out_t) out_t += L;
-                        if (++k_in_st == P.nw) { k_in_st = 0; st++; }
-                        if (walk < nwalks) {
-                            const uint2 rec = __ldg(&P.noderec[st]);
-                            off = rec.x; deg = rec.y;
-                            u = st;
+                        if (++k_in_st == P.nw) {           // next start node
+                            k_in_st = 0; st++;
+                            if (walk < nwalks) rec = __ldg(&P.noderec[st]);
                         }
+                        off = rec.x; deg = rec.y;
+                        u = st;
                     }
                 }
             }
@@ -515,7 +529,7 @@ static int plan_walk(WalkParams &P, int32_t n, int32_t nw, int32_t L, int64_t ep
     P.wpe = wpe;
     // chunk size: enough chunks to fill the machine, at most 64 walks per thread
     // (amortises the jump-ahead, ~45 % of a warp's instructions at 16), at least 4
-    int wpt = 64;
+    int wpt = 32;
     const int64_t want_threads = (int64_t)148 * 2048;
     while (wpt > 4 && E * ceil_div(wpe, wpt) < want_threads) wpt >>= 1;
     P.wpt = wpt;
