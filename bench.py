@@ -33,8 +33,16 @@ import torch
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-WORKLOAD = dict(name="pubmed-shaped", n=19717, undirected_edges=44324, F=500, C=3, H=128, nw=40, L=4,
-                S=9463, variant="homo", dropout=0.7)
+WORKLOADS = {
+    # BASELINE.json configs[2] (the default; the metric is quoted on it), [1] and [3]; shapes from SURVEY §8(d)
+    "pubmed": dict(name="pubmed-shaped", n=19717, undirected_edges=44324, F=500, C=3, H=128, nw=40, L=4, S=9463,
+                   variant="homo", dropout=0.7),
+    "cora": dict(name="cora-shaped", n=2708, undirected_edges=5278, F=1433, C=7, H=128, nw=40, L=4, S=1192,
+                 variant="homo", dropout=0.7),
+    "bgp": dict(name="bgp-shaped", n=63977, undirected_edges=142814, F=287, C=8, H=128, nw=40, L=6, S=4884,
+                variant="hetero", dropout=0.7),
+}
+WORKLOAD = dict(WORKLOADS["pubmed"])
 MERW_EPOCHS_PER_STEP = 16
 
 
@@ -155,7 +163,7 @@ def cpu_pagg_baseline(sample_rows=512, repeats=2, threads=None):
     lt = torch.randint(0, L, (S, nw, L), generator=g)
     import pathnet_b200.pagg as pg
     torch.manual_seed(0)
-    mod = pg.PathNet_homo(w["F"], w["H"], w["C"], L)
+    mod = (pg.PathNet_homo if w["variant"] == "homo" else pg.PathNet)(w["F"], w["H"], w["C"], L)
     params = {k: v.detach().clone().requires_grad_(True) for k, v in mod.state_dict().items()}
     opt = torch.optim.Adam(params.values(), lr=0.005, weight_decay=0.0005)
     p_drop = w["dropout"]
@@ -164,7 +172,7 @@ def cpu_pagg_baseline(sample_rows=512, repeats=2, threads=None):
         t0 = time.perf_counter()
         ms = (torch.rand(L, S * nw, w["H"]) >= p_drop).float() / (1 - p_drop)
         mc = (torch.rand(S, 2 * w["H"]) >= p_drop).float() / (1 - p_drop)
-        out = po.pagg_forward("homo", params, X, neis, nw, L, m2, lt, mask_seq=ms, mask_cat=mc)
+        out = po.pagg_forward(w["variant"], params, X, neis, nw, L, m2, lt, mask_seq=ms, mask_cat=mc)
         loss = torch.nn.functional.cross_entropy(out, y[m2])
         opt.zero_grad()
         loss.backward()
@@ -220,7 +228,7 @@ def run_reference_arm(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": best * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{w['name']} N={w['n']} F={w['F']} H={w['H']} C={w['C']} path_num={w['nw']} "
-                               f"path_len={w['L']} S={w['S']} (PathNet_homo, dropout {w['dropout']}); "
+                               f"path_len={w['L']} S={w['S']} ({'PathNet_homo' if w['variant'] == 'homo' else 'PathNet'}, dropout {w['dropout']}); "
                                f"bounded sample: {paths} paths/step"},
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": "paths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -238,7 +246,11 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--math", default=os.environ.get("PN_BENCH_MATH", "tc"), choices=["fp32", "tc"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="pubmed", choices=sorted(WORKLOADS),
+                    help="pubmed (default, BASELINE configs[2]) | cora (configs[1]) | bgp (configs[3], hetero, L=6)")
     args = ap.parse_args()
+    WORKLOAD.clear()
+    WORKLOAD.update(WORKLOADS[args.workload])
     if args.impl == "reference":
         return run_reference_arm(args)
     args.warmup = max(args.warmup, 3)
@@ -271,7 +283,8 @@ def main():
     ltype_host = types[0].long().cpu()[mask].contiguous().pin_memory()
     Xd, yd = X.to(dev), y.to(dev)[mask.to(dev)]
     torch.manual_seed(0)
-    model = pb.PathNet_homo(w["F"], H, w["C"], L_, dropout=w["dropout"], math_mode=args.math).to(dev).train()
+    cls = pb.PathNet_homo if w["variant"] == "homo" else pb.PathNet
+    model = cls(w["F"], H, w["C"], L_, dropout=w["dropout"], math_mode=args.math).to(dev).train()
     opt = torch.optim.Adam(model.parameters(), lr=0.005, weight_decay=0.0005)
     reducer = FlatGradAllReduce(model.parameters()) if world > 1 else None
     lossf = torch.nn.CrossEntropyLoss(reduction="sum")
@@ -398,7 +411,7 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.math == "fp32" else "f16xf32acc",
         "data": "synthetic",
         "config": {"workload": f"{w['name']} N={w['n']} F={w['F']} H={w['H']} C={w['C']} path_num={nw} path_len={L_} "
-                               f"S={S} rows/GPU -> {P} paths/step/GPU (PathNet_homo, train mode, dropout {w['dropout']}, "
+                               f"S={S} rows/GPU -> {P} paths/step/GPU ({'PathNet_homo' if w['variant'] == 'homo' else 'PathNet'}, train mode, dropout {w['dropout']}, "
                                f"CE + Adam), paths drawn by the on-GPU MERW sampler",
                    "parallelism": f"dp{world} (rows sharded, flat NCCL grad all-reduce)" if world > 1 else "single GPU",
                    "l2": "per-step working set ~9 GB >> 126 MB L2 (no explicit flush for PAGG); MERW leg flushes L2 "

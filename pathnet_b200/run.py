@@ -29,6 +29,8 @@ def _fused_forward(variant):
         mod = sys.modules.get(type(self).__module__)
         drop = float(getattr(mod, "dropout", 0.0)) if mod is not None else 0.0
         dev = X.device
+        if dev.type != "cuda":
+            raise RuntimeError("pathnet_b200 PAGG runs on CUDA only (no CPU fallback); X is on %s" % dev)
         if torch.is_tensor(indices):
             mask = indices.to(dev)
         else:
@@ -73,12 +75,20 @@ def install_stubs():
     class _Anything:
         def __init__(self, *a, **k): pass
         def __call__(self, *a, **k): return self
-        def __getattr__(self, k): return _Anything()
+        def __getattr__(self, k):
+            if k.startswith("__"):          # keep inspect / copy / pickle protocols honest
+                raise AttributeError(k)
+            return _Anything()
+
+    def _module_getattr(k):
+        if k.startswith("__"):
+            raise AttributeError(k)
+        return _Anything()
 
     try:
         import matplotlib  # noqa: F401
     except ImportError:
-        mod("matplotlib", pyplot=mod("matplotlib.pyplot", __getattr__=lambda k: _Anything()))
+        mod("matplotlib", pyplot=mod("matplotlib.pyplot", __getattr__=_module_getattr))
         mod("mpl_toolkits"); mod("mpl_toolkits.mplot3d", Axes3D=_Anything)
     try:
         import torch_geometric  # noqa: F401
