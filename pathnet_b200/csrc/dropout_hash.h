@@ -24,11 +24,19 @@ PN_HD uint32_t fmix32(uint32_t h)
 }
 
 // one 32-bit hash serves the element PAIR (idx>>1): even idx uses the low 16
-// bits, odd idx the high 16 bits
+// bits, odd idx the high 16 bits.  key = dropout_key(seed, stream) is computed
+// once per kernel; per pair the cost is one multiply + one murmur3 finalizer.
+PN_HD uint32_t dropout_key(uint64_t seed, uint32_t stream_id)
+{
+    return fmix32((uint32_t)seed ^ 0x6a09e667u) ^ fmix32((uint32_t)(seed >> 32) + stream_id * 0x7f4a7c15u + 0x3c6ef372u);
+}
+PN_HD uint32_t dropout_hash_pair_k(uint32_t key, uint64_t pair)
+{
+    return fmix32(((uint32_t)pair * 0x9e3779b1u) ^ key ^ ((uint32_t)(pair >> 32) * 0x85ebca77u));
+}
 PN_HD uint32_t dropout_hash_pair(uint64_t seed, uint32_t stream_id, uint64_t pair)
 {
-    uint32_t h = fmix32((uint32_t)pair ^ (uint32_t)seed);
-    return fmix32(h ^ ((uint32_t)(pair >> 32) * 0x9e3779b9u) ^ (uint32_t)(seed >> 32) ^ (stream_id * 0x7f4a7c15u) ^ 0x6a09e667u);
+    return dropout_hash_pair_k(dropout_key(seed, stream_id), pair);
 }
 
 // 16-bit value in [0, 65536) for element idx

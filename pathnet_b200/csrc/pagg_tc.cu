@@ -277,18 +277,20 @@ __device__ __forceinline__ void tc_gather_quarter(const LstmTcArgs &a, unsigned 
 {
     const bool valid = row_off >= 0;
     const float *src = a.T + (int64_t)(valid ? row_off : 0) * TC_H;
-#pragma unroll 2
-    for (int k8 = cq * 4; k8 < cq * 4 + 4; k8++) {
-        float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const uint32_t key = dropout_key(a.drop_seed, 0);
+    float4 ld[8];   // all eight 16-byte loads of the quarter row in flight together
+#pragma unroll
+    for (int i = 0; i < 8; i++) ld[i] = valid ? __ldg(reinterpret_cast<const float4 *>(src + cq * 32 + i * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int kk = 0; kk < 4; kk++) {
+        const int k8 = cq * 4 + kk;
+        float f[8] = {ld[2 * kk].x, ld[2 * kk].y, ld[2 * kk].z, ld[2 * kk].w, ld[2 * kk + 1].x, ld[2 * kk + 1].y, ld[2 * kk + 1].z, ld[2 * kk + 1].w};
         if (valid) {
-            const float4 u = __ldg(reinterpret_cast<const float4 *>(src + k8 * 8));
-            const float4 w = __ldg(reinterpret_cast<const float4 *>(src + k8 * 8 + 4));
-            f[0] = u.x; f[1] = u.y; f[2] = u.z; f[3] = u.w; f[4] = w.x; f[5] = w.y; f[6] = w.z; f[7] = w.w;
             if (a.drop_thr) {
                 const uint64_t pair = (elem0 + k8 * 8) >> 1;
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
-                    const uint32_t h = dropout_hash_pair(a.drop_seed, 0, pair + q);
+                    const uint32_t h = dropout_hash_pair_k(key, pair + q);
                     f[2 * q] = (h & 0xFFFFu) < a.drop_thr ? 0.f : f[2 * q] * a.drop_scale;
                     f[2 * q + 1] = (h >> 16) < a.drop_thr ? 0.f : f[2 * q + 1] * a.drop_scale;
                 }
@@ -668,6 +670,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
         const bool valid = p < a.P;
         const uint32_t lane_base = taddr + ((uint32_t)(lq * 32) << 16);
         const float scale = a.gscale[0], inv_scale = a.gscale[1];
+        const uint32_t dkey = dropout_key(a.drop_seed, 0);
         const bool tr = a.trace && blockIdx.x == a.trace_block && tid == 0;
         for (int s = 0; s < L; s++) {
             const int t = L - 1 - s;
@@ -768,7 +771,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
                             const uint64_t pair = ((uint64_t)e * TC_H + cb * 8) >> 1;
 #pragma unroll
                             for (int q = 0; q < 4; q++) {
-                                const uint32_t h = dropout_hash_pair(a.drop_seed, 0, pair + q);
+                                const uint32_t h = dropout_hash_pair_k(dkey, pair + q);
                                 f[2 * q] = (h & 0xFFFFu) < a.drop_thr ? 0.f : f[2 * q] * a.drop_scale;
                                 f[2 * q + 1] = (h >> 16) < a.drop_thr ? 0.f : f[2 * q + 1] * a.drop_scale;
                             }

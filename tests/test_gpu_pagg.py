@@ -127,14 +127,22 @@ def _np_fmix32(h):
     return h
 
 
+def _fmix_scalar(h):
+    h &= 0xFFFFFFFF
+    h ^= h >> 16; h = (h * 0x85ebca6b) & 0xFFFFFFFF
+    h ^= h >> 13; h = (h * 0xc2b2ae35) & 0xFFFFFFFF
+    h ^= h >> 16
+    return h
+
+
 def np_dropout_hash(seed, stream_id, idx):
     """numpy restatement of csrc/dropout_hash.h (checked against pn_dropout_hash below)"""
+    key = _fmix_scalar((seed & 0xFFFFFFFF) ^ 0x6a09e667) ^ _fmix_scalar(((seed >> 32) & 0xFFFFFFFF) + stream_id * 0x7f4a7c15 + 0x3c6ef372)
     idx = idx.astype(np.uint64)
     pair = idx >> np.uint64(1)
     lo, hi = pair & np.uint64(0xFFFFFFFF), pair >> np.uint64(32)
-    h = _np_fmix32(lo ^ np.uint64(seed & 0xFFFFFFFF))
-    h = _np_fmix32(h ^ ((hi * np.uint64(0x9e3779b9)) & np.uint64(0xFFFFFFFF)) ^ np.uint64((seed >> 32) & 0xFFFFFFFF)
-                   ^ np.uint64((stream_id * 0x7f4a7c15) & 0xFFFFFFFF) ^ np.uint64(0x6a09e667))
+    x = ((lo * np.uint64(0x9e3779b1)) & np.uint64(0xFFFFFFFF)) ^ np.uint64(key) ^ ((hi * np.uint64(0x85ebca77)) & np.uint64(0xFFFFFFFF))
+    h = _np_fmix32(x)
     return np.where(idx & np.uint64(1), h >> np.uint64(16), h & np.uint64(0xFFFF))
 
 
