@@ -15,6 +15,7 @@
 //           the (offset, degree) of both candidate next nodes.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -53,6 +54,7 @@ struct pn_graph {
     uint32_t *d_rowptr = nullptr; // [n+1] for the distance-table build
     int32_t *d_adj = nullptr;     // [m] E[u] in file-row order
     uint8_t *d_dist = nullptr;    // [n][n] hop distance, saturated
+    int *d_overflow = nullptr;    // sparse-label kernel's ball-capacity flag
     int32_t dist_L = 0;           // walk length the table is valid for
 };
 
@@ -168,6 +170,11 @@ struct WalkParams {
     int64_t wpe;             // walks per epoch in this call = n' * nw
     int64_t cpe;             // chunks per epoch = ceil(wpe / wpt)
     int64_t total_chunks;    // E * cpe
+    // root-centric (sparse label) kernel only
+    const uint32_t *rowptr;  // [n+1]
+    const int32_t *adj;      // [m]
+    int64_t epochs;          // E
+    int *overflow;           // set to 1 when a start node's radius-(L-2) ball exceeds the shared-memory table
     // jump-ahead tables (host-computed per call); chunk stride = 2L*wpt draws
     uint32_t base[lfg::DEG];               // window whose first generated word is the
                                            // first rand() of (epoch_begin, node_begin, walk 0)
@@ -354,6 +361,148 @@ k_merw_walk(const __grid_constant__ WalkParams P)
     }
 }
 
+
+// ----------------------------------------------------------------------------
+// root-centric walk kernel with sparse labels: for graphs whose dense n x n
+// distance table does not fit.  CTA = one start node:
+//   1. truncated BFS of radius L-2 from the start node into a shared-memory hash
+//      set (key = node, value = hop distance) — the ball the reference reads out
+//      of dis[st][*] (gen_merw.cpp:101-123, :193);
+//   2. the node's nw walks for every epoch: lane = walk, its 2L draws are the
+//      first 2L words of the window at the walk's stream offset, each word one
+//      31-term dot product of the lane's jump polynomial with the warp's window;
+//   3. labels by hash lookup: found -> distance, not found -> position (= L-1).
+// ----------------------------------------------------------------------------
+constexpr int ROOT_THREADS = 128;
+constexpr int ROOT_HASH = 8192;    // slots (power of two); ball capacity = ROOT_QCAP
+constexpr int ROOT_QCAP = 4096;
+constexpr int ROOT_SMEM = (ROOT_HASH + ROOT_QCAP + (ROOT_THREADS / 32) * 64 + 32 * lfg::DEG) * 4;
+
+__device__ __forceinline__ uint32_t hash_node(uint32_t v) { return (v * 0x9e3779b1u) >> 19; }  // 13 bits
+
+__global__ void __launch_bounds__(ROOT_THREADS)
+k_merw_walk_root(const __grid_constant__ WalkParams P)
+{
+    extern __shared__ __align__(16) uint32_t root_smem[];
+    uint32_t *htab = root_smem;                                            // [ROOT_HASH] 0 = empty, else (node + 1) | dist << 28
+    int32_t *queue = reinterpret_cast<int32_t *>(htab + ROOT_HASH);        // [ROOT_QCAP]
+    uint32_t(*scratch)[64] = reinterpret_cast<uint32_t(*)[64]>(queue + ROOT_QCAP);                    // [warps][64]
+    uint32_t(*lane_poly)[lfg::DEG] = reinterpret_cast<uint32_t(*)[lfg::DEG]>(scratch + ROOT_THREADS / 32);   // [32][31]
+    __shared__ int q_tail, q_overflow;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int32_t st = P.node_begin + blockIdx.x;
+    const int L = P.L, R = L - 2;
+    for (int i = tid; i < ROOT_HASH; i += ROOT_THREADS) htab[i] = 0;
+    for (int i = tid; i < 32 * lfg::DEG; i += ROOT_THREADS) lane_poly[i / lfg::DEG][i % lfg::DEG] = P.jlane[i / lfg::DEG][i % lfg::DEG];
+    if (tid == 0) { q_tail = 1; q_overflow = 0; queue[0] = st; }
+    __syncthreads();
+    if (tid == 0) htab[hash_node((uint32_t)st)] = ((uint32_t)st + 1u);   // distance 0
+    __syncthreads();
+    // ---- 1. BFS, one level per iteration, one warp per frontier node ----
+    if (P.types) {
+        int lvl_begin = 0;
+        for (int level = 0; level < R; level++) {
+            const int lvl_end = q_tail;
+            __syncthreads();
+            for (int qi = lvl_begin + warp; qi < lvl_end && qi < ROOT_QCAP; qi += ROOT_THREADS / 32) {
+                const int32_t v = queue[qi];
+                const uint32_t e1 = P.rowptr[v + 1];
+                for (uint32_t e = P.rowptr[v] + lane; e < e1; e += 32) {
+                    const uint32_t w = (uint32_t)P.adj[e];
+                    const uint32_t val = (w + 1u) | ((uint32_t)(level + 1) << 28);
+                    uint32_t slot = hash_node(w);
+                    for (int probe = 0; probe < ROOT_HASH; probe++) {
+                        const uint32_t cur = htab[slot];
+                        if ((cur & 0x0FFFFFFFu) == w + 1u) break;             // already known (at a smaller or equal distance)
+                        if (cur == 0) {
+                            const uint32_t old = atomicCAS(&htab[slot], 0u, val);
+                            if (old == 0) {                                    // newly discovered
+                                const int pos = atomicAdd(&q_tail, 1);
+                                if (pos < ROOT_QCAP) queue[pos] = (int32_t)w; else q_overflow = 1;
+                                break;
+                            }
+                            if ((old & 0x0FFFFFFFu) == w + 1u) break;
+                        }
+                        slot = (slot + 1) & (ROOT_HASH - 1);
+                    }
+                }
+            }
+            __syncthreads();
+            lvl_begin = lvl_end;
+        }
+        if (q_overflow) { if (tid == 0) *P.overflow = 1; return; }
+    }
+    // ---- 2./3. walks: group g = 32 consecutive walks of this start node, lane = walk ----
+    const uint2 rec0 = __ldg(&P.noderec[st]);
+    const int64_t c_root = (int64_t)(st - P.node_begin) * P.nw;          // chunk (= walk) index of the node's first walk
+    for (int g = warp; g * 32 < P.nw; g += ROOT_THREADS / 32) {
+        // warp window at (epoch 0, walk c_root + 32 g)
+        uint32_t w = lane < lfg::DEG ? P.base[lane] : 0u;
+        {
+            uint64_t cb = (uint64_t)(c_root + g * 32);
+            for (int i = 0; cb; i++, cb >>= 4)
+                if (cb & 15) w = warp_window_apply(P.jchunk16[i][(cb & 15) - 1], w, scratch[warp], lane);
+        }
+        const int wi = g * 32 + lane;                                      // walk index within the start node
+        const bool active = wi < P.nw;
+        uint32_t cf[lfg::DEG];
+#pragma unroll
+        for (int i = 0; i < lfg::DEG; i++) cf[i] = lane_poly[lane][i];
+        for (int64_t ep = 0; ep < P.epochs; ep++) {
+            if (ep > 0) w = warp_window_apply(P.jepoch[0], w, scratch[warp], lane);   // + one epoch
+            // extended window e_0..e_60 in shared memory
+            uint32_t *ext = scratch[warp];
+            __syncwarp();
+            if (lane < lfg::DEG) ext[lane] = w;
+            __syncwarp();
+            for (int d0 = 0; d0 < 30; d0 += 3) {
+                if (lane < 3) ext[31 + d0 + lane] = ext[d0 + lane] + ext[28 + d0 + lane];
+                __syncwarp();
+            }
+            int32_t *out_n = P.nodes + ((ep * P.wpe) + c_root + wi) * L;
+            uint8_t *out_t = P.types ? P.types + ((ep * P.wpe) + c_root + wi) * L : nullptr;
+            int32_t u = st;
+            uint32_t off = rec0.x, deg = rec0.y;
+            for (int t = 0; t < L; t++) {
+                // the walk's draws 2t and 2t+1: words 2t, 2t+1 of the lane's window = dot(cf, ext[i .. i+30])
+                uint32_t r1 = 0, r2 = 0;
+#pragma unroll
+                for (int j = 0; j < lfg::DEG; j++) { r1 += cf[j] * ext[2 * t + j]; r2 += cf[j] * ext[2 * t + 1 + j]; }
+                r1 >>= 1; r2 >>= 1;
+                if (active) {
+                    out_n[t] = u;
+                    if (out_t) {
+                        uint32_t lab = 0;
+                        if (t >= 1 && u != st) {
+                            lab = (uint32_t)t;                             // not in the ball: distance = position
+                            uint32_t slot = hash_node((uint32_t)u);
+                            for (int probe = 0; probe < ROOT_HASH; probe++) {
+                                const uint32_t cur = htab[slot];
+                                if (cur == 0) break;
+                                if ((cur & 0x0FFFFFFFu) == (uint32_t)u + 1u) { lab = min(lab, cur >> 28); break; }
+                                slot = (slot + 1) & (ROOT_HASH - 1);
+                            }
+                        }
+                        out_t[t] = (uint8_t)lab;
+                    }
+                    if (t + 1 < L) {
+                        const uint32_t x = r1 % deg;
+                        uint32_t c0, c1, c2, c3, c4, c5, c6, c7;
+                        asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                                     : "=r"(c0), "=r"(c1), "=r"(c2), "=r"(c3), "=r"(c4), "=r"(c5), "=r"(c6), "=r"(c7)
+                                     : "l"(P.cells + (off + x)));
+                        const bool takeA = (int32_t)r2 > (int32_t)c2;
+                        u = takeA ? (int32_t)c0 : (int32_t)c1;
+                        off = takeA ? c3 : c5;
+                        deg = takeA ? c4 : c6;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
 }  // namespace pn
 
 // ============================================================================
@@ -455,7 +604,7 @@ extern "C" int pn_graph_free(pn_graph *g)
     if (g->device < 0) { delete g; return PN_OK; }
     cudaSetDevice(g->device);
     cudaFree(g->d_noderec); cudaFree(g->d_cells); cudaFree(g->d_rowptr); cudaFree(g->d_adj);
-    cudaFree(g->d_dist);
+    cudaFree(g->d_dist); cudaFree(g->d_overflow);
     delete g;
     return PN_OK;
 }
@@ -521,7 +670,7 @@ static void copy_poly(uint32_t dst[lfg::DEG], const lfg::Poly &p) { memcpy(dst, 
 
 // Chunking + jump-ahead tables of one pn_merw_sample call (host).
 static int plan_walk(WalkParams &P, int32_t n, int32_t nw, int32_t L, int64_t epoch_begin,
-                     int64_t E, int32_t node_begin, int64_t np, uint64_t seed)
+                     int64_t E, int32_t node_begin, int64_t np, uint64_t seed, bool root_mode = false)
 {
     memset(&P, 0, sizeof(P));
     const int64_t wpe = np * nw;
@@ -532,6 +681,7 @@ static int plan_walk(WalkParams &P, int32_t n, int32_t nw, int32_t L, int64_t ep
     int wpt = 32;
     const int64_t want_threads = (int64_t)148 * 2048;
     while (wpt > 4 && E * ceil_div(wpe, wpt) < want_threads) wpt >>= 1;
+    if (root_mode) wpt = 1;  // one walk per lane; the window is taken AT the walk's first draw (see below)
     P.wpt = wpt;
     P.cpe = ceil_div(wpe, wpt);
     P.total_chunks = E * P.cpe;
@@ -546,7 +696,8 @@ static int plan_walk(WalkParams &P, int32_t n, int32_t nw, int32_t L, int64_t ep
     // window is s_{310 + first_draw .. 340 + first_draw}
     __uint128_t first = (__uint128_t)((uint64_t)epoch_begin) * epoch_stride +
                         (__uint128_t)((uint64_t)node_begin * (uint64_t)nw) * draws_per_walk;
-    first += (uint64_t)(lfg::FIRST_OUTPUT - lfg::DEG);
+    // root mode: window words 0..2L-1 ARE the walk's draws (no generation step), so no -31
+    first += (uint64_t)(root_mode ? lfg::FIRST_OUTPUT : lfg::FIRST_OUTPUT - lfg::DEG);
     PN_REQUIRE((first >> 64) == 0, "pn_merw_sample: stream offset exceeds 2^64");
     lfg::window_apply(lfg::poly_xpow((uint64_t)first), s0, P.base);
     lfg::Poly pc = lfg::poly_xpow(chunk_stride), pe = lfg::poly_xpow(epoch_stride);
@@ -605,19 +756,49 @@ extern "C" int pn_merw_sample(pn_graph *g, int32_t nw, int32_t L, int64_t epoch_
     if (E == 0 || wpe == 0) return PN_OK;
     PN_REQUIRE(nodes != nullptr, "pn_merw_sample: nodes is NULL");
     PN_CUDA(cudaSetDevice(g->device));
-    if (types) {
-        int rc = pn_graph_prepare_labels(g, L, 0, stream_);
-        if (rc != PN_OK) return rc;
+    // label source: the dense table when it fits (24 GiB budget), else per-start-node balls in shared
+    // memory (root-centric kernel); PN_MERW_SPARSE=1 forces the latter (tests)
+    bool sparse = false;
+    if (types && L > 2) {
+        const char *force = getenv("PN_MERW_SPARSE");
+        if (force && force[0] == '1') sparse = true;
+        else {
+            int rc = pn_graph_prepare_labels(g, L, 0, stream_);
+            if (rc == PN_ERR_UNSUPPORTED) sparse = true;
+            else if (rc != PN_OK) return rc;
+        }
     }
     WalkParams P;
     {
-        int rc = plan_walk(P, g->n, nw, L, epoch_begin, E, node_begin, np, seed);
+        int rc = plan_walk(P, g->n, nw, L, epoch_begin, E, node_begin, np, seed, sparse);
         if (rc != PN_OK) return rc;
     }
     P.noderec = g->d_noderec; P.cells = g->d_cells;
-    P.dist = (types && L > 2) ? g->d_dist : nullptr;
+    P.dist = (types && L > 2 && !sparse) ? g->d_dist : nullptr;
     P.dist_pitch = ceil_div(g->n, 16) * 16;
     P.nodes = nodes; P.types = types;
+    if (sparse) {
+        PN_REQUIRE(2 * L <= 30, "pn_merw_sample: sparse-label mode supports path_len <= 15 (got %d)", L);
+        PN_REQUIRE(np < ((int64_t)1 << 31), "pn_merw_sample: too many start nodes in one call");
+        if (!g->d_overflow) PN_CUDA(cudaMalloc(&g->d_overflow, sizeof(int)));
+        PN_CUDA(cudaMemsetAsync(g->d_overflow, 0, sizeof(int), stream));
+        P.rowptr = g->d_rowptr; P.adj = g->d_adj; P.epochs = E; P.overflow = g->d_overflow;
+        {
+            ProfScope prof("merw_walk", stream);
+            PN_CUDA(cudaFuncSetAttribute(k_merw_walk_root, cudaFuncAttributeMaxDynamicSharedMemorySize, ROOT_SMEM));
+            k_merw_walk_root<<<(unsigned)np, ROOT_THREADS, ROOT_SMEM, stream>>>(P);
+        }
+        PN_LAUNCH_CHECK();
+        int h = 0;   // the ball-capacity check needs the result: sparse mode synchronises the stream
+        PN_CUDA(cudaMemcpyAsync(&h, g->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        PN_CUDA(cudaStreamSynchronize(stream));
+        if (h) {
+            set_error("pn_merw_sample: a start node's radius-%d ball has more than %d nodes; the sparse label "
+                      "path keeps it in shared memory (dense table needs n*n bytes <= 24 GiB)", L - 2, ROOT_QCAP);
+            return PN_ERR_UNSUPPORTED;
+        }
+        return PN_OK;
+    }
     const int64_t blocks = ceil_div(P.total_chunks, WALK_THREADS);
     PN_REQUIRE(blocks < ((int64_t)1 << 31), "pn_merw_sample: grid too large; split the epoch range");
     ProfScope prof("merw_walk", stream);

@@ -58,3 +58,27 @@ def messy_graph(n, avg_deg, seed, hubs=2, neg_frac=0.05, zero_frac=0.05, dup_fra
     p[r < neg_frac] *= -1.0
     p[(r >= neg_frac) & (r < neg_frac + zero_frac)] = 0.0
     return n, u, v, p
+
+
+def lattice_graph(side, seed=0, shuffle=True):
+    """side x side torus, 16 neighbours per node (the 5x5 block around it minus the 8 outermost
+    corner/knight cells ... here: all cells with |dx|,|dy| <= 2 except |dx|=|dy|=2 and the centre,
+    i.e. 20 - 4 = 16), ids randomly permuted so memory access is random while radius-r balls stay
+    small ((4r+1)^2 nodes at most).  p: random positive, rows not normalised."""
+    rng = np.random.default_rng(seed)
+    n = side * side
+    ids = rng.permutation(n).astype(np.int64) if shuffle else np.arange(n, dtype=np.int64)
+    x, y = np.meshgrid(np.arange(side), np.arange(side), indexing="ij")
+    us, vs = [], []
+    for dx in range(-2, 3):
+        for dy in range(-2, 3):
+            if (dx == 0 and dy == 0) or (abs(dx) == 2 and abs(dy) == 2):
+                continue
+            us.append(ids[(x * side + y).ravel()])
+            vs.append(ids[(((x + dx) % side) * side + (y + dy) % side).ravel()])
+    u = np.concatenate(us).astype(np.int32)
+    v = np.concatenate(vs).astype(np.int32)
+    perm = rng.permutation(len(u))
+    u, v = u[perm], v[perm]
+    p = rng.random(len(u)) * 0.12 + 0.001
+    return n, u, v, p

@@ -132,3 +132,51 @@ def test_dead_end_graph_is_an_error():
     with pytest.raises(_lib.PnError) as ei:
         g.sample(2, 3)
     assert ei.value.code == -3
+
+
+# ---------------------------------------------------------------- sparse-label (root-centric) path --
+@pytest.fixture
+def force_sparse(monkeypatch):
+    monkeypatch.setenv("PN_MERW_SPARSE", "1")
+
+
+@pytest.mark.parametrize("n,deg,nw,L,E,seed", [(300, 8, 5, 3, 3, 1), (300, 8, 40, 4, 2, 2), (257, 4, 33, 4, 2, 5),
+                                              (64, 3, 70, 4, 2, 6)])
+def test_sparse_label_path_matches_oracle_on_messy_graphs(force_sparse, n, deg, nw, L, E, seed):
+    gr = messy_graph(n, deg, seed)
+    want_n, want_t = mo.OracleGraph(*gr).sample(nw, L, 2000 + seed, 0, E)
+    got_n, got_t = _gpu_sample(sampler.MerwGraph(*gr), nw, L, 2000 + seed, epochs=E)
+    assert (got_n == want_n).all()
+    assert (got_t == want_t).all()
+
+
+@pytest.mark.parametrize("side,nw,L,E", [(40, 64, 8, 2), (33, 40, 6, 3), (25, 7, 5, 2)])
+def test_sparse_label_path_matches_oracle_on_lattices(force_sparse, side, nw, L, E):
+    from tests.helpers import lattice_graph
+    gr = lattice_graph(side, seed=side)
+    g = sampler.MerwGraph(*gr)
+    want_n, want_t = mo.OracleGraph(*gr).sample(nw, L, 99, 1, 1 + E)
+    got_n, got_t = _gpu_sample(g, nw, L, 99, epochs=E, epoch_begin=1)
+    assert (got_n == want_n).all()
+    assert (got_t == want_t).all()
+    assert got_t.max() == L - 1                       # far enough to leave the radius-(L-2) ball sometimes
+    a_n, a_t = _gpu_sample(g, nw, L, 99, epochs=E, epoch_begin=1, node_begin=100, node_end=333)
+    assert (a_n == want_n[:, 100:333]).all() and (a_t == want_t[:, 100:333]).all()
+
+
+def test_sparse_and_dense_paths_agree(monkeypatch):
+    from tests.helpers import lattice_graph
+    gr = lattice_graph(60, seed=4)
+    g = sampler.MerwGraph(*gr)
+    d_n, d_t = _gpu_sample(g, 16, 6, 5, epochs=2)
+    monkeypatch.setenv("PN_MERW_SPARSE", "1")
+    s_n, s_t = _gpu_sample(g, 16, 6, 5, epochs=2)
+    assert (d_n == s_n).all() and (d_t == s_t).all()
+
+
+def test_sparse_label_path_reports_ball_overflow(force_sparse):
+    gr = messy_graph(20000, 12, 3, hubs=4)            # radius-4 balls cover the whole graph
+    g = sampler.MerwGraph(*gr)
+    with pytest.raises(_lib.PnError) as ei:
+        g.sample(4, 6, epochs=1, node_begin=0, node_end=64)
+    assert ei.value.code == -5 and "ball" in str(ei.value)
