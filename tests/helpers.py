@@ -61,10 +61,9 @@ def messy_graph(n, avg_deg, seed, hubs=2, neg_frac=0.05, zero_frac=0.05, dup_fra
 
 
 def lattice_graph(side, seed=0, shuffle=True):
-    """side x side torus, 16 neighbours per node (the 5x5 block around it minus the 8 outermost
-    corner/knight cells ... here: all cells with |dx|,|dy| <= 2 except |dx|=|dy|=2 and the centre,
-    i.e. 20 - 4 = 16), ids randomly permuted so memory access is random while radius-r balls stay
-    small ((4r+1)^2 nodes at most).  p: random positive, rows not normalised."""
+    """side x side torus, 20 neighbours per node (all cells with |dx|,|dy| <= 2 except the four
+    corners |dx|=|dy|=2 and the centre), ids randomly permuted so memory access is random while
+    radius-r balls stay small ((4r+1)^2 nodes at most).  p: random positive, rows not normalised."""
     rng = np.random.default_rng(seed)
     n = side * side
     ids = rng.permutation(n).astype(np.int64) if shuffle else np.arange(n, dtype=np.int64)

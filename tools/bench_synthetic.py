@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """MERW on the synthetic large-graph config of BASELINE.json (configs[4]: 10 M nodes, degree 16,
-path_num = 64, path_len = 8): a randomly relabelled 2-D torus with 16 neighbours per node
+path_num = 64, path_len = 8): a randomly relabelled 2-D torus with 20 neighbours per node
 (tests/helpers.lattice_graph) — memory access is random, radius-6 balls stay small (<= 625 nodes), so
 the sparse-label kernel applies (the dense n x n table would need 10^14 bytes).
 
