@@ -57,6 +57,12 @@ typedef struct pn_graph pn_graph;
  * for every rand() output r, and uploads everything to `device`. */
 int pn_graph_from_edges(int32_t n, int64_t m, const int32_t *u, const int32_t *v,
                         const double *p, int device, pn_graph **out);
+/* Uniform-random-walk variant of the sampler (preprocess/gen.cpp, the "RW-PathNet" ablation): rows are the
+ * 2-column `<name>_nsl.in` rows; adjacency = self loop per node, then both directions of every row with
+ * u != v (gen.cpp:83-94); a roll draws ONE rand() (`rand() % deg`, :112-114).  pn_merw_sample on such a
+ * graph reproduces gen.cpp's output for srand(seed). */
+int pn_graph_from_edges_uniform(int32_t n, int64_t m, const int32_t *u, const int32_t *v, int device,
+                                pn_graph **out);
 int pn_graph_free(pn_graph *g);
 
 /* n, rows, max out-degree, and the first node without out-rows (-1 if none). */

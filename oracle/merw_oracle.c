@@ -80,6 +80,7 @@ typedef struct {
     /* alias cells, CSR aligned with the rows (gen_merw.cpp:23-79) */
     int *A, *B;
     double *S;
+    int uniform; /* 1: the uniform-random-walk variant preprocess/gen.cpp (one rand() per roll) */
 } merw_graph;
 
 /* AliasTable::init, gen_merw.cpp:23-79, for one node's rows.
@@ -163,6 +164,33 @@ merw_graph *merw_oracle_graph(int n, long m, const int *u, const int *v,
     return g;
 }
 
+/* Adjacency of the uniform-random-walk sampler, preprocess/gen.cpp:83-94: a self loop for every
+ * node first (link(i,i)), then for every input row (u,v) with u != v: link(u,v) and link(v,u).
+ * Rows are 2-column (`<name>_nsl.in`).  A walk step is `u = E[u][rand() % E[u].size()]` (:112-114). */
+merw_graph *merw_oracle_graph_uniform(int n, long m, const int *u, const int *v)
+{
+    merw_graph *g = (merw_graph *)calloc(1, sizeof(*g));
+    g->n = n; g->uniform = 1;
+    long rows = n;
+    for (long e = 0; e < m; e++) if (u[e] != v[e]) rows += 2;
+    g->m = rows;
+    g->off = (long *)calloc((size_t)n + 1, sizeof(long));
+    g->adj = (int *)malloc(sizeof(int) * (size_t)rows);
+    for (int i = 0; i < n; i++) g->off[i + 1] = 1;
+    for (long e = 0; e < m; e++) if (u[e] != v[e]) { g->off[u[e] + 1]++; g->off[v[e] + 1]++; }
+    for (int i = 0; i < n; i++) g->off[i + 1] += g->off[i];
+    long *cur = (long *)malloc(sizeof(long) * (size_t)n);
+    memcpy(cur, g->off, sizeof(long) * (size_t)n);
+    for (int i = 0; i < n; i++) g->adj[cur[i]++] = i;
+    for (long e = 0; e < m; e++) if (u[e] != v[e]) { g->adj[cur[u[e]]++] = v[e]; g->adj[cur[v[e]]++] = u[e]; }
+    free(cur);
+    g->A = (int *)malloc(sizeof(int) * (size_t)rows);
+    g->B = (int *)malloc(sizeof(int) * (size_t)rows);
+    g->S = (double *)malloc(sizeof(double) * (size_t)rows);
+    for (long k = 0; k < rows; k++) { g->A[k] = g->B[k] = g->adj[k]; g->S[k] = 1.0; }
+    return g;
+}
+
 void merw_oracle_graph_free(merw_graph *g)
 {
     if (!g) return;
@@ -186,6 +214,7 @@ static int alias_roll(const merw_graph *g, int u, glibc_rng *rng)
     long o = g->off[u];
     int cells = (int)(g->off[u + 1] - o);
     if (cells == 0) return -1;
+    if (g->uniform) return g->adj[o + glibc_rand(rng) % cells]; /* gen.cpp:112-114: one draw */
     int x = glibc_rand(rng) % cells;
     double p = 1.0 * glibc_rand(rng) / 2147483647; /* RAND_MAX */
     return p > g->S[o + x] ? g->A[o + x] : g->B[o + x];
@@ -238,13 +267,13 @@ int merw_oracle_sample_range(const merw_graph *g, int nw, int L, unsigned int se
     const long np = node_end - node_begin;
     for (long epoch = 0; epoch < epoch_end; epoch++) {
         if (epoch < epoch_begin) {
-            long draws = (long)n * nw * L * 2;
+            long draws = (long)n * nw * L * (g->uniform ? 1 : 2);
             for (long k = 0; k < draws; k++) (void)glibc_rand(&rng);
             continue;
         }
         for (int st = 0; st < n; st++) {
             if (st < node_begin || st >= node_end) {
-                long draws = (long)nw * L * 2;
+                long draws = (long)nw * L * (g->uniform ? 1 : 2);
                 for (long k = 0; k < draws; k++) (void)glibc_rand(&rng);
                 continue;
             }

@@ -41,12 +41,43 @@ def have_ref() -> bool:
     return all((HERE / "_ref" / f).exists() for f in ("gen_merw", "gen_epoch_merw", "faketime.so"))
 
 
+def have_ref_uniform() -> bool:
+    return all((HERE / "_ref" / f).exists() for f in ("gen", "faketime.so"))
+
+
+def read_edge_input_nsl(path):
+    """2-column `<name>_nsl.in`: header `n m`, then m rows `u v` (gen.cpp:79-94)."""
+    with open(path) as f:
+        n, m = (int(x) for x in f.readline().split()[:2])
+        arr = np.loadtxt(f, dtype=np.int64, ndmin=2, max_rows=m) if m else np.zeros((0, 2), dtype=np.int64)
+    return n, arr[:, 0].astype(np.int32), arr[:, 1].astype(np.int32)
+
+
+def run_reference_uniform(edge_file, nw, L, seed, epochs=1, name="g", timeout=3600) -> bytes:
+    """Run the unmodified uniform-RW binary (oracle/_ref/gen from preprocess/gen.cpp): reads
+    ../edge_input/<name>_nsl.in, writes ./<name>_<nw>_<L>_nsl.txt (all 1000 epochs)."""
+    n = int(open(edge_file).readline().split()[0])
+    with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as W:
+        os.makedirs(f"{W}/preprocess"); os.makedirs(f"{W}/edge_input")
+        os.symlink(os.path.abspath(edge_file), f"{W}/edge_input/{name}_nsl.in")
+        env = dict(os.environ, FAKE_TIME=str(seed), LD_PRELOAD=str(HERE / "_ref" / "faketime.so"))
+        subprocess.run([str(HERE / "_ref" / "gen"), name, str(nw), str(L)], cwd=f"{W}/preprocess", env=env, check=True,
+                       timeout=timeout, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        out = bytearray()
+        with open(f"{W}/preprocess/{name}_{nw}_{L}_nsl.txt", "rb") as f:
+            for _ in range(n * nw * epochs):
+                out += f.readline()
+        return bytes(out)
+
+
 def lib():
     global _LIB
     if _LIB is None:
         L = C.CDLL(str(build()))
         L.merw_oracle_graph.restype = C.c_void_p
         L.merw_oracle_graph.argtypes = [C.c_int, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.merw_oracle_graph_uniform.restype = C.c_void_p
+        L.merw_oracle_graph_uniform.argtypes = [C.c_int, C.c_long, C.c_void_p, C.c_void_p]
         L.merw_oracle_graph_free.argtypes = [C.c_void_p]
         L.merw_oracle_graph_cells.argtypes = [C.c_void_p] + [C.c_void_p] * 4
         L.merw_oracle_sample.restype = C.c_int
@@ -79,17 +110,25 @@ def write_edge_input(path, n, u, v, p) -> None:
 
 
 class OracleGraph:
-    def __init__(self, n, u, v, p):
+    def __init__(self, n, u, v, p=None):
+        """p=None: the uniform-random-walk variant (preprocess/gen.cpp) on 2-column rows."""
         self.n, self.m = int(n), int(len(u))
         self._u = np.ascontiguousarray(u, dtype=np.int32)
         self._v = np.ascontiguousarray(v, dtype=np.int32)
+        if p is None:
+            self._h = lib().merw_oracle_graph_uniform(self.n, self.m, self._u.ctypes.data, self._v.ctypes.data)
+            self.m = self.n + 2 * int((self._u != self._v).sum())   # rows of gen.cpp's adjacency
+            return
         self._p = np.ascontiguousarray(p, dtype=np.float64)
         self._h = lib().merw_oracle_graph(self.n, self.m, self._u.ctypes.data,
                                           self._v.ctypes.data, self._p.ctypes.data)
 
     def __del__(self):
         if getattr(self, "_h", None):
-            lib().merw_oracle_graph_free(self._h)
+            try:
+                lib().merw_oracle_graph_free(self._h)
+            except Exception:   # interpreter shutdown
+                pass
             self._h = None
 
     def cells(self):

@@ -49,6 +49,7 @@ def lib():
     L.pn_dropout_hash.restype = C.c_uint32
     L.pn_dropout_hash.argtypes = [u64, C.c_uint32, u64]
     L.pn_graph_from_edges.argtypes = [i32, i64, vp, vp, vp, C.c_int, C.POINTER(vp)]
+    L.pn_graph_from_edges_uniform.argtypes = [i32, i64, vp, vp, C.c_int, C.POINTER(vp)]
     L.pn_graph_free.argtypes = [vp]
     L.pn_graph_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i64), C.POINTER(i32), C.POINTER(i32)]
     L.pn_graph_cells_host.argtypes = [vp, vp, vp, vp, vp, vp]
@@ -84,7 +85,7 @@ def check(rc: int) -> int:
 
 
 # symbols include/pathnet_b200.h declares (tests assert the .so exports each)
-EXPORTS = ("pn_version", "pn_last_error", "pn_graph_from_edges", "pn_graph_free", "pn_graph_info",
+EXPORTS = ("pn_version", "pn_last_error", "pn_graph_from_edges", "pn_graph_from_edges_uniform", "pn_graph_free", "pn_graph_info",
            "pn_graph_cells_host", "pn_graph_prepare_labels", "pn_merw_sample", "pn_merw_probabilities",
            "pn_paths_format_txt", "pn_paths_parse_txt", "pn_pagg_canonicalize",
            "pn_pagg_workspace_bytes", "pn_pagg_forward", "pn_pagg_backward", "pn_dropout_hash",

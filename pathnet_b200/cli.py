@@ -17,7 +17,7 @@ import time
 
 def main(argv=None) -> int:
     argv = list(sys.argv[1:] if argv is None else argv)
-    if not argv or argv[0] not in ("gen_merw", "gen_epoch_merw"):
+    if not argv or argv[0] not in ("gen_merw", "gen_epoch_merw", "gen", "gen_epoch"):
         print(__doc__, file=sys.stderr)
         return 2
     tool, rest = argv[0], argv[1:]
@@ -36,18 +36,24 @@ def main(argv=None) -> int:
         print("ERROR: Incorrect number of parameters. ", file=sys.stderr)
         return 0
     name, nw, L = pos[0], int(pos[1]), int(pos[2])
-    fin = f"../edge_input/{name}.in"
+    uniform = tool in ("gen", "gen_epoch")                 # preprocess/gen.cpp / gen_epoch.cpp (uniform random walk)
+    fin = f"../edge_input/{name}_nsl.in" if uniform else f"../edge_input/{name}.in"
     if seed is None:
         seed = int(time.time())
     from . import sampler
     from ._lib import PnError
-    if tool == "gen_merw":                             # :156-157 (gen_epoch_merw prints nothing)
+    suffix = "nsl" if uniform else "merw"
+    if tool in ("gen_merw", "gen"):                    # :156-157 (the per-epoch variants print nothing)
         print(f"File input: {fin}")
-        print(f"File output: ./{name}_{nw}_{L}_merw.txt")
-    g = sampler.MerwGraph.from_file(fin, device=device)
-    print(f"{name}: {g.n}", file=sys.stderr)          # :164
+        print(f"File output: ./{name}_{nw}_{L}_{suffix}.txt")
+    if uniform:
+        g = sampler.MerwGraph(*sampler.read_edge_input_nsl(fin), device=device)
+        print(f"{g.n}", file=sys.stderr)               # gen.cpp:81
+    else:
+        g = sampler.MerwGraph.from_file(fin, device=device)
+        print(f"{name}: {g.n}", file=sys.stderr)      # gen_merw.cpp:164
     batch = max(1, min(epochs, (64 << 20) // max(1, g.n * nw * L)))
-    out = open(f"./{name}_{nw}_{L}_merw.txt", "wb") if tool == "gen_merw" else None
+    out = open(f"./{name}_{nw}_{L}_{suffix}.txt", "wb") if tool in ("gen_merw", "gen") else None
     try:
         for e0 in range(0, epochs, batch):
             e1 = min(epochs, e0 + batch)
@@ -63,7 +69,7 @@ def main(argv=None) -> int:
                 out.write(sampler.format_paths_txt(nodes, types))
             else:
                 for e in range(e0, e1):
-                    with open(f"./{name}_{nw}_{L}_{e}_merw.txt", "wb") as f:
+                    with open(f"./{name}_{nw}_{L}_{e}_merw.txt" if not uniform else f"./{name}_{nw}_{L}_{e}.txt", "wb") as f:
                         f.write(sampler.format_paths_txt(nodes[e - e0], types[e - e0]))
     finally:
         if out is not None:

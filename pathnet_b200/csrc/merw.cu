@@ -44,6 +44,7 @@ struct pn_graph {
     int64_t m = 0;
     int32_t max_deg = 0;
     int32_t dead_end = -1;
+    bool uniform = false;         // uniform-random-walk variant (preprocess/gen.cpp): one rand() per roll
     // host copies (parity tests, text tools)
     std::vector<int64_t> off;
     std::vector<int32_t> A, B, thr;
@@ -167,6 +168,7 @@ struct WalkParams {
     uint8_t *types;
     int32_t n, nw, L, wpt;
     int32_t node_begin;
+    int32_t dpr;             // rand() draws per roll: 2 (MERW alias roll, gen_merw.cpp:88-89) or 1 (uniform, gen.cpp:112-113)
     int64_t wpe;             // walks per epoch in this call = n' * nw
     int64_t cpe;             // chunks per epoch = ceil(wpe / wpt)
     int64_t total_chunks;    // E * cpe
@@ -295,7 +297,8 @@ k_merw_walk(const __grid_constant__ WalkParams P)
     const bool vec4 = (L & 3) == 0;                        // walk outputs are 16-byte (ids) / 4-byte (labels) aligned groups
     int32_t pk_n[4] = {0, 0, 0, 0};
     uint32_t pk_t = 0;
-    const int total_draws = P.wpt * 2 * L;                 // uniform across the warp
+    const int total_draws = P.wpt * P.dpr * L;             // uniform across the warp
+    const bool one_draw = P.dpr == 1;
     int drawn = 0;
     bool second = false;                                   // false: next draw is r1, true: r2
     while (drawn < total_draws) {
@@ -305,8 +308,9 @@ k_merw_walk(const __grid_constant__ WalkParams P)
             if (drawn < total_draws) {                     // uniform
                 const uint32_t o = s[j] >> 1;
                 drawn++;
-                if (!second) { r1 = o; second = true; }
+                if (!second && !one_draw) { r1 = o; second = true; }
                 else {
+                    if (one_draw) r1 = o;                  // gen.cpp: the single draw picks the neighbour (cells have A == B)
                     second = false;
                     const bool active = walk < nwalks;
                     if (active) {
@@ -466,8 +470,9 @@ k_merw_walk_root(const __grid_constant__ WalkParams P)
             for (int t = 0; t < L; t++) {
                 // the walk's draws 2t and 2t+1: words 2t, 2t+1 of the lane's window = dot(cf, ext[i .. i+30])
                 uint32_t r1 = 0, r2 = 0;
+                const int i1 = P.dpr * t, i2 = P.dpr == 2 ? i1 + 1 : i1;
 #pragma unroll
-                for (int j = 0; j < lfg::DEG; j++) { r1 += cf[j] * ext[2 * t + j]; r2 += cf[j] * ext[2 * t + 1 + j]; }
+                for (int j = 0; j < lfg::DEG; j++) { r1 += cf[j] * ext[i1 + j]; r2 += cf[j] * ext[i2 + j]; }
                 r1 >>= 1; r2 >>= 1;
                 if (active) {
                     out_n[t] = u;
@@ -598,6 +603,34 @@ extern "C" int pn_graph_from_edges(int32_t n, int64_t m, const int32_t *u, const
     return PN_OK;
 }
 
+// Uniform-random-walk variant (preprocess/gen.cpp:83-94): adjacency = a self loop per node first, then
+// (u,v) and (v,u) for every input row with u != v; a roll is `E[u][rand() % E[u].size()]` (:112-114).
+// Implemented as degenerate alias cells (A = B = neighbour) plus one draw per roll.
+extern "C" int pn_graph_from_edges_uniform(int32_t n, int64_t m, const int32_t *u, const int32_t *v, int device,
+                                           pn_graph **out)
+{
+    PN_REQUIRE(out != nullptr, "pn_graph_from_edges_uniform: out is NULL");
+    *out = nullptr;
+    PN_REQUIRE(n > 0 && m >= 0 && (m == 0 || (u && v)), "pn_graph_from_edges_uniform: bad arguments");
+    std::vector<std::vector<int32_t>> E((size_t)n);
+    for (int32_t i = 0; i < n; i++) E[i].push_back(i);
+    for (int64_t e = 0; e < m; e++) {
+        PN_REQUIRE(u[e] >= 0 && u[e] < n && v[e] >= 0 && v[e] < n, "pn_graph_from_edges_uniform: row %lld outside [0,%d)", (long long)e, n);
+        if (u[e] == v[e]) continue;
+        E[u[e]].push_back(v[e]);
+        E[v[e]].push_back(u[e]);
+    }
+    std::vector<int32_t> ru, rv;
+    std::vector<double> rp;
+    for (int32_t i = 0; i < n; i++)
+        for (int32_t w : E[i]) { ru.push_back(i); rv.push_back(w); rp.push_back(0.0); }
+    // p = 0 for every row: the two-queue construction then emits each row as the cell (id, id, 1.0)
+    // in row order, i.e. A = B = E[u][x] — exactly the table a uniform pick indexes
+    int rc = pn_graph_from_edges(n, (int64_t)ru.size(), ru.data(), rv.data(), rp.data(), device, out);
+    if (rc == PN_OK) (*out)->uniform = true;
+    return rc;
+}
+
 extern "C" int pn_graph_free(pn_graph *g)
 {
     if (!g) return PN_OK;
@@ -670,11 +703,11 @@ static void copy_poly(uint32_t dst[lfg::DEG], const lfg::Poly &p) { memcpy(dst, 
 
 // Chunking + jump-ahead tables of one pn_merw_sample call (host).
 static int plan_walk(WalkParams &P, int32_t n, int32_t nw, int32_t L, int64_t epoch_begin,
-                     int64_t E, int32_t node_begin, int64_t np, uint64_t seed, bool root_mode = false)
+                     int64_t E, int32_t node_begin, int64_t np, uint64_t seed, bool root_mode = false, int dpr = 2)
 {
     memset(&P, 0, sizeof(P));
     const int64_t wpe = np * nw;
-    P.n = n; P.nw = nw; P.L = L; P.node_begin = node_begin;
+    P.n = n; P.nw = nw; P.L = L; P.node_begin = node_begin; P.dpr = dpr;
     P.wpe = wpe;
     // chunk size: enough chunks to fill the machine, at most 64 walks per thread
     // (amortises the jump-ahead, ~45 % of a warp's instructions at 16), at least 4
@@ -687,7 +720,7 @@ static int plan_walk(WalkParams &P, int32_t n, int32_t nw, int32_t L, int64_t ep
     P.total_chunks = E * P.cpe;
     PN_REQUIRE(P.cpe < ((int64_t)1 << (4 * NDIGITS)) && E < ((int64_t)1 << NPOLY_BITS),
                "pn_merw_sample: too many chunks/epochs in one call");
-    const uint64_t draws_per_walk = 2ull * (uint64_t)L;  // every roll draws twice, L rolls
+    const uint64_t draws_per_walk = (uint64_t)dpr * (uint64_t)L;  // every roll draws dpr times, L rolls
     const uint64_t chunk_stride = draws_per_walk * (uint64_t)wpt;
     const uint64_t epoch_stride = draws_per_walk * (uint64_t)n * (uint64_t)nw;
     uint32_t s0[lfg::DEG];
@@ -770,7 +803,7 @@ extern "C" int pn_merw_sample(pn_graph *g, int32_t nw, int32_t L, int64_t epoch_
     }
     WalkParams P;
     {
-        int rc = plan_walk(P, g->n, nw, L, epoch_begin, E, node_begin, np, seed, sparse);
+        int rc = plan_walk(P, g->n, nw, L, epoch_begin, E, node_begin, np, seed, sparse, g->uniform ? 1 : 2);
         if (rc != PN_OK) return rc;
     }
     P.noderec = g->d_noderec; P.cells = g->d_cells;

@@ -26,6 +26,17 @@ VARIANT = {"hetero": 0, "homo": 1}
 MATH = {"fp32": 0, "tc": 1}
 
 
+def resolve_math_mode(mode: str, H: int, L: int) -> str:
+    """"auto" (the default): tensor-core kernels where they exist (hidden 128, path_len <= 8), else the fp32
+    CUDA-core kernels.  "fp32" = strict-parity mode (1e-4 against the reference's CPU fp32 math); "tc" =
+    tensor cores or an error if the shape is unsupported."""
+    if mode == "auto":
+        return "tc" if (H == 128 and L <= 8) else "fp32"
+    if mode not in MATH:
+        raise ValueError(f"math_mode must be 'auto', 'fp32' or 'tc' (got {mode!r})")
+    return mode
+
+
 def _stream_ptr():
     return torch.cuda.current_stream().cuda_stream
 
@@ -69,7 +80,7 @@ class _PaggFunction(torch.autograd.Function):
         S, nw, L = seq_node.shape
         H, Fd = params[0].shape
         cfg = PaggCfg(N=X.shape[0], F=Fd, H=H, C=params[10].shape[0], S=S, nw=nw, L=L,
-                      variant=VARIANT[meta["variant"]], math_mode=MATH[meta["math_mode"]],
+                      variant=VARIANT[meta["variant"]], math_mode=MATH[resolve_math_mode(meta["math_mode"], H, L)],
                       training=int(meta["training"]), dropout_p=float(meta["dropout"]),
                       dropout_seed=int(meta["seed"]))
         with torch.cuda.device(dev):
@@ -102,7 +113,7 @@ class _PaggFunction(torch.autograd.Function):
 
 
 def pagg_forward(variant, X, params: dict, seq_node, seq_type, partner, rows, *, dropout=0.0,
-                 training=False, seed=0, math_mode="fp32"):
+                 training=False, seed=0, math_mode="auto"):
     """Functional form over a dict with the reference's state_dict keys."""
     L = seq_node.shape[2]
     nets_w = torch.stack([params[f"nets.{d}.weight"] for d in range(L)])
@@ -122,7 +133,7 @@ class _PathNetBase(nn.Module):
     def __init__(self, feature_length, hidden_size, out_size, wl, **kwargs):
         # kwargs mirrors the reference signature (`aggr` is set and ignored there, :156-157)
         self.dropout = float(kwargs.pop("dropout", 0.0))
-        self.math_mode = kwargs.pop("math_mode", "fp32")
+        self.math_mode = kwargs.pop("math_mode", "auto")   # "auto" | "fp32" (strict parity) | "tc"
         kwargs.setdefault("aggr", "mean")
         super().__init__()
         self.feature_length, self.hidden_size, self.out_size = feature_length, hidden_size, out_size

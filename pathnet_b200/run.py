@@ -43,7 +43,7 @@ def _fused_forward(variant):
         seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if (self.training and drop > 0) else 0
         return pagg.pagg_forward(variant, X, dict(self.named_parameters()), sn, st, pt, rows, dropout=drop,
                                  training=self.training, seed=seed,
-                                 math_mode=os.environ.get("PN_MATH_MODE", "fp32"))
+                                 math_mode=os.environ.get("PN_MATH_MODE", "auto"))
     return forward
 
 

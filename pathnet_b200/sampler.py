@@ -30,18 +30,34 @@ def read_edge_input(path):
             np.ascontiguousarray(arr[:, 1], dtype=np.int32), np.ascontiguousarray(arr[:, 2]))
 
 
+def read_edge_input_nsl(path):
+    """2-column `<name>_nsl.in` of the uniform-RW sampler: header `n m`, then m rows `u v` (gen.cpp:79-94)."""
+    with open(path) as f:
+        n, m = (int(x) for x in f.readline().split()[:2])
+        arr = np.loadtxt(f, dtype=np.int64, ndmin=2, max_rows=m) if m else np.zeros((0, 2), dtype=np.int64)
+    return n, np.ascontiguousarray(arr[:, 0], dtype=np.int32), np.ascontiguousarray(arr[:, 1], dtype=np.int32)
+
+
 class MerwGraph:
     """CSR + alias cells of one `<name>.in`, resident on one GPU."""
 
-    def __init__(self, n, u, v, p, device="cuda:0"):
+    def __init__(self, n, u, v, p=None, device="cuda:0"):
+        """p=None: the uniform-random-walk variant of the sampler (preprocess/gen.cpp) on 2-column rows."""
         u = np.ascontiguousarray(u, dtype=np.int32)
         v = np.ascontiguousarray(v, dtype=np.int32)
-        p = np.ascontiguousarray(p, dtype=np.float64)
-        if not (len(u) == len(v) == len(p)):
-            raise ValueError("u, v, p must have the same length")
         self.device = None if device in (None, "host") else torch.device(device)
         dev_index = -1 if self.device is None else (self.device.index or 0)
         h = C.c_void_p()
+        if p is None:
+            if len(u) != len(v):
+                raise ValueError("u, v must have the same length")
+            check(lib().pn_graph_from_edges_uniform(int(n), len(u), u.ctypes.data, v.ctypes.data, dev_index, C.byref(h)))
+            self._h = h
+            self.n, self.m = int(n), self.info()["m"]
+            return
+        p = np.ascontiguousarray(p, dtype=np.float64)
+        if not (len(u) == len(v) == len(p)):
+            raise ValueError("u, v, p must have the same length")
         check(lib().pn_graph_from_edges(int(n), len(u), u.ctypes.data, v.ctypes.data, p.ctypes.data,
                                         dev_index, C.byref(h)))
         self._h = h
@@ -54,7 +70,10 @@ class MerwGraph:
     def __del__(self):
         h = getattr(self, "_h", None)
         if h:
-            lib().pn_graph_free(h)
+            try:
+                lib().pn_graph_free(h)
+            except Exception:   # interpreter shutdown
+                pass
             self._h = None
 
     def info(self):

@@ -29,6 +29,7 @@ def _fixture(path):
 
 def _module_for(variant, F, H, Cc, L, params, **kw):
     cls = pagg.PathNet if variant == "hetero" else pagg.PathNet_homo
+    kw.setdefault("math_mode", "fp32")   # strict-parity mode for the 1e-4 comparisons in this file
     m = cls(F, H, Cc, L, **kw)
     m.load_state_dict(params)
     return m.to(DEV)
@@ -83,7 +84,7 @@ def _random_case(variant, N, Fd, H, Cc, nw, L, S, seed):
     g = torch.Generator().manual_seed(seed)
     torch.manual_seed(seed)
     cls = pagg.PathNet if variant == "hetero" else pagg.PathNet_homo
-    m = cls(Fd, H, Cc, L)
+    m = cls(Fd, H, Cc, L, math_mode="fp32")   # strict-parity mode unless a test switches it
     X = torch.randn(N, Fd, generator=g)
     mask = torch.zeros(N, dtype=torch.bool)
     mask[torch.randperm(N, generator=g)[:S]] = True
@@ -181,7 +182,8 @@ def test_training_mode_with_identical_dropout_masks(variant):
     dev = lambda a, dt: torch.tensor(a, device=DEV, dtype=dt)
     sd = dict(m.named_parameters())
     y = pagg.pagg_forward(variant, X.to(DEV), sd, dev(sn, torch.int32), dev(st, torch.uint8),
-                          dev(pt, torch.int32), dev(rows, torch.int32), dropout=p, training=True, seed=seed)
+                          dev(pt, torch.int32), dev(rows, torch.int32), dropout=p, training=True, seed=seed,
+                          math_mode="fp32")
     torch.testing.assert_close(y.cpu(), y_ref.detach().float(), **FWD_TOL)
     (y * G.to(DEV)).sum().backward()
     for k, pr in m.named_parameters():
@@ -249,7 +251,7 @@ def test_empty_and_error_cases():
     with pytest.raises(RuntimeError):
         pagg.PathNet_homo(8, 32, 3, 2)(X.cpu(), torch.zeros((1, 6), dtype=torch.int64), 3, 2,
                                        np.ones(10, dtype=bool), torch.zeros((1, 3, 2), dtype=torch.int64), None)
-    bad = pagg.PathNet_homo(8, 48, 3, 2).to(DEV)   # H not a multiple of 32
+    bad = pagg.PathNet_homo(8, 48, 3, 2).to(DEV)   # H not a multiple of 32 (auto -> fp32 kernels -> rejected)
     mk = np.zeros(10, dtype=bool); mk[0] = True
     with pytest.raises(_lib.PnError):
         bad(X, torch.zeros((1, 6), dtype=torch.int64), 3, 2, mk, torch.zeros((1, 3, 2), dtype=torch.int64), None)

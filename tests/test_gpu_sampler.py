@@ -180,3 +180,25 @@ def test_sparse_label_path_reports_ball_overflow(force_sparse):
     with pytest.raises(_lib.PnError) as ei:
         g.sample(4, 6, epochs=1, node_begin=0, node_end=64)
     assert ei.value.code == -5 and "ball" in str(ei.value)
+
+
+# --------------------------------------------------- uniform random walk variant (preprocess/gen.cpp) --
+def test_uniform_rw_matches_reference_gen_fixture_and_oracle(monkeypatch):
+    z = np.load(GOLDEN / "uniform_rw_reference.npz")
+    n, u, v, nw, L, seed, E = int(z["n"]), z["u"], z["v"], int(z["nw"]), int(z["L"]), int(z["seed"]), int(z["epochs"])
+    g = sampler.MerwGraph(n, u, v, None)
+    nodes, types = _gpu_sample(g, nw, L, seed, epochs=E)
+    txt = sampler.format_paths_txt(nodes, types)
+    assert len(txt) == int(z["nbytes"]) and sha256(txt) == str(z["sha256"])          # == reference gen binary
+    monkeypatch.setenv("PN_MERW_SPARSE", "1")                                          # and through the sparse-label kernel
+    s_n, s_t = _gpu_sample(g, nw, L, seed, epochs=E)
+    assert (s_n == nodes).all() and (s_t == types).all()
+
+
+def test_uniform_rw_on_a_larger_graph_matches_oracle():
+    rng = np.random.default_rng(5)
+    n, m = 5000, 30000
+    u, v = rng.integers(0, n, m).astype(np.int32), rng.integers(0, n, m).astype(np.int32)
+    want_n, want_t = mo.OracleGraph(n, u, v).sample(40, 4, 321, 0, 2)
+    got_n, got_t = _gpu_sample(sampler.MerwGraph(n, u, v, None), 40, 4, 321, epochs=2)
+    assert (got_n == want_n).all() and (got_t == want_t).all()

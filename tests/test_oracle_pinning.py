@@ -189,3 +189,20 @@ def test_shipped_edge_inputs_are_not_a_golden_for_the_builder():
     uk, idx = np.unique(key, return_index=True)
     pp, _, lam = mpo.compute_merw(n, uk // n, uk % n)
     assert np.abs(pp - p[idx]).max() > 1e-2 and abs(lam - 11.0787866794) < 1e-8
+
+
+# ------------------------------------------------ uniform random walk (gen.cpp) --
+def test_uniform_rw_oracle_matches_reference_gen_binary_fixture():
+    """oracle restatement of preprocess/gen.cpp against the sha256 of the reference `gen` binary's text
+    (tests/golden/uniform_rw_reference.npz holds the 2-column input rows and the hash)."""
+    z = np.load(GOLDEN / "uniform_rw_reference.npz")
+    g = mo.OracleGraph(int(z["n"]), z["u"], z["v"])          # p=None -> uniform variant
+    nodes, types = g.sample(int(z["nw"]), int(z["L"]), int(z["seed"]), 0, int(z["epochs"]))
+    txt = mo.format_txt(nodes, types)
+    assert len(txt) == int(z["nbytes"]) and sha256(txt) == str(z["sha256"])
+    if mo.have_ref_uniform():
+        import tempfile
+        with tempfile.TemporaryDirectory() as d:
+            f = f"{d}/u_nsl.in"
+            open(f, "w").write(f"{int(z['n'])} {len(z['u'])}\n" + "".join(f"{a} {b}\n" for a, b in zip(z["u"], z["v"])))
+            assert mo.run_reference_uniform(f, int(z["nw"]), int(z["L"]), int(z["seed"]), epochs=int(z["epochs"]), name="u") == txt
