@@ -143,6 +143,9 @@ typedef struct {
     int32_t training;        /* F.dropout(training=...) (:194,:209,:264,:276) */
     float dropout_p;         /* the reference's module-global `dropout` (:71) */
     uint64_t dropout_seed;   /* counter-based mask stream    */
+    int32_t no_backward;     /* 1: inference only — forward skips saving activations / gradient operands;
+                                pn_pagg_backward on such a workspace is an error (PN_ERR_INVALID)       */
+    int32_t reserved;
 } pn_pagg_cfg;
 
 /* Parameter (or gradient) block, fp32 device pointers, PyTorch layouts

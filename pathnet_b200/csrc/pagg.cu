@@ -100,7 +100,7 @@ struct LstmArgs {
     const int32_t *seq_node; // [P,L]
     const uint8_t *seq_type; // [P,L]
     const float *Wp, *WpT, *bp;
-    float *acts;             // [L][P][5][H]
+    float *acts;             // [L][P][5][H] (null: inference, nothing saved)
     float *hfin;             // [P,H]
     int64_t P;
     int L;
@@ -217,8 +217,10 @@ __global__ void __launch_bounds__(256) k_lstm_fwd_f32(LstmArgs a)
                 const float h = og * tanhf(cn);
                 As[row * AP + H + unit] = h;
                 if (p < a.P) {
-                    float *act = a.acts + (((int64_t)t * a.P + p) * 5) * H + unit;
-                    act[0] = ig; act[H] = fg; act[2 * H] = gg; act[3 * H] = og; act[4 * H] = cn;
+                    if (a.acts) {
+                        float *act = a.acts + (((int64_t)t * a.P + p) * 5) * H + unit;
+                        act[0] = ig; act[H] = fg; act[2 * H] = gg; act[3 * H] = og; act[4 * H] = cn;
+                    }
                     if (t == a.L - 1) a.hfin[p * H + unit] = h;
                 }
             }
@@ -679,7 +681,7 @@ extern "C" int pn_pagg_forward(const pn_pagg_cfg *cfg, const pn_pagg_params *prm
     // K2: gather + dropout + LSTM                                  (:194-195 / :264-265)
     LstmArgs la{};
     la.T = w.T; la.seq_node = seq_node; la.seq_type = seq_type; la.Wp = w.Wp; la.WpT = w.WpT; la.bp = w.bp;
-    la.acts = w.acts; la.hfin = w.hfin; la.P = P; la.L = (int)L;
+    la.acts = c.no_backward ? nullptr : w.acts; la.hfin = w.hfin; la.P = P; la.L = (int)L;
     la.drop_thr = thr; la.drop_scale = scale; la.drop_seed = c.dropout_seed;
     if (c.math_mode == PN_MATH_TC) {
         rc = pagg_tc_forward_lstm(c, w, *prm, seq_node, seq_type, st);
@@ -714,6 +716,7 @@ extern "C" int pn_pagg_backward(const pn_pagg_cfg *cfg, const pn_pagg_params *pr
     if (rc != PN_OK) return rc;
     const pn_pagg_cfg &c = *cfg;
     PN_REQUIRE(prm && X && workspace && grads, "pagg_backward: NULL pointer");
+    PN_REQUIRE(!cfg->no_backward, "pagg_backward: the forward ran with no_backward = 1 (nothing was saved)");
     cudaStream_t st = (cudaStream_t)stream;
     const PaggWs w = carve_workspace(c, (void *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255));
     const int64_t N = c.N, F = c.F, H = c.H, L = c.L, S = c.S, C = c.C, P = (int64_t)c.S * c.nw;

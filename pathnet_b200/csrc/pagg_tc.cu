@@ -249,6 +249,7 @@ struct LstmTcArgs {
     int L;
     uint32_t drop_thr; float drop_scale; uint64_t drop_seed;
     unsigned char *xh_img;    // wgrad operand images [x_t | h_{t-1}] (see LstmBwdTcArgs), written here
+    int save;                 // 0: inference only, skip activations and operand images
     long long *trace;         // optional clock64() trace of CTA `trace_block` (debug)
     int trace_block;
 };
@@ -298,7 +299,7 @@ __device__ __forceinline__ void tc_gather_quarter(const LstmTcArgs &a, unsigned 
         }
         const uint4 pk = pack8_f16(f);
         *reinterpret_cast<uint4 *>(Xs + canon_off(r, k8 * 8, TC_H)) = pk;
-        *reinterpret_cast<uint4 *>(xh_blk + (size_t)k8 * 2048 + r * 16) = pk;   // x half of the wgrad operand image
+        if (a.save) *reinterpret_cast<uint4 *>(xh_blk + (size_t)k8 * 2048 + r * 16) = pk;   // x half of the wgrad operand image
     }
 }
 
@@ -399,7 +400,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_fwd_tc(LstmTcArgs a)
         // h_{-1} = 0: h half of step 0's image
 #pragma unroll
         for (int k8 = 16 + cq * 4; k8 < 16 + cq * 4 + 4; k8++)
-            *reinterpret_cast<uint4 *>(a.xh_img + (int64_t)blockIdx.x * XH_BLOCK_BYTES + (size_t)k8 * 2048 + r * 16) = make_uint4(0, 0, 0, 0);
+            if (a.save) *reinterpret_cast<uint4 *>(a.xh_img + (int64_t)blockIdx.x * XH_BLOCK_BYTES + (size_t)k8 * 2048 + r * 16) = make_uint4(0, 0, 0, 0);
         for (int t = 0; t < L; t++) {
             if (tr) a.trace[t * 8 + 0] = clock64();
             fence_proxy_async();   // generic-proxy smem writes (x_t, h_{t-1}) -> async proxy (tcgen05.mma)
@@ -465,9 +466,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_fwd_tc(LstmTcArgs a)
                 if (!t_is_last) {
                     const uint4 hpk = make_uint4(ph[0], ph[1], ph[2], ph[3]);
                     *reinterpret_cast<uint4 *>(Hs + canon_off(r, c0 / 4, TC_H)) = hpk;
-                    *reinterpret_cast<uint4 *>(a.xh_img + ((int64_t)(t + 1) * ntiles + blockIdx.x) * XH_BLOCK_BYTES + (size_t)(16 + c0 / 32) * 2048 + r * 16) = hpk;
+                    if (a.save) *reinterpret_cast<uint4 *>(a.xh_img + ((int64_t)(t + 1) * ntiles + blockIdx.x) * XH_BLOCK_BYTES + (size_t)(16 + c0 / 32) * 2048 + r * 16) = hpk;
                 }
-                if (valid) {
+                if (valid && a.save) {
                     const int ub = (c0 / 32) * 1024;  // unit8 block of 128 rows x 8 halves
                     *reinterpret_cast<uint4 *>(act + 0 * 16384 + ub) = make_uint4(pi[0], pi[1], pi[2], pi[3]);
                     *reinterpret_cast<uint4 *>(act + 1 * 16384 + ub) = make_uint4(pf[0], pf[1], pf[2], pf[3]);
@@ -513,7 +514,7 @@ int pagg_tc_forward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_pa
     }
     const int64_t P = (int64_t)c.S * c.nw;
     LstmTcArgs a{w.T, seq_node, seq_type, Wh, w.bp, reinterpret_cast<__half *>(w.acts), w.hfin, P, c.L, thr, scale, c.dropout_seed,
-                 reinterpret_cast<unsigned char *>(w.XH), nullptr, 0};
+                 reinterpret_cast<unsigned char *>(w.XH), c.no_backward ? 0 : 1, nullptr, 0};
     long long *d_trace = nullptr;
     const char *trace_env = getenv("PN_TRACE_FWD");
     if (trace_env) {

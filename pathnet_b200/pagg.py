@@ -82,7 +82,7 @@ class _PaggFunction(torch.autograd.Function):
         cfg = PaggCfg(N=X.shape[0], F=Fd, H=H, C=params[10].shape[0], S=S, nw=nw, L=L,
                       variant=VARIANT[meta["variant"]], math_mode=MATH[resolve_math_mode(meta["math_mode"], H, L)],
                       training=int(meta["training"]), dropout_p=float(meta["dropout"]),
-                      dropout_seed=int(meta["seed"]))
+                      dropout_seed=int(meta["seed"]), no_backward=int(not meta.get("need_backward", True)))
         with torch.cuda.device(dev):
             ws_bytes = lib().pn_pagg_workspace_bytes(C.byref(cfg))
             if ws_bytes == 0:
@@ -118,7 +118,8 @@ def pagg_forward(variant, X, params: dict, seq_node, seq_type, partner, rows, *,
     L = seq_node.shape[2]
     nets_w = torch.stack([params[f"nets.{d}.weight"] for d in range(L)])
     nets_b = torch.stack([params[f"nets.{d}.bias"] for d in range(L)])
-    meta = dict(variant=variant, math_mode=math_mode, training=training, dropout=dropout, seed=seed)
+    need_bwd = torch.is_grad_enabled() and any(t.requires_grad for t in params.values() if torch.is_tensor(t))
+    meta = dict(variant=variant, math_mode=math_mode, training=training, dropout=dropout, seed=seed, need_backward=need_bwd)
     return _PaggFunction.apply(X, params["fc0.weight"], params["fc0.bias"], nets_w, nets_b,
                                params["LSTM.weight_ih_l0"], params["LSTM.weight_hh_l0"],
                                params["LSTM.bias_ih_l0"], params["LSTM.bias_hh_l0"],

@@ -255,3 +255,16 @@ def test_empty_and_error_cases():
     mk = np.zeros(10, dtype=bool); mk[0] = True
     with pytest.raises(_lib.PnError):
         bad(X, torch.zeros((1, 6), dtype=torch.int64), 3, 2, mk, torch.zeros((1, 3, 2), dtype=torch.int64), None)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tc"])
+def test_no_grad_inference_matches_and_saves_nothing(mode):
+    """torch.no_grad() forwards set cfg.no_backward: same logits, no activations written."""
+    m, X, mask, neis, lt = _random_case("homo", 300, 20, 128, 4, 6, 4, 150, seed=21)
+    m = m.to(DEV).eval()
+    m.math_mode = mode
+    y_grad = m(X.to(DEV), neis, 6, 4, mask, lt, None)
+    with torch.no_grad():
+        y_inf = m(X.to(DEV), neis, 6, 4, mask, lt, None)
+    assert not y_inf.requires_grad and y_grad.requires_grad
+    torch.testing.assert_close(y_inf, y_grad.detach(), rtol=0, atol=0)
