@@ -626,7 +626,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t taddr = s_taddr;  // cols [0,128) dx, [128,256) dh_{t-1}, [256,384) dc
+    // TMEM columns: [0,128) / [128,256): dx of even / odd steps (ping-pong, so step s's dx can be scattered while the
+    // tensor core already works on step s+1), [256,384): dh_{t-1}, [384,512): running dc
+    const uint32_t taddr = s_taddr;
 
     if (warp == TC_CWARPS + 1) {
         if (lane == 0) {
@@ -646,7 +648,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
                 const int t = L - 1 - s;
                 mbar_wait(&a_ready, s & 1);
                 tc_fence_after();
-                const uint32_t idesc = t == 0 ? make_idesc_f16(128, 128) : make_idesc_f16(128, 256);  // t = 0: dh_{-1} unused
+                constexpr uint32_t idesc = make_idesc_f16(128, 128);
+                const uint32_t dx_col = (uint32_t)(s & 1) * 128;
                 for (int c = 0; c < TCB_NCHUNK; c++) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
@@ -654,8 +657,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
 #pragma unroll
                     for (int ks = 0; ks < TCB_KC / 16; ks++) {
                         const uint64_t ad = make_smem_desc(smem_u32(As) + (uint32_t)(c * (TCB_KC / 8) + ks * 2) * 128, 128, (TC_G4 / 8) * 128);
-                        const uint64_t bd = make_smem_desc(wbase + (uint32_t)ks * 256, 128, (TCB_KC / 8) * 128);
-                        mma_f16(taddr, ad, bd, idesc, (c > 0) || (ks > 0));
+                        // rows 0..127 of W' give dx, rows 128..255 (16 row groups further) give dh_{t-1} (unused at t = 0)
+                        const uint64_t bd_x = make_smem_desc(wbase + (uint32_t)ks * 256, 128, (TCB_KC / 8) * 128);
+                        mma_f16(taddr + dx_col, ad, bd_x, idesc, (c > 0) || (ks > 0));
+                        if (t > 0) {
+                            const uint64_t bd_h = make_smem_desc(wbase + 16u * ((TCB_KC / 8) * 128) + (uint32_t)ks * 256, 128, (TCB_KC / 8) * 128);
+                            mma_f16(taddr + 256, ad, bd_h, idesc, (c > 0) || (ks > 0));
+                        }
                     }
                     mma_commit(&empty_bar[stage]);
                     if (++stage == TCB_NSTAGE) { stage = 0; phase ^= 1; }
@@ -672,6 +680,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
         const uint32_t lane_base = taddr + ((uint32_t)(lq * 32) << 16);
         const float scale = a.gscale[0], inv_scale = a.gscale[1];
         const uint32_t dkey = dropout_key(a.drop_seed, 0);
+        // dx of step `ss` (time tt = L-1-ss) -> dT with the forward's dropout mask; reads the dx region of that step
+        auto scatter_dx = [&](int ss) {
+            const int tt = L - 1 - ss;
+            const uint32_t dx_col = (uint32_t)(ss & 1) * 128;
+            // tcgen05.ld is warp-collective (.sync.aligned): every lane loads, only valid rows scatter
+            const int64_t e = valid ? p * L + tt : 0;
+            float *dst = valid ? a.dT + ((int64_t)a.seq_node[e] * L + a.seq_type[e]) * TC_H : nullptr;
+#pragma unroll
+            for (int cb = cq * 4; cb < cq * 4 + 4; cb++) {
+                uint32_t v[8];
+                tmem_ld8(lane_base + dx_col + cb * 8, v);
+                tmem_ld_wait();
+                if (valid) {
+                    float f[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) f[j] = __uint_as_float(v[j]) * inv_scale;
+                    if (a.drop_thr) {
+                        const uint64_t pair = ((uint64_t)e * TC_H + cb * 8) >> 1;
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const uint32_t h = dropout_hash_pair_k(dkey, pair + q);
+                            f[2 * q] = (h & 0xFFFFu) < a.drop_thr ? 0.f : f[2 * q] * a.drop_scale;
+                            f[2 * q + 1] = (h >> 16) < a.drop_thr ? 0.f : f[2 * q + 1] * a.drop_scale;
+                        }
+                    }
+                    atomicAdd(reinterpret_cast<float4 *>(dst + cb * 8), make_float4(f[0], f[1], f[2], f[3]));
+                    atomicAdd(reinterpret_cast<float4 *>(dst + cb * 8 + 4), make_float4(f[4], f[5], f[6], f[7]));
+                }
+                __syncwarp();
+            }
+        };
         const bool tr = a.trace && blockIdx.x == a.trace_block && tid == 0;
         for (int s = 0; s < L; s++) {
             const int t = L - 1 - s;
@@ -696,8 +735,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
                     }
                 } else {
                     uint32_t v0[8], v1[8];
-                    tmem_ld8(lane_base + 128 + u0, v0);
-                    tmem_ld8(lane_base + 256 + u0, v1);
+                    tmem_ld8(lane_base + 256 + u0, v0);
+                    tmem_ld8(lane_base + 384 + u0, v1);
                     tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 8; j++) { dh[j] = __uint_as_float(v0[j]); dc[j] = __uint_as_float(v1[j]); }
@@ -728,7 +767,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
                     da[j >> 1][(j & 1) * 4 + 0] = d_i; da[j >> 1][(j & 1) * 4 + 1] = d_f;
                     da[j >> 1][(j & 1) * 4 + 2] = d_g; da[j >> 1][(j & 1) * 4 + 3] = d_o;
                 }
-                tmem_st8(lane_base + 256 + u0, dcn_bits);
+                tmem_st8(lane_base + 384 + u0, dcn_bits);
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
                     const uint4 pk = pack8_f16(da[q]);
@@ -751,41 +790,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
                 }
             }
             if (tr) a.trace[s * 8 + 2] = clock64();
-            // ---- [dx | dh_{t-1}] = da . W' ----
+            // ---- while the tensor core computes [dx | dh_{t-1}] = da . W' for this step: scatter the PREVIOUS step's dx ----
+            if (s > 0) scatter_dx(s - 1);
             mbar_wait(&acc_full, s & 1);
             tc_fence_after();
             if (tr) a.trace[s * 8 + 3] = clock64();
-            {
-                // tcgen05.ld is warp-collective (.sync.aligned): every lane loads, only valid rows scatter
-                const int64_t e = valid ? p * L + t : 0;
-                float *dst = valid ? a.dT + ((int64_t)a.seq_node[e] * L + a.seq_type[e]) * TC_H : nullptr;
-#pragma unroll
-                for (int cb = cq * 4; cb < cq * 4 + 4; cb++) {
-                    uint32_t v[8];
-                    tmem_ld8(lane_base + cb * 8, v);
-                    tmem_ld_wait();
-                    if (valid) {
-                        float f[8];
-#pragma unroll
-                        for (int j = 0; j < 8; j++) f[j] = __uint_as_float(v[j]) * inv_scale;
-                        if (a.drop_thr) {
-                            const uint64_t pair = ((uint64_t)e * TC_H + cb * 8) >> 1;
-#pragma unroll
-                            for (int q = 0; q < 4; q++) {
-                                const uint32_t h = dropout_hash_pair_k(dkey, pair + q);
-                                f[2 * q] = (h & 0xFFFFu) < a.drop_thr ? 0.f : f[2 * q] * a.drop_scale;
-                                f[2 * q + 1] = (h >> 16) < a.drop_thr ? 0.f : f[2 * q + 1] * a.drop_scale;
-                            }
-                        }
-                        atomicAdd(reinterpret_cast<float4 *>(dst + cb * 8), make_float4(f[0], f[1], f[2], f[3]));
-                        atomicAdd(reinterpret_cast<float4 *>(dst + cb * 8 + 4), make_float4(f[4], f[5], f[6], f[7]));
-                    }
-                    __syncwarp();
-                }
-            }
-            tc_fence_before();  // the TMEM reads above precede the next step's MMA (ordered through a_ready)
             if (tr) a.trace[s * 8 + 4] = clock64();
         }
+        scatter_dx(L - 1);   // the last step's dx (nothing left to overlap it with)
     }
     tc_fence_before();
     __syncthreads();
