@@ -548,18 +548,9 @@ int pagg_tc_forward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_pa
 // tensor-core backward
 // ===========================================================================
 // Gradients travel as fp16 multiplied by a power-of-two scale chosen from
-// max|dh_final| (so the largest gate gradient sits near 2^4): the same 11-bit
+// max|dh_final| (taken by k_pool_bwd; the largest gate gradient then sits near 2^4): the same 11-bit
 // significand as the forward operands, with 2^12 of head-room against growth
 // through the recurrence and 2^-28 relative before flush-to-zero.
-__global__ void k_absmax_bits(const float *__restrict__ x, int64_t n, unsigned int *__restrict__ out)
-{
-    float m = 0.f;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        m = fmaxf(m, fabsf(x[i]));
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
-}
 __global__ void k_make_scale(float *gscale)
 {
     const float m = __uint_as_float(*reinterpret_cast<unsigned int *>(gscale));
@@ -914,55 +905,6 @@ __global__ void __launch_bounds__(192, 1) k_wgrad_tc(WgradTcArgs a)
     tc_fence_before();
     __syncthreads();
     if (warp == 4) { __syncwarp(); tmem_dealloc<512>(taddr); }
-}
-
-// bias gradient: dbp[col] = (1/scale) * sum over all rows of all da blocks.
-// One warp per (block, col8 group of 4): 16 independent 16-byte loads in flight per lane.
-__global__ void __launch_bounds__(256) k_colsum_da_img(const unsigned char *__restrict__ da_img, int64_t nblocks,
-                                                        const float *__restrict__ gscale, float *__restrict__ dbp)
-{
-    __shared__ float acc[TC_G4];
-    for (int i = threadIdx.x; i < TC_G4; i += 256) acc[i] = 0.f;
-    __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // work item = (block b, group g of 4 col8): 16 groups per block
-    const int64_t nitems = nblocks * 16;
-    for (int64_t it = (int64_t)blockIdx.x * 8 + warp; it < nitems; it += (int64_t)gridDim.x * 8) {
-        const int64_t b = it >> 4;
-        const int g = (int)(it & 15);
-        const unsigned char *blk = da_img + b * DA_BLOCK_BYTES + (size_t)g * 4 * 2048;
-        uint4 ld[4][4];
-#pragma unroll
-        for (int c = 0; c < 4; c++)
-#pragma unroll
-            for (int rr = 0; rr < 4; rr++)
-                ld[c][rr] = __ldg(reinterpret_cast<const uint4 *>(blk + (size_t)c * 2048 + (rr * 32 + lane) * 16));
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-            float s8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int rr = 0; rr < 4; rr++) {
-                float f[8];
-                unpack8_f16(ld[c][rr], f);
-#pragma unroll
-                for (int j = 0; j < 8; j++) s8[j] += f[j];
-            }
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) s8[j] += __shfl_xor_sync(0xffffffffu, s8[j], o);
-            }
-            if (lane < 8) {
-                float v = s8[0];
-#pragma unroll
-                for (int j = 1; j < 8; j++) v = lane == j ? s8[j] : v;
-                atomicAdd(&acc[(g * 4 + c) * 8 + lane], v);
-            }
-        }
-    }
-    __syncthreads();
-    const float inv_scale = gscale[1];
-    for (int i = threadIdx.x; i < TC_G4; i += 256) atomicAdd(dbp + i, acc[i] * inv_scale);
 }
 
 // LSTM backward in tensor-core mode: fills w.dWp [2H][4H] and w.dbp [4H] (packed
