@@ -590,26 +590,38 @@ struct LstmBwdTcArgs {
     long long *trace;
     int trace_block;
 };
-constexpr int TCB_NSTAGE = 3;
+constexpr int TCB_NSTAGE = 4;   // 64 KB of W' in flight beside the 128 KB operand tile: the deepest ring that stays inside the 196 KB
+                                // shared-memory carve-out (6 stages -> 228 KB carve-out, the smaller L1 costs more than the depth wins)
 constexpr int TCB_A_BYTES = 128 * TC_G4 * 2;  // 128 KB: da tile [128][512] fp16 canonical
-constexpr int TCB_SMEM = TCB_A_BYTES + TCB_NSTAGE * TCB_CHUNK_BYTES + 1024;
+constexpr int TCB_SMEM_FIXED = TCB_A_BYTES + TCB_NSTAGE * TCB_CHUNK_BYTES + 128 /*align*/;   // + 128 * L * 4 bytes of row offsets
 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+// (Measured and dropped: pairing neighbouring tiles in a cluster that multicasts the W' stream halves its L2 traffic but
+// couples the two CTAs chunk by chunk -- 5 % slower.  The stream is latency-, not bandwidth-limited: depth helps.)
 __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
 {
     extern __shared__ unsigned char smem_dyn[];
-    unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    // no-swizzle UMMA operands and bulk copies need 16-byte alignment only; 128 keeps the tiles on line boundaries
+    unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 127) & ~(uintptr_t)127);
     unsigned char *As = base;                 // da_t, [128][512] fp16 canonical K-major
     unsigned char *Ws = base + TCB_A_BYTES;   // ring of W' chunks
-    __shared__ uint64_t full_bar[TCB_NSTAGE], empty_bar[TCB_NSTAGE], a_ready, acc_full;
+    int32_t *rowoff_s = reinterpret_cast<int32_t *>(Ws + TCB_NSTAGE * TCB_CHUNK_BYTES);   // [128][L]: dT row of (sequence, step)
+    __shared__ uint64_t full_bar[TCB_NSTAGE], empty_bar[TCB_NSTAGE], a_ready[4], acc_full;
     __shared__ uint32_t s_taddr;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t tile = blockIdx.x, p0 = tile * 128;
     const int L = a.L;
+    for (int i = tid; i < 128 * L; i += TC_THREADS) {
+        const int rr = i / L, tt = i % L;
+        const int64_t pp = p0 + rr;
+        int32_t off = -1;
+        if (pp < a.P) { const int64_t e = pp * L + tt; off = a.seq_node[e] * L + a.seq_type[e]; }
+        rowoff_s[rr * L + tt] = off;
+    }
     if (tid == 0) {
         for (int s = 0; s < TCB_NSTAGE; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(&a_ready, TC_CWARPS * 32);
+        for (int i = 0; i < 4; i++) mbar_init(&a_ready[i], TC_CWARPS * 32);
         mbar_init(&acc_full, 1);
         fence_mbar_init();
     }
@@ -617,15 +629,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    // TMEM columns: [0,128) / [128,256): dx of even / odd steps (ping-pong, so step s's dx can be scattered while the
-    // tensor core already works on step s+1), [256,384): dh_{t-1}, [384,512): running dc
+    // TMEM columns: [0,128): dx of the step, [128,256) / [256,384): dh_{t-1} written by even / odd steps (ping-pong: the
+    // tensor core already accumulates this step's dh while the gate-gradient loop still reads the previous one),
+    // [384,512): running dc.
+    // Pipelining inside a step: the gate-gradient loop produces da in four quarters (iteration i of every warp fills
+    // K-chunks {i, 4+i, 8+i, 12+i} of the operand tile); the MMA warp starts on a quarter as soon as it is complete, so
+    // the weight streaming and the tensor-core time hide under the remaining gate-gradient work.
     const uint32_t taddr = s_taddr;
 
     if (warp == TC_CWARPS + 1) {
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
             for (int s = 0; s < L; s++)
-                for (int c = 0; c < TCB_NCHUNK; c++) {
+                for (int j = 0; j < TCB_NCHUNK; j++) {
+                    const int c = 4 * (j & 3) + (j >> 2);   // quarter-major order, the order the MMA warp consumes them in
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_arrive_expect_tx(&full_bar[stage], TCB_CHUNK_BYTES);
                     bulk_g2s(Ws + stage * TCB_CHUNK_BYTES, a.WhT + (size_t)c * TCB_CHUNK_BYTES, TCB_CHUNK_BYTES, &full_bar[stage]);
@@ -637,11 +654,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
             uint32_t stage = 0, phase = 0;
             for (int s = 0; s < L; s++) {
                 const int t = L - 1 - s;
-                mbar_wait(&a_ready, s & 1);
-                tc_fence_after();
                 constexpr uint32_t idesc = make_idesc_f16(128, 128);
-                const uint32_t dx_col = (uint32_t)(s & 1) * 128;
-                for (int c = 0; c < TCB_NCHUNK; c++) {
+                const uint32_t dh_col = 128u + (uint32_t)(s & 1) * 128u;
+                for (int j = 0; j < TCB_NCHUNK; j++) {
+                    const int c = 4 * (j & 3) + (j >> 2);
+                    if ((j & 3) == 0) { mbar_wait(&a_ready[j >> 2], s & 1); tc_fence_after(); }
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t wbase = smem_u32(Ws + stage * TCB_CHUNK_BYTES);
@@ -650,10 +667,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
                         const uint64_t ad = make_smem_desc(smem_u32(As) + (uint32_t)(c * (TCB_KC / 8) + ks * 2) * 128, 128, (TC_G4 / 8) * 128);
                         // rows 0..127 of W' give dx, rows 128..255 (16 row groups further) give dh_{t-1} (unused at t = 0)
                         const uint64_t bd_x = make_smem_desc(wbase + (uint32_t)ks * 256, 128, (TCB_KC / 8) * 128);
-                        mma_f16(taddr + dx_col, ad, bd_x, idesc, (c > 0) || (ks > 0));
+                        mma_f16(taddr, ad, bd_x, idesc, (j > 0) || (ks > 0));
                         if (t > 0) {
                             const uint64_t bd_h = make_smem_desc(wbase + 16u * ((TCB_KC / 8) * 128) + (uint32_t)ks * 256, 128, (TCB_KC / 8) * 128);
-                            mma_f16(taddr + 256, ad, bd_h, idesc, (c > 0) || (ks > 0));
+                            mma_f16(taddr + dh_col, ad, bd_h, idesc, (j > 0) || (ks > 0));
                         }
                     }
                     mma_commit(&empty_bar[stage]);
@@ -671,24 +688,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
         const uint32_t lane_base = taddr + ((uint32_t)(lq * 32) << 16);
         const float scale = a.gscale[0], inv_scale = a.gscale[1];
         const uint32_t dkey = dropout_key(a.drop_seed, 0);
-        // dx of step `ss` (time tt = L-1-ss) -> dT with the forward's dropout mask; reads the dx region of that step
+        // dx of step `ss` (time tt = L-1-ss) -> dT with the forward's dropout mask
         auto scatter_dx = [&](int ss) {
             const int tt = L - 1 - ss;
-            const uint32_t dx_col = (uint32_t)(ss & 1) * 128;
             // tcgen05.ld is warp-collective (.sync.aligned): every lane loads, only valid rows scatter
-            const int64_t e = valid ? p * L + tt : 0;
-            float *dst = valid ? a.dT + ((int64_t)a.seq_node[e] * L + a.seq_type[e]) * TC_H : nullptr;
+            uint32_t v[32];
+            tmem_ld32(lane_base + cq * 32, v);   // dx region = columns [0,128)
+            tmem_ld_wait();
+            if (valid) {
+                const int64_t e = p * L + tt;
+                float *dst = a.dT + (int64_t)rowoff_s[r * L + tt] * TC_H + cq * 32;
 #pragma unroll
-            for (int cb = cq * 4; cb < cq * 4 + 4; cb++) {
-                uint32_t v[8];
-                tmem_ld8(lane_base + dx_col + cb * 8, v);
-                tmem_ld_wait();
-                if (valid) {
+                for (int c8 = 0; c8 < 4; c8++) {
                     float f[8];
 #pragma unroll
-                    for (int j = 0; j < 8; j++) f[j] = __uint_as_float(v[j]) * inv_scale;
+                    for (int j = 0; j < 8; j++) f[j] = __uint_as_float(v[c8 * 8 + j]) * inv_scale;
                     if (a.drop_thr) {
-                        const uint64_t pair = ((uint64_t)e * TC_H + cb * 8) >> 1;
+                        const uint64_t pair = ((uint64_t)e * TC_H + cq * 32 + c8 * 8) >> 1;
 #pragma unroll
                         for (int q = 0; q < 4; q++) {
                             const uint32_t h = dropout_hash_pair_k(dkey, pair + q);
@@ -696,11 +712,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
                             f[2 * q + 1] = (h >> 16) < a.drop_thr ? 0.f : f[2 * q + 1] * a.drop_scale;
                         }
                     }
-                    atomicAdd(reinterpret_cast<float4 *>(dst + cb * 8), make_float4(f[0], f[1], f[2], f[3]));
-                    atomicAdd(reinterpret_cast<float4 *>(dst + cb * 8 + 4), make_float4(f[4], f[5], f[6], f[7]));
+                    if (a.drop_thr) {   // most elements are dropped (p = 0.7 upstream): only touch the pairs that carry anything
+#pragma unroll
+                        for (int q = 0; q < 4; q++)
+                            if (f[2 * q] != 0.f || f[2 * q + 1] != 0.f)
+                                atomicAdd(reinterpret_cast<float2 *>(dst + c8 * 8 + 2 * q), make_float2(f[2 * q], f[2 * q + 1]));
+                    } else {
+                        atomicAdd(reinterpret_cast<float4 *>(dst + c8 * 8), make_float4(f[0], f[1], f[2], f[3]));
+                        atomicAdd(reinterpret_cast<float4 *>(dst + c8 * 8 + 4), make_float4(f[4], f[5], f[6], f[7]));
+                    }
                 }
-                __syncwarp();
             }
+            __syncwarp();
         };
         const bool tr = a.trace && blockIdx.x == a.trace_block && tid == 0;
         for (int s = 0; s < L; s++) {
@@ -710,7 +733,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
             unsigned char *da_blk = a.da_img + blk * DA_BLOCK_BYTES;
             const __half *act = a.acts + ((int64_t)tile * L + t) * ACT_BLOCK_HALFS + r * 8;
             const __half *actp = act - ACT_BLOCK_HALFS;  // step t-1 (only read when t > 0)
-            // ---- gate gradients ----
+            // ---- pull the next step's activations towards L2 (a whole step ahead) ----
+            if (valid && t > 0) {
+#pragma unroll
+                for (int cb = cq * 4; cb < cq * 4 + 4; cb++) {
+#pragma unroll
+                    for (int q = 0; q < 5; q++) prefetch_l2(actp + q * 16384 + cb * 1024);
+                    if (t > 1) prefetch_l2(actp - ACT_BLOCK_HALFS + 4 * 16384 + cb * 1024);
+                }
+            }
+            // ---- the previous step's dx (complete since acc_full) -> dT, before this step's MMAs overwrite the region ----
+            if (s > 0) scatter_dx(s - 1);
+            if (tr) a.trace[s * 8 + 1] = clock64();
+            const uint32_t dh_rd = 128u + (uint32_t)((s - 1) & 1) * 128u;
+            // ---- gate gradients, one K-quarter of the operand tile per iteration ----
 #pragma unroll 1
             for (int cb = cq * 4; cb < cq * 4 + 4; cb++) {
                 const int u0 = cb * 8;
@@ -726,7 +762,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
                     }
                 } else {
                     uint32_t v0[8], v1[8];
-                    tmem_ld8(lane_base + 256 + u0, v0);
+                    tmem_ld8(lane_base + dh_rd + u0, v0);
                     tmem_ld8(lane_base + 384 + u0, v1);
                     tmem_ld_wait();
 #pragma unroll
@@ -765,24 +801,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
                     *reinterpret_cast<uint4 *>(As + canon_off(r, cb * 32 + q * 8, TC_G4)) = pk;          // dgrad operand
                     *reinterpret_cast<uint4 *>(da_blk + (size_t)(cb * 4 + q) * 2048 + r * 16) = pk;       // wgrad operand image
                 }
+                // this quarter of the operand tile is written: let the tensor core start on it
+                fence_proxy_async();
+                tc_fence_before();
+                mbar_arrive(&a_ready[cb - cq * 4]);
             }
             tmem_st_wait();
-            fence_proxy_async();
-            tc_fence_before();
-            mbar_arrive(&a_ready);
-            if (tr) a.trace[s * 8 + 1] = clock64();
-            // ---- while the tensor core works: pull the next step's activations towards L2 ... ----
-            if (valid && t > 0) {
-#pragma unroll
-                for (int cb = cq * 4; cb < cq * 4 + 4; cb++) {
-#pragma unroll
-                    for (int q = 0; q < 5; q++) prefetch_l2(actp + q * 16384 + cb * 1024);
-                    if (t > 1) prefetch_l2(actp - ACT_BLOCK_HALFS + 4 * 16384 + cb * 1024);
-                }
-            }
             if (tr) a.trace[s * 8 + 2] = clock64();
-            // ---- while the tensor core computes [dx | dh_{t-1}] = da . W' for this step: scatter the PREVIOUS step's dx ----
-            if (s > 0) scatter_dx(s - 1);
             mbar_wait(&acc_full, s & 1);
             tc_fence_after();
             if (tr) a.trace[s * 8 + 3] = clock64();
@@ -797,8 +822,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
 
 // ---------------------------------------------------------------------------
 // weight gradients: dWp[k][col] (+)= sum over blocks  XH_blk^T . dA_blk
-// CTA = one 128 (k) x 256 (col) output tile (blockIdx.y) x one split of the
-// block list (blockIdx.x); operands are bulk-copied images (MN-major UMMA).
+// CTA = one 128 (k) x 256 (col) output tile x one split of the block list;
+// operands are bulk-copied images (MN-major UMMA).  The four tiles of a split
+// form a thread-block cluster (1 x 4): tile (mt, nt) needs XH half mt and dA
+// half nt, so each CTA fetches ONE quarter of the block (16 KB of XH, 32 KB of
+// dA) and multicasts it to the two CTAs that use it -- every byte of the
+// images is read from HBM/L2 once per block instead of twice.
 // ---------------------------------------------------------------------------
 struct WgradTcArgs {
     const unsigned char *xh_img, *da_img;
@@ -819,10 +848,13 @@ __global__ void __launch_bounds__(192, 1) k_wgrad_tc(WgradTcArgs a)
     __shared__ uint64_t full_bar[2], empty_bar[2], acc_full;
     __shared__ uint32_t s_taddr;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int mt = blockIdx.y >> 1, nt = blockIdx.y & 1;
-    const bool do_bias = mt == 0;   // the mt = 0 CTAs also produce the column sums of their 256 da columns
+    const uint32_t rank = cluster_ctarank();          // == blockIdx.y (cluster = the 4 tiles of one split)
+    const int mt = rank >> 1, nt = rank & 1;
+    // who shares what: XH half mt is used by ranks {2mt, 2mt+1}; dA half nt by ranks {nt, 2+nt}
+    const uint16_t xh_mask = (uint16_t)(3u << (2 * mt)), da_mask = (uint16_t)(5u << nt);
+    const uint16_t peers = (uint16_t)(xh_mask | da_mask);   // self + the two CTAs whose copies land in my stages
     if (tid == 0) {
-        for (int s = 0; s < 2; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 3); }
         mbar_init(&acc_full, 1);
         fence_mbar_init();
     }
@@ -836,25 +868,29 @@ __global__ void __launch_bounds__(192, 1) k_wgrad_tc(WgradTcArgs a)
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();   // every CTA's mbarriers are initialised before any peer's copy or commit can reach them
     tc_fence_after();
-    const uint32_t taddr = s_taddr;   // cols [0,256): dWp tile, cols [256,512): bias rows (lane 0 = column sums)
+    const uint32_t taddr = s_taddr;   // cols [0,256): dWp tile, cols [256,384): bias rows (lane 0 = column sums of 128 da columns)
     const int64_t first = blockIdx.x, step = gridDim.x;
     if (warp == 5) {
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
             for (int64_t b = first; b < a.nblocks; b += step) {
                 unsigned char *dst = base + stage * WG_STAGE_BYTES;
-                mbar_wait(&empty_bar[stage], phase ^ 1);
+                mbar_wait(&empty_bar[stage], phase ^ 1);   // this stage is free in all three CTAs my copies land in
                 mbar_arrive_expect_tx(&full_bar[stage], WG_STAGE_BYTES);
-                bulk_g2s(dst, a.xh_img + b * XH_BLOCK_BYTES + (size_t)mt * 32768, 32768, &full_bar[stage]);
-                bulk_g2s(dst + 32768, a.da_img + b * DA_BLOCK_BYTES + (size_t)nt * 65536, 32768, &full_bar[stage]);
-                bulk_g2s(dst + 65536, a.da_img + b * DA_BLOCK_BYTES + (size_t)nt * 65536 + 32768, 32768, &full_bar[stage]);
+                // my quarter of XH half mt (piece nt) -> both CTAs of row mt
+                bulk_g2s_mc(dst + nt * 16384, a.xh_img + b * XH_BLOCK_BYTES + (size_t)mt * 32768 + (size_t)nt * 16384, 16384,
+                            &full_bar[stage], xh_mask);
+                // my quarter of dA half nt (piece mt) -> both CTAs of column nt
+                bulk_g2s_mc(dst + 32768 + mt * 32768, a.da_img + b * DA_BLOCK_BYTES + (size_t)nt * 65536 + (size_t)mt * 32768, 32768,
+                            &full_bar[stage], da_mask);
                 if (++stage == 2) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 4) {
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_f16_mn(128, 256);
+            constexpr uint32_t idesc = make_idesc_f16_mn(128, 256), idesc_b = make_idesc_f16_mn(128, 128);
             uint32_t stage = 0, phase = 0;
             bool first_blk = true;
             for (int64_t b = first; b < a.nblocks; b += step) {
@@ -866,10 +902,12 @@ __global__ void __launch_bounds__(192, 1) k_wgrad_tc(WgradTcArgs a)
                     const uint64_t ad = make_smem_desc(abase + ks * 256, 128, 2048);
                     const uint64_t bd = make_smem_desc(bbase + ks * 256, 128, 2048);
                     mma_f16(taddr, ad, bd, idesc, !first_blk || ks > 0);
-                    if (do_bias) mma_f16(taddr + 256, make_smem_desc(obase + ks * 256, 128, 2048), bd, idesc, !first_blk || ks > 0);
+                    // bias: ones . dA over this CTA's share of the columns (mt picks which 128 of the 256)
+                    mma_f16(taddr + 256, make_smem_desc(obase + ks * 256, 128, 2048),
+                            make_smem_desc(bbase + mt * 32768 + ks * 256, 128, 2048), idesc_b, !first_blk || ks > 0);
                 }
                 first_blk = false;
-                mma_commit(&empty_bar[stage]);
+                mma_commit_mc(&empty_bar[stage], peers);
                 if (++stage == 2) { stage = 0; phase ^= 1; }
             }
             mma_commit(&acc_full);
@@ -890,20 +928,21 @@ __global__ void __launch_bounds__(192, 1) k_wgrad_tc(WgradTcArgs a)
                               make_float4(__uint_as_float(v[j]) * inv_scale, __uint_as_float(v[j + 1]) * inv_scale,
                                           __uint_as_float(v[j + 2]) * inv_scale, __uint_as_float(v[j + 3]) * inv_scale));
             }
-            if (do_bias && warp == 0) {   // TMEM lane 0 of the second accumulator = sum over rows of da[:, col]
-                for (int c0 = 0; c0 < 256; c0 += 32) {
+            if (warp == 0) {   // TMEM lane 0 of the second accumulator = sum over rows of da[:, col]
+                for (int c0 = 0; c0 < 128; c0 += 32) {
                     uint32_t v[32];
                     tmem_ld32(taddr + 256 + (uint32_t)c0, v);
                     tmem_ld_wait();
                     if (lane == 0)
 #pragma unroll
-                        for (int j = 0; j < 32; j++) atomicAdd(a.dbp + nt * 256 + c0 + j, __uint_as_float(v[j]) * inv_scale);
+                        for (int j = 0; j < 32; j++) atomicAdd(a.dbp + nt * 256 + mt * 128 + c0 + j, __uint_as_float(v[j]) * inv_scale);
                 }
             }
         }
     }
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();   // no CTA leaves while a peer's multicast copy or commit may still target it
     if (warp == 4) { __syncwarp(); tmem_dealloc<512>(taddr); }
 }
 
@@ -939,10 +978,11 @@ int pagg_tc_backward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_p
         a.trace = d_trace;
         a.trace_block = atoi(trace_env);
     }
-    PN_CUDA(cudaFuncSetAttribute(k_lstm_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TCB_SMEM));
+    const int bwd_smem = TCB_SMEM_FIXED + 128 * c.L * (int)sizeof(int32_t);
+    PN_CUDA(cudaFuncSetAttribute(k_lstm_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TCB_SMEM_FIXED + 128 * TC_MAX_L * (int)sizeof(int32_t)));
     {
         ProfScope prof("lstm_bwd", st);
-        k_lstm_bwd_tc<<<(unsigned)ntiles, TC_THREADS, TCB_SMEM, st>>>(a);
+        k_lstm_bwd_tc<<<(unsigned)ntiles, TC_THREADS, bwd_smem, st>>>(a);
     }
     PN_LAUNCH_CHECK();
     if (d_trace) {  // debug only
@@ -952,7 +992,7 @@ int pagg_tc_backward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_p
         cudaFree(d_trace);
         const long long t00 = h[0];
         for (int q = 0; q < c.L && q < 64; q++)
-            fprintf(stderr, "[trace bwd cta %d] s=%d  begin %lld | da staged+arrive %lld | regather/prefetch done %lld | acc_full seen %lld | dx scattered %lld\n",
+            fprintf(stderr, "[trace bwd cta %d] s=%d  begin %lld | prev dx scattered %lld | 4 da quarters arrived %lld | acc_full seen %lld | %lld\n",
                     a.trace_block, q, h[q * 8 + 0] - t00, h[q * 8 + 1] - t00, h[q * 8 + 2] - t00, h[q * 8 + 3] - t00, h[q * 8 + 4] - t00);
     }
     PN_CUDA(cudaMemsetAsync(w.dWp, 0, sizeof(float) * TC_K2 * TC_G4, st));
@@ -961,8 +1001,24 @@ int pagg_tc_backward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_p
     PN_CUDA(cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
     {
         ProfScope prof("wgrad", st);
-        const unsigned nsplit = (unsigned)std::max<int64_t>(1, std::min<int64_t>(37, nblocks));
-        k_wgrad_tc<<<dim3(nsplit, 4), 192, WG_SMEM, st>>>(wa);
+        // one cluster of 4 CTAs per split; as many splits as clusters fit on the device at once (a second wave would double the time)
+        cudaLaunchConfig_t lc = {};
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 4; attr[0].val.clusterDim.z = 1;
+        lc.gridDim = dim3(1, 4); lc.blockDim = dim3(192); lc.dynamicSmemBytes = WG_SMEM; lc.stream = st;
+        lc.attrs = attr; lc.numAttrs = 1;
+        static int max_clusters = 0;
+        if (max_clusters == 0) {
+            int mc = 0;
+            lc.gridDim = dim3(64, 4);
+            PN_CUDA(cudaOccupancyMaxActiveClusters(&mc, k_wgrad_tc, &lc));
+            max_clusters = std::max(1, std::min(mc, 64));
+            if (getenv("PN_TRACE_BWD")) fprintf(stderr, "[wgrad] max active clusters of 4 = %d\n", mc);
+        }
+        const unsigned nsplit = (unsigned)std::max<int64_t>(1, std::min<int64_t>(max_clusters, nblocks));
+        lc.gridDim = dim3(nsplit, 4);
+        PN_CUDA(cudaLaunchKernelEx(&lc, k_wgrad_tc, wa));
     }
     PN_LAUNCH_CHECK();
     return PN_OK;
