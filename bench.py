@@ -285,7 +285,7 @@ def main():
     torch.manual_seed(0)
     cls = pb.PathNet_homo if w["variant"] == "homo" else pb.PathNet
     model = cls(w["F"], H, w["C"], L_, dropout=w["dropout"], math_mode=args.math).to(dev).train()
-    opt = torch.optim.Adam(model.parameters(), lr=0.005, weight_decay=0.0005)
+    opt = torch.optim.Adam(model.parameters(), lr=0.005, weight_decay=0.0005, fused=True)   # same update as PathNet_run.py:295, one kernel
     reducer = FlatGradAllReduce(model.parameters()) if world > 1 else None
     lossf = torch.nn.CrossEntropyLoss(reduction="sum")
     S_global = S * world
@@ -296,7 +296,7 @@ def main():
     def step(neis, ltype, read_loss):
         out = model(Xd, neis, nw, L_, mask, ltype, None)
         loss = lossf(out, yd) / S_global
-        opt.zero_grad(set_to_none=False)
+        opt.zero_grad()   # as PathNet_run.py:350 (grads set to None: autograd assigns instead of accumulating)
         loss.backward()
         if reducer is not None:
             reducer()

@@ -799,7 +799,9 @@ extern "C" int pn_pagg_backward(const pn_pagg_cfg *cfg, const pn_pagg_params *pr
     }
     const bool tcm = c.math_mode == PN_MATH_TC;
     {
-        int splitk = (int)std::max<int64_t>(1, std::min<int64_t>(64, N / 1024));
+        // split the reduction over N so the (L*H/128) x (H/128) output tiles fill one wave of the 148 SMs
+        int splitk = (int)std::max<int64_t>(1, std::min<int64_t>(tcm ? 148 / std::max<int64_t>(1, ceil_div(L * H, 128) * ceil_div(H, 128)) : 64, N / 256));
+        if (!tcm) splitk = (int)std::max<int64_t>(1, std::min<int64_t>(64, N / 1024));
         if (splitk > 1) ZERO(g.nets_w, L * H * H);
         // dWn[m][i] = sum_n dT[n][m] Z[n][i]: both operands have the reduction index as their row (MN-major);
         // raw gradients go through bf16 (fp16 would underflow), fp32 accumulate
@@ -818,7 +820,8 @@ extern "C" int pn_pagg_backward(const pn_pagg_cfg *cfg, const pn_pagg_params *pr
         PN_LAUNCH_CHECK();
     }
     {
-        int splitk = (int)std::max<int64_t>(1, std::min<int64_t>(64, N / 1024));
+        int splitk = (int)std::max<int64_t>(1, std::min<int64_t>(tcm ? 148 / std::max<int64_t>(1, ceil_div(H, 128) * ceil_div(F, 128)) : 64, N / 256));
+        if (!tcm) splitk = (int)std::max<int64_t>(1, std::min<int64_t>(64, N / 1024));
         if (splitk > 1) ZERO(g.fc0_w, H * F);
         rc = tcm ? launch_gemm_tc(st, w.dZ, H, X, F, g.fc0_w, F, H, F, N, nullptr, false, true, true, true, false, splitk)
                  : launch_gemm(st, w.dZ, 1, H, X, F, 1, g.fc0_w, F, H, F, N, nullptr, false, false, splitk);  // dW0 = dZ^T X
