@@ -356,6 +356,11 @@ def main():
         ms, n = prof[name]
         if n:
             kern[name] = {"ms": ms / n, "tflops": fl / (ms / n * 1e-3) / 1e12}
+            tr = ncu_traffic(name) if args.workload == "pubmed" and args.math == "tc" else None
+            if tr:   # second roof: the kernel's DRAM traffic (committed ncu capture of this workload) over the live duration
+                kern[name]["dram_gbs"] = tr / (ms / n * 1e-3) / 1e9
+                kern[name]["hbm_frac"] = kern[name]["dram_gbs"] / peaks["hbm"]
+            kern[name]["tensor_frac"] = kern[name]["tflops"] / (peaks["bf16_sustained"] or peaks["bf16"])
     dom = max(kern, key=lambda k: kern[k]["ms"]) if kern else None
     peak = peaks["bf16_sustained"] or peaks["bf16"]
     roofline = None
@@ -367,7 +372,8 @@ def main():
                     "math_mode": args.math, "kernels": kern,
                     "note": "algorithmic FLOPs = 16*L*H^2 per path per LSTM GEMM pass (SURVEY 8d): forward gates, "
                             "backward dgrad, backward wgrad; math_mode tc = tcgen05 fp16 operands / fp32 accumulate, "
-                            "fp32 = CUDA-core FMA (strict parity mode)"}
+                            "fp32 = CUDA-core FMA (strict parity mode).  kernels[*].hbm_frac = the same kernels against "
+                            "the HBM roof (saved-activation / operand-image traffic): the LSTM kernels sit between the two roofs"}
 
     # ---- MERW walks/sec (labels included), same graph ----
     E = MERW_EPOCHS_PER_STEP

@@ -793,9 +793,10 @@ extern "C" int pn_pagg_backward(const pn_pagg_cfg *cfg, const pn_pagg_params *pr
     k_unpack_lstm_grads<<<(unsigned)ceil_div(4 * H * H, 256), 256, 0, st>>>((int)H, w.dWp, w.dbp, g.w_ih, g.w_hh, g.b_ih, g.b_hh);
     PN_LAUNCH_CHECK();
     // ---- table projection: T = act(Z Wn^T + bn) ----
+    // homo: ReLU backward fused with the bias gradient (column sums) of the table projection
     if (homo) {
-        k_relu_mask<<<(unsigned)ceil_div(N * L * H, 256), 256, 0, st>>>(w.dT, w.T, N * L * H);
-        PN_LAUNCH_CHECK();
+        rc = launch_relu_mask_colsum(st, w.dT, w.T, N, L * H, g.nets_b);
+        if (rc) return rc;
     }
     const bool tcm = c.math_mode == PN_MATH_TC;
     {
@@ -809,15 +810,17 @@ extern "C" int pn_pagg_backward(const pn_pagg_cfg *cfg, const pn_pagg_params *pr
                  : launch_gemm(st, w.dT, 1, L * H, w.Z, H, 1, g.nets_w, H, L * H, H, N, nullptr, false, false, splitk);
         if (rc) return rc;
     }
-    rc = launch_colsum(st, w.dT, N, L * H, L * H, g.nets_b);
-    if (rc) return rc;
+    if (!homo) {
+        rc = launch_colsum(st, w.dT, N, L * H, L * H, g.nets_b);
+        if (rc) return rc;
+    }
     rc = tcm ? launch_gemm_tc(st, w.dT, L * H, prm->nets_w, H, w.dZ, H, N, H, L * H, nullptr, false, false, true, true, true, 1)
              : launch_gemm(st, w.dT, L * H, 1, prm->nets_w, H, 1, w.dZ, H, N, H, L * H, nullptr, false, true);  // dZ += dT Wn
     if (rc) return rc;
     // ---- fc0: Z = act(X W0^T + b0) ----
     if (homo) {
-        k_relu_mask<<<(unsigned)ceil_div(N * H, 256), 256, 0, st>>>(w.dZ, w.Z, N * H);
-        PN_LAUNCH_CHECK();
+        rc = launch_relu_mask_colsum(st, w.dZ, w.Z, N, H, g.fc0_b);
+        if (rc) return rc;
     }
     {
         int splitk = (int)std::max<int64_t>(1, std::min<int64_t>(tcm ? 148 / std::max<int64_t>(1, ceil_div(H, 128) * ceil_div(F, 128)) : 64, N / 256));
@@ -827,7 +830,7 @@ extern "C" int pn_pagg_backward(const pn_pagg_cfg *cfg, const pn_pagg_params *pr
                  : launch_gemm(st, w.dZ, 1, H, X, F, 1, g.fc0_w, F, H, F, N, nullptr, false, false, splitk);  // dW0 = dZ^T X
         if (rc) return rc;
     }
-    rc = launch_colsum(st, w.dZ, N, H, H, g.fc0_b);
+    if (!homo) rc = launch_colsum(st, w.dZ, N, H, H, g.fc0_b);
 #undef ZERO
     return rc;
 }

@@ -192,11 +192,44 @@ inline int launch_colsum(cudaStream_t st, const float *A, int64_t M, int64_t N, 
     return PN_OK;
 }
 
-// g[i] = (y[i] > 0) ? g[i] : 0
-static __global__ void k_relu_mask(float *__restrict__ g, const float *__restrict__ y, int64_t n)
+// ReLU backward and the bias gradient in one pass over a dense [M][N] gradient: g = (y > 0) ? g : 0, out[n] = sum_m g[m][n].
+// (The two used to be separate sweeps of the same 40 MB table gradient.)
+static __global__ void k_relu_mask_colsum(float *__restrict__ g, const float *__restrict__ y, int64_t M, int64_t N,
+                                          float *__restrict__ out)
 {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n && !(y[i] > 0.f)) g[i] = 0.f;
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const int64_t rows_per = (M + gridDim.y - 1) / gridDim.y;
+    const int64_t m0 = (int64_t)blockIdx.y * rows_per, m1 = min(M, m0 + rows_per);
+    float s = 0.f;
+    // batches of 8 rows: all 16 loads are issued before the first (possibly aliasing, as far as the compiler knows) store
+    for (int64_t mb = m0; mb < m1; mb += 8) {
+        float v[8], a[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const bool in = mb + i < m1;
+            v[i] = in ? g[(mb + i) * N + n] : 0.f;
+            a[i] = in ? y[(mb + i) * N + n] : 1.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            if (a[i] > 0.f) s += v[i];
+            else g[(mb + i) * N + n] = 0.f;   // never taken for the padding entries (a = 1)
+        }
+    }
+    atomicAdd(out + n, s);
+}
+
+inline int launch_relu_mask_colsum(cudaStream_t st, float *g, const float *y, int64_t M, int64_t N, float *out)
+{
+    if (N <= 0) return PN_OK;
+    PN_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)N, st));
+    if (M <= 0) return PN_OK;
+    const int64_t yb = std::max<int64_t>(1, std::min<int64_t>(2048, M / 64));
+    dim3 grid((unsigned)ceil_div(N, 128), (unsigned)yb);
+    k_relu_mask_colsum<<<grid, 128, 0, st>>>(g, y, M, N, out);
+    PN_LAUNCH_CHECK();
+    return PN_OK;
 }
 
 }  // namespace pn

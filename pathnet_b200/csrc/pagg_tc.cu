@@ -153,26 +153,31 @@ __global__ void __launch_bounds__(128) k_gemm_tc(GemmTcArgs g)
     if (it >= 2) { const int b = it & 1; mbar_wait(&bar[b], phase[b]); }
     if (it >= 1) { const int b = (it - 1) & 1; mbar_wait(&bar[b], phase[b]); }
     tc_fence_after();
-    // epilogue: warp w owns TMEM lanes 32w..32w+31 = rows m0+32w+lane
-    const int64_t row = m0 + warp * 32 + lane;
+    // epilogue: warp w owns TMEM lanes 32w..32w+31 = rows m0+32w..+31.  tcgen05.ld hands each lane one ROW; written out like
+    // that every store instruction would touch 32 different lines, so each 32 x 32 block is transposed through shared memory
+    // (the operand stages are idle: every MMA has committed) and leaves as whole 128-byte row segments.
     const bool atomic = gridDim.z > 1 || g.accumulate;
     if (kbeg < kend) {
+        float *stg = reinterpret_cast<float *>(smem_raw) + warp * (32 * 33);
         for (int c0 = 0; c0 < BN; c0 += 32) {
             uint32_t v[32];
             tmem_ld32(taddr + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
             tmem_ld_wait();
-            if (row < g.M) {
 #pragma unroll
-                for (int j = 0; j < 32; j++) {
-                    const int64_t n = n0 + c0 + j;
-                    if (n < g.N) {
-                        float x = __uint_as_float(v[j]);
-                        if (g.bias && blockIdx.z == 0) x += g.bias[n];
-                        if (atomic) atomicAdd(g.C + row * g.ldc + n, x);
-                        else g.C[row * g.ldc + n] = g.relu ? fmaxf(x, 0.f) : x;
-                    }
+            for (int j = 0; j < 32; j++) stg[lane * 33 + j] = __uint_as_float(v[j]);
+            __syncwarp();
+            const int64_t n = n0 + c0 + lane;
+            if (n < g.N) {
+                const float bn = (g.bias && blockIdx.z == 0) ? g.bias[n] : 0.f;
+                const int64_t rmax = min((int64_t)32, g.M - (m0 + warp * 32));
+                float *dst = g.C + (m0 + warp * 32) * g.ldc + n;
+                for (int rr = 0; rr < rmax; rr++) {
+                    const float x = stg[rr * 33 + lane] + bn;
+                    if (atomic) atomicAdd(dst + (int64_t)rr * g.ldc, x);
+                    else dst[(int64_t)rr * g.ldc] = g.relu ? fmaxf(x, 0.f) : x;
                 }
             }
+            __syncwarp();
         }
     }
     tc_fence_before();
@@ -180,6 +185,10 @@ __global__ void __launch_bounds__(128) k_gemm_tc(GemmTcArgs g)
     if (warp == 0) { __syncwarp(); tmem_dealloc<BN>(taddr); }
 }
 
+// (Measured and dropped: a kind::tf32 variant that cp.async-copies the fp32 operands straight into the UMMA layout -- no
+// conversion pass, 4 x 32 KB in flight per CTA.  Its 192 KB ring allows one CTA per SM; this kernel's 64 KB allows three,
+// which matters more for these short-K GEMMs: 75 us vs 44 us on the fc0 / table projections.  MN-major tf32 operands
+// also failed to validate with the layout that is correct for 16-bit types.)
 // a_mn / b_mn: operand given as [K][M] / [K][N]; bf16: 16-bit format of the operands;
 // splitk > 1 or accumulate: results are atomically added to C (no ReLU then).
 int launch_gemm_tc(cudaStream_t st, const float *A, int64_t lda, const float *B, int64_t ldb, float *C, int64_t ldc,
