@@ -137,6 +137,7 @@ class _PathNetBase(nn.Module):
         self.math_mode = kwargs.pop("math_mode", "auto")   # "auto" | "fp32" (strict parity) | "tc"
         kwargs.setdefault("aggr", "mean")
         super().__init__()
+        self._rows_cache = {}
         self.feature_length, self.hidden_size, self.out_size = feature_length, hidden_size, out_size
         # construction order = the reference's (:162-170), so a given torch seed
         # yields the same initial weights
@@ -151,16 +152,31 @@ class _PathNetBase(nn.Module):
         # nn.LSTM would otherwise try cudnn weight flattening on .to(device); harmless
         return super()._apply(fn, *a, **k)
 
-    def forward(self, X, neis, num_w, walk_len, indices, layer_type, indxx=None):
-        dev = X.device
-        if dev.type != "cuda":
-            raise RuntimeError("pathnet_b200 PAGG runs on CUDA only (no CPU fallback); X is on %s" % dev)
+    def _rows_of(self, indices, dev):
+        """Row numbers selected by the node mask `indices` (int32, on dev).  torch.nonzero synchronises with the device,
+        and training passes the same mask tensor every step (PathNet_run.py:345-347), so the result is kept per mask
+        TENSOR OBJECT (held alive, so its identity cannot be recycled) for as long as its in-place version counter is
+        unchanged.  numpy masks are not cached (their mutations cannot be seen)."""
         if torch.is_tensor(indices):
+            ent = self._rows_cache.get(id(indices))
+            if ent is not None and ent[0] is indices and ent[1] == indices._version and ent[2] == str(dev):
+                return ent[3]
             mask = indices.to(dev)
         else:
             mask = torch.as_tensor(np.asarray(indices), device=dev)
         rows = (torch.nonzero(mask.reshape(-1), as_tuple=False).reshape(-1) if mask.dtype == torch.bool
                 else torch.nonzero(mask.reshape(-1) != 0, as_tuple=False).reshape(-1)).to(torch.int32)
+        if torch.is_tensor(indices):
+            if len(self._rows_cache) >= 8:   # train / val / test masks and a few more; never grows without bound
+                self._rows_cache.pop(next(iter(self._rows_cache)))
+            self._rows_cache[id(indices)] = (indices, indices._version, str(dev), rows)
+        return rows
+
+    def forward(self, X, neis, num_w, walk_len, indices, layer_type, indxx=None):
+        dev = X.device
+        if dev.type != "cuda":
+            raise RuntimeError("pathnet_b200 PAGG runs on CUDA only (no CPU fallback); X is on %s" % dev)
+        rows = self._rows_of(indices, dev)
         S = rows.numel()
         neis = torch.as_tensor(neis).to(dev, dtype=torch.int64)            # reference: neis.to(device) (:176,:244)
         layer_type = torch.as_tensor(layer_type).to(dev, dtype=torch.int64)  # (:184,:248)

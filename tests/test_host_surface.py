@@ -76,3 +76,23 @@ def test_cli_argument_errors_mirror_reference(capsys):
     assert cli.main(["gen_merw", "cornell", "40"]) == 0           # gen_merw.cpp:128-132
     assert "ERROR: Incorrect number of parameters." in capsys.readouterr().err
     assert cli.main(["nonsense"]) == 2
+
+
+def test_mask_rows_cache_follows_in_place_changes():
+    """PathNet._rows_of keeps nonzero(mask) per mask tensor object and drops it when the tensor is modified in place."""
+    import torch
+    from pathnet_b200.pagg import PathNet_homo
+    m = PathNet_homo(8, 16, 3, 4)
+    mask = torch.tensor([True, False, True, True])
+    r1 = m._rows_of(mask, torch.device("cpu"))
+    assert r1.dtype == torch.int32 and r1.tolist() == [0, 2, 3]
+    assert m._rows_of(mask, torch.device("cpu")) is r1            # same object, same version: reused
+    mask[1] = True                                                 # in-place edit bumps the version counter
+    assert m._rows_of(mask, torch.device("cpu")).tolist() == [0, 1, 2, 3]
+    other = torch.tensor([False, True, False, False])              # a different tensor never hits another's entry
+    assert m._rows_of(other, torch.device("cpu")).tolist() == [1]
+    import numpy as np
+    assert m._rows_of(np.array([0, 1, 1, 0]), torch.device("cpu")).tolist() == [1, 2]
+    for _ in range(20):                                            # bounded
+        m._rows_of(torch.tensor([True]), torch.device("cpu"))
+    assert len(m._rows_cache) <= 8
