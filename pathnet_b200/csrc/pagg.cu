@@ -567,6 +567,160 @@ __global__ void __launch_bounds__(256) k_pool_bwd(PoolArgs a)
 }
 
 // ---------------------------------------------------------------------------
+// H = 128 versions of the two pooling kernels: a lane owns 4 CONSECUTIVE hidden units, so every row of hfin / T / Z /
+// dhfin moves as one 16-byte access per lane (512 B per warp instruction) instead of four 4-byte ones.  Same math.
+// The partner vector is looked up once per run of equal partner rows (homo: the row's own step-0 entry for all its paths).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float dot4(const float4 &a, const float4 &b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+__device__ __forceinline__ float4 ld4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+
+__global__ void __launch_bounds__(256) k_pool_fwd128(PoolArgs a)
+{
+    constexpr int H = 128;
+    const int lane = threadIdx.x & 31;
+    const int64_t s = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (s >= a.S) return;
+    const int nw = a.nw;
+    const float bias = a.attw_b[0];
+    const float4 wh = ld4(a.attw_w + 4 * lane), wp = ld4(a.attw_w + H + 4 * lane);
+    float mx = -INFINITY;
+    const float *pv_last = nullptr;
+    float pd_last = 0.f;
+#pragma unroll 4
+    for (int w = 0; w < nw; w++) {
+        const int64_t p = s * nw + w;
+        const float4 h4 = ld4(a.hfin + p * H + 4 * lane);
+        const float *pv = partner_vec(a, p);
+        if (pv != pv_last) { pd_last = dot4(wp, ld4(pv + 4 * lane)); pv_last = pv; }
+        const float d = warp_sum(dot4(wh, h4) + pd_last) + bias;
+        if (lane == 0) a.score[p] = d;
+        mx = fmaxf(mx, d > 0.f ? d : 0.01f * d);
+    }
+    __syncwarp();
+    float denom = 0.f;
+    if (a.variant == PN_VARIANT_HETERO) {
+        for (int w = lane; w < nw; w += 32) {
+            const float d = a.score[s * nw + w];
+            denom += expf((d > 0.f ? d : 0.01f * d) - mx);
+        }
+        denom = warp_sum(denom);
+    }
+    for (int w = lane; w < nw; w += 32) {
+        const int64_t p = s * nw + w;
+        const float d = a.score[p];
+        a.att[p] = a.variant == PN_VARIANT_HETERO ? expf((d > 0.f ? d : 0.01f * d) - mx) / denom : 1.f + d;
+    }
+    __syncwarp();
+    float4 pooled = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+    for (int w = 0; w < nw; w++) {
+        const float at = a.att[s * nw + w];
+        const float4 h4 = ld4(a.hfin + (s * nw + w) * H + 4 * lane);
+        pooled.x += at * h4.x; pooled.y += at * h4.y; pooled.z += at * h4.z; pooled.w += at * h4.w;
+    }
+    const float inv_nw = 1.f / (float)nw;
+    float po[4] = {pooled.x * inv_nw, pooled.y * inv_nw, pooled.z * inv_nw, pooled.w * inv_nw};
+    const float4 e4 = ld4(a.Z + (int64_t)a.rows[s] * H + 4 * lane);
+    float eg[4] = {e4.x, e4.y, e4.z, e4.w};
+    if (a.drop_thr) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int j = 4 * lane + q;
+            eg[q] = dropout_hash(a.drop_seed, 1, (uint64_t)s * 2 * H + j) < a.drop_thr ? 0.f : eg[q] * a.drop_scale;
+            po[q] = dropout_hash(a.drop_seed, 1, (uint64_t)s * 2 * H + H + j) < a.drop_thr ? 0.f : po[q] * a.drop_scale;
+        }
+    }
+    *reinterpret_cast<float4 *>(a.cat + s * 2 * H + 4 * lane) = make_float4(eg[0], eg[1], eg[2], eg[3]);
+    *reinterpret_cast<float4 *>(a.cat + s * 2 * H + H + 4 * lane) = make_float4(po[0], po[1], po[2], po[3]);
+}
+
+__global__ void __launch_bounds__(256) k_pool_bwd128(PoolArgs a)
+{
+    constexpr int H = 128;
+    extern __shared__ float s_dattw[];  // [2H+1]
+    const int nw = a.nw;
+    for (int i = threadIdx.x; i < 2 * H + 1; i += blockDim.x) s_dattw[i] = 0.f;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t s = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (s < a.S) {
+        const float inv_nw = 1.f / (float)nw;
+        const int64_t node = a.rows[s];
+        // gradient wrt the pooled half of the concat, dropout applied once
+        float4 g4 = ld4(a.dcat + s * 2 * H + H + 4 * lane);
+        float4 e4 = ld4(a.dcat + s * 2 * H + 4 * lane);   // and wrt the ego half
+        if (a.drop_thr) {
+            float *gp = &g4.x, *ep = &e4.x;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int j = 4 * lane + q;
+                gp[q] = dropout_hash(a.drop_seed, 1, (uint64_t)s * 2 * H + H + j) < a.drop_thr ? 0.f : gp[q] * a.drop_scale;
+                ep[q] = dropout_hash(a.drop_seed, 1, (uint64_t)s * 2 * H + j) < a.drop_thr ? 0.f : ep[q] * a.drop_scale;
+            }
+        }
+        atomicAdd(reinterpret_cast<float4 *>(a.dZ + node * H + 4 * lane), e4);
+        // da_w = inv_nw * <dpooled, h_w>, kept by lane (w mod 32) for w < 64, else recomputed
+        float da_keep0 = 0.f, da_keep1 = 0.f;
+        float dot_sum = 0.f;  // sum_v att_v * da_v (softmax backward), hetero only
+#pragma unroll 4
+        for (int w = 0; w < nw; w++) {
+            const int64_t p = s * nw + w;
+            const float d = warp_sum(dot4(g4, ld4(a.hfin + p * H + 4 * lane))) * inv_nw;
+            if ((w & 31) == lane) { if (w < 32) da_keep0 = d; else if (w < 64) da_keep1 = d; }
+            dot_sum += a.att[p] * d;
+        }
+        const float4 wh = ld4(a.attw_w + 4 * lane), wp = ld4(a.attw_w + H + 4 * lane);
+        float dbias = 0.f, amax = 0.f;
+        float4 dw_h = make_float4(0.f, 0.f, 0.f, 0.f), dw_p = dw_h, dp_acc = dw_h;
+        float *dp_cur = nullptr;
+        const float *pv_last = nullptr;
+        float4 pv4 = dw_h;
+#pragma unroll 2
+        for (int w = 0; w < nw; w++) {
+            const int64_t p = s * nw + w;
+            const float4 h4 = ld4(a.hfin + p * H + 4 * lane);
+            const float *pv = partner_vec(a, p);
+            if (pv != pv_last) { pv4 = ld4(pv + 4 * lane); pv_last = pv; }
+            float da;
+            if (w < 64) da = __shfl_sync(0xffffffffu, w < 32 ? da_keep0 : da_keep1, w & 31);
+            else da = warp_sum(dot4(g4, h4)) * inv_nw;
+            const float raw = a.score[p], att = a.att[p];
+            float dscore;
+            if (a.variant == PN_VARIANT_HETERO) dscore = att * (da - dot_sum) * (raw > 0.f ? 1.f : 0.01f);
+            else dscore = da;  // weight = 1 + score
+            dbias += dscore;
+            float *dpv = a.variant == PN_VARIANT_HOMO
+                             ? a.dT + ((int64_t)a.seq_node[p * a.L] * a.L + a.seq_type[p * a.L]) * H
+                             : a.dZ + (int64_t)a.partner[p] * H;
+            if (dpv != dp_cur) {
+                if (dp_cur) atomicAdd(reinterpret_cast<float4 *>(dp_cur + 4 * lane), dp_acc);
+                dp_acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                dp_cur = dpv;
+            }
+            const float k = inv_nw * att;
+            const float4 dh = make_float4(k * g4.x + dscore * wh.x, k * g4.y + dscore * wh.y, k * g4.z + dscore * wh.z, k * g4.w + dscore * wh.w);
+            *reinterpret_cast<float4 *>(a.dhfin + p * H + 4 * lane) = dh;
+            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(dh.x), fabsf(dh.y)), fmaxf(fabsf(dh.z), fabsf(dh.w))));
+            dw_h.x += dscore * h4.x; dw_h.y += dscore * h4.y; dw_h.z += dscore * h4.z; dw_h.w += dscore * h4.w;
+            dw_p.x += dscore * pv4.x; dw_p.y += dscore * pv4.y; dw_p.z += dscore * pv4.z; dw_p.w += dscore * pv4.w;
+            dp_acc.x += dscore * wp.x; dp_acc.y += dscore * wp.y; dp_acc.z += dscore * wp.z; dp_acc.w += dscore * wp.w;
+        }
+        if (dp_cur) atomicAdd(reinterpret_cast<float4 *>(dp_cur + 4 * lane), dp_acc);
+        atomicAdd(&s_dattw[4 * lane + 0], dw_h.x); atomicAdd(&s_dattw[4 * lane + 1], dw_h.y);
+        atomicAdd(&s_dattw[4 * lane + 2], dw_h.z); atomicAdd(&s_dattw[4 * lane + 3], dw_h.w);
+        atomicAdd(&s_dattw[H + 4 * lane + 0], dw_p.x); atomicAdd(&s_dattw[H + 4 * lane + 1], dw_p.y);
+        atomicAdd(&s_dattw[H + 4 * lane + 2], dw_p.z); atomicAdd(&s_dattw[H + 4 * lane + 3], dw_p.w);
+        if (lane == 0) atomicAdd(&s_dattw[2 * H], dbias);
+        if (a.absmax_bits) {
+            amax = warp_max(amax);
+            if (lane == 0 && amax > 0.f) atomicMax(a.absmax_bits, __float_as_uint(amax));
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * H + 1; i += blockDim.x) atomicAdd(a.dattw + i, s_dattw[i]);
+}
+
+// ---------------------------------------------------------------------------
 // host orchestration
 // ---------------------------------------------------------------------------
 static int check_cfg(const pn_pagg_cfg *c)
@@ -701,7 +855,8 @@ extern "C" int pn_pagg_forward(const pn_pagg_cfg *cfg, const pn_pagg_params *prm
     pa.seq_type = seq_type; pa.attw_w = prm->attw_w; pa.attw_b = prm->attw_b;
     pa.score = w.score; pa.att = w.att; pa.cat = w.cat;
     pa.drop_thr = thr; pa.drop_scale = scale; pa.drop_seed = c.dropout_seed;
-    k_pool_fwd<<<(unsigned)ceil_div(S, 8), 256, 0, st>>>(pa);
+    if (H == 128) k_pool_fwd128<<<(unsigned)ceil_div(S, 8), 256, 0, st>>>(pa);
+    else k_pool_fwd<<<(unsigned)ceil_div(S, 8), 256, 0, st>>>(pa);
     PN_LAUNCH_CHECK();
     // K4: logits = cat fc2_w^T + fc2_b                             (:210 / :277)
     return launch_gemm(st, w.cat, 2 * H, 1, prm->fc2_w, 1, 2 * H, logits, c.C, S, c.C, 2 * H, prm->fc2_b, false, false);
@@ -757,7 +912,8 @@ extern "C" int pn_pagg_backward(const pn_pagg_cfg *cfg, const pn_pagg_params *pr
         ZERO(w.gscale, 2);
         pa.absmax_bits = reinterpret_cast<unsigned int *>(w.gscale);
     }
-    k_pool_bwd<<<(unsigned)ceil_div(S, 8), 256, sizeof(float) * (2 * H + 1), st>>>(pa);
+    if (H == 128) k_pool_bwd128<<<(unsigned)ceil_div(S, 8), 256, sizeof(float) * (2 * H + 1), st>>>(pa);
+    else k_pool_bwd<<<(unsigned)ceil_div(S, 8), 256, sizeof(float) * (2 * H + 1), st>>>(pa);
     PN_LAUNCH_CHECK();
     PN_CUDA(cudaMemcpyAsync(g.attw_w, w.dattw, sizeof(float) * 2 * H, cudaMemcpyDeviceToDevice, st));
     PN_CUDA(cudaMemcpyAsync(g.attw_b, w.dattw + 2 * H, sizeof(float), cudaMemcpyDeviceToDevice, st));
