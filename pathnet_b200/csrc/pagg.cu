@@ -372,7 +372,14 @@ struct PoolArgs {
     const float *dcat;   // [S,2H] grad wrt the dropped concat
     float *dhfin, *dZ, *dT, *dattw;
     unsigned int *absmax_bits;  // max |dhfin| as float bits (tensor-core backward's gradient scale), may be null
+    // classifier fused into the H = 128 kernels (few classes: each warp already holds its whole concat row)
+    int C;
+    const float *fc2_w, *fc2_b;   // [C][2H], [C]
+    float *logits;                // forward: [S][C], null = not fused
+    const float *dlogits;         // backward: [S][C], null = not fused (dcat is read instead)
+    float *dfc2_w, *dfc2_b;       // backward: atomically accumulated
 };
+constexpr int POOL_FUSE_MAX_C = 16;
 
 __device__ __forceinline__ float warp_sum(float v)
 {
@@ -630,16 +637,26 @@ __global__ void __launch_bounds__(256) k_pool_fwd128(PoolArgs a)
             po[q] = dropout_hash(a.drop_seed, 1, (uint64_t)s * 2 * H + H + j) < a.drop_thr ? 0.f : po[q] * a.drop_scale;
         }
     }
-    *reinterpret_cast<float4 *>(a.cat + s * 2 * H + 4 * lane) = make_float4(eg[0], eg[1], eg[2], eg[3]);
-    *reinterpret_cast<float4 *>(a.cat + s * 2 * H + H + 4 * lane) = make_float4(po[0], po[1], po[2], po[3]);
+    const float4 eg4 = make_float4(eg[0], eg[1], eg[2], eg[3]), po4 = make_float4(po[0], po[1], po[2], po[3]);
+    *reinterpret_cast<float4 *>(a.cat + s * 2 * H + 4 * lane) = eg4;
+    *reinterpret_cast<float4 *>(a.cat + s * 2 * H + H + 4 * lane) = po4;
+    if (a.logits) {   // logits = cat W2^T + b2   (:210 / :277)
+        for (int c = 0; c < a.C; c++) {
+            const float *wc = a.fc2_w + (int64_t)c * 2 * H;
+            const float d = warp_sum(dot4(eg4, ld4(wc + 4 * lane)) + dot4(po4, ld4(wc + H + 4 * lane)));
+            if (lane == 0) a.logits[s * a.C + c] = d + a.fc2_b[c];
+        }
+    }
 }
 
 __global__ void __launch_bounds__(256) k_pool_bwd128(PoolArgs a)
 {
     constexpr int H = 128;
-    extern __shared__ float s_dattw[];  // [2H+1]
+    extern __shared__ float s_dattw[];  // [2H+1], then (fused classifier) dW2 [C][2H] and db2 [C]
     const int nw = a.nw;
-    for (int i = threadIdx.x; i < 2 * H + 1; i += blockDim.x) s_dattw[i] = 0.f;
+    const int nfuse = a.dlogits ? a.C * (2 * H + 1) : 0;
+    float *s_dw2 = s_dattw + 2 * H + 1, *s_db2 = s_dw2 + a.C * 2 * H;
+    for (int i = threadIdx.x; i < 2 * H + 1 + nfuse; i += blockDim.x) s_dattw[i] = 0.f;
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int64_t s = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -647,8 +664,28 @@ __global__ void __launch_bounds__(256) k_pool_bwd128(PoolArgs a)
         const float inv_nw = 1.f / (float)nw;
         const int64_t node = a.rows[s];
         // gradient wrt the pooled half of the concat, dropout applied once
-        float4 g4 = ld4(a.dcat + s * 2 * H + H + 4 * lane);
-        float4 e4 = ld4(a.dcat + s * 2 * H + 4 * lane);   // and wrt the ego half
+        float4 g4, e4;   // ... and wrt the ego half
+        if (a.dlogits) {   // dcat = dY W2, dW2 += dY^T cat, db2 += dY  -- this row's share
+            g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            e4 = g4;
+            const float4 ce = ld4(a.cat + s * 2 * H + 4 * lane), cp = ld4(a.cat + s * 2 * H + H + 4 * lane);
+            for (int c = 0; c < a.C; c++) {
+                const float dl = a.dlogits[s * a.C + c];
+                const float *wc = a.fc2_w + (int64_t)c * 2 * H;
+                const float4 we = ld4(wc + 4 * lane), wq = ld4(wc + H + 4 * lane);
+                e4.x += dl * we.x; e4.y += dl * we.y; e4.z += dl * we.z; e4.w += dl * we.w;
+                g4.x += dl * wq.x; g4.y += dl * wq.y; g4.z += dl * wq.z; g4.w += dl * wq.w;
+                float *dw = s_dw2 + c * 2 * H;
+                atomicAdd(dw + 4 * lane + 0, dl * ce.x); atomicAdd(dw + 4 * lane + 1, dl * ce.y);
+                atomicAdd(dw + 4 * lane + 2, dl * ce.z); atomicAdd(dw + 4 * lane + 3, dl * ce.w);
+                atomicAdd(dw + H + 4 * lane + 0, dl * cp.x); atomicAdd(dw + H + 4 * lane + 1, dl * cp.y);
+                atomicAdd(dw + H + 4 * lane + 2, dl * cp.z); atomicAdd(dw + H + 4 * lane + 3, dl * cp.w);
+                if (lane == 0) atomicAdd(s_db2 + c, dl);
+            }
+        } else {
+            g4 = ld4(a.dcat + s * 2 * H + H + 4 * lane);
+            e4 = ld4(a.dcat + s * 2 * H + 4 * lane);
+        }
         if (a.drop_thr) {
             float *gp = &g4.x, *ep = &e4.x;
 #pragma unroll
@@ -718,6 +755,10 @@ __global__ void __launch_bounds__(256) k_pool_bwd128(PoolArgs a)
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 2 * H + 1; i += blockDim.x) atomicAdd(a.dattw + i, s_dattw[i]);
+    if (a.dlogits) {
+        for (int i = threadIdx.x; i < a.C * 2 * H; i += blockDim.x) atomicAdd(a.dfc2_w + i, s_dw2[i]);
+        for (int i = threadIdx.x; i < a.C; i += blockDim.x) atomicAdd(a.dfc2_b + i, s_db2[i]);
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -855,10 +896,14 @@ extern "C" int pn_pagg_forward(const pn_pagg_cfg *cfg, const pn_pagg_params *prm
     pa.seq_type = seq_type; pa.attw_w = prm->attw_w; pa.attw_b = prm->attw_b;
     pa.score = w.score; pa.att = w.att; pa.cat = w.cat;
     pa.drop_thr = thr; pa.drop_scale = scale; pa.drop_seed = c.dropout_seed;
-    if (H == 128) k_pool_fwd128<<<(unsigned)ceil_div(S, 8), 256, 0, st>>>(pa);
+    // the H = 128 kernels use 16-byte accesses: parameter pointers handed in through the C ABI must be aligned for that
+    const bool pool128 = H == 128 && ((reinterpret_cast<uintptr_t>(prm->attw_w) | reinterpret_cast<uintptr_t>(prm->fc2_w)) & 15) == 0;
+    const bool fuse_fc2 = pool128 && c.C <= POOL_FUSE_MAX_C;   // K4 (logits = cat fc2_w^T + fc2_b, :210 / :277) inside the pooling kernel
+    if (fuse_fc2) { pa.C = c.C; pa.fc2_w = prm->fc2_w; pa.fc2_b = prm->fc2_b; pa.logits = logits; }
+    if (pool128) k_pool_fwd128<<<(unsigned)ceil_div(S, 8), 256, 0, st>>>(pa);
     else k_pool_fwd<<<(unsigned)ceil_div(S, 8), 256, 0, st>>>(pa);
     PN_LAUNCH_CHECK();
-    // K4: logits = cat fc2_w^T + fc2_b                             (:210 / :277)
+    if (fuse_fc2) return PN_OK;
     return launch_gemm(st, w.cat, 2 * H, 1, prm->fc2_w, 1, 2 * H, logits, c.C, S, c.C, 2 * H, prm->fc2_b, false, false);
 }
 
@@ -887,17 +932,21 @@ extern "C" int pn_pagg_backward(const pn_pagg_cfg *cfg, const pn_pagg_params *pr
         return PN_OK;
     }
     PN_REQUIRE(seq_node && seq_type && partner && rows && dlogits, "pagg_backward: NULL pointer");
-    // ---- fc2 ----
-    {
+    // ---- fc2 ---- (H = 128 and few classes: done inside the pooling kernel, which holds every concat row anyway)
+    const bool pool128 = H == 128 && ((reinterpret_cast<uintptr_t>(prm->attw_w) | reinterpret_cast<uintptr_t>(prm->fc2_w)) & 15) == 0;
+    const bool fuse_fc2 = pool128 && C <= POOL_FUSE_MAX_C;
+    if (fuse_fc2) {
+        ZERO(g.fc2_w, C * 2 * H); ZERO(g.fc2_b, C);
+    } else {
         const int splitk = (int)std::max<int64_t>(1, std::min<int64_t>(128, S / 128));  // K = S on very few output tiles
         if (splitk > 1) ZERO(g.fc2_w, C * 2 * H);
         rc = launch_gemm(st, dlogits, 1, C, w.cat, 2 * H, 1, g.fc2_w, 2 * H, C, 2 * H, S, nullptr, false, false, splitk);  // dW2 = dY^T cat
         if (rc) return rc;
+        rc = launch_colsum(st, dlogits, S, C, C, g.fc2_b);
+        if (rc) return rc;
+        rc = launch_gemm(st, dlogits, C, 1, prm->fc2_w, 2 * H, 1, w.dcat, 2 * H, S, 2 * H, C, nullptr, false, false);  // dcat = dY W2
+        if (rc) return rc;
     }
-    rc = launch_colsum(st, dlogits, S, C, C, g.fc2_b);
-    if (rc) return rc;
-    rc = launch_gemm(st, dlogits, C, 1, prm->fc2_w, 2 * H, 1, w.dcat, 2 * H, S, 2 * H, C, nullptr, false, false);  // dcat = dY W2
-    if (rc) return rc;
     // ---- attention / pooling ----
     ZERO(w.dZ, N * H); ZERO(w.dT, N * L * H); ZERO(w.dattw, 2 * H + 1);
     PoolArgs pa{};
@@ -912,7 +961,8 @@ extern "C" int pn_pagg_backward(const pn_pagg_cfg *cfg, const pn_pagg_params *pr
         ZERO(w.gscale, 2);
         pa.absmax_bits = reinterpret_cast<unsigned int *>(w.gscale);
     }
-    if (H == 128) k_pool_bwd128<<<(unsigned)ceil_div(S, 8), 256, sizeof(float) * (2 * H + 1), st>>>(pa);
+    if (fuse_fc2) { pa.C = (int)C; pa.fc2_w = prm->fc2_w; pa.dlogits = dlogits; pa.dfc2_w = g.fc2_w; pa.dfc2_b = g.fc2_b; }
+    if (pool128) k_pool_bwd128<<<(unsigned)ceil_div(S, 8), 256, sizeof(float) * (2 * H + 1 + (fuse_fc2 ? C * (2 * H + 1) : 0)), st>>>(pa);
     else k_pool_bwd<<<(unsigned)ceil_div(S, 8), 256, sizeof(float) * (2 * H + 1), st>>>(pa);
     PN_LAUNCH_CHECK();
     PN_CUDA(cudaMemcpyAsync(g.attw_w, w.dattw, sizeof(float) * 2 * H, cudaMemcpyDeviceToDevice, st));
