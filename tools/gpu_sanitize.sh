@@ -14,5 +14,5 @@ for variant in ("homo", "hetero"):
     assert all(torch.isfinite(p.grad).all() for p in m.parameters())
 print("tc path ran")
 PY
-echo "== memcheck tc"; timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python /tmp/san.py > gpurun_out/memcheck_tc.log 2>&1; echo "rc=$?"; tail -4 gpurun_out/memcheck_tc.log
-echo "== racecheck tc"; timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python /tmp/san.py > gpurun_out/racecheck_tc.log 2>&1; echo "rc=$?"; tail -6 gpurun_out/racecheck_tc.log
+echo "== memcheck tc"; timeout 100 compute-sanitizer --tool memcheck --error-exitcode 9 python /tmp/san.py > gpurun_out/memcheck_tc.log 2>&1; echo "rc=$?"; tail -4 gpurun_out/memcheck_tc.log
+echo "== racecheck tc"; timeout 100 compute-sanitizer --tool racecheck --error-exitcode 9 python /tmp/san.py > gpurun_out/racecheck_tc.log 2>&1; echo "rc=$?"; tail -6 gpurun_out/racecheck_tc.log
