@@ -64,13 +64,13 @@ def main(argv=None) -> int:
                     print("ERROR:: A.size() == 0 in Alias Table", file=sys.stderr)
                     return 0
                 raise
-            nodes, types = nodes.cpu().numpy(), types.cpu().numpy()
+            nodes, types = nodes.cpu().numpy(), types.cpu().numpy()      # int32 / uint8, C-contiguous
             if out is not None:
-                out.write(sampler.format_paths_txt(nodes, types))
+                out.write(memoryview(sampler.format_paths_array(nodes, types)))
             else:
                 for e in range(e0, e1):
                     with open(f"./{name}_{nw}_{L}_{e}_merw.txt" if not uniform else f"./{name}_{nw}_{L}_{e}.txt", "wb") as f:
-                        f.write(sampler.format_paths_txt(nodes[e - e0], types[e - e0]))
+                        f.write(memoryview(sampler.format_paths_array(nodes[e - e0], types[e - e0])))
     finally:
         if out is not None:
             out.close()

@@ -154,20 +154,31 @@ def format_paths_txt(nodes, types) -> bytes:
     """Text of gen_merw.cpp:188-206 for walks in (..., L) arrays."""
     nodes = np.ascontiguousarray(torch.as_tensor(nodes).cpu().numpy(), dtype=np.int32)
     types = np.ascontiguousarray(torch.as_tensor(types).cpu().numpy(), dtype=np.uint8)
+    return format_paths_array(nodes, types).tobytes()
+
+
+def format_paths_array(nodes: np.ndarray, types: np.ndarray) -> np.ndarray:
+    """The text as a uint8 array (no bytes copy; sized exactly by a first, output-less call; both passes use all host
+    threads).  `nodes` int32 / `types` uint8 C-contiguous numpy arrays of shape (..., L)."""
+    nodes = np.ascontiguousarray(nodes, dtype=np.int32)   # no copies when already in that form
+    types = np.ascontiguousarray(types, dtype=np.uint8)
     L = nodes.shape[-1]
     walks = nodes.size // L
-    cap = walks * (2 + L * 13 + L * 5)
-    buf = C.create_string_buffer(cap)
-    k = check(lib().pn_paths_format_txt(nodes.ctypes.data, types.ctypes.data, walks, L, buf, cap))
-    return buf.raw[:k]
+    size = check(lib().pn_paths_format_txt(nodes.ctypes.data, types.ctypes.data, walks, L, None, 0))
+    buf = np.empty(size, dtype=np.uint8)
+    k = check(lib().pn_paths_format_txt(nodes.ctypes.data, types.ctypes.data, walks, L, buf.ctypes.data, size))
+    assert k == size
+    return buf
 
 
 def write_paths_txt(path, nodes, types) -> int:
     """Write walks in the reference's text format; returns bytes written."""
-    txt = format_paths_txt(nodes, types)
+    nodes = np.ascontiguousarray(torch.as_tensor(nodes).cpu().numpy(), dtype=np.int32)
+    types = np.ascontiguousarray(torch.as_tensor(types).cpu().numpy(), dtype=np.uint8)
+    buf = format_paths_array(nodes, types)
     with open(path, "wb") as f:
-        f.write(txt)
-    return len(txt)
+        f.write(memoryview(buf))
+    return int(buf.size)
 
 
 def parse_paths_txt(txt: bytes, L: int):

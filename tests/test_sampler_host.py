@@ -153,6 +153,40 @@ def test_parse_rejects_garbage():
         sampler.parse_paths_txt(b"hello\n", 2)
 
 
+def test_text_io_is_independent_of_the_host_thread_count(monkeypatch):
+    """The writer / reader split their input over host threads (PN_HOST_THREADS): same bytes, same arrays, and the
+    earliest malformed byte is the one reported, whatever the split."""
+    rng = np.random.default_rng(11)
+    W, L = 120_000, 4                                     # ~3.5 MB of text: several reader pieces (>= 1 MiB each)
+    nodes = rng.integers(0, 20_000_000, (W, L)).astype(np.int32)
+    types = rng.integers(0, 9, (W, L)).astype(np.uint8)
+    nodes[0, 0], nodes[1, 1], nodes[2, 2], nodes[3, 3] = 0, 2147483647, -2147483648, -5   # digit-count edges, signs
+    types[4, 0], types[5, 1], types[6, 2] = 255, 100, 10
+    want = mo.format_txt(nodes[:3000], types[:3000])
+    outs = []
+    for t in ("1", "3", "16"):
+        monkeypatch.setenv("PN_HOST_THREADS", t)
+        txt = sampler.format_paths_txt(nodes, types)
+        assert txt[:len(want)] == want
+        outs.append(txt)
+        n2, t2 = sampler.parse_paths_txt(txt, L)
+        assert n2.shape == (W, L) and (n2 == nodes).all() and (t2 == types).all()
+    assert outs[0] == outs[1] == outs[2]
+    size = _lib.lib().pn_paths_format_txt(nodes.ctypes.data, types.ctypes.data, W, L, None, 0)   # size query
+    assert size == len(outs[0])
+    bad = bytearray(outs[0])
+    pos = len(bad) * 2 // 3
+    pos = bad.index(b"[", pos) + 1
+    bad[pos:pos + 1] = b"x"                                # a non-digit where a field must start, in a late piece
+    for t in ("1", "5"):
+        monkeypatch.setenv("PN_HOST_THREADS", t)
+        with pytest.raises(_lib.PnError, match=f"expected digit at byte {pos}"):
+            sampler.parse_paths_txt(bytes(bad), L)
+    with pytest.raises(_lib.PnError, match="more than"):  # output arrays too small
+        n_small = np.zeros((10, L), np.int32); t_small = np.zeros((10, L), np.uint8)
+        _lib.check(_lib.lib().pn_paths_parse_txt(outs[0], len(outs[0]), L, n_small.ctypes.data, t_small.ctypes.data, 10))
+
+
 def test_abi_exports_every_declared_symbol():
     import re
     from pathlib import Path
