@@ -124,6 +124,13 @@ int64_t pn_paths_format_txt(const int32_t *nodes, const uint8_t *types, int64_t 
 int64_t pn_paths_parse_txt(const char *txt, int64_t bytes, int32_t L, int32_t *nodes,
                            uint8_t *types, int64_t max_walks);
 
+/* Reader of the sampler's input files (what gen_merw.cpp:162-172 / gen.cpp:79-94 read with fscanf): header "n m",
+ * then m rows "u v p" (cols = 3) or "u v" (cols = 2).  Host buffers; the doubles are correctly rounded like strtod's.
+ * With u == NULL only the header is read (*n_out, *m_out) and 0 is returned; otherwise returns m (rows stored; rows
+ * beyond m are ignored as in the reference), < 0 on error (fewer than m rows, m > max_rows, malformed header). */
+int64_t pn_edges_parse_txt(const char *txt, int64_t bytes, int32_t cols, int64_t max_rows, int32_t *n_out,
+                           int64_t *m_out, int32_t *u, int32_t *v, double *p);
+
 /* ------------------------------------------------------------------ *
  *  PAGG operator  (replaces PathNet.forward / PathNet_homo.forward and
  *  their autograd backward, PathNet_run.py:172-211, :239-278, :351)

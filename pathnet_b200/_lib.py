@@ -62,6 +62,8 @@ def lib():
     L.pn_paths_format_txt.argtypes = [vp, vp, i64, i32, vp, i64]
     L.pn_paths_parse_txt.restype = i64
     L.pn_paths_parse_txt.argtypes = [vp, i64, i32, vp, vp, i64]
+    L.pn_edges_parse_txt.restype = i64
+    L.pn_edges_parse_txt.argtypes = [vp, i64, i32, i64, C.POINTER(i32), C.POINTER(i64), vp, vp, vp]
     L.pn_debug_gemm_tc.argtypes = [vp, vp, vp, vp, i64, i64, i64, C.c_int, vp]
     L.pn_debug_gemm_tc2.argtypes = [vp, vp, vp, i64, i64, i64, C.c_int, C.c_int, vp]
     L.pn_profile_enable.argtypes = [C.c_int]
@@ -87,7 +89,7 @@ def check(rc: int) -> int:
 # symbols include/pathnet_b200.h declares (tests assert the .so exports each)
 EXPORTS = ("pn_version", "pn_last_error", "pn_graph_from_edges", "pn_graph_from_edges_uniform", "pn_graph_free", "pn_graph_info",
            "pn_graph_cells_host", "pn_graph_prepare_labels", "pn_merw_sample", "pn_merw_probabilities",
-           "pn_paths_format_txt", "pn_paths_parse_txt", "pn_pagg_canonicalize",
+           "pn_paths_format_txt", "pn_paths_parse_txt", "pn_edges_parse_txt", "pn_pagg_canonicalize",
            "pn_pagg_workspace_bytes", "pn_pagg_forward", "pn_pagg_backward", "pn_dropout_hash",
            "pn_launch_count", "pn_profile_enable", "pn_profile_read")
 

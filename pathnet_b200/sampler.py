@@ -19,23 +19,33 @@ import torch
 from ._lib import check, lib
 
 
+def _read_edges(path, cols: int):
+    """(n, u int32[m], v int32[m], p float64[m] | None) through pn_edges_parse_txt (all host threads; doubles rounded
+    like the reference's fscanf("%lf"))."""
+    txt = np.fromfile(path, dtype=np.uint8)
+    n, m = C.c_int32(0), C.c_int64(0)
+    check(lib().pn_edges_parse_txt(txt.ctypes.data, txt.size, cols, 0, C.byref(n), C.byref(m), None, None, None))
+    m_ = int(m.value)
+    u, v = np.empty(m_, dtype=np.int32), np.empty(m_, dtype=np.int32)
+    p = np.empty(m_, dtype=np.float64) if cols == 3 else None
+    try:
+        check(lib().pn_edges_parse_txt(txt.ctypes.data, txt.size, cols, m_, C.byref(n), C.byref(m), u.ctypes.data,
+                                       v.ctypes.data, p.ctypes.data if p is not None else None))
+    except Exception as ex:   # same exception type as before for short files
+        raise ValueError(f"{path}: {ex}") from None
+    return int(n.value), u, v, p
+
+
 def read_edge_input(path):
     """`<name>.in`: header `n m`, then m rows `u v p` (gen_merw.cpp:162-172)."""
-    with open(path) as f:
-        n, m = (int(x) for x in f.readline().split()[:2])
-        arr = np.loadtxt(f, dtype=np.float64, ndmin=2, max_rows=m) if m else np.zeros((0, 3))
-    if arr.shape[0] != m:
-        raise ValueError(f"{path}: header says {m} rows, found {arr.shape[0]}")
-    return (n, np.ascontiguousarray(arr[:, 0], dtype=np.int32),
-            np.ascontiguousarray(arr[:, 1], dtype=np.int32), np.ascontiguousarray(arr[:, 2]))
+    n, u, v, p = _read_edges(path, 3)
+    return n, u, v, p
 
 
 def read_edge_input_nsl(path):
     """2-column `<name>_nsl.in` of the uniform-RW sampler: header `n m`, then m rows `u v` (gen.cpp:79-94)."""
-    with open(path) as f:
-        n, m = (int(x) for x in f.readline().split()[:2])
-        arr = np.loadtxt(f, dtype=np.int64, ndmin=2, max_rows=m) if m else np.zeros((0, 2), dtype=np.int64)
-    return n, np.ascontiguousarray(arr[:, 0], dtype=np.int32), np.ascontiguousarray(arr[:, 1], dtype=np.int32)
+    n, u, v, _ = _read_edges(path, 2)
+    return n, u, v
 
 
 class MerwGraph:

@@ -187,6 +187,45 @@ def test_text_io_is_independent_of_the_host_thread_count(monkeypatch):
         _lib.check(_lib.lib().pn_paths_parse_txt(outs[0], len(outs[0]), L, n_small.ctypes.data, t_small.ctypes.data, 10))
 
 
+def test_edge_file_reader_matches_fscanf_semantics(tmp_path, monkeypatch):
+    """pn_edges_parse_txt: header + m rows, doubles bit-identical to strtod, rows past m ignored, blank lines / CRLF /
+    tabs accepted, rows that span lines read as a token stream (fscanf), short files rejected; thread-count invariant."""
+    rng = np.random.default_rng(5)
+    m = 60_000                                            # ~2.5 MB: several pieces
+    u = rng.integers(0, 99_999, m).astype(np.int32)
+    v = rng.integers(0, 99_999, m).astype(np.int32)
+    p = rng.random(m) * 10.0 ** rng.integers(-12, 3, m)
+    p[:4] = [0.0, 1.0, 5e-324, 1.7976931348623157e308]
+    lines = [f"{a} {b} {repr(float(c))}" for a, b, c in zip(u, v, p)]
+    lines[7] = f"{u[7]}\t{v[7]}  {repr(float(p[7]))}  "    # tabs, trailing blanks
+    lines[9] = lines[9] + "\r"                            # CRLF
+    lines[11] = "\n" + lines[11]                          # blank line
+    lines[13] = f"+{u[13]} {v[13]} {float(p[13]):.17e}"    # explicit sign, exponent form
+    f = tmp_path / "g.in"
+    f.write_text("100000 %d\n" % m + "\n".join(lines) + "\n" + "1 2 0.5\n" * 3)   # 3 rows beyond m: ignored
+    want_p = np.array([float(x.split()[2]) for x in lines])                        # Python float() == strtod
+    for t in ("1", "4"):
+        monkeypatch.setenv("PN_HOST_THREADS", t)
+        n, uu, vv, pp = sampler.read_edge_input(f)
+        assert n == 100000 and len(uu) == m
+        assert (uu == u).all() and (vv == v).all()
+        assert (pp.view(np.uint64) == want_p.view(np.uint64)).all()
+    # token stream: a row broken over two lines still reads (fscanf does not care about line ends)
+    g = tmp_path / "h.in"
+    g.write_text("5 3\n0 1\n0.25\n1 2 0.5 2\n3 0.125\n")
+    n, uu, vv, pp = sampler.read_edge_input(g)
+    assert n == 5 and uu.tolist() == [0, 1, 2] and vv.tolist() == [1, 2, 3] and pp.tolist() == [0.25, 0.5, 0.125]
+    # 2-column variant
+    h = tmp_path / "k_nsl.in"
+    h.write_text("4 3\n0 1\n1 2\n2 3\n")
+    n, uu, vv = sampler.read_edge_input_nsl(h)
+    assert n == 4 and uu.tolist() == [0, 1, 2] and vv.tolist() == [1, 2, 3]
+    short = tmp_path / "s.in"
+    short.write_text("4 3\n0 1 0.5\n1 2 0.5\n")
+    with pytest.raises(ValueError, match="header says 3 rows, found 2"):
+        sampler.read_edge_input(short)
+
+
 def test_abi_exports_every_declared_symbol():
     import re
     from pathlib import Path
