@@ -2,6 +2,7 @@
 """Benchmark of the PathNet hot path (MERW sampler -> PAGG fwd+bwd) on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--workload pubmed|cora|bgp] [--scaling weak|strong] [--math tc|fp32]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
 Headline (`value`): PAGG paths aggregated per second, forward+backward of one
@@ -12,9 +13,10 @@ P=378 520 paths per step and per GPU).  The second metric of BASELINE.json,
 MERW walks/sec (labels included), is measured in the same run on the same
 graph and reported under "merw".  Data are synthetic (seeded) at those shapes.
 
-A "step" = one pass over one batch: inputs resident in HBM for `value`; host
-index tensors copied in and the loss read back every step for `e2e`.
-Prints ONE JSON line (rank 0).
+A "step" = one pass over one batch through pathnet_b200.train.TrainStep (the
+whole step captured as one CUDA graph): inputs resident in HBM for `value`;
+pinned HOST index tensors copied in and the loss read back every step for
+`e2e`.  Prints ONE JSON line (rank 0).
 """
 from __future__ import annotations
 
@@ -44,13 +46,23 @@ WORKLOADS = {
 }
 WORKLOAD = dict(WORKLOADS["pubmed"])
 MERW_EPOCHS_PER_STEP = 16
+STAGED_REF = ROOT / "oracle" / "_ref" / "pathnet" / "PathNet_run.py"
+
+
+def config_of(world, scaling):
+    """The SAME dict in both arms (the driver compares them): what is computed, not how."""
+    w = WORKLOAD
+    rows = f"S={w['S']} rows" + ("/GPU" if scaling == "weak" and world > 1 else " in total" if world > 1 else "")
+    return {"workload": f"{w['name']} N={w['n']} F={w['F']} H={w['H']} C={w['C']} path_num={w['nw']} path_len={w['L']} {rows} "
+                        f"-> {w['S'] * w['nw']} paths/step ({'PathNet_homo' if w['variant'] == 'homo' else 'PathNet'}, train mode, "
+                        f"dropout {w['dropout']}, CE + Adam)",
+            "parallelism": f"dp{world} ({scaling} scaling)" if world > 1 else "single GPU"}
 
 
 # --------------------------------------------------------------------------- data
-def pubmed_shaped_graph(seed=0):
-    """n = 19 717, 216 730 rows like edge_input/pubmed.in: every
-    directed edge and every self loop appears twice, skewed degrees, p > 0 with
-    row sums 2."""
+def shaped_graph(seed=0):
+    """n nodes, rows like edge_input/pubmed.in: every directed edge and every self loop appears
+    twice, skewed degrees, p > 0 with row sums 2."""
     w = WORKLOAD
     rng = np.random.default_rng(seed)
     n, ne = w["n"], w["undirected_edges"]
@@ -101,7 +113,7 @@ class ClockSampler:
                     self.rows.append(parts)
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.1)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -123,14 +135,15 @@ class ClockSampler:
 
 
 def ncu_traffic(slot):
-    """DRAM bytes per launch of a kernel from the committed `ncu --set full` capture
-    (profiles/r01/ncu_traffic.json, written by tools/ncu_summary.py), or None."""
-    f = ROOT / "profiles" / "r01" / "ncu_traffic.json"
-    if f.exists():
-        d = json.loads(f.read_text()).get(slot)
-        if d:
-            return d["dram_bytes_per_launch"]
-    return None
+    """DRAM bytes per launch of a kernel from the newest committed `ncu --set full` capture
+    (profiles/r0X/ncu_traffic.json, written by tools/ncu_summary.py), or None."""
+    for rnd in ("r02", "r01"):
+        f = ROOT / "profiles" / rnd / "ncu_traffic.json"
+        if f.exists():
+            d = json.loads(f.read_text()).get(slot)
+            if d:
+                return d["dram_bytes_per_launch"], rnd
+    return None, None
 
 
 def measured_peaks():
@@ -142,47 +155,131 @@ def measured_peaks():
 
 
 # ------------------------------------------------------------------ reference arm
-def cpu_pagg_baseline(sample_rows=512, repeats=2, threads=None):
-    """The oracle port of the reference PAGG train step (torch CPU fp32, all host
-    threads) on a bounded sample of the same workload: the first `sample_rows`
-    of the S rows (same N, F, H, nw, L)."""
-    from oracle import pagg_oracle as po
+def reference_classes(device, dropout):
+    """The reference's OWN PathNet / PathNet_homo classes, AST-extracted from the staged, unmodified script
+    (oracle/_ref/pathnet/PathNet_run.py, see oracle/stage_reference.py); None when it did not travel."""
+    if not STAGED_REF.exists():
+        return None
+    import ast
+    import torch.nn as nn
+    import torch.nn.functional as F
+    tree = ast.parse(STAGED_REF.read_text())
+    keep = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name in ("PathNet", "PathNet_homo")]
+
+    class MessagePassing(nn.Module):   # the reference subclasses torch_geometric's class and never calls propagate()
+        def __init__(self, *a, **k):
+            super().__init__()
+
+    ns = dict(torch=torch, nn=nn, F=F, MessagePassing=MessagePassing, device=device, dropout=dropout)
+    exec(compile(ast.Module(body=keep, type_ignores=[]), "PathNet_run.py", "exec"), ns)
+    return ns
+
+
+def reference_train_step_fn(device, rows_limit=None, seed=5):
+    """One training step of the reference (PathNet_run.py:345-352) with its own classes on `device`: returns
+    (step_fn, paths_per_step, description).  Falls back to the oracle port when the script is not staged."""
     w = WORKLOAD
-    # all the host threads it can use, but not past the point where torch's CPU
-    # kernels stop scaling on these small per-op shapes (measured on the box:
-    # 128 threads were 40x slower than 8-32)
-    threads = threads or min(os.cpu_count(), 32)
-    torch.set_num_threads(threads)
     X, mask, y = synthetic_inputs()
-    rows = torch.nonzero(mask).reshape(-1)[:sample_rows]
+    rows = torch.nonzero(mask).reshape(-1)
+    if rows_limit is not None:
+        rows = rows[:rows_limit]
     m2 = torch.zeros_like(mask)
     m2[rows] = True
     S, nw, L = rows.numel(), w["nw"], w["L"]
-    g = torch.Generator().manual_seed(5)
-    neis = torch.randint(0, w["n"], (S, nw * L), generator=g)
+    g = torch.Generator().manual_seed(seed)
+    neis = torch.randint(0, w["n"], (S, nw * L), generator=g)          # CPU int64, as the reference holds them
     lt = torch.randint(0, L, (S, nw, L), generator=g)
-    import pathnet_b200.pagg as pg
+    ns = reference_classes(device, w["dropout"])
     torch.manual_seed(0)
+    Xd, yd = X.to(device), y[m2].to(device)
+    if ns is not None:
+        cls = ns["PathNet_homo"] if w["variant"] == "homo" else ns["PathNet"]
+        model = cls(w["F"], w["H"], w["C"], L).to(device).train()
+        opt = torch.optim.Adam(model.parameters(), lr=0.005, weight_decay=0.0005)
+        lossf = torch.nn.CrossEntropyLoss()
+        m2_np = m2.numpy()
+
+        def step():
+            indxx = torch.arange(S * nw * L, dtype=torch.long, device=device)       # :342-343
+            out = model(Xd, neis, nw, L, m2_np, lt, indxx)                            # :345-347
+            loss = lossf(out, yd)
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            return float(loss.item())
+        return step, S * nw, "reference", "unmodified PathNet_run.py classes (AST-extracted from oracle/_ref/pathnet), torch Adam + CrossEntropyLoss"
+    from oracle import pagg_oracle as po
+    import pathnet_b200.pagg as pg
     mod = (pg.PathNet_homo if w["variant"] == "homo" else pg.PathNet)(w["F"], w["H"], w["C"], L)
-    params = {k: v.detach().clone().requires_grad_(True) for k, v in mod.state_dict().items()}
+    params = {k: v.detach().clone().to(device).requires_grad_(True) for k, v in mod.state_dict().items()}
     opt = torch.optim.Adam(params.values(), lr=0.005, weight_decay=0.0005)
     p_drop = w["dropout"]
-    best = None
-    for it in range(repeats + 1):
-        t0 = time.perf_counter()
-        ms = (torch.rand(L, S * nw, w["H"]) >= p_drop).float() / (1 - p_drop)
-        mc = (torch.rand(S, 2 * w["H"]) >= p_drop).float() / (1 - p_drop)
-        out = po.pagg_forward(w["variant"], params, X, neis, nw, L, m2, lt, mask_seq=ms, mask_cat=mc)
-        loss = torch.nn.functional.cross_entropy(out, y[m2])
+
+    def step():
+        ms = (torch.rand(L, S * nw, w["H"], device=device) >= p_drop).float() / (1 - p_drop)
+        mc = (torch.rand(S, 2 * w["H"], device=device) >= p_drop).float() / (1 - p_drop)
+        out = po.pagg_forward(w["variant"], params, Xd, neis.to(device), nw, L, m2, lt.to(device), mask_seq=ms, mask_cat=mc)
+        loss = torch.nn.functional.cross_entropy(out, yd)
         opt.zero_grad()
         loss.backward()
         opt.step()
-        dt = time.perf_counter() - t0
-        if it > 0:
-            best = dt if best is None else min(best, dt)
-    return dict(value=S * nw / best, unit="paths/s", cores=threads, kind="port",
-                sample=f"{S} of {w['S']} rows ({S * nw} paths) of the same workload, best of {repeats} after 1 warm-up, "
-                       f"oracle/pagg_oracle.py (torch CPU fp32) train step incl. dropout masks + Adam"), best, S * nw
+        return float(loss.item())
+    return step, S * nw, "port", "oracle/pagg_oracle.py (torch restatement of the reference forward), torch Adam"
+
+
+def cpu_pagg_baseline(steps=2, warmup=1, budget_s=150.0, threads=None):
+    """The reference PAGG train step on the host cores: full S when it fits the time budget, else a bounded
+    prefix of the rows (same N, F, H, nw, L)."""
+    w = WORKLOAD
+    # all the host threads it can use, but not past the point where torch's CPU kernels stop scaling on these
+    # per-op shapes (measured on the box: 128 threads were 40x slower than 8-32)
+    threads = threads or min(os.cpu_count() or 1, 32)
+    torch.set_num_threads(threads)
+    rows_limit = None
+    step, paths, kind, what = reference_train_step_fn("cpu", rows_limit)
+    t0 = time.perf_counter()
+    step()
+    first = time.perf_counter() - t0
+    if first * (steps + warmup) > budget_s:       # too slow for the budget: shrink the sample proportionally
+        rows_limit = max(64, int(w["S"] * budget_s / (first * (steps + warmup + 1))))
+        step, paths, kind, what = reference_train_step_fn("cpu", rows_limit)
+        step()
+    for _ in range(max(0, warmup - 1)):
+        step()
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+    mean = sum(times) / len(times)
+    S_used = paths // w["nw"]
+    base = dict(value=paths / mean, unit="paths/s", cores=threads, kind=kind,
+                sample=f"{S_used} of {w['S']} rows ({paths} paths/step), mean of {steps} step(s) after {warmup} warm-up, {what}, "
+                       f"torch CPU fp32 on {threads} threads (best {paths / min(times):.0f} paths/s)")
+    return base, mean, paths
+
+
+def gpu_status_quo(dev, steps=5, warmup=2):
+    """BASELINE.md §3 PAGG-2: the reference module itself on the same B200 through stock PyTorch (cuBLAS / cuDNN)."""
+    w = WORKLOAD
+    try:
+        step, paths, kind, what = reference_train_step_fn(dev)
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        return {"value": paths / (ms * 1e-3), "unit": "paths/s", "ms_per_step": ms, "kind": kind, "what": what,
+                "note": f"stock PyTorch {torch.__version__} ops on the same GPU, host int64 index tensors in + loss.item() per step "
+                        f"(its own e2e), matmul TF32 {'on' if torch.backends.cuda.matmul.allow_tf32 else 'off'}, cuDNN TF32 "
+                        f"{'on' if torch.backends.cudnn.allow_tf32 else 'off'}"}
+    except Exception as ex:   # out of memory on the 3 GB stack etc.: report, never fail the bench
+        return {"unavailable": f"{type(ex).__name__}: {str(ex)[:200]}"}
 
 
 def cpu_merw_baseline(graph, epochs=1):
@@ -221,15 +318,13 @@ def run_reference_arm(args):
     if rank != 0:
         return
     w = WORKLOAD
-    base, best, paths = cpu_pagg_baseline(sample_rows=512, repeats=max(1, min(args.steps, 3)))
-    merw = cpu_merw_baseline(pubmed_shaped_graph())
+    base, mean, paths = cpu_pagg_baseline(steps=max(1, args.steps), warmup=max(1, args.warmup), budget_s=200.0)
+    merw = cpu_merw_baseline(shaped_graph())
     line = {
         "impl": "reference", "metric": "pagg_paths_per_sec_fwd_bwd", "value": base["value"], "unit": "paths/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": best * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{w['name']} N={w['n']} F={w['F']} H={w['H']} C={w['C']} path_num={w['nw']} "
-                               f"path_len={w['L']} S={w['S']} ({'PathNet_homo' if w['variant'] == 'homo' else 'PathNet'}, dropout {w['dropout']}); "
-                               f"bounded sample: {paths} paths/step"},
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": mean * 1e3,
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_of(max(1, args.gpus), args.scaling),
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": "paths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "merw": {"metric": "merw_walks_per_sec", "value": merw["value"], "unit": "walks/s", "cpu_baseline": merw},
@@ -246,6 +341,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--math", default=os.environ.get("PN_BENCH_MATH", "tc"), choices=["fp32", "tc"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the strict / module-API / status-quo / MERW legs")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="multi-GPU: weak = every rank its own S rows; strong = the S rows of ONE batch sharded across ranks")
     ap.add_argument("--workload", default="pubmed", choices=sorted(WORKLOADS),
                     help="pubmed (default, BASELINE configs[2]) | cora (configs[1]) | bgp (configs[3], hetero, L=6)")
     args = ap.parse_args()
@@ -258,7 +356,8 @@ def main():
     import torch.distributed as dist
     import pathnet_b200 as pb
     from pathnet_b200 import _lib
-    from pathnet_b200.dist import FlatGradAllReduce
+    from pathnet_b200.dist import FlatGradAllReduce, shard_bounds
+    from pathnet_b200.train import TrainStep
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -272,36 +371,31 @@ def main():
     w = WORKLOAD
     peaks = measured_peaks()
     L_, nw, S, H = w["L"], w["nw"], w["S"], w["H"]
-    P = S * nw
-
-    # ---- data: graph + one epoch of OUR sampled paths per rank (weak scaling) ----
-    graph = pubmed_shaped_graph()
-    g = pb.MerwGraph(*graph, device=dev)
-    X, mask, y = synthetic_inputs(rank)
-    nodes, types = g.sample(nw, L_, epochs=1, seed=12345, epoch_begin=rank)
-    neis_host = nodes[0].view(w["n"], nw * L_).long().cpu()[mask].contiguous().pin_memory()
-    ltype_host = types[0].long().cpu()[mask].contiguous().pin_memory()
-    Xd, yd = X.to(dev), y.to(dev)[mask.to(dev)]
-    torch.manual_seed(0)
+    strong = args.scaling == "strong" and world > 1
+    lo, hi = shard_bounds(S, rank, world) if strong else (0, S)
+    S_local = hi - lo
+    P_local, P_job = S_local * nw, (S * nw if strong else S * nw * world)
     cls = pb.PathNet_homo if w["variant"] == "homo" else pb.PathNet
-    model = cls(w["F"], H, w["C"], L_, dropout=w["dropout"], math_mode=args.math).to(dev).train()
-    opt = torch.optim.Adam(model.parameters(), lr=0.005, weight_decay=0.0005, fused=True)   # same update as PathNet_run.py:295, one kernel
-    reducer = FlatGradAllReduce(model.parameters()) if world > 1 else None
-    lossf = torch.nn.CrossEntropyLoss(reduction="sum")
-    S_global = S * world
 
-    # device-resident inputs for `value`
-    neis_dev, ltype_dev = neis_host.to(dev), ltype_host.to(dev)
+    # ---- data: graph + one epoch of OUR sampled paths per rank ----
+    graph = shaped_graph()
+    g = pb.MerwGraph(*graph, device=dev)
+    X, mask, y = synthetic_inputs(0 if strong else rank)
+    nodes, types = g.sample(nw, L_, epochs=1, seed=12345, epoch_begin=0 if strong else rank)
+    maskd = mask.to(dev)
+    neis_dev = nodes[0].view(w["n"], nw * L_)[maskd].contiguous()           # int32 [S, nw*L]: the sampler's own dtypes,
+    ltype_dev = types[0][maskd].contiguous()                                #   uint8 [S, nw, L]: resident in HBM
+    neis_host = neis_dev.cpu().pin_memory()                                 # 4 + 1 bytes per path position in pinned host memory
+    ltype_host = ltype_dev.cpu().pin_memory()
+    Xd, y_rows = X.to(dev), y[mask]
+    S_global = S if strong else S * world
 
-    def step(neis, ltype, read_loss):
-        out = model(Xd, neis, nw, L_, mask, ltype, None)
-        loss = lossf(out, yd) / S_global
-        opt.zero_grad()   # as PathNet_run.py:350 (grads set to None: autograd assigns instead of accumulating)
-        loss.backward()
-        if reducer is not None:
-            reducer()
-        opt.step()
-        return loss.item() if read_loss else loss
+    def make_step(math, graph_mode=True, seed=7):
+        torch.manual_seed(0)
+        model = cls(w["F"], H, w["C"], L_, dropout=w["dropout"], math_mode=math).to(dev).train()
+        ts = TrainStep(model, Xd, mask, y_rows, nw, L_, lr=0.005, weight_decay=0.0005, seed=seed + rank, graph=graph_mode,
+                       s_global=S_global, shard=(lo, hi) if strong else None)     # Adam as PathNet_run.py:295
+        return model, ts
 
     def barrier():
         if world > 1:
@@ -321,118 +415,195 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    # ---- value: inputs resident in HBM, K graph-launched steps ----
+    model, ts = make_step(args.math)
     for _ in range(args.warmup):
-        step(neis_dev, ltype_dev, False)
-    launches0 = _lib.lib().pn_launch_count()
+        ts.step(neis_dev, ltype_dev)
     with ClockSampler(local) as clocks:
-        total_ms = timed(lambda: step(neis_dev, ltype_dev, False), args.steps)
-    launches = _lib.lib().pn_launch_count() - launches0
+        total_ms = timed(lambda: ts.step(neis_dev, ltype_dev), args.steps)
     ms_per_step = total_ms / args.steps
-    value = world * P / (ms_per_step * 1e-3)
+    value = P_job / (ms_per_step * 1e-3)
+    launches = ts.launches_per_step * args.steps      # kernels of libpathnet_b200.so per step (graph nodes replayed) x steps
 
-    # ---- e2e: host index tensors in (pinned), loss out, every step ----
+    # ---- e2e: the public training-step call with pinned HOST index tensors in and the loss out, every step.  The
+    #      H2D copy of step k+1 is issued (prefetch) before step k's loss is read, so it overlaps step k's kernels;
+    #      every step's copy and read-back happen inside the timed region ----
+    def e2e_step():
+        ts.step()
+        ts.prefetch(neis_host, ltype_host)
+        return float(ts.loss.item())
+    ts.prefetch(neis_host, ltype_host)
     for _ in range(2):
-        step(neis_host, ltype_host, True)
-    e2e_ms = timed(lambda: step(neis_host, ltype_host, True), args.steps) / args.steps
-    h2d = neis_host.numel() * 8 + ltype_host.numel() * 8
-    e2e = {"value": world * P / (e2e_ms * 1e-3), "unit": "paths/s", "h2d_bytes_per_step": int(h2d),
+        e2e_step()
+    e2e_ms = timed(e2e_step, args.steps) / args.steps
+    ts.step()   # consume the last prefetch
+    h2d = neis_host.numel() * neis_host.element_size() + ltype_host.numel() * ltype_host.element_size()
+    e2e = {"value": P_job / (e2e_ms * 1e-3), "unit": "paths/s", "h2d_bytes_per_step": int(h2d),
            "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms,
-           "note": "module.forward with CPU int64 neis/layer_type (as PathNet_run.py passes them) + loss.item(); "
-                   "X stays resident as in the reference (:300)"}
+           "note": "pathnet_b200.train.TrainStep: prefetch(pinned host int32 node ids + uint8 labels, the dtypes gen_merw() hands over) "
+                   "-> step() (one CUDA graph: canonicalize, forward, CE, backward, Adam) -> loss.item(); the copy of the next step's "
+                   "indices overlaps the current step; X stays resident as in the reference (:300)"}
 
-    # ---- roofline of the dominant kernels (in-stream CUDA events inside the library) ----
-    _lib.profile_enable(True)
-    nprof = 3
-    for _ in range(nprof):
-        step(neis_dev, ltype_dev, False)
-    torch.cuda.synchronize()
-    prof = {k: _lib.profile_read(k) for k in ("lstm_fwd", "lstm_bwd", "wgrad")}
-    _lib.profile_enable(False)
-    flop_fwd = 16.0 * L_ * H * H * P            # 16 L H^2 per path forward
-    flop_bwd_dgrad = 16.0 * L_ * H * H * P      # da . Wp^T
-    flop_wgrad = 16.0 * L_ * H * H * P          # [x;h]^T da
-    kern = {}
-    for name, fl in (("lstm_fwd", flop_fwd), ("lstm_bwd", flop_bwd_dgrad), ("wgrad", flop_wgrad)):
-        ms, n = prof[name]
-        if n:
-            kern[name] = {"ms": ms / n, "tflops": fl / (ms / n * 1e-3) / 1e12}
-            tr = ncu_traffic(name) if args.workload == "pubmed" and args.math == "tc" else None
-            if tr:   # second roof: the kernel's DRAM traffic (committed ncu capture of this workload) over the live duration
-                kern[name]["dram_gbs"] = tr / (ms / n * 1e-3) / 1e9
-                kern[name]["hbm_frac"] = kern[name]["dram_gbs"] / peaks["hbm"]
-            kern[name]["tensor_frac"] = kern[name]["tflops"] / (peaks["bf16_sustained"] or peaks["bf16"])
-    dom = max(kern, key=lambda k: kern[k]["ms"]) if kern else None
-    peak = peaks["bf16_sustained"] or peaks["bf16"]
+    extras = {}
     roofline = None
-    if dom:
-        roofline = {"kernel": dom, "bound": "tensor", "achieved": kern[dom]["tflops"], "peak": peak,
-                    "unit": "TFLOP/s", "frac": kern[dom]["tflops"] / peak, "traffic": ncu_traffic(dom),
-                    "traffic_note": "DRAM read+write bytes per launch from the committed ncu --set full capture (profiles/r01)",
-                    "peak_source": f"{peaks['src']} bf16 sustained (MEASURED_PEAKS.json)",
-                    "math_mode": args.math, "kernels": kern,
-                    "note": "algorithmic FLOPs = 16*L*H^2 per path per LSTM GEMM pass (SURVEY 8d): forward gates, "
-                            "backward dgrad, backward wgrad; math_mode tc = tcgen05 fp16 operands / fp32 accumulate, "
-                            "fp32 = CUDA-core FMA (strict parity mode).  kernels[*].hbm_frac = the same kernels against "
-                            "the HBM roof (saved-activation / operand-image traffic): the LSTM kernels sit between the two roofs"}
+    merw = None
+    if not args.no_extras:
+        # ---- the reference's own calling convention: module.forward with CPU int64 tensors, torch CE + Adam (autograd path) ----
+        neis64, ltype64 = neis_host.long().pin_memory(), ltype_host.long().pin_memory()
+        torch.manual_seed(0)
+        model2 = cls(w["F"], H, w["C"], L_, dropout=w["dropout"], math_mode=args.math).to(dev).train()
+        opt = torch.optim.Adam(model2.parameters(), lr=0.005, weight_decay=0.0005, fused=True)
+        reducer = FlatGradAllReduce(model2.parameters(), sink=model2.grad_sink) if world > 1 else None
+        lossf = torch.nn.CrossEntropyLoss(reduction="sum")
+        yd = y_rows.to(dev)
+        if not strong:
+            def module_step():
+                out = model2(Xd, neis64, nw, L_, mask, ltype64, None)
+                loss = lossf(out, yd) / S_global
+                opt.zero_grad()
+                loss.backward()
+                if reducer is not None:
+                    reducer()
+                opt.step()
+                return loss.item()
+            for _ in range(2):
+                module_step()
+            mod_ms = timed(module_step, args.steps) / args.steps
+            extras["module_api"] = {"value": P_job / (mod_ms * 1e-3), "unit": "paths/s", "ms_per_step": mod_ms,
+                                    "h2d_bytes_per_step": int(neis64.numel() * 16),
+                                    "note": "nn.Module.forward with CPU int64 neis/layer_type exactly as PathNet_run.py:345-352 passes them, "
+                                            "torch CrossEntropyLoss + autograd + fused torch Adam, loss.item() every step"
+                                            + (f"; zero-copy flat all-reduce used on {reducer.zero_copy_steps} steps" if reducer else "")}
+        del model2, opt
 
-    # ---- MERW walks/sec (labels included), same graph ----
-    E = MERW_EPOCHS_PER_STEP
-    out_n = torch.empty((E, w["n"], nw, L_), dtype=torch.int32, device=dev)
-    out_t = torch.empty((E, w["n"], nw, L_), dtype=torch.uint8, device=dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    for i in range(3):
-        g.sample(nw, L_, epochs=E, seed=777, epoch_begin=i * E, out=(out_n, out_t))
-    merw_ms = []
-    _lib.profile_enable(True)
-    for i in range(args.steps):
-        flush.fill_(i & 0xFF)          # evict L2 between timed launches
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        g.sample(nw, L_, epochs=E, seed=777, epoch_begin=(3 + i) * E, out=(out_n, out_t))
-        e1.record()
+        # ---- roofline of the dominant kernels (in-stream CUDA events inside the library; eager launches, not the graph) ----
+        _, ts_prof = make_step(args.math, graph_mode=False)
+        for _ in range(2):
+            ts_prof.step(neis_dev, ltype_dev)
+        _lib.profile_enable(True)
+        for _ in range(3):
+            ts_prof.step(neis_dev, ltype_dev)
         torch.cuda.synchronize()
-        merw_ms.append(e0.elapsed_time(e1))
-    kms, kn = _lib.profile_read("merw_walk")
-    _lib.profile_enable(False)
-    walks = E * w["n"] * nw
-    merw_step = sum(merw_ms) / len(merw_ms)
-    t_m = torch.tensor([merw_step], device=dev)
-    if world > 1:
-        dist.all_reduce(t_m, op=dist.ReduceOp.MAX)
-    merw_step = float(t_m.item())
-    bytes_per_walk = (L_ - 1) * (8 + 16) + L_ * (4 + 1)   # 92 B at L = 4
-    merw = {"metric": "merw_walks_per_sec", "value": world * walks / (merw_step * 1e-3), "unit": "walks/s",
-            "ms_per_step": merw_step, "walks_per_step": walks, "epochs_per_step": E,
-            "labels_included": True, "rng": "glibc_compat (bit-exact srand/rand stream)", "l2_flush": True,
-            "roofline": {"kernel": "k_merw_walk", "bound": "hbm",
-                         "achieved": walks * bytes_per_walk / ((kms / max(kn, 1)) * 1e-3) / 1e9 if kn else None,
-                         "peak": peaks["hbm"], "unit": "GB/s",
-                         "frac": (walks * bytes_per_walk / ((kms / kn) * 1e-3) / 1e9 / peaks["hbm"]) if kn else None,
-                         "traffic": ncu_traffic("merw_walk"), "bytes_per_walk": bytes_per_walk,
-                         "peak_source": f"{peaks['src']} HBM copy bandwidth"}}
+        prof = {k: _lib.profile_read(k) for k in ("lstm_fwd", "lstm_bwd", "wgrad")}
+        _lib.profile_enable(False)
+        del ts_prof
+        flop_pass = 16.0 * L_ * H * H * P_local      # 16 L H^2 per path per LSTM GEMM pass (forward gates, dgrad, wgrad)
+        peak = peaks["bf16_sustained"] or peaks["bf16"]
+        kern = {}
+        for name in ("lstm_fwd", "lstm_bwd", "wgrad"):
+            ms, n = prof[name]
+            if n:
+                kern[name] = {"ms": ms / n, "tflops": flop_pass / (ms / n * 1e-3) / 1e12}
+                tr, rnd = ncu_traffic(name) if args.workload == "pubmed" and args.math == "tc" else (None, None)
+                if tr:   # second roof: the kernel's DRAM traffic (committed ncu capture of this workload) over the live duration
+                    kern[name]["dram_gbs"] = tr / (ms / n * 1e-3) / 1e9
+                    kern[name]["hbm_frac"] = kern[name]["dram_gbs"] / peaks["hbm"]
+                kern[name]["tensor_frac"] = kern[name]["tflops"] / peak
+        dom = max(kern, key=lambda k: kern[k]["ms"]) if kern else None
+        if dom:
+            tr, rnd = ncu_traffic(dom)
+            roofline = {"kernel": dom, "bound": "tensor", "achieved": kern[dom]["tflops"], "peak": peak,
+                        "unit": "TFLOP/s", "frac": kern[dom]["tflops"] / peak, "traffic": tr,
+                        "traffic_note": f"DRAM read+write bytes per launch from the committed ncu --set full capture (profiles/{rnd})",
+                        "peak_source": f"{peaks['src']} bf16 sustained under the power cap (MEASURED_PEAKS.json); these kernels run at full clock",
+                        "math_mode": args.math, "kernels": kern,
+                        "whole_step_tflops": 3 * flop_pass / (ms_per_step * 1e-3) / 1e12,
+                        "note": "algorithmic FLOPs = 16*L*H^2 per path per LSTM GEMM pass (SURVEY 8d): forward gates, "
+                                "backward dgrad, backward wgrad; math_mode tc = tcgen05 fp16 operands / fp32 accumulate, "
+                                "fp32 = CUDA-core FMA (strict parity mode).  kernels[*].hbm_frac = the same kernels against "
+                                "the HBM roof (saved-activation / operand-image traffic)"}
+
+        # ---- strict-parity mode (CUDA-core fp32, 1e-4 against the reference) on the same step ----
+        if args.math == "tc" and world == 1:
+            _, ts32 = make_step("fp32")
+            for _ in range(2):
+                ts32.step(neis_dev, ltype_dev)
+            n32 = max(3, min(args.steps, 5))
+            ms32 = timed(lambda: ts32.step(neis_dev, ltype_dev), n32) / n32
+            ts32.prefetch(neis_host, ltype_host)
+
+            def e2e32():
+                ts32.step()
+                ts32.prefetch(neis_host, ltype_host)
+                return float(ts32.loss.item())
+            e2e32()
+            ms32e = timed(e2e32, n32) / n32
+            extras["strict"] = {"math_mode": "fp32", "dtype": "f32", "value": P_job / (ms32 * 1e-3), "ms_per_step": ms32,
+                                "e2e": P_job / (ms32e * 1e-3), "e2e_ms_per_step": ms32e, "unit": "paths/s", "steps": n32,
+                                "note": "same step in the strict-parity math mode (CUDA-core fp32 FMA; logits within 1e-4 of the reference's fp32 math)"}
+            del ts32
+
+        # ---- MERW walks/sec (labels included), same graph ----
+        E = MERW_EPOCHS_PER_STEP
+        out_n = torch.empty((E, w["n"], nw, L_), dtype=torch.int32, device=dev)
+        out_t = torch.empty((E, w["n"], nw, L_), dtype=torch.uint8, device=dev)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        for i in range(3):
+            g.sample(nw, L_, epochs=E, seed=777, epoch_begin=i * E, out=(out_n, out_t))
+        merw_ms = []
+        _lib.profile_enable(True)
+        for i in range(args.steps):
+            flush.fill_(i & 0xFF)          # evict L2 between timed launches
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            g.sample(nw, L_, epochs=E, seed=777, epoch_begin=(3 + i) * E, out=(out_n, out_t))
+            e1.record()
+            torch.cuda.synchronize()
+            merw_ms.append(e0.elapsed_time(e1))
+        kms, kn = _lib.profile_read("merw_walk")
+        _lib.profile_enable(False)
+        walks = E * w["n"] * nw
+        merw_step = sum(merw_ms) / len(merw_ms)
+        t_m = torch.tensor([merw_step], device=dev)
+        if world > 1:
+            dist.all_reduce(t_m, op=dist.ReduceOp.MAX)
+        merw_step = float(t_m.item())
+        # e2e of the sampler = the hand-off the next stage consumes: the tensors stay on the device (gen_merw() -> TrainStep);
+        # for the reference's text boundary, D2H + the threaded text writer are timed by tools/bench_handoff.py
+        bytes_per_walk = (L_ - 1) * (8 + 16) + L_ * (4 + 1)   # 92 B at L = 4
+        mtr, mrnd = ncu_traffic("merw_walk")
+        merw = {"metric": "merw_walks_per_sec", "value": world * walks / (merw_step * 1e-3), "unit": "walks/s",
+                "ms_per_step": merw_step, "walks_per_step": walks, "epochs_per_step": E,
+                "labels_included": True, "rng": "glibc_compat (bit-exact srand/rand stream)", "l2_flush": True,
+                "roofline": {"kernel": "k_merw_walk", "bound": "hbm",
+                             "achieved": walks * bytes_per_walk / ((kms / max(kn, 1)) * 1e-3) / 1e9 if kn else None,
+                             "peak": peaks["hbm"], "unit": "GB/s",
+                             "frac": (walks * bytes_per_walk / ((kms / kn) * 1e-3) / 1e9 / peaks["hbm"]) if kn else None,
+                             "traffic": mtr, "bytes_per_walk": bytes_per_walk,
+                             "peak_source": f"{peaks['src']} HBM copy bandwidth"}}
+        del out_n, out_t, flush
 
     line = {
         "metric": "pagg_paths_per_sec_fwd_bwd", "value": value, "unit": "paths/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.math == "fp32" else "f16xf32acc",
-        "data": "synthetic",
-        "config": {"workload": f"{w['name']} N={w['n']} F={w['F']} H={w['H']} C={w['C']} path_num={nw} path_len={L_} "
-                               f"S={S} rows/GPU -> {P} paths/step/GPU ({'PathNet_homo' if w['variant'] == 'homo' else 'PathNet'}, train mode, dropout {w['dropout']}, "
-                               f"CE + Adam), paths drawn by the on-GPU MERW sampler",
-                   "parallelism": f"dp{world} (rows sharded, flat NCCL grad all-reduce)" if world > 1 else "single GPU",
-                   "l2": "per-step working set ~9 GB >> 126 MB L2 (no explicit flush for PAGG); MERW leg flushes L2 "
-                         "with a 256 MiB write between launches",
-                   "math_mode": args.math},
-        "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches),
+        "scaling": args.scaling if world > 1 else "weak", "vs_baseline": None,
+        "dtype": "f32" if args.math == "fp32" else "f16xf32acc", "data": "synthetic",
+        "config": config_of(world, args.scaling),
+        "math_mode": args.math,
+        "l2": "per-step working set ~9 GB >> 126 MB L2 (no explicit flush for PAGG); MERW leg flushes L2 with a 256 MiB write between launches",
+        "inputs": "paths drawn by the on-GPU MERW sampler (int32 node ids, uint8 labels); one CUDA graph per step",
+        "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "launches_per_step": ts.launches_per_step,
         "roofline": roofline, "merw": merw,
     }
+    if strong:
+        line["rows_per_rank"] = [shard_bounds(S, r, world)[1] - shard_bounds(S, r, world)[0] for r in range(world)]
+    line.update(extras)
+    if roofline is not None and merw is not None:
+        roofline["merw"] = {"value": merw["value"], "unit": "walks/s", "frac_of_hbm_roof": merw["roofline"]["frac"]}
+    if "strict" in extras:
+        e2e["strict"] = extras["strict"]
     if world > 1:
         dist.barrier()
     if rank == 0:
-        if not args.no_cpu_baseline and world == 1:
-            base, _, _ = cpu_pagg_baseline(sample_rows=512, repeats=2)
+        if not args.no_cpu_baseline and not args.no_extras and world == 1:
+            del ts, model
+            torch.cuda.empty_cache()
+            line["gpu_status_quo"] = gpu_status_quo(dev)
+            base, _, _ = cpu_pagg_baseline(steps=2, warmup=1, budget_s=40.0)
+            base["gpu_status_quo"] = line["gpu_status_quo"]
             line["cpu_baseline"] = base
-            line["merw"]["cpu_baseline"] = cpu_merw_baseline(graph)
+            if merw is not None:
+                line["merw"]["cpu_baseline"] = cpu_merw_baseline(graph)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

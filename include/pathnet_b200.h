@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PN_VERSION 100 /* 0.1.0 */
+#define PN_VERSION 200 /* 0.2.0 */
 
 typedef enum {
     PN_OK = 0,
@@ -152,7 +152,17 @@ typedef struct {
     uint64_t dropout_seed;   /* counter-based mask stream    */
     int32_t no_backward;     /* 1: inference only — forward skips saving activations / gradient operands;
                                 pn_pagg_backward on such a workspace is an error (PN_ERR_INVALID)       */
-    int32_t reserved;
+    int32_t row_chunk;       /* output rows processed per pass over the LSTM / pooling kernels.  0 = all S rows at
+                                once (the workspace then scales with S*nw sequences).  > 0: the per-sequence part of
+                                the workspace is sized for row_chunk rows; forward loops over chunks sharing one Z / T
+                                table, backward RECOMPUTES each chunk's forward before its backward (activation
+                                checkpointing by row chunk), so 10^8-path calls run in a bounded workspace.          */
+    const uint64_t *dropout_seed_dev; /* optional device word ADDED to dropout_seed inside the kernels (NULL = none):
+                                lets a captured CUDA graph draw fresh masks on every replay                         */
+    const void *x16;         /* optional device copy of X as fp16 [N][F16] row-major, F16 = F rounded up to 8 (zero
+                                padded), e.g. made once by pn_pagg_pack_x16: the tensor-core mode then TMA-loads it
+                                instead of re-reading and re-converting the fp32 X on every call (X is constant over
+                                a training run, PathNet_run.py:300).  NULL = convert per call.                       */
 } pn_pagg_cfg;
 
 /* Parameter (or gradient) block, fp32 device pointers, PyTorch layouts
@@ -165,18 +175,31 @@ typedef struct {
         *fc2_w, *fc2_b;
 } pn_pagg_params;
 
+typedef enum { PN_IDX_I64 = 0, PN_IDX_I32 = 1, PN_IDX_U8 = 2 } pn_index_dtype;
+
 /* Integer-only canonicalisation of the reference's index tensors into the
  * form one fused kernel serves for both variants (DESIGN.md §PAGG canonical
- * form).  neis[S, nw*L] and layer_type[S, nw, L] are the int64 tensors the
- * reference's forward() receives (device copies); outputs, device:
+ * form).  neis[S, nw*L] and layer_type[S, nw, L] are the index tensors the
+ * reference's forward() receives (device copies): int64 as the reference
+ * passes them, or the sampler's own int32 node ids / uint8 labels
+ * (`*_dtype` = pn_index_dtype; node ids: i64 or i32, labels: i64, i32 or u8).
+ * Outputs, device:
  *   seq_node[S][nw][L] int32, seq_type[S][nw][L] uint8 : the L (type,node)
  *       table entries fed to the LSTM for the w-th sequence pooled into row s
  *   partner[S][nw] int32 : node whose embedding joins h_n in the attention
  * hetero reproduces the flip/reshape/view re-interpretations of
- * PathNet_run.py:179-199 exactly. */
-int pn_pagg_canonicalize(int32_t variant, int32_t S, int32_t nw, int32_t L,
-                         const int64_t *neis, const int64_t *layer_type, int32_t *seq_node,
-                         uint8_t *seq_type, int32_t *partner, void *stream);
+ * PathNet_run.py:179-199 exactly.
+ * Range check (the reference raises IndexError / a device assert on X[neis],
+ * nei[indxx, layer_type]): a node id outside [0,N) or a label outside [0,L)
+ * sets bit 0 / bit 1 of *status and is replaced by 0, so no later kernel ever
+ * indexes out of bounds.  `status` is one int32 the kernel can write — device
+ * memory or pinned host memory (readable by the host without a
+ * synchronisation once the kernel has run); NULL skips the report (the
+ * sanitisation still happens).  The caller zeroes it. */
+int pn_pagg_canonicalize(int32_t variant, int32_t N, int32_t S, int32_t nw, int32_t L,
+                         const void *neis, int32_t neis_dtype, const void *layer_type,
+                         int32_t type_dtype, int32_t *seq_node, uint8_t *seq_type,
+                         int32_t *partner, int32_t *status, void *stream);
 
 /* Bytes of device workspace forward/backward need for this cfg (saved
  * activations + scratch).  The same workspace must be passed to forward and
@@ -195,6 +218,33 @@ int pn_pagg_backward(const pn_pagg_cfg *cfg, const pn_pagg_params *params, const
                      const int32_t *seq_node, const uint8_t *seq_type, const int32_t *partner,
                      const int32_t *rows, void *workspace, const float *dlogits,
                      const pn_pagg_params *grads, void *stream);
+
+/* ------------------------------------------------------------------ *
+ *  Rest of the training step on the device (PathNet_run.py:345-352), so that
+ *  forward -> loss -> backward -> optimizer is one stream of device work
+ *  (capturable as one CUDA graph)
+ * ------------------------------------------------------------------ */
+
+/* Per-step device state: `step` (Adam's t) and `seed_add` (added to
+ * cfg.dropout_seed inside the kernels when cfg.dropout_seed_dev points at it).
+ * pn_step_advance increments both on the device, so a captured graph draws
+ * fresh dropout masks and uses the right bias correction on every replay. */
+typedef struct { uint64_t seed_add; int64_t step; } pn_step_state;
+int pn_step_advance(pn_step_state *state /* device */, void *stream);
+
+/* Replaces lossfunc(y_hat, Y[train_indices]) and its autograd (torch.nn.CrossEntropyLoss, :297,:348,:351):
+ *   *loss += inv_count * sum_s [ logsumexp(logits[s]) - logits[s][labels[s]] ]   (device float, caller zeroes it)
+ *   dlogits[s][c] = inv_count * (softmax(logits[s])[c] - [c == labels[s]])        (may be NULL: loss only)
+ * inv_count = 1 / (number of rows of the GLOBAL batch), so shards of a data-parallel step add up to the mean.
+ * labels: device int64 or int32 (`label_dtype` = pn_index_dtype), one per row. */
+int pn_ce_loss_grad(int64_t S, int32_t C, const float *logits, const void *labels, int32_t label_dtype,
+                    float inv_count, float *loss, float *dlogits, void *stream);
+
+/* Replaces optimizer.step() of torch.optim.Adam(params, lr, weight_decay) (:295-296,:352) over flat fp32 buffers
+ * (params, grads, exp_avg, exp_avg_sq: device, n elements each); t = state->step (device). */
+typedef struct { float lr, beta1, beta2, eps, weight_decay; } pn_adam_cfg;
+int pn_adam_step(int64_t n, float *params, const float *grads, float *exp_avg, float *exp_avg_sq,
+                 const pn_adam_cfg *cfg, const pn_step_state *state /* device */, void *stream);
 
 /* The 16-bit dropout hash the kernels use for element `idx` (dropped iff
  * hash < floor(p*65536)) of mask

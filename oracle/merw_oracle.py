@@ -34,6 +34,8 @@ def build_ref() -> bool:
     if not Path("/root/reference/preprocess/gen_merw.cpp").exists():
         return have_ref()
     subprocess.check_call(["make", "-C", str(HERE), "ref"], stdout=subprocess.DEVNULL)
+    from oracle import stage_reference
+    stage_reference.stage()   # the reference's Python driver + cornell data, for the reference arm / launcher test on the GPU box
     return have_ref()
 
 

@@ -22,11 +22,17 @@ class PaggCfg(C.Structure):
     _fields_ = [("N", C.c_int32), ("F", C.c_int32), ("H", C.c_int32), ("C", C.c_int32),
                 ("S", C.c_int32), ("nw", C.c_int32), ("L", C.c_int32), ("variant", C.c_int32),
                 ("math_mode", C.c_int32), ("training", C.c_int32), ("dropout_p", C.c_float),
-                ("dropout_seed", C.c_uint64), ("no_backward", C.c_int32), ("reserved", C.c_int32)]
+                ("dropout_seed", C.c_uint64), ("no_backward", C.c_int32), ("row_chunk", C.c_int32),
+                ("dropout_seed_dev", C.c_void_p), ("x16", C.c_void_p)]
 
 
 PARAM_NAMES = ("fc0_w", "fc0_b", "nets_w", "nets_b", "w_ih", "w_hh", "b_ih", "b_hh", "attw_w",
                "attw_b", "fc2_w", "fc2_b")
+
+
+class AdamCfg(C.Structure):
+    _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+                ("weight_decay", C.c_float)]
 
 
 class PaggParams(C.Structure):
@@ -69,13 +75,16 @@ def lib():
     L.pn_profile_enable.argtypes = [C.c_int]
     L.pn_profile_read.argtypes = [C.c_char_p, C.POINTER(C.c_double), C.POINTER(i64)]
     if hasattr(L, "pn_pagg_forward"):
-        L.pn_pagg_canonicalize.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]
+        L.pn_pagg_canonicalize.argtypes = [i32, i32, i32, i32, i32, vp, i32, vp, i32, vp, vp, vp, vp, vp]
         L.pn_pagg_workspace_bytes.restype = C.c_size_t
         L.pn_pagg_workspace_bytes.argtypes = [C.POINTER(PaggCfg)]
         L.pn_pagg_forward.argtypes = [C.POINTER(PaggCfg), C.POINTER(PaggParams), vp, vp, vp, vp, vp,
                                       vp, vp, vp]
         L.pn_pagg_backward.argtypes = [C.POINTER(PaggCfg), C.POINTER(PaggParams), vp, vp, vp, vp,
                                        vp, vp, vp, C.POINTER(PaggParams), vp]
+        L.pn_step_advance.argtypes = [vp, vp]
+        L.pn_ce_loss_grad.argtypes = [i64, i32, vp, vp, i32, C.c_float, vp, vp, vp]
+        L.pn_adam_step.argtypes = [i64, vp, vp, vp, vp, C.POINTER(AdamCfg), vp, vp]
     _LIB = L
     return L
 
@@ -90,7 +99,8 @@ def check(rc: int) -> int:
 EXPORTS = ("pn_version", "pn_last_error", "pn_graph_from_edges", "pn_graph_from_edges_uniform", "pn_graph_free", "pn_graph_info",
            "pn_graph_cells_host", "pn_graph_prepare_labels", "pn_merw_sample", "pn_merw_probabilities",
            "pn_paths_format_txt", "pn_paths_parse_txt", "pn_edges_parse_txt", "pn_pagg_canonicalize",
-           "pn_pagg_workspace_bytes", "pn_pagg_forward", "pn_pagg_backward", "pn_dropout_hash",
+           "pn_pagg_workspace_bytes", "pn_pagg_forward", "pn_pagg_backward", "pn_step_advance", "pn_ce_loss_grad",
+           "pn_adam_step", "pn_dropout_hash",
            "pn_launch_count", "pn_profile_enable", "pn_profile_read")
 
 

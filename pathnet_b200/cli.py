@@ -3,6 +3,9 @@ names (preprocess/gen_merw.cpp:125-213, gen_epoch_merw.cpp):
 
     python -m pathnet_b200.cli gen_merw       <data_name> <path_num> <path_len> [--seed N] [--epochs N]
     python -m pathnet_b200.cli gen_epoch_merw <data_name> <path_num> <path_len> [--seed N] [--epochs N]
+    python -m pathnet_b200.cli gen | gen_epoch <data_name> <path_num> <path_len> ...   uniform-random-walk variants
+        (preprocess/gen.cpp reads ../edge_input/<name>_nsl.in -> ./<name>_<nw>_<L>_nsl.txt;
+         preprocess/gen_epoch.cpp reads ../edge_input/<name>.in (2 columns) -> ./<name>_<nw>_<L>_<epoch>.txt)
 
 Run from `preprocess/`: reads `../edge_input/<name>.in`, writes
 `./<name>_<nw>_<L>_merw.txt` (gen_merw) or `./<name>_<nw>_<L>_<epoch>_merw.txt`
@@ -37,7 +40,8 @@ def main(argv=None) -> int:
         return 0
     name, nw, L = pos[0], int(pos[1]), int(pos[2])
     uniform = tool in ("gen", "gen_epoch")                 # preprocess/gen.cpp / gen_epoch.cpp (uniform random walk)
-    fin = f"../edge_input/{name}_nsl.in" if uniform else f"../edge_input/{name}.in"
+    # gen.cpp:57-60 opens ../edge_input/<name>_nsl.in; gen_epoch.cpp:52-54 and both MERW tools open ../edge_input/<name>.in
+    fin = f"../edge_input/{name}_nsl.in" if tool == "gen" else f"../edge_input/{name}.in"
     if seed is None:
         seed = int(time.time())
     from . import sampler
@@ -47,8 +51,12 @@ def main(argv=None) -> int:
         print(f"File input: {fin}")
         print(f"File output: ./{name}_{nw}_{L}_{suffix}.txt")
     if uniform:
-        g = sampler.MerwGraph(*sampler.read_edge_input_nsl(fin), device=device)
-        print(f"{g.n}", file=sys.stderr)               # gen.cpp:81
+        n_, u_, v_ = sampler.read_edge_input_nsl(fin)
+        g = sampler.MerwGraph(n_, u_, v_, device=device)
+        if tool == "gen":
+            print(f"{g.n}", file=sys.stderr)           # gen.cpp:81
+        else:
+            print(f"{n_} {len(u_)}")                   # gen_epoch.cpp:64 prints "n m" to stdout before the first freopen
     else:
         g = sampler.MerwGraph.from_file(fin, device=device)
         print(f"{name}: {g.n}", file=sys.stderr)      # gen_merw.cpp:164

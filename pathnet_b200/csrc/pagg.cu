@@ -19,23 +19,30 @@
 
 namespace pn {
 
+// effective dropout seed of a kernel-argument struct (see pn_pagg_cfg.dropout_seed_dev)
+#define PN_SEED(a) ((a).seed_dev ? (a).drop_seed + *(a).seed_dev : (a).drop_seed)
+
 // ---------------------------------------------------------------------------
 // canonicalisation (integer only)
 // ---------------------------------------------------------------------------
-__global__ void k_canonicalize(int variant, int64_t S, int nw, int L, const int64_t *__restrict__ neis,
-                               const int64_t *__restrict__ ltype, int32_t *__restrict__ seq_node,
-                               uint8_t *__restrict__ seq_type, int32_t *__restrict__ partner)
+// NT / TT: element types of the caller's index tensors (int64 as the reference passes them, or the sampler's
+// int32 node ids / uint8 labels).  Out-of-range entries set *status and become 0 (see the header).
+template <typename NT, typename TT>
+__global__ void k_canonicalize(int variant, int64_t N, int64_t S, int nw, int L, const NT *__restrict__ neis,
+                               const TT *__restrict__ ltype, int32_t *__restrict__ seq_node,
+                               uint8_t *__restrict__ seq_type, int32_t *__restrict__ partner, int32_t *status)
 {
     const int64_t P = S * nw;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // over S*nw*L
     if (i >= P * L) return;
     const int t = (int)(i % L);
     const int64_t sw = i / L;  // s*nw + w
+    int64_t node, type, pnode = 0;
     if (variant == PN_VARIANT_HOMO) {
         // sequence (s,w) = path p = s*nw+w in natural order (:246-265)
-        seq_node[i] = (int32_t)neis[i];
-        seq_type[i] = (uint8_t)ltype[i];
-        if (t == 0) partner[sw] = (int32_t)neis[sw * L];  // step-0 entry of the same path (:259-260)
+        node = (int64_t)neis[i];
+        type = (int64_t)ltype[i];
+        if (t == 0) pnode = (int64_t)neis[sw * L];  // step-0 entry of the same path (:259-260)
     } else {
         // output row s pools LSTM batch elements b = w*S + s (:196-197); batch
         // element b, step t is flat row r = b*L + t of the flipped/reshaped
@@ -43,10 +50,18 @@ __global__ void k_canonicalize(int variant, int64_t S, int nw, int L, const int6
         const int64_t s = sw / nw, w = sw % nw;
         const int64_t b = w * S + s;
         const int64_t r = b * L + t;
-        seq_node[i] = (int32_t)neis[(r % P) * L + (L - 1 - r / P)];
-        seq_type[i] = (uint8_t)ltype[r];
-        if (t == 0) partner[sw] = (int32_t)neis[b * L];  // neis[0] row b (:199)
+        node = (int64_t)neis[(r % P) * L + (L - 1 - r / P)];
+        type = (int64_t)ltype[r];
+        if (t == 0) pnode = (int64_t)neis[b * L];  // neis[0] row b (:199)
     }
+    int bad = 0;
+    if (node < 0 || node >= N) { bad |= 1; node = 0; }
+    if (type < 0 || type >= L) { bad |= 2; type = 0; }
+    if (t == 0 && (pnode < 0 || pnode >= N)) { bad |= 1; pnode = 0; }
+    seq_node[i] = (int32_t)node;
+    seq_type[i] = (uint8_t)type;
+    if (t == 0) partner[sw] = (int32_t)pnode;
+    if (bad && status) atomicOr(status, bad);
 }
 
 // ---------------------------------------------------------------------------
@@ -108,6 +123,8 @@ struct LstmArgs {
     uint32_t drop_thr;       // drop iff hash < thr; 0 = no dropout
     float drop_scale;
     uint64_t drop_seed;
+    const uint64_t *seed_dev; // optional device word added to drop_seed (CUDA-graph replay)
+    int64_t p_base;          // global index of this chunk's first sequence (row-chunked calls): mask indices are global
     // backward only
     const float *dhfin;      // [P,H]
     float *dT;               // [N,L,H]
@@ -133,8 +150,9 @@ __device__ __forceinline__ void gather_x_tile(const LstmArgs &a, float *As, int 
             for (int j = tx * 4; j < H; j += 128) {
                 float4 v = __ldg(reinterpret_cast<const float4 *>(src + j));
                 if (a.drop_thr) {
-                    const uint64_t pair = ((uint64_t)e * H + j) >> 1;  // (e*H + j) is even
-                    const uint32_t h0 = dropout_hash_pair(a.drop_seed, 0, pair), h1 = dropout_hash_pair(a.drop_seed, 0, pair + 1);
+                    const uint64_t pair = ((uint64_t)(e + a.p_base * a.L) * H + j) >> 1;  // (e*H + j) is even
+                    const uint64_t seed = PN_SEED(a);
+                    const uint32_t h0 = dropout_hash_pair(seed, 0, pair), h1 = dropout_hash_pair(seed, 0, pair + 1);
                     v.x = (h0 & 0xFFFFu) < a.drop_thr ? 0.f : v.x * a.drop_scale;
                     v.y = (h0 >> 16) < a.drop_thr ? 0.f : v.y * a.drop_scale;
                     v.z = (h1 & 0xFFFFu) < a.drop_thr ? 0.f : v.z * a.drop_scale;
@@ -299,7 +317,7 @@ __global__ void __launch_bounds__(256) k_lstm_bwd_f32(LstmArgs a)
                 float *dst = a.XH + ((int64_t)t * a.P + p) * K2;
                 for (int j = tx; j < H; j += 32) {
                     float v = __ldg(src + j);
-                    if (a.drop_thr) v = dropout_hash(a.drop_seed, 0, (uint64_t)e * H + j) < a.drop_thr ? 0.f : v * a.drop_scale;
+                    if (a.drop_thr) v = dropout_hash(PN_SEED(a), 0, (uint64_t)(e + a.p_base * a.L) * H + j) < a.drop_thr ? 0.f : v * a.drop_scale;
                     dst[j] = v;
                 }
             }
@@ -348,7 +366,7 @@ __global__ void __launch_bounds__(256) k_lstm_bwd_f32(LstmArgs a)
                 for (int q = 0; q < UPT; q++) {
                     const int j = q * 32 + tx;
                     float v = acc[pp][q];
-                    if (a.drop_thr) v = dropout_hash(a.drop_seed, 0, (uint64_t)e * H + j) < a.drop_thr ? 0.f : v * a.drop_scale;
+                    if (a.drop_thr) v = dropout_hash(PN_SEED(a), 0, (uint64_t)(e + a.p_base * a.L) * H + j) < a.drop_thr ? 0.f : v * a.drop_scale;
                     atomicAdd(dst + j, v);
                 }
             }
@@ -368,6 +386,8 @@ struct PoolArgs {
     const float *attw_w, *attw_b;
     float *score, *att, *cat;
     uint32_t drop_thr; float drop_scale; uint64_t drop_seed;
+    const uint64_t *seed_dev;   // optional device word added to drop_seed
+    int64_t s_base;             // global index of this chunk's first output row (mask indices are global)
     // backward
     const float *dcat;   // [S,2H] grad wrt the dropped concat
     float *dhfin, *dZ, *dT, *dattw;
@@ -445,8 +465,8 @@ __global__ void __launch_bounds__(256) k_pool_fwd(PoolArgs a)
         pooled *= inv_nw;
         float ego = a.Z[node * H + j];
         if (a.drop_thr) {
-            ego = dropout_hash(a.drop_seed, 1, (uint64_t)s * 2 * H + j) < a.drop_thr ? 0.f : ego * a.drop_scale;
-            pooled = dropout_hash(a.drop_seed, 1, (uint64_t)s * 2 * H + H + j) < a.drop_thr ? 0.f : pooled * a.drop_scale;
+            ego = dropout_hash(PN_SEED(a), 1, (uint64_t)(s + a.s_base) * 2 * H + j) < a.drop_thr ? 0.f : ego * a.drop_scale;
+            pooled = dropout_hash(PN_SEED(a), 1, (uint64_t)(s + a.s_base) * 2 * H + H + j) < a.drop_thr ? 0.f : pooled * a.drop_scale;
         }
         a.cat[s * 2 * H + j] = ego;
         a.cat[s * 2 * H + H + j] = pooled;
@@ -473,7 +493,7 @@ __global__ void __launch_bounds__(256) k_pool_bwd(PoolArgs a)
             float g = 0.f;
             if (j < H) {
                 g = a.dcat[s * 2 * H + H + j];
-                if (a.drop_thr) g = dropout_hash(a.drop_seed, 1, (uint64_t)s * 2 * H + H + j) < a.drop_thr ? 0.f : g * a.drop_scale;
+                if (a.drop_thr) g = dropout_hash(PN_SEED(a), 1, (uint64_t)(s + a.s_base) * 2 * H + H + j) < a.drop_thr ? 0.f : g * a.drop_scale;
             }
             gq[q] = g;
         }
@@ -495,7 +515,7 @@ __global__ void __launch_bounds__(256) k_pool_bwd(PoolArgs a)
         }
         for (int j = lane; j < H; j += 32) {  // ego gradient
             float g = a.dcat[s * 2 * H + j];
-            if (a.drop_thr) g = dropout_hash(a.drop_seed, 1, (uint64_t)s * 2 * H + j) < a.drop_thr ? 0.f : g * a.drop_scale;
+            if (a.drop_thr) g = dropout_hash(PN_SEED(a), 1, (uint64_t)(s + a.s_base) * 2 * H + j) < a.drop_thr ? 0.f : g * a.drop_scale;
             atomicAdd(a.dZ + node * H + j, g);
         }
         float dbias = 0.f, amax = 0.f;
@@ -633,8 +653,8 @@ __global__ void __launch_bounds__(256) k_pool_fwd128(PoolArgs a)
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             const int j = 4 * lane + q;
-            eg[q] = dropout_hash(a.drop_seed, 1, (uint64_t)s * 2 * H + j) < a.drop_thr ? 0.f : eg[q] * a.drop_scale;
-            po[q] = dropout_hash(a.drop_seed, 1, (uint64_t)s * 2 * H + H + j) < a.drop_thr ? 0.f : po[q] * a.drop_scale;
+            eg[q] = dropout_hash(PN_SEED(a), 1, (uint64_t)(s + a.s_base) * 2 * H + j) < a.drop_thr ? 0.f : eg[q] * a.drop_scale;
+            po[q] = dropout_hash(PN_SEED(a), 1, (uint64_t)(s + a.s_base) * 2 * H + H + j) < a.drop_thr ? 0.f : po[q] * a.drop_scale;
         }
     }
     const float4 eg4 = make_float4(eg[0], eg[1], eg[2], eg[3]), po4 = make_float4(po[0], po[1], po[2], po[3]);
@@ -691,8 +711,8 @@ __global__ void __launch_bounds__(256) k_pool_bwd128(PoolArgs a)
 #pragma unroll
             for (int q = 0; q < 4; q++) {
                 const int j = 4 * lane + q;
-                gp[q] = dropout_hash(a.drop_seed, 1, (uint64_t)s * 2 * H + H + j) < a.drop_thr ? 0.f : gp[q] * a.drop_scale;
-                ep[q] = dropout_hash(a.drop_seed, 1, (uint64_t)s * 2 * H + j) < a.drop_thr ? 0.f : ep[q] * a.drop_scale;
+                gp[q] = dropout_hash(PN_SEED(a), 1, (uint64_t)(s + a.s_base) * 2 * H + H + j) < a.drop_thr ? 0.f : gp[q] * a.drop_scale;
+                ep[q] = dropout_hash(PN_SEED(a), 1, (uint64_t)(s + a.s_base) * 2 * H + j) < a.drop_thr ? 0.f : ep[q] * a.drop_scale;
             }
         }
         atomicAdd(reinterpret_cast<float4 *>(a.dZ + node * H + 4 * lane), e4);
@@ -774,6 +794,8 @@ static int check_cfg(const pn_pagg_cfg *c)
     PN_REQUIRE(c->variant == PN_VARIANT_HETERO || c->variant == PN_VARIANT_HOMO, "pagg: bad variant %d", c->variant);
     PN_REQUIRE(c->math_mode == PN_MATH_FP32 || c->math_mode == PN_MATH_TC, "pagg: bad math_mode %d", c->math_mode);
     PN_REQUIRE(c->dropout_p >= 0.f && c->dropout_p <= 1.f, "pagg: dropout p=%f outside [0,1]", (double)c->dropout_p);
+    PN_REQUIRE(c->row_chunk >= 0, "pagg: row_chunk %d < 0", c->row_chunk);
+    PN_REQUIRE((int64_t)c->N * c->L < ((int64_t)1 << 31), "pagg: N*L = %lld table rows exceed int32 row offsets", (long long)c->N * c->L);
     return PN_OK;
 }
 
@@ -809,30 +831,45 @@ static int launch_lstm_bwd(const LstmArgs &a, cudaStream_t st)
     return PN_OK;
 }
 
-int pagg_tc_forward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_params &prm,
-                         const int32_t *seq_node, const uint8_t *seq_type, cudaStream_t st);  // pagg_tc.cu
-int pagg_tc_backward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_params &prm,
-                          const int32_t *seq_node, const uint8_t *seq_type, cudaStream_t st);  // pagg_tc.cu
-int launch_gemm_tc(cudaStream_t st, const float *A, int64_t lda, const float *B, int64_t ldb, float *C, int64_t ldc,
-                   int64_t M, int64_t N, int64_t K, const float *bias, bool relu, bool a_mn = false, bool b_mn = false,
-                   bool bf16 = false, bool accumulate = false, int splitk = 1);                  // pagg_tc.cu
+int pagg_tc_forward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_params &prm, const int32_t *seq_node,
+                         const uint8_t *seq_type, const PaggChunk &ck, cudaStream_t st);   // pagg_tc.cu
+int pagg_tc_backward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_params &prm, const int32_t *seq_node,
+                          const uint8_t *seq_type, const PaggChunk &ck, cudaStream_t st);  // pagg_tc.cu
+int pagg_tc_project(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_params &prm, const float *X, cudaStream_t st);          // pagg_tc.cu
+int pagg_tc_project_backward(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_params &prm, const float *X,
+                             const pn_pagg_params &g, cudaStream_t st);                                                          // pagg_tc.cu
 
 }  // namespace pn
 
 using namespace pn;
 
-extern "C" int pn_pagg_canonicalize(int32_t variant, int32_t S, int32_t nw, int32_t L,
-                                    const int64_t *neis, const int64_t *layer_type,
-                                    int32_t *seq_node, uint8_t *seq_type, int32_t *partner,
-                                    void *stream)
+extern "C" int pn_pagg_canonicalize(int32_t variant, int32_t N, int32_t S, int32_t nw, int32_t L,
+                                    const void *neis, int32_t neis_dtype, const void *layer_type,
+                                    int32_t type_dtype, int32_t *seq_node, uint8_t *seq_type, int32_t *partner,
+                                    int32_t *status, void *stream)
 {
     PN_REQUIRE(variant == PN_VARIANT_HETERO || variant == PN_VARIANT_HOMO, "canonicalize: bad variant %d", variant);
-    PN_REQUIRE(S >= 0 && nw > 0 && L > 0, "canonicalize: bad sizes S=%d nw=%d L=%d", S, nw, L);
+    PN_REQUIRE(N > 0 && S >= 0 && nw > 0 && L > 0 && L <= 255, "canonicalize: bad sizes N=%d S=%d nw=%d L=%d", N, S, nw, L);
+    PN_REQUIRE(neis_dtype == PN_IDX_I64 || neis_dtype == PN_IDX_I32, "canonicalize: node ids must be int64 or int32 (dtype code %d)", neis_dtype);
+    PN_REQUIRE(type_dtype == PN_IDX_I64 || type_dtype == PN_IDX_I32 || type_dtype == PN_IDX_U8,
+               "canonicalize: labels must be int64, int32 or uint8 (dtype code %d)", type_dtype);
     if (S == 0) return PN_OK;
     PN_REQUIRE(neis && layer_type && seq_node && seq_type && partner, "canonicalize: NULL pointer");
     const int64_t total = (int64_t)S * nw * L;
-    k_canonicalize<<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        variant, S, nw, L, neis, layer_type, seq_node, seq_type, partner);
+    const unsigned grid = (unsigned)ceil_div(total, 256);
+    cudaStream_t st = (cudaStream_t)stream;
+#define PN_CANON(NT, TT) \
+    k_canonicalize<NT, TT><<<grid, 256, 0, st>>>(variant, N, S, nw, L, (const NT *)neis, (const TT *)layer_type, seq_node, seq_type, partner, status)
+    if (neis_dtype == PN_IDX_I64) {
+        if (type_dtype == PN_IDX_I64) PN_CANON(int64_t, int64_t);
+        else if (type_dtype == PN_IDX_I32) PN_CANON(int64_t, int32_t);
+        else PN_CANON(int64_t, uint8_t);
+    } else {
+        if (type_dtype == PN_IDX_I64) PN_CANON(int32_t, int64_t);
+        else if (type_dtype == PN_IDX_I32) PN_CANON(int32_t, int32_t);
+        else PN_CANON(int32_t, uint8_t);
+    }
+#undef PN_CANON
     PN_LAUNCH_CHECK();
     return PN_OK;
 }
@@ -842,6 +879,78 @@ extern "C" size_t pn_pagg_workspace_bytes(const pn_pagg_cfg *cfg)
     if (check_cfg(cfg) != PN_OK) return 0;
     return carve_workspace(*cfg, nullptr).bytes + 256;
 }
+
+namespace {
+
+// rows [s0, s0 + Sc) of the call: the chunk's slice of the index tensors
+struct ChunkPtrs {
+    const int32_t *seq_node, *partner, *rows;
+    const uint8_t *seq_type;
+};
+ChunkPtrs chunk_ptrs(const pn_pagg_cfg &c, const PaggChunk &ck, const int32_t *seq_node, const uint8_t *seq_type,
+                     const int32_t *partner, const int32_t *rows)
+{
+    const int64_t p0 = ck.s0 * c.nw;
+    return {seq_node + p0 * c.L, partner + p0, rows + ck.s0, seq_type + p0 * c.L};
+}
+
+// K2 of one chunk: gather + dropout + LSTM                         (:194-195 / :264-265)
+int lstm_forward_chunk(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_params &prm, const ChunkPtrs &ix,
+                       const PaggChunk &ck, cudaStream_t st)
+{
+    if (c.math_mode == PN_MATH_TC) return pagg_tc_forward_lstm(c, w, prm, ix.seq_node, ix.seq_type, ck, st);
+    uint32_t thr; float scale;
+    drop_params(c, thr, scale);
+    LstmArgs la{};
+    la.T = w.T; la.seq_node = ix.seq_node; la.seq_type = ix.seq_type; la.Wp = w.Wp; la.WpT = w.WpT; la.bp = w.bp;
+    la.acts = ck.save ? w.acts : nullptr; la.hfin = w.hfin; la.P = ck.Sc * c.nw; la.L = c.L;
+    la.drop_thr = thr; la.drop_scale = scale; la.drop_seed = c.dropout_seed; la.seed_dev = c.dropout_seed_dev;
+    la.p_base = ck.s0 * c.nw;
+    switch (c.H / 32) {
+        case 1: return launch_lstm_fwd<1>(la, st);
+        case 2: return launch_lstm_fwd<2>(la, st);
+        case 3: return launch_lstm_fwd<3>(la, st);
+        default: return launch_lstm_fwd<4>(la, st);
+    }
+}
+
+PoolArgs pool_args(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_params &prm, const ChunkPtrs &ix, const PaggChunk &ck)
+{
+    uint32_t thr; float scale;
+    drop_params(c, thr, scale);
+    PoolArgs pa{};
+    pa.variant = c.variant; pa.H = c.H; pa.nw = c.nw; pa.L = c.L; pa.S = ck.Sc;
+    pa.Z = w.Z; pa.T = w.T; pa.hfin = w.hfin; pa.seq_node = ix.seq_node; pa.partner = ix.partner; pa.rows = ix.rows;
+    pa.seq_type = ix.seq_type; pa.attw_w = prm.attw_w; pa.attw_b = prm.attw_b;
+    pa.score = w.score; pa.att = w.att; pa.cat = w.cat;
+    pa.drop_thr = thr; pa.drop_scale = scale; pa.drop_seed = c.dropout_seed; pa.seed_dev = c.dropout_seed_dev;
+    pa.s_base = ck.s0;
+    return pa;
+}
+
+// the H = 128 pooling kernels use 16-byte accesses: parameter pointers handed in through the C ABI must be aligned for that
+bool pool128_ok(const pn_pagg_cfg &c, const pn_pagg_params &prm)
+{
+    return c.H == 128 && ((reinterpret_cast<uintptr_t>(prm.attw_w) | reinterpret_cast<uintptr_t>(prm.fc2_w)) & 15) == 0;
+}
+
+// K3 (+K4) of one chunk: attention + pool + concat + dropout (+ classifier) (:196-210 / :266-277).
+// logits == nullptr: recompute pass of the chunked backward (only score / att / cat are needed).
+int pool_forward_chunk(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_params &prm, const ChunkPtrs &ix,
+                       const PaggChunk &ck, float *logits, cudaStream_t st)
+{
+    PoolArgs pa = pool_args(c, w, prm, ix, ck);
+    const bool pool128 = pool128_ok(c, prm);
+    const bool fuse_fc2 = pool128 && c.C <= POOL_FUSE_MAX_C && logits != nullptr;
+    if (fuse_fc2) { pa.C = c.C; pa.fc2_w = prm.fc2_w; pa.fc2_b = prm.fc2_b; pa.logits = logits; }
+    if (pool128) k_pool_fwd128<<<(unsigned)ceil_div(ck.Sc, 8), 256, 0, st>>>(pa);
+    else k_pool_fwd<<<(unsigned)ceil_div(ck.Sc, 8), 256, 0, st>>>(pa);
+    PN_LAUNCH_CHECK();
+    if (fuse_fc2 || logits == nullptr) return PN_OK;
+    return launch_gemm(st, w.cat, 2 * c.H, 1, prm.fc2_w, 1, 2 * c.H, logits, c.C, ck.Sc, c.C, 2 * c.H, prm.fc2_b, false, false);
+}
+
+}  // namespace
 
 extern "C" int pn_pagg_forward(const pn_pagg_cfg *cfg, const pn_pagg_params *prm, const float *X,
                                const int32_t *seq_node, const uint8_t *seq_type,
@@ -856,55 +965,36 @@ extern "C" int pn_pagg_forward(const pn_pagg_cfg *cfg, const pn_pagg_params *prm
     PN_REQUIRE(seq_node && seq_type && partner && rows && logits, "pagg_forward: NULL pointer");
     cudaStream_t st = (cudaStream_t)stream;
     const PaggWs w = carve_workspace(c, (void *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255));
-    const int64_t N = c.N, F = c.F, H = c.H, L = c.L, S = c.S, P = (int64_t)c.S * c.nw;
+    const int64_t N = c.N, F = c.F, H = c.H, L = c.L;
     const bool homo = c.variant == PN_VARIANT_HOMO;
-    uint32_t thr; float scale;
-    drop_params(c, thr, scale);
+    const bool tcm = c.math_mode == PN_MATH_TC;
 
     // K0: Z = act(X W0^T + b0)                                     (:175 / :242-243)
-    const bool tcm = c.math_mode == PN_MATH_TC;
-    rc = tcm ? launch_gemm_tc(st, X, F, prm->fc0_w, F, w.Z, H, N, H, F, prm->fc0_b, homo)
-             : launch_gemm(st, X, F, 1, prm->fc0_w, 1, F, w.Z, H, N, H, F, prm->fc0_b, homo, false);
-    if (rc) return rc;
     // K1: T[n, d*H + j] = act(Z nets_w[d]^T + nets_b[d])           (:185-191 / :249-257, hoisted)
-    rc = tcm ? launch_gemm_tc(st, w.Z, H, prm->nets_w, H, w.T, L * H, N, L * H, H, prm->nets_b, homo)
-             : launch_gemm(st, w.Z, H, 1, prm->nets_w, 1, H, w.T, L * H, N, L * H, H, prm->nets_b, homo, false);
-    if (rc) return rc;
+    if (tcm) {
+        rc = pagg_tc_project(c, w, *prm, X, st);
+        if (rc) return rc;
+    } else {
+        rc = launch_gemm(st, X, F, 1, prm->fc0_w, 1, F, w.Z, H, N, H, F, prm->fc0_b, homo, false);
+        if (rc) return rc;
+        rc = launch_gemm(st, w.Z, H, 1, prm->nets_w, 1, H, w.T, L * H, N, L * H, H, prm->nets_b, homo, false);
+        if (rc) return rc;
+    }
     k_pack_lstm<<<(unsigned)ceil_div(2 * H * 4 * H, 256), 256, 0, st>>>((int)H, prm->w_ih, prm->w_hh, prm->b_ih,
                                                                       prm->b_hh, w.Wp, w.WpT, w.bp);
     PN_LAUNCH_CHECK();
-    // K2: gather + dropout + LSTM                                  (:194-195 / :264-265)
-    LstmArgs la{};
-    la.T = w.T; la.seq_node = seq_node; la.seq_type = seq_type; la.Wp = w.Wp; la.WpT = w.WpT; la.bp = w.bp;
-    la.acts = c.no_backward ? nullptr : w.acts; la.hfin = w.hfin; la.P = P; la.L = (int)L;
-    la.drop_thr = thr; la.drop_scale = scale; la.drop_seed = c.dropout_seed;
-    if (c.math_mode == PN_MATH_TC) {
-        rc = pagg_tc_forward_lstm(c, w, *prm, seq_node, seq_type, st);
-    } else {
-        switch (H / 32) {
-            case 1: rc = launch_lstm_fwd<1>(la, st); break;
-            case 2: rc = launch_lstm_fwd<2>(la, st); break;
-            case 3: rc = launch_lstm_fwd<3>(la, st); break;
-            default: rc = launch_lstm_fwd<4>(la, st); break;
-        }
+    const int64_t rows_per = chunk_rows(c);
+    const bool single = rows_per >= c.S;
+    for (int64_t s0 = 0; s0 < c.S; s0 += rows_per) {
+        // a chunked call saves nothing in the forward: its backward recomputes chunk by chunk
+        const PaggChunk ck{s0, std::min<int64_t>(rows_per, c.S - s0), single && !c.no_backward, s0 == 0};
+        const ChunkPtrs ix = chunk_ptrs(c, ck, seq_node, seq_type, partner, rows);
+        rc = lstm_forward_chunk(c, w, *prm, ix, ck, st);
+        if (rc) return rc;
+        rc = pool_forward_chunk(c, w, *prm, ix, ck, logits + s0 * c.C, st);
+        if (rc) return rc;
     }
-    if (rc) return rc;
-    // K3: attention + pool + concat + dropout                      (:196-209 / :266-276)
-    PoolArgs pa{};
-    pa.variant = c.variant; pa.H = (int)H; pa.nw = c.nw; pa.L = (int)L; pa.S = S;
-    pa.Z = w.Z; pa.T = w.T; pa.hfin = w.hfin; pa.seq_node = seq_node; pa.partner = partner; pa.rows = rows;
-    pa.seq_type = seq_type; pa.attw_w = prm->attw_w; pa.attw_b = prm->attw_b;
-    pa.score = w.score; pa.att = w.att; pa.cat = w.cat;
-    pa.drop_thr = thr; pa.drop_scale = scale; pa.drop_seed = c.dropout_seed;
-    // the H = 128 kernels use 16-byte accesses: parameter pointers handed in through the C ABI must be aligned for that
-    const bool pool128 = H == 128 && ((reinterpret_cast<uintptr_t>(prm->attw_w) | reinterpret_cast<uintptr_t>(prm->fc2_w)) & 15) == 0;
-    const bool fuse_fc2 = pool128 && c.C <= POOL_FUSE_MAX_C;   // K4 (logits = cat fc2_w^T + fc2_b, :210 / :277) inside the pooling kernel
-    if (fuse_fc2) { pa.C = c.C; pa.fc2_w = prm->fc2_w; pa.fc2_b = prm->fc2_b; pa.logits = logits; }
-    if (pool128) k_pool_fwd128<<<(unsigned)ceil_div(S, 8), 256, 0, st>>>(pa);
-    else k_pool_fwd<<<(unsigned)ceil_div(S, 8), 256, 0, st>>>(pa);
-    PN_LAUNCH_CHECK();
-    if (fuse_fc2) return PN_OK;
-    return launch_gemm(st, w.cat, 2 * H, 1, prm->fc2_w, 1, 2 * H, logits, c.C, S, c.C, 2 * H, prm->fc2_b, false, false);
+    return PN_OK;
 }
 
 extern "C" int pn_pagg_backward(const pn_pagg_cfg *cfg, const pn_pagg_params *prm, const float *X,
@@ -919,10 +1009,9 @@ extern "C" int pn_pagg_backward(const pn_pagg_cfg *cfg, const pn_pagg_params *pr
     PN_REQUIRE(!cfg->no_backward, "pagg_backward: the forward ran with no_backward = 1 (nothing was saved)");
     cudaStream_t st = (cudaStream_t)stream;
     const PaggWs w = carve_workspace(c, (void *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255));
-    const int64_t N = c.N, F = c.F, H = c.H, L = c.L, S = c.S, C = c.C, P = (int64_t)c.S * c.nw;
+    const int64_t N = c.N, F = c.F, H = c.H, L = c.L, S = c.S, C = c.C;
     const bool homo = c.variant == PN_VARIANT_HOMO;
-    uint32_t thr; float scale;
-    drop_params(c, thr, scale);
+    const bool tcm = c.math_mode == PN_MATH_TC;
     const pn_pagg_params &g = *grads;
 #define ZERO(ptr, n) PN_CUDA(cudaMemsetAsync((ptr), 0, sizeof(float) * (size_t)(n), st))
     if (S == 0) {  // no rows: every gradient is zero
@@ -932,96 +1021,102 @@ extern "C" int pn_pagg_backward(const pn_pagg_cfg *cfg, const pn_pagg_params *pr
         return PN_OK;
     }
     PN_REQUIRE(seq_node && seq_type && partner && rows && dlogits, "pagg_backward: NULL pointer");
-    // ---- fc2 ---- (H = 128 and few classes: done inside the pooling kernel, which holds every concat row anyway)
-    const bool pool128 = H == 128 && ((reinterpret_cast<uintptr_t>(prm->attw_w) | reinterpret_cast<uintptr_t>(prm->fc2_w)) & 15) == 0;
-    const bool fuse_fc2 = pool128 && C <= POOL_FUSE_MAX_C;
-    if (fuse_fc2) {
-        ZERO(g.fc2_w, C * 2 * H); ZERO(g.fc2_b, C);
-    } else {
-        const int splitk = (int)std::max<int64_t>(1, std::min<int64_t>(128, S / 128));  // K = S on very few output tiles
-        if (splitk > 1) ZERO(g.fc2_w, C * 2 * H);
-        rc = launch_gemm(st, dlogits, 1, C, w.cat, 2 * H, 1, g.fc2_w, 2 * H, C, 2 * H, S, nullptr, false, false, splitk);  // dW2 = dY^T cat
-        if (rc) return rc;
-        rc = launch_colsum(st, dlogits, S, C, C, g.fc2_b);
-        if (rc) return rc;
-        rc = launch_gemm(st, dlogits, C, 1, prm->fc2_w, 2 * H, 1, w.dcat, 2 * H, S, 2 * H, C, nullptr, false, false);  // dcat = dY W2
-        if (rc) return rc;
-    }
-    // ---- attention / pooling ----
+    const bool pool128 = pool128_ok(c, *prm);
+    const bool fuse_fc2 = pool128 && C <= POOL_FUSE_MAX_C;   // fc2 backward inside the pooling kernel (it holds every concat row anyway)
+    // accumulators shared by all chunks (the chunk kernels add into them atomically)
     ZERO(w.dZ, N * H); ZERO(w.dT, N * L * H); ZERO(w.dattw, 2 * H + 1);
-    PoolArgs pa{};
-    pa.variant = c.variant; pa.H = (int)H; pa.nw = c.nw; pa.L = (int)L; pa.S = S;
-    pa.Z = w.Z; pa.T = w.T; pa.hfin = w.hfin; pa.seq_node = seq_node; pa.partner = partner; pa.rows = rows;
-    pa.seq_type = seq_type; pa.attw_w = prm->attw_w; pa.attw_b = prm->attw_b;
-    pa.score = w.score; pa.att = w.att; pa.cat = w.cat;
-    pa.drop_thr = thr; pa.drop_scale = scale; pa.drop_seed = c.dropout_seed;
-    pa.dcat = w.dcat; pa.dhfin = w.dhfin; pa.dZ = w.dZ; pa.dT = w.dT; pa.dattw = w.dattw;
-    pa.absmax_bits = nullptr;
-    if (c.math_mode == PN_MATH_TC) {
-        ZERO(w.gscale, 2);
-        pa.absmax_bits = reinterpret_cast<unsigned int *>(w.gscale);
+    ZERO(w.dWp, 2 * H * 4 * H); ZERO(w.dbp, 4 * H);
+    ZERO(g.fc2_w, C * 2 * H); ZERO(g.fc2_b, C);
+    uint32_t thr; float scale;
+    drop_params(c, thr, scale);
+    const int64_t rows_per = chunk_rows(c);
+    const bool single = rows_per >= S;
+    for (int64_t s0 = 0; s0 < S; s0 += rows_per) {
+        const PaggChunk ck{s0, std::min<int64_t>(rows_per, S - s0), true, s0 == 0};
+        const ChunkPtrs ix = chunk_ptrs(c, ck, seq_node, seq_type, partner, rows);
+        const int64_t Sc = ck.Sc, Pc = Sc * c.nw;
+        const float *dl = dlogits + s0 * C;
+        if (!single) {   // recompute this chunk's forward (same masks: mask indices are global)
+            rc = lstm_forward_chunk(c, w, *prm, ix, ck, st);
+            if (rc) return rc;
+            rc = pool_forward_chunk(c, w, *prm, ix, ck, nullptr, st);
+            if (rc) return rc;
+        }
+        // ---- fc2 ----
+        if (!fuse_fc2) {
+            const int splitk = (int)std::max<int64_t>(1, std::min<int64_t>(128, Sc / 128));  // K = Sc on very few output tiles
+            rc = launch_gemm(st, dl, 1, C, w.cat, 2 * H, 1, g.fc2_w, 2 * H, C, 2 * H, Sc, nullptr, false, splitk == 1, splitk);  // dW2 += dY^T cat
+            if (rc) return rc;
+            rc = launch_colsum(st, dl, Sc, C, C, g.fc2_b, /*accumulate=*/true);
+            if (rc) return rc;
+            rc = launch_gemm(st, dl, C, 1, prm->fc2_w, 2 * H, 1, w.dcat, 2 * H, Sc, 2 * H, C, nullptr, false, false);  // dcat = dY W2
+            if (rc) return rc;
+        }
+        // ---- attention / pooling ----
+        PoolArgs pa = pool_args(c, w, *prm, ix, ck);
+        pa.dcat = w.dcat; pa.dhfin = w.dhfin; pa.dZ = w.dZ; pa.dT = w.dT; pa.dattw = w.dattw;
+        pa.absmax_bits = nullptr;
+        if (tcm) {
+            ZERO(w.gscale, 2);
+            pa.absmax_bits = reinterpret_cast<unsigned int *>(w.gscale);
+        }
+        if (fuse_fc2) { pa.C = (int)C; pa.fc2_w = prm->fc2_w; pa.dlogits = dl; pa.dfc2_w = g.fc2_w; pa.dfc2_b = g.fc2_b; }
+        if (pool128) k_pool_bwd128<<<(unsigned)ceil_div(Sc, 8), 256, sizeof(float) * (2 * H + 1 + (fuse_fc2 ? C * (2 * H + 1) : 0)), st>>>(pa);
+        else k_pool_bwd<<<(unsigned)ceil_div(Sc, 8), 256, sizeof(float) * (2 * H + 1), st>>>(pa);
+        PN_LAUNCH_CHECK();
+        // ---- LSTM BPTT ----
+        if (tcm) {
+            rc = pagg_tc_backward_lstm(c, w, *prm, ix.seq_node, ix.seq_type, ck, st);
+            if (rc) return rc;
+        } else {
+            LstmArgs la{};
+            la.T = w.T; la.seq_node = ix.seq_node; la.seq_type = ix.seq_type; la.Wp = w.Wp; la.WpT = w.WpT; la.bp = w.bp;
+            la.acts = w.acts; la.hfin = w.hfin; la.P = Pc; la.L = (int)L;
+            la.drop_thr = thr; la.drop_scale = scale; la.drop_seed = c.dropout_seed; la.seed_dev = c.dropout_seed_dev;
+            la.p_base = s0 * c.nw;
+            la.dhfin = w.dhfin; la.dT = w.dT; la.dA = w.dA; la.XH = w.XH;
+            switch (H / 32) {
+                case 1: rc = launch_lstm_bwd<1>(la, st); break;
+                case 2: rc = launch_lstm_bwd<2>(la, st); break;
+                case 3: rc = launch_lstm_bwd<3>(la, st); break;
+                default: rc = launch_lstm_bwd<4>(la, st); break;
+            }
+            if (rc) return rc;
+            // dWp[k][col] += sum_r XH[r][k] dA[r][col];  dbp += colsum(dA)
+            const int64_t R = L * Pc;
+            const int splitk = (int)std::max<int64_t>(1, std::min<int64_t>(256, R / 2048));
+            {
+                ProfScope prof("wgrad", st);
+                rc = launch_gemm(st, w.XH, 1, 2 * H, w.dA, 4 * H, 1, w.dWp, 4 * H, 2 * H, 4 * H, R, nullptr, false, splitk == 1, splitk);
+            }
+            if (rc) return rc;
+            rc = launch_colsum(st, w.dA, R, 4 * H, 4 * H, w.dbp, /*accumulate=*/true);
+            if (rc) return rc;
+        }
     }
-    if (fuse_fc2) { pa.C = (int)C; pa.fc2_w = prm->fc2_w; pa.dlogits = dlogits; pa.dfc2_w = g.fc2_w; pa.dfc2_b = g.fc2_b; }
-    if (pool128) k_pool_bwd128<<<(unsigned)ceil_div(S, 8), 256, sizeof(float) * (2 * H + 1 + (fuse_fc2 ? C * (2 * H + 1) : 0)), st>>>(pa);
-    else k_pool_bwd<<<(unsigned)ceil_div(S, 8), 256, sizeof(float) * (2 * H + 1), st>>>(pa);
-    PN_LAUNCH_CHECK();
     PN_CUDA(cudaMemcpyAsync(g.attw_w, w.dattw, sizeof(float) * 2 * H, cudaMemcpyDeviceToDevice, st));
     PN_CUDA(cudaMemcpyAsync(g.attw_b, w.dattw + 2 * H, sizeof(float), cudaMemcpyDeviceToDevice, st));
-    // ---- LSTM BPTT ----
-    LstmArgs la{};
-    la.T = w.T; la.seq_node = seq_node; la.seq_type = seq_type; la.Wp = w.Wp; la.WpT = w.WpT; la.bp = w.bp;
-    la.acts = w.acts; la.hfin = w.hfin; la.P = P; la.L = (int)L;
-    la.drop_thr = thr; la.drop_scale = scale; la.drop_seed = c.dropout_seed;
-    la.dhfin = w.dhfin; la.dT = w.dT; la.dA = w.dA; la.XH = w.XH;
-    if (c.math_mode == PN_MATH_TC) {
-        rc = pagg_tc_backward_lstm(c, w, *prm, seq_node, seq_type, st);
-        if (rc) return rc;
-    } else {
-        switch (H / 32) {
-            case 1: rc = launch_lstm_bwd<1>(la, st); break;
-            case 2: rc = launch_lstm_bwd<2>(la, st); break;
-            case 3: rc = launch_lstm_bwd<3>(la, st); break;
-            default: rc = launch_lstm_bwd<4>(la, st); break;
-        }
-        if (rc) return rc;
-        // dWp[k][col] = sum_r XH[r][k] dA[r][col];  dbp = colsum(dA)
-        ZERO(w.dWp, 2 * H * 4 * H);
-        const int64_t R = L * P;
-        int splitk = (int)std::max<int64_t>(1, std::min<int64_t>(256, R / 2048));
-        {
-            ProfScope prof("wgrad", st);
-            rc = launch_gemm(st, w.XH, 1, 2 * H, w.dA, 4 * H, 1, w.dWp, 4 * H, 2 * H, 4 * H, R, nullptr, false, false, splitk);
-        }
-        if (rc) return rc;
-        rc = launch_colsum(st, w.dA, R, 4 * H, 4 * H, w.dbp);
-        if (rc) return rc;
-    }
     k_unpack_lstm_grads<<<(unsigned)ceil_div(4 * H * H, 256), 256, 0, st>>>((int)H, w.dWp, w.dbp, g.w_ih, g.w_hh, g.b_ih, g.b_hh);
     PN_LAUNCH_CHECK();
+    if (tcm) return pagg_tc_project_backward(c, w, *prm, X, g, st);
     // ---- table projection: T = act(Z Wn^T + bn) ----
     // homo: ReLU backward fused with the bias gradient (column sums) of the table projection
     if (homo) {
         rc = launch_relu_mask_colsum(st, w.dT, w.T, N, L * H, g.nets_b);
         if (rc) return rc;
     }
-    const bool tcm = c.math_mode == PN_MATH_TC;
     {
-        // split the reduction over N so the (L*H/128) x (H/128) output tiles fill one wave of the 148 SMs
-        int splitk = (int)std::max<int64_t>(1, std::min<int64_t>(tcm ? 148 / std::max<int64_t>(1, ceil_div(L * H, 128) * ceil_div(H, 128)) : 64, N / 256));
-        if (!tcm) splitk = (int)std::max<int64_t>(1, std::min<int64_t>(64, N / 1024));
+        const int splitk = (int)std::max<int64_t>(1, std::min<int64_t>(64, N / 1024));
         if (splitk > 1) ZERO(g.nets_w, L * H * H);
-        // dWn[m][i] = sum_n dT[n][m] Z[n][i]: both operands have the reduction index as their row (MN-major);
-        // raw gradients go through bf16 (fp16 would underflow), fp32 accumulate
-        rc = tcm ? launch_gemm_tc(st, w.dT, L * H, w.Z, H, g.nets_w, H, L * H, H, N, nullptr, false, true, true, true, false, splitk)
-                 : launch_gemm(st, w.dT, 1, L * H, w.Z, H, 1, g.nets_w, H, L * H, H, N, nullptr, false, false, splitk);
+        // dWn[m][i] = sum_n dT[n][m] Z[n][i]
+        rc = launch_gemm(st, w.dT, 1, L * H, w.Z, H, 1, g.nets_w, H, L * H, H, N, nullptr, false, false, splitk);
         if (rc) return rc;
     }
     if (!homo) {
         rc = launch_colsum(st, w.dT, N, L * H, L * H, g.nets_b);
         if (rc) return rc;
     }
-    rc = tcm ? launch_gemm_tc(st, w.dT, L * H, prm->nets_w, H, w.dZ, H, N, H, L * H, nullptr, false, false, true, true, true, 1)
-             : launch_gemm(st, w.dT, L * H, 1, prm->nets_w, H, 1, w.dZ, H, N, H, L * H, nullptr, false, true);  // dZ += dT Wn
+    rc = launch_gemm(st, w.dT, L * H, 1, prm->nets_w, H, 1, w.dZ, H, N, H, L * H, nullptr, false, true);  // dZ += dT Wn
     if (rc) return rc;
     // ---- fc0: Z = act(X W0^T + b0) ----
     if (homo) {
@@ -1029,11 +1124,9 @@ extern "C" int pn_pagg_backward(const pn_pagg_cfg *cfg, const pn_pagg_params *pr
         if (rc) return rc;
     }
     {
-        int splitk = (int)std::max<int64_t>(1, std::min<int64_t>(tcm ? 148 / std::max<int64_t>(1, ceil_div(H, 128) * ceil_div(F, 128)) : 64, N / 256));
-        if (!tcm) splitk = (int)std::max<int64_t>(1, std::min<int64_t>(64, N / 1024));
+        const int splitk = (int)std::max<int64_t>(1, std::min<int64_t>(64, N / 1024));
         if (splitk > 1) ZERO(g.fc0_w, H * F);
-        rc = tcm ? launch_gemm_tc(st, w.dZ, H, X, F, g.fc0_w, F, H, F, N, nullptr, false, true, true, true, false, splitk)
-                 : launch_gemm(st, w.dZ, 1, H, X, F, 1, g.fc0_w, F, H, F, N, nullptr, false, false, splitk);  // dW0 = dZ^T X
+        rc = launch_gemm(st, w.dZ, 1, H, X, F, 1, g.fc0_w, F, H, F, N, nullptr, false, false, splitk);  // dW0 = dZ^T X
         if (rc) return rc;
     }
     if (!homo) rc = launch_colsum(st, w.dZ, N, H, H, g.fc0_b);

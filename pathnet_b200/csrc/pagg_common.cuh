@@ -1,6 +1,8 @@
 // Shared pieces of the PAGG kernels: workspace layout, generic fp32 GEMM,
 // small elementwise kernels.  See pagg.cu for the operator itself.
 #pragma once
+#include <algorithm>
+
 #include "common.h"
 #include "dropout_hash.h"
 
@@ -31,18 +33,36 @@ struct PaggWs {
     float *dWp;      // [2H][4H]
     float *dbp;      // [4H]
     float *dattw;    // [2H+1]
-    float *gscale;   // [2] gradient scale of the tensor-core backward (scale, 1/scale)
+    float *gscale;   // [8] gradient scales {s, 1/s} of the tensor-core backward: [0,1] LSTM (max |dh_final|), [2,3] dT, [4,5] dZ
+    // tensor-core mode only (fp16 storage)
+    float *x16;      // [N][F16] fp16 copy of X (unless the caller supplied cfg.x16)
+    float *z16;      // [N][H]   fp16 copy of Z written by the fc0 epilogue
+    float *w16;      // fc0_w [H][F16] then nets_w [L*H][H], fp16
     size_t bytes;
 };
 
 inline size_t ws_align(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// rows per pass over the per-sequence kernels (pn_pagg_cfg.row_chunk; 0 = the whole call)
+inline int64_t chunk_rows(const pn_pagg_cfg &c)
+{
+    return (c.row_chunk > 0 && c.row_chunk < c.S) ? (int64_t)c.row_chunk : (int64_t)std::max(c.S, 1);
+}
+
+// one pass: output rows [s0, s0 + Sc) of the call
+struct PaggChunk {
+    int64_t s0, Sc;
+    bool save;    // keep activations / gradient operands for this chunk's backward
+    bool first;   // first chunk of the call: weight packing happens here
+};
 
 inline PaggWs carve_workspace(const pn_pagg_cfg &c, void *base)
 {
     PaggWs w{};
     char *p = (char *)base;
     size_t off = 0;
-    const size_t N = c.N, H = c.H, L = c.L, S = c.S, P = (size_t)c.S * c.nw;
+    // per-node regions are whole-call; per-sequence regions are sized for one row chunk
+    const size_t N = c.N, H = c.H, L = c.L, S = (size_t)chunk_rows(c), P = S * c.nw;
     const size_t P128 = (P + 127) / 128 * 128;  // the tensor-core kernels work on whole 128-sequence tiles
     auto take = [&](float *&dst, size_t nfloats) {
         dst = (float *)(p + off);
@@ -67,7 +87,12 @@ inline PaggWs carve_workspace(const pn_pagg_cfg &c, void *base)
     take(w.dWp, 2 * H * 4 * H);
     take(w.dbp, 4 * H);
     take(w.dattw, 2 * H + 1);
-    take(w.gscale, 2);
+    take(w.gscale, 8);
+    // tensor-core mode: 16-bit copies feeding the TMA-loaded projection GEMMs (see pagg_tc.cu)
+    const size_t F16 = ((size_t)c.F + 7) / 8 * 8;
+    take(w.x16, c.math_mode == PN_MATH_TC && !c.x16 ? (N * F16 + 1) / 2 : 0);
+    take(w.z16, c.math_mode == PN_MATH_TC ? (N * H + 1) / 2 : 0);
+    take(w.w16, c.math_mode == PN_MATH_TC ? (H * F16 + L * H * H + 1) / 2 : 0);
     w.bytes = off;
     return w;
 }
@@ -167,27 +192,39 @@ inline int launch_gemm(cudaStream_t st, const float *A, int64_t sAm, int64_t sAk
     return PN_OK;
 }
 
-// column sums: out[n] = sum_m A[m*ld + n]   (out pre-zeroed; atomics across row blocks)
-static __global__ void k_colsum(const float *__restrict__ A, int64_t M, int64_t N, int64_t ld,
-                         float *__restrict__ out)
+// max |v| of a block's values -> atomicMax on the float's bit pattern (non-negative floats order like unsigned ints)
+__device__ __forceinline__ void block_absmax(float m, unsigned int *absmax_bits)
 {
-    int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
-    int64_t rows_per = (M + gridDim.y - 1) / gridDim.y;
-    int64_t m0 = (int64_t)blockIdx.y * rows_per, m1 = min(M, m0 + rows_per);
-    float s = 0.f;
-    for (int64_t m = m0; m < m1; m++) s += A[m * ld + n];
-    atomicAdd(out + n, s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(absmax_bits, __float_as_uint(m));
 }
 
-inline int launch_colsum(cudaStream_t st, const float *A, int64_t M, int64_t N, int64_t ld, float *out)
+// column sums: out[n] = sum_m A[m*ld + n]   (out pre-zeroed; atomics across row blocks);
+// optionally max |A| -> *absmax_bits (pre-zeroed)
+static __global__ void k_colsum(const float *__restrict__ A, int64_t M, int64_t N, int64_t ld,
+                         float *__restrict__ out, unsigned int *absmax_bits)
+{
+    int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float s = 0.f, mx = 0.f;
+    if (n < N) {
+        int64_t rows_per = (M + gridDim.y - 1) / gridDim.y;
+        int64_t m0 = (int64_t)blockIdx.y * rows_per, m1 = min(M, m0 + rows_per);
+        for (int64_t m = m0; m < m1; m++) { const float v = A[m * ld + n]; s += v; mx = fmaxf(mx, fabsf(v)); }
+        atomicAdd(out + n, s);
+    }
+    if (absmax_bits) block_absmax(mx, absmax_bits);
+}
+
+inline int launch_colsum(cudaStream_t st, const float *A, int64_t M, int64_t N, int64_t ld, float *out, bool accumulate = false,
+                         unsigned int *absmax_bits = nullptr)
 {
     if (N <= 0) return PN_OK;
-    PN_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)N, st));
+    if (!accumulate) PN_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)N, st));
     if (M <= 0) return PN_OK;
     int64_t yb = std::max<int64_t>(1, std::min<int64_t>(1024, M / 256));
     dim3 grid((unsigned)ceil_div(N, 128), (unsigned)yb);
-    k_colsum<<<grid, 128, 0, st>>>(A, M, N, ld, out);
+    k_colsum<<<grid, 128, 0, st>>>(A, M, N, ld, out, absmax_bits);
     PN_LAUNCH_CHECK();
     return PN_OK;
 }
@@ -195,39 +232,42 @@ inline int launch_colsum(cudaStream_t st, const float *A, int64_t M, int64_t N, 
 // ReLU backward and the bias gradient in one pass over a dense [M][N] gradient: g = (y > 0) ? g : 0, out[n] = sum_m g[m][n].
 // (The two used to be separate sweeps of the same 40 MB table gradient.)
 static __global__ void k_relu_mask_colsum(float *__restrict__ g, const float *__restrict__ y, int64_t M, int64_t N,
-                                          float *__restrict__ out)
+                                          float *__restrict__ out, unsigned int *absmax_bits)
 {
     const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
-    const int64_t rows_per = (M + gridDim.y - 1) / gridDim.y;
-    const int64_t m0 = (int64_t)blockIdx.y * rows_per, m1 = min(M, m0 + rows_per);
-    float s = 0.f;
-    // batches of 8 rows: all 16 loads are issued before the first (possibly aliasing, as far as the compiler knows) store
-    for (int64_t mb = m0; mb < m1; mb += 8) {
-        float v[8], a[8];
+    float s = 0.f, mx = 0.f;
+    if (n < N) {
+        const int64_t rows_per = (M + gridDim.y - 1) / gridDim.y;
+        const int64_t m0 = (int64_t)blockIdx.y * rows_per, m1 = min(M, m0 + rows_per);
+        // batches of 8 rows: all 16 loads are issued before the first (possibly aliasing, as far as the compiler knows) store
+        for (int64_t mb = m0; mb < m1; mb += 8) {
+            float v[8], a[8];
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const bool in = mb + i < m1;
-            v[i] = in ? g[(mb + i) * N + n] : 0.f;
-            a[i] = in ? y[(mb + i) * N + n] : 1.f;
-        }
+            for (int i = 0; i < 8; i++) {
+                const bool in = mb + i < m1;
+                v[i] = in ? g[(mb + i) * N + n] : 0.f;
+                a[i] = in ? y[(mb + i) * N + n] : 1.f;
+            }
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            if (a[i] > 0.f) s += v[i];
-            else g[(mb + i) * N + n] = 0.f;   // never taken for the padding entries (a = 1)
+            for (int i = 0; i < 8; i++) {
+                if (a[i] > 0.f) { s += v[i]; mx = fmaxf(mx, fabsf(v[i])); }
+                else g[(mb + i) * N + n] = 0.f;   // never taken for the padding entries (a = 1)
+            }
         }
+        atomicAdd(out + n, s);
     }
-    atomicAdd(out + n, s);
+    if (absmax_bits) block_absmax(mx, absmax_bits);   // max |g| after masking: the tensor-core GEMMs scale their fp16 operand by it
 }
 
-inline int launch_relu_mask_colsum(cudaStream_t st, float *g, const float *y, int64_t M, int64_t N, float *out)
+inline int launch_relu_mask_colsum(cudaStream_t st, float *g, const float *y, int64_t M, int64_t N, float *out,
+                                   unsigned int *absmax_bits = nullptr)
 {
     if (N <= 0) return PN_OK;
     PN_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)N, st));
     if (M <= 0) return PN_OK;
     const int64_t yb = std::max<int64_t>(1, std::min<int64_t>(2048, M / 64));
     dim3 grid((unsigned)ceil_div(N, 128), (unsigned)yb);
-    k_relu_mask_colsum<<<grid, 128, 0, st>>>(g, y, M, N, out);
+    k_relu_mask_colsum<<<grid, 128, 0, st>>>(g, y, M, N, out, absmax_bits);
     PN_LAUNCH_CHECK();
     return PN_OK;
 }

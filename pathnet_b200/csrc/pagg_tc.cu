@@ -41,6 +41,8 @@ struct GemmTcArgs {
     const float *bias;   // [N] or null
     int64_t M, N, K, lda, ldb, ldc;
     int relu, accumulate;
+    const float *a_scale;   // optional device {s, 1/s}: A is staged as fp16(A * s) and the result multiplied by 1/s (raw
+                            // gradients would underflow fp16; s is a power of two taken from max |A|, see k_absmax_scale)
 };
 
 template <bool BF16>
@@ -59,7 +61,7 @@ __device__ __forceinline__ uint4 pack8_half_or_bf16(const float (&f)[8])
 // Two phases so that all of a thread's global loads are in flight together.
 template <int ROWS, int NTHREADS, bool MN, bool BF16>
 __device__ __forceinline__ void stage_tile(unsigned char *dst, const float *__restrict__ src, int64_t ld, int64_t row0,
-                                           int64_t nrows, int64_t k0, int64_t kend, int tid)
+                                           int64_t nrows, int64_t k0, int64_t kend, int tid, float mul = 1.f)
 {
     constexpr int CHUNKS = ROWS * 8;  // 16-byte chunks (8 elements)
     constexpr int PER = CHUNKS / NTHREADS;
@@ -101,7 +103,7 @@ __device__ __forceinline__ void stage_tile(unsigned char *dst, const float *__re
         const int c = tid + i * NTHREADS;
         const uint32_t off = !MN ? canon_off(c % ROWS, (c / ROWS) * 8, 64)
                                  : (uint32_t)((c / 64) * 1024 + ((c % 64) >> 3) * 128 + ((c % 64) & 7) * 16);
-        const float f[8] = {lo[i].x, lo[i].y, lo[i].z, lo[i].w, hi[i].x, hi[i].y, hi[i].z, hi[i].w};
+        const float f[8] = {lo[i].x * mul, lo[i].y * mul, lo[i].z * mul, lo[i].w * mul, hi[i].x * mul, hi[i].y * mul, hi[i].z * mul, hi[i].w * mul};
         *reinterpret_cast<uint4 *>(dst + off) = pack8_half_or_bf16<BF16>(f);
     }
 }
@@ -131,11 +133,12 @@ __global__ void __launch_bounds__(128) k_gemm_tc(GemmTcArgs g)
     // read it (two tiles earlier) have committed
     uint32_t phase[2] = {0, 0};
     int it = 0;
+    const float a_mul = g.a_scale ? g.a_scale[0] : 1.f, out_mul = g.a_scale ? g.a_scale[1] : 1.f;
     for (int64_t k0 = kbeg; k0 < kend; k0 += BK, it++) {
         const int b = it & 1;
         unsigned char *As = smem_raw + b * STAGE, *Bs = As + BM * BK * 2;
         if (it >= 2) { mbar_wait(&bar[b], phase[b]); phase[b] ^= 1; }
-        stage_tile<BM, 128, A_MN, BF16>(As, g.A, g.lda, m0, g.M, k0, kend, tid);
+        stage_tile<BM, 128, A_MN, BF16>(As, g.A, g.lda, m0, g.M, k0, kend, tid, a_mul);
         stage_tile<BN, 128, B_MN, BF16>(Bs, g.B, g.ldb, n0, g.N, k0, kend, tid);
         fence_proxy_async();
         __syncthreads();
@@ -172,7 +175,7 @@ __global__ void __launch_bounds__(128) k_gemm_tc(GemmTcArgs g)
                 const int64_t rmax = min((int64_t)32, g.M - (m0 + warp * 32));
                 float *dst = g.C + (m0 + warp * 32) * g.ldc + n;
                 for (int rr = 0; rr < rmax; rr++) {
-                    const float x = stg[rr * 33 + lane] + bn;
+                    const float x = stg[rr * 33 + lane] * out_mul + bn;
                     if (atomic) atomicAdd(dst + (int64_t)rr * g.ldc, x);
                     else dst[(int64_t)rr * g.ldc] = g.relu ? fmaxf(x, 0.f) : x;
                 }
@@ -193,11 +196,11 @@ __global__ void __launch_bounds__(128) k_gemm_tc(GemmTcArgs g)
 // splitk > 1 or accumulate: results are atomically added to C (no ReLU then).
 int launch_gemm_tc(cudaStream_t st, const float *A, int64_t lda, const float *B, int64_t ldb, float *C, int64_t ldc,
                    int64_t M, int64_t N, int64_t K, const float *bias, bool relu, bool a_mn, bool b_mn, bool bf16,
-                   bool accumulate, int splitk)
+                   bool accumulate, int splitk, const float *a_scale)
 {
     if (M <= 0 || N <= 0) return PN_OK;
     if ((splitk > 1 || accumulate) && relu) { set_error("launch_gemm_tc: ReLU with atomic accumulation"); return PN_ERR_INVALID; }
-    GemmTcArgs g{A, B, C, bias, M, N, K, lda, ldb, ldc, relu ? 1 : 0, accumulate ? 1 : 0};
+    GemmTcArgs g{A, B, C, bias, M, N, K, lda, ldb, ldc, relu ? 1 : 0, accumulate ? 1 : 0, a_scale};
     constexpr int BN = 128;
     const size_t smem = 2 * (128 + BN) * 64 * 2;
     dim3 grid((unsigned)ceil_div(N, BN), (unsigned)ceil_div(M, 128), (unsigned)std::max(1, splitk));
@@ -257,6 +260,8 @@ struct LstmTcArgs {
     int64_t P;
     int L;
     uint32_t drop_thr; float drop_scale; uint64_t drop_seed;
+    const uint64_t *seed_dev; // optional device word added to drop_seed (CUDA-graph replay)
+    int64_t p_base;           // global index of this call's first sequence (row-chunked calls)
     unsigned char *xh_img;    // wgrad operand images [x_t | h_{t-1}] (see LstmBwdTcArgs), written here
     int save;                 // 0: inference only, skip activations and operand images
     long long *trace;         // optional clock64() trace of CTA `trace_block` (debug)
@@ -287,7 +292,7 @@ __device__ __forceinline__ void tc_gather_quarter(const LstmTcArgs &a, unsigned 
 {
     const bool valid = row_off >= 0;
     const float *src = a.T + (int64_t)(valid ? row_off : 0) * TC_H;
-    const uint32_t key = dropout_key(a.drop_seed, 0);
+    const uint32_t key = dropout_key(a.seed_dev ? a.drop_seed + *a.seed_dev : a.drop_seed, 0);
     float4 ld[8];   // all eight 16-byte loads of the quarter row in flight together
 #pragma unroll
     for (int i = 0; i < 8; i++) ld[i] = valid ? __ldg(reinterpret_cast<const float4 *>(src + cq * 32 + i * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -404,7 +409,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_fwd_tc(LstmTcArgs a)
         const bool tr = a.trace && blockIdx.x == a.trace_block && tid == 0;
         if (tr) a.trace[6] = clock64();
         const int64_t ntiles = gridDim.x;
-        tc_gather_quarter(a, Xs, r, cq, rowoff_s[r * TC_MAX_L + 0], (uint64_t)(p * L + 0) * TC_H,
+        tc_gather_quarter(a, Xs, r, cq, rowoff_s[r * TC_MAX_L + 0], (uint64_t)((p + a.p_base) * L + 0) * TC_H,
                           a.xh_img + ((int64_t)0 * ntiles + blockIdx.x) * XH_BLOCK_BYTES);
         // h_{-1} = 0: h half of step 0's image
 #pragma unroll
@@ -419,7 +424,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_fwd_tc(LstmTcArgs a)
             // reader of that buffer, completed before acc_full(t-1) was observed)
             if (t + 1 < L)
                 tc_gather_quarter(a, Xs + ((t + 1) & 1) * TC_XBYTES, r, cq, rowoff_s[r * TC_MAX_L + t + 1],
-                                  (uint64_t)(p * L + t + 1) * TC_H, a.xh_img + ((int64_t)(t + 1) * ntiles + blockIdx.x) * XH_BLOCK_BYTES);
+                                  (uint64_t)((p + a.p_base) * L + t + 1) * TC_H, a.xh_img + ((int64_t)(t + 1) * ntiles + blockIdx.x) * XH_BLOCK_BYTES);
             if (tr) a.trace[t * 8 + 1] = clock64();
             // ---- wait for the gate pre-activations ----
             mbar_wait(&acc_full, t & 1);
@@ -506,7 +511,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_fwd_tc(LstmTcArgs a)
 
 // Forward LSTM in tensor-core mode (called from pn_pagg_forward).
 int pagg_tc_forward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_params &prm,
-                         const int32_t *seq_node, const uint8_t *seq_type, cudaStream_t st)
+                         const int32_t *seq_node, const uint8_t *seq_type, const PaggChunk &ck, cudaStream_t st)
 {
     if (c.H != TC_H || c.L > TC_MAX_L) {
         set_error("PN_MATH_TC: the tensor-core LSTM is built for hidden size 128 and path_len <= %d (got H=%d L=%d)", TC_MAX_L, c.H, c.L);
@@ -514,16 +519,18 @@ int pagg_tc_forward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_pa
     }
     // packed fp16 weights live in the (otherwise unused in this mode) Wp/WpT region: 2 x 256 KB fp32 >= 256 KB fp16
     unsigned char *Wh = reinterpret_cast<unsigned char *>(w.Wp);
-    k_pack_lstm_tc<<<(unsigned)ceil_div(TC_G4 * TC_K2, 256), 256, 0, st>>>(prm.w_ih, prm.w_hh, prm.b_ih, prm.b_hh, Wh, w.bp);
-    PN_LAUNCH_CHECK();
+    if (ck.first) {
+        k_pack_lstm_tc<<<(unsigned)ceil_div(TC_G4 * TC_K2, 256), 256, 0, st>>>(prm.w_ih, prm.w_hh, prm.b_ih, prm.b_hh, Wh, w.bp);
+        PN_LAUNCH_CHECK();
+    }
     uint32_t thr = 0; float scale = 1.f;
     if (c.training && c.dropout_p > 0.f) {
         thr = dropout_threshold(c.dropout_p);
         scale = c.dropout_p >= 1.f ? 0.f : 1.f / (1.f - c.dropout_p);
     }
-    const int64_t P = (int64_t)c.S * c.nw;
+    const int64_t P = ck.Sc * c.nw;
     LstmTcArgs a{w.T, seq_node, seq_type, Wh, w.bp, reinterpret_cast<__half *>(w.acts), w.hfin, P, c.L, thr, scale, c.dropout_seed,
-                 reinterpret_cast<unsigned char *>(w.XH), c.no_backward ? 0 : 1, nullptr, 0};
+                 c.dropout_seed_dev, ck.s0 * c.nw, reinterpret_cast<unsigned char *>(w.XH), ck.save ? 1 : 0, nullptr, 0};
     long long *d_trace = nullptr;
     const char *trace_env = getenv("PN_TRACE_FWD");
     if (trace_env) {
@@ -596,6 +603,8 @@ struct LstmBwdTcArgs {
     int64_t P, ntiles;
     int L;
     uint32_t drop_thr; float drop_scale; uint64_t drop_seed;
+    const uint64_t *seed_dev;
+    int64_t p_base;
     long long *trace;
     int trace_block;
 };
@@ -696,7 +705,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
         const bool valid = p < a.P;
         const uint32_t lane_base = taddr + ((uint32_t)(lq * 32) << 16);
         const float scale = a.gscale[0], inv_scale = a.gscale[1];
-        const uint32_t dkey = dropout_key(a.drop_seed, 0);
+        const uint32_t dkey = dropout_key(a.seed_dev ? a.drop_seed + *a.seed_dev : a.drop_seed, 0);
         // dx of step `ss` (time tt = L-1-ss) -> dT with the forward's dropout mask
         auto scatter_dx = [&](int ss) {
             const int tt = L - 1 - ss;
@@ -713,7 +722,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
 #pragma unroll
                     for (int j = 0; j < 8; j++) f[j] = __uint_as_float(v[c8 * 8 + j]) * inv_scale;
                     if (a.drop_thr) {
-                        const uint64_t pair = ((uint64_t)e * TC_H + cq * 32 + c8 * 8) >> 1;
+                        const uint64_t pair = ((uint64_t)(e + a.p_base * L) * TC_H + cq * 32 + c8 * 8) >> 1;
 #pragma unroll
                         for (int q = 0; q < 4; q++) {
                             const uint32_t h = dropout_hash_pair_k(dkey, pair + q);
@@ -958,19 +967,21 @@ __global__ void __launch_bounds__(192, 1) k_wgrad_tc(WgradTcArgs a)
 // LSTM backward in tensor-core mode: fills w.dWp [2H][4H] and w.dbp [4H] (packed
 // layouts, same as the fp32 path) and scatters dx into w.dT.
 int pagg_tc_backward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_params &prm,
-                          const int32_t *seq_node, const uint8_t *seq_type, cudaStream_t st)
+                          const int32_t *seq_node, const uint8_t *seq_type, const PaggChunk &ck, cudaStream_t st)
 {
     if (c.H != TC_H) {
         set_error("PN_MATH_TC: the tensor-core LSTM is built for hidden size 128 (got %d)", c.H);
         return PN_ERR_UNSUPPORTED;
     }
-    const int64_t P = (int64_t)c.S * c.nw, ntiles = ceil_div(P, 128), nblocks = ntiles * c.L;
+    const int64_t P = ck.Sc * c.nw, ntiles = ceil_div(P, 128), nblocks = ntiles * c.L;
     // max |dh_final| was accumulated into gscale[0] (as float bits) by k_pool_bwd
     k_make_scale<<<1, 1, 0, st>>>(w.gscale);
     PN_LAUNCH_CHECK();
     unsigned char *WhT = reinterpret_cast<unsigned char *>(w.WpT);  // 256 KB of the 512 KB fp32 region
-    k_pack_lstm_tc_bwd<<<(unsigned)ceil_div(TC_G4 * TC_K2, 256), 256, 0, st>>>(prm.w_ih, prm.w_hh, WhT);
-    PN_LAUNCH_CHECK();
+    if (ck.first) {
+        k_pack_lstm_tc_bwd<<<(unsigned)ceil_div(TC_G4 * TC_K2, 256), 256, 0, st>>>(prm.w_ih, prm.w_hh, WhT);
+        PN_LAUNCH_CHECK();
+    }
     uint32_t thr = 0; float scale = 1.f;
     if (c.training && c.dropout_p > 0.f) {
         thr = dropout_threshold(c.dropout_p);
@@ -978,7 +989,7 @@ int pagg_tc_backward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_p
     }
     unsigned char *da_img = reinterpret_cast<unsigned char *>(w.dA), *xh_img = reinterpret_cast<unsigned char *>(w.XH);
     LstmBwdTcArgs a{w.T, seq_node, seq_type, WhT, reinterpret_cast<const __half *>(w.acts), w.dhfin, w.gscale, w.dT,
-                    da_img, xh_img, P, ntiles, c.L, thr, scale, c.dropout_seed, nullptr, 0};
+                    da_img, xh_img, P, ntiles, c.L, thr, scale, c.dropout_seed, c.dropout_seed_dev, ck.s0 * c.nw, nullptr, 0};
     long long *d_trace = nullptr;
     const char *trace_env = getenv("PN_TRACE_BWD");
     if (trace_env) {
@@ -1004,8 +1015,7 @@ int pagg_tc_backward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_p
             fprintf(stderr, "[trace bwd cta %d] s=%d  begin %lld | prev dx scattered %lld | 4 da quarters arrived %lld | acc_full seen %lld | %lld\n",
                     a.trace_block, q, h[q * 8 + 0] - t00, h[q * 8 + 1] - t00, h[q * 8 + 2] - t00, h[q * 8 + 3] - t00, h[q * 8 + 4] - t00);
     }
-    PN_CUDA(cudaMemsetAsync(w.dWp, 0, sizeof(float) * TC_K2 * TC_G4, st));
-    PN_CUDA(cudaMemsetAsync(w.dbp, 0, sizeof(float) * TC_G4, st));
+    // dWp / dbp are zeroed once per call by pn_pagg_backward: every chunk adds into them
     WgradTcArgs wa{xh_img, da_img, nblocks, w.gscale, w.dWp, w.dbp};
     PN_CUDA(cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
     {
@@ -1033,6 +1043,71 @@ int pagg_tc_backward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_p
     return PN_OK;
 }
 
+// ---------------------------------------------------------------------------
+// projections around the LSTM in tensor-core mode
+// ---------------------------------------------------------------------------
+// {s, 1/s} with s a power of two that maps max |v| (float bits in slot[0], from the column-sum sweeps) to (2^13, 2^14]:
+// the fp16 copy of a raw gradient then keeps 11 significant bits down to 2^-28 of its largest entry.
+__global__ void k_absmax_scale(float *slot)
+{
+    const float m = __uint_as_float(*reinterpret_cast<unsigned int *>(slot));
+    float sc = 1.f;
+    if (m > 0.f && isfinite(m)) sc = exp2f(14.f - ceilf(log2f(m)));
+    slot[0] = sc;
+    slot[1] = 1.f / sc;
+}
+
+// K0: Z = act(X W0^T + b0) (:175 / :242-243);  K1: T[n, d*H + j] = act(Z nets_w[d]^T + nets_b[d]) (:185-191 / :249-257, hoisted)
+int pagg_tc_project(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_params &prm, const float *X, cudaStream_t st)
+{
+    const int64_t N = c.N, F = c.F, H = c.H, L = c.L;
+    const bool homo = c.variant == PN_VARIANT_HOMO;
+    int rc = launch_gemm_tc(st, X, F, prm.fc0_w, F, w.Z, H, N, H, F, prm.fc0_b, homo, false, false, false, false, 1, nullptr);
+    if (rc) return rc;
+    return launch_gemm_tc(st, w.Z, H, prm.nets_w, H, w.T, L * H, N, L * H, H, prm.nets_b, homo, false, false, false, false, 1, nullptr);
+}
+
+// backward of the two projections: nets_w/nets_b, fc0_w/fc0_b from dT, dZ (w.dT / w.dZ hold the scattered gradients).
+// The raw gradients are staged as fp16 times a power-of-two scale taken from their largest entry (the column-sum
+// sweeps that produce the bias gradients also take that maximum), fp32 accumulation.
+int pagg_tc_project_backward(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_params &prm, const float *X,
+                             const pn_pagg_params &g, cudaStream_t st)
+{
+    const int64_t N = c.N, F = c.F, H = c.H, L = c.L;
+    const bool homo = c.variant == PN_VARIANT_HOMO;
+    float *sc_T = w.gscale + 2, *sc_Z = w.gscale + 4;
+    PN_CUDA(cudaMemsetAsync(w.gscale + 2, 0, sizeof(float) * 4, st));
+    int rc;
+    // ---- table projection: T = act(Z Wn^T + bn) ----  (homo: ReLU backward fused with the bias gradient sweep)
+    rc = homo ? launch_relu_mask_colsum(st, w.dT, w.T, N, L * H, g.nets_b, reinterpret_cast<unsigned int *>(sc_T))
+              : launch_colsum(st, w.dT, N, L * H, L * H, g.nets_b, false, reinterpret_cast<unsigned int *>(sc_T));
+    if (rc) return rc;
+    k_absmax_scale<<<1, 1, 0, st>>>(sc_T);
+    PN_LAUNCH_CHECK();
+    {
+        // split the reduction over N so the (L*H/128) x (H/128) output tiles fill one wave of the 148 SMs
+        const int splitk = (int)std::max<int64_t>(1, std::min<int64_t>(148 / std::max<int64_t>(1, ceil_div(L * H, 128) * ceil_div(H, 128)), N / 256));
+        if (splitk > 1) PN_CUDA(cudaMemsetAsync(g.nets_w, 0, sizeof(float) * (size_t)(L * H * H), st));
+        // dWn[m][i] = sum_n dT[n][m] Z[n][i]: both operands have the reduction index as their row (MN-major)
+        rc = launch_gemm_tc(st, w.dT, L * H, w.Z, H, g.nets_w, H, L * H, H, N, nullptr, false, true, true, false, false, splitk, sc_T);
+        if (rc) return rc;
+    }
+    rc = launch_gemm_tc(st, w.dT, L * H, prm.nets_w, H, w.dZ, H, N, H, L * H, nullptr, false, false, true, false, true, 1, sc_T);  // dZ += dT Wn
+    if (rc) return rc;
+    // ---- fc0: Z = act(X W0^T + b0) ----
+    rc = homo ? launch_relu_mask_colsum(st, w.dZ, w.Z, N, H, g.fc0_b, reinterpret_cast<unsigned int *>(sc_Z))
+              : launch_colsum(st, w.dZ, N, H, H, g.fc0_b, false, reinterpret_cast<unsigned int *>(sc_Z));
+    if (rc) return rc;
+    k_absmax_scale<<<1, 1, 0, st>>>(sc_Z);
+    PN_LAUNCH_CHECK();
+    {
+        const int splitk = (int)std::max<int64_t>(1, std::min<int64_t>(148 / std::max<int64_t>(1, ceil_div(H, 128) * ceil_div(F, 128)), N / 256));
+        if (splitk > 1) PN_CUDA(cudaMemsetAsync(g.fc0_w, 0, sizeof(float) * (size_t)(H * F), st));
+        rc = launch_gemm_tc(st, w.dZ, H, X, F, g.fc0_w, F, H, F, N, nullptr, false, true, true, false, false, splitk, sc_Z);  // dW0 = dZ^T X
+    }
+    return rc;
+}
+
 }  // namespace pn
 
 // stand-alone entry for the tcgen05 GEMM (unit-tested against fp64 math).  flags: bit0 A given as [K][M],
@@ -1040,12 +1115,12 @@ int pagg_tc_backward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_p
 extern "C" int pn_debug_gemm_tc(const float *A, const float *B, float *C, const float *bias, int64_t M, int64_t N,
                                 int64_t K, int relu, void *stream)
 {
-    return pn::launch_gemm_tc((cudaStream_t)stream, A, K, B, K, C, N, M, N, K, bias, relu != 0, false, false, false, false, 1);
+    return pn::launch_gemm_tc((cudaStream_t)stream, A, K, B, K, C, N, M, N, K, bias, relu != 0, false, false, false, false, 1, nullptr);
 }
 extern "C" int pn_debug_gemm_tc2(const float *A, const float *B, float *C, int64_t M, int64_t N, int64_t K, int flags,
                                  int splitk, void *stream)
 {
     const bool a_mn = flags & 1, b_mn = flags & 2, bf16 = flags & 4, acc = flags & 8;
     return pn::launch_gemm_tc((cudaStream_t)stream, A, a_mn ? M : K, B, b_mn ? N : K, C, N, M, N, K, nullptr, false, a_mn,
-                              b_mn, bf16, acc, splitk);
+                              b_mn, bf16, acc, splitk, nullptr);
 }

@@ -27,23 +27,13 @@ def _fused_forward(variant):
     def forward(self, X, neis, num_w, walk_len, indices, layer_type, indxx=None):
         from . import pagg
         mod = sys.modules.get(type(self).__module__)
-        drop = float(getattr(mod, "dropout", 0.0)) if mod is not None else 0.0
-        dev = X.device
-        if dev.type != "cuda":
-            raise RuntimeError("pathnet_b200 PAGG runs on CUDA only (no CPU fallback); X is on %s" % dev)
-        if torch.is_tensor(indices):
-            mask = indices.to(dev)
-        else:
-            mask = torch.as_tensor(np.asarray(indices), device=dev)
-        rows = torch.nonzero(mask.reshape(-1) != 0, as_tuple=False).reshape(-1).to(torch.int32)
-        S = rows.numel()
-        neis = torch.as_tensor(neis).to(dev, dtype=torch.int64)
-        layer_type = torch.as_tensor(layer_type).to(dev, dtype=torch.int64)
-        sn, st, pt = pagg.canonicalize(variant, neis, layer_type.view(S, num_w, walk_len), num_w, walk_len)
-        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if (self.training and drop > 0) else 0
-        return pagg.pagg_forward(variant, X, dict(self.named_parameters()), sn, st, pt, rows, dropout=drop,
-                                 training=self.training, seed=seed,
-                                 math_mode=os.environ.get("PN_MATH_MODE", "auto"))
+        drop = float(getattr(mod, "dropout", 0.0)) if mod is not None else 0.0   # the script's module global (:71)
+        st = self.__dict__.get("_pn_state")
+        if st is None:   # per-module state of the fused path: mask -> rows cache (no per-call nonzero sync), index guard
+            st = self.__dict__["_pn_state"] = dict(rows=pagg.RowsCache(), guard=pagg.IndexGuard(X.device), sink=pagg.GradSink())
+        return pagg.fused_forward(self, variant, X, neis, num_w, walk_len, indices, layer_type, dropout=drop,
+                                  math_mode=os.environ.get("PN_MATH_MODE", "auto"), rows_cache=st["rows"],
+                                  guard=st["guard"], grad_sink=st["sink"])
     return forward
 
 

@@ -79,20 +79,47 @@ def test_cli_argument_errors_mirror_reference(capsys):
 
 
 def test_mask_rows_cache_follows_in_place_changes():
-    """PathNet._rows_of keeps nonzero(mask) per mask tensor object and drops it when the tensor is modified in place."""
+    """RowsCache keeps nonzero(mask) per mask (torch: tensor object + in-place version; numpy: by content)."""
     import torch
-    from pathnet_b200.pagg import PathNet_homo
-    m = PathNet_homo(8, 16, 3, 4)
-    mask = torch.tensor([True, False, True, True])
-    r1 = m._rows_of(mask, torch.device("cpu"))
-    assert r1.dtype == torch.int32 and r1.tolist() == [0, 2, 3]
-    assert m._rows_of(mask, torch.device("cpu")) is r1            # same object, same version: reused
-    mask[1] = True                                                 # in-place edit bumps the version counter
-    assert m._rows_of(mask, torch.device("cpu")).tolist() == [0, 1, 2, 3]
-    other = torch.tensor([False, True, False, False])              # a different tensor never hits another's entry
-    assert m._rows_of(other, torch.device("cpu")).tolist() == [1]
     import numpy as np
-    assert m._rows_of(np.array([0, 1, 1, 0]), torch.device("cpu")).tolist() == [1, 2]
+    from pathnet_b200.pagg import PathNet_homo, RowsCache
+    m = PathNet_homo(8, 16, 3, 4)
+    rc, cpu = m._rows_cache, torch.device("cpu")
+    assert isinstance(rc, RowsCache)
+    mask = torch.tensor([True, False, True, True])
+    r1 = rc.get(mask, cpu)
+    assert r1.dtype == torch.int32 and r1.tolist() == [0, 2, 3]
+    assert rc.get(mask, cpu) is r1                                 # same object, same version: reused
+    mask[1] = True                                                 # in-place edit bumps the version counter
+    assert rc.get(mask, cpu).tolist() == [0, 1, 2, 3]
+    other = torch.tensor([False, True, False, False])              # a different tensor never hits another's entry
+    assert rc.get(other, cpu).tolist() == [1]
+    a = np.array([0, 1, 1, 0])
+    r2 = rc.get(a, cpu)
+    assert r2.tolist() == [1, 2]
+    assert rc.get(np.array([0, 1, 1, 0]), cpu) is r2               # numpy masks: by content (the reference passes numpy bool masks)
+    a[0] = 1
+    assert rc.get(a, cpu).tolist() == [0, 1, 2]                    # a mutated array is a different key
     for _ in range(20):                                            # bounded
-        m._rows_of(torch.tensor([True]), torch.device("cpu"))
-    assert len(m._rows_cache) <= 8
+        rc.get(torch.tensor([True]), cpu)
+    assert len(rc.ents) <= 8
+
+
+def test_math_mode_resolution(monkeypatch):
+    import warnings
+    import pytest
+    from pathnet_b200 import pagg
+    assert pagg.resolve_math_mode("fp32", 128, 4) == "fp32"
+    assert pagg.resolve_math_mode("tc", 128, 4) == "tc"
+    assert pagg.resolve_math_mode("auto", 64, 4) == "fp32"        # no tensor-core kernels at this hidden size
+    monkeypatch.setenv("PN_MATH_MODE", "fp32")
+    assert pagg.resolve_math_mode("auto", 128, 4) == "fp32"       # env override of the default
+    monkeypatch.delenv("PN_MATH_MODE")
+    pagg._warned_auto_tc = False
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        assert pagg.resolve_math_mode("auto", 128, 4) == "tc"
+        assert pagg.resolve_math_mode("auto", 128, 4) == "tc"
+    assert len(w) == 1 and "fp32" in str(w[0].message)            # one notice naming the strict mode
+    with pytest.raises(ValueError):
+        pagg.resolve_math_mode("bf16", 128, 4)

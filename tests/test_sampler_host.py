@@ -235,4 +235,4 @@ def test_abi_exports_every_declared_symbol():
     missing = [s for s in sorted(declared) if not hasattr(L, s)]
     assert not missing, missing
     assert set(_lib.EXPORTS) <= declared
-    assert L.pn_version() == 100
+    assert L.pn_version() == 200
