@@ -201,6 +201,12 @@ int pn_pagg_canonicalize(int32_t variant, int32_t N, int32_t S, int32_t nw, int3
                          int32_t type_dtype, int32_t *seq_node, uint8_t *seq_type,
                          int32_t *partner, int32_t *status, void *stream);
 
+/* fp16 copy of X for pn_pagg_cfg.x16: [N][F16] row-major, F16 = F rounded up to a multiple of 8, zero padded
+ * (pn_pagg_x16_bytes(N, F) bytes, 16-byte aligned).  X does not change during training (PathNet_run.py:300), so a
+ * caller makes this once and the tensor-core mode TMA-loads it on every step instead of re-reading fp32 X. */
+size_t pn_pagg_x16_bytes(int32_t N, int32_t F);
+int pn_pagg_pack_x16(int32_t N, int32_t F, const float *X, void *x16, void *stream);
+
 /* Bytes of device workspace forward/backward need for this cfg (saved
  * activations + scratch).  The same workspace must be passed to forward and
  * to the matching backward, untouched in between. */
@@ -260,6 +266,12 @@ int pn_debug_gemm_tc(const float *A, const float *B, float *C, const float *bias
  * bit3 accumulate into C (atomics); splitk >= 1 splits K across CTAs (C pre-zeroed). */
 int pn_debug_gemm_tc2(const float *A, const float *B, float *C, int64_t M, int64_t N, int64_t K,
                       int flags, int splitk, void *stream);
+
+/* Unit-test entry of the TMA-fed GEMM (gemm_tma.cu): C[M,N] (fp32, may be NULL) and C16[M,N] (fp16 of the value times
+ * c16_scale, may be NULL) = act(A[M,K] B[N,K]^T + bias); fp32 device inputs are converted to fp16 in `scratch`
+ * ((M + N) * roundup8(K) halves) first. */
+int pn_debug_gemm_tma(const float *A, const float *B, float *C, void *C16, const float *bias, int64_t M, int64_t N,
+                      int64_t K, int relu, float c16_scale, void *scratch, void *stream);
 
 /* In-stream kernel timing for bench.py's roofline: when enabled, the library
  * brackets its dominant kernels with CUDA events on the launching stream.

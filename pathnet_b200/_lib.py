@@ -82,6 +82,10 @@ def lib():
                                       vp, vp, vp]
         L.pn_pagg_backward.argtypes = [C.POINTER(PaggCfg), C.POINTER(PaggParams), vp, vp, vp, vp,
                                        vp, vp, vp, C.POINTER(PaggParams), vp]
+        L.pn_pagg_x16_bytes.restype = C.c_size_t
+        L.pn_pagg_x16_bytes.argtypes = [i32, i32]
+        L.pn_pagg_pack_x16.argtypes = [i32, i32, vp, vp, vp]
+        L.pn_debug_gemm_tma.argtypes = [vp, vp, vp, vp, vp, i64, i64, i64, C.c_int, C.c_float, vp, vp]
         L.pn_step_advance.argtypes = [vp, vp]
         L.pn_ce_loss_grad.argtypes = [i64, i32, vp, vp, i32, C.c_float, vp, vp, vp]
         L.pn_adam_step.argtypes = [i64, vp, vp, vp, vp, C.POINTER(AdamCfg), vp, vp]
@@ -99,7 +103,8 @@ def check(rc: int) -> int:
 EXPORTS = ("pn_version", "pn_last_error", "pn_graph_from_edges", "pn_graph_from_edges_uniform", "pn_graph_free", "pn_graph_info",
            "pn_graph_cells_host", "pn_graph_prepare_labels", "pn_merw_sample", "pn_merw_probabilities",
            "pn_paths_format_txt", "pn_paths_parse_txt", "pn_edges_parse_txt", "pn_pagg_canonicalize",
-           "pn_pagg_workspace_bytes", "pn_pagg_forward", "pn_pagg_backward", "pn_step_advance", "pn_ce_loss_grad",
+           "pn_pagg_workspace_bytes", "pn_pagg_forward", "pn_pagg_backward", "pn_pagg_x16_bytes", "pn_pagg_pack_x16",
+           "pn_step_advance", "pn_ce_loss_grad",
            "pn_adam_step", "pn_dropout_hash",
            "pn_launch_count", "pn_profile_enable", "pn_profile_read")
 

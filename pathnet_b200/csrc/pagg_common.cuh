@@ -38,6 +38,7 @@ struct PaggWs {
     float *x16;      // [N][F16] fp16 copy of X (unless the caller supplied cfg.x16)
     float *z16;      // [N][H]   fp16 copy of Z written by the fc0 epilogue
     float *w16;      // fc0_w [H][F16] then nets_w [L*H][H], fp16
+    float *t16;      // [N][L*H] fp16 copy of T times the dropout scale (what the LSTM kernel gathers)
     size_t bytes;
 };
 
@@ -93,6 +94,7 @@ inline PaggWs carve_workspace(const pn_pagg_cfg &c, void *base)
     take(w.x16, c.math_mode == PN_MATH_TC && !c.x16 ? (N * F16 + 1) / 2 : 0);
     take(w.z16, c.math_mode == PN_MATH_TC ? (N * H + 1) / 2 : 0);
     take(w.w16, c.math_mode == PN_MATH_TC ? (H * F16 + L * H * H + 1) / 2 : 0);
+    take(w.t16, c.math_mode == PN_MATH_TC ? (N * L * H + 1) / 2 : 0);
     w.bytes = off;
     return w;
 }

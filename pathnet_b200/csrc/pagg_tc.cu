@@ -221,6 +221,15 @@ int launch_gemm_tc(cudaStream_t st, const float *A, int64_t lda, const float *B,
     return PN_OK;
 }
 
+int launch_f32_to_f16_rows(cudaStream_t st, const float *src, int64_t rows, int64_t K, int64_t ld_src, __half *dst, int64_t K16);   // gemm_tma.cu
+int launch_gemm_tma(cudaStream_t st, const __half *A16, const __half *B16, int64_t M, int64_t N, int64_t K16, const float *bias,
+                    bool relu, float *C, int64_t ldc, __half *C16, int64_t ldc16, float c16_scale);                                  // gemm_tma.cu
+static bool tc_legacy_gemm()
+{
+    static const bool legacy = [] { const char *e = getenv("PN_TC_GEMM"); return e && e[0] == 'l'; }();
+    return legacy;
+}
+
 // ---------------------------------------------------------------------------
 // LSTM weights -> fp16, canonical layout, cut into 16 K-chunks of 16 so each
 // chunk ([512 cols][16 k], 16 KB) is one contiguous bulk copy.
@@ -250,6 +259,7 @@ __global__ void k_pack_lstm_tc(const float *__restrict__ w_ih, const float *__re
 }
 
 struct LstmTcArgs {
+    const __half *T16;        // [N,L,H] fp16 table, pre-multiplied by the dropout scale (null: gather the fp32 table below)
     const float *T;           // [N,L,H] fp32 table
     const int32_t *seq_node;  // [P,L]
     const uint8_t *seq_type;  // [P,L]
@@ -286,13 +296,39 @@ __device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_
 constexpr int TC_CWARPS = 16;                    // compute warps: 4 TMEM lane quarters x 4 column quarters
 constexpr int TC_THREADS = (TC_CWARPS + 2) * 32;  // + MMA warp + weight-producer warp
 
-// this thread's quarter (32 floats) of table row `row_off` -> dropout -> fp16 -> x tile (canonical, K extent 128)
+// this thread's quarter (32 values) of table row `row_off` -> dropout -> fp16 -> x tile (canonical, K extent 128).
+// With the fp16 table (written by the projection GEMM's epilogue, already times 1/(1-p)) the row is 4 x 16 bytes and
+// dropout is a bit mask on the packed halves; the fp32 table costs 8 loads, the scale multiply and the conversion.
 __device__ __forceinline__ void tc_gather_quarter(const LstmTcArgs &a, unsigned char *Xs, int r, int cq, int32_t row_off,
                                                    uint64_t elem0 /* (p*L + t) * H */, unsigned char *xh_blk)
 {
     const bool valid = row_off >= 0;
-    const float *src = a.T + (int64_t)(valid ? row_off : 0) * TC_H;
     const uint32_t key = dropout_key(a.seed_dev ? a.drop_seed + *a.seed_dev : a.drop_seed, 0);
+    if (a.T16) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(a.T16 + (int64_t)(valid ? row_off : 0) * TC_H + cq * 32);
+        uint4 ld[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) ld[i] = valid ? __ldg(src + i) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++) {
+            const int k8 = cq * 4 + kk;
+            uint32_t wv[4] = {ld[kk].x, ld[kk].y, ld[kk].z, ld[kk].w};
+            if (valid && a.drop_thr) {
+                const uint64_t pair = (elem0 + k8 * 8) >> 1;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const uint32_t h = dropout_hash_pair_k(key, pair + q);
+                    const uint32_t keep = ((h & 0xFFFFu) < a.drop_thr ? 0u : 0x0000FFFFu) | ((h >> 16) < a.drop_thr ? 0u : 0xFFFF0000u);
+                    wv[q] &= keep;
+                }
+            }
+            const uint4 pk = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+            *reinterpret_cast<uint4 *>(Xs + canon_off(r, k8 * 8, TC_H)) = pk;
+            if (a.save) *reinterpret_cast<uint4 *>(xh_blk + (size_t)k8 * 2048 + r * 16) = pk;   // x half of the wgrad operand image
+        }
+        return;
+    }
+    const float *src = a.T + (int64_t)(valid ? row_off : 0) * TC_H;
     float4 ld[8];   // all eight 16-byte loads of the quarter row in flight together
 #pragma unroll
     for (int i = 0; i < 8; i++) ld[i] = valid ? __ldg(reinterpret_cast<const float4 *>(src + cq * 32 + i * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -529,7 +565,8 @@ int pagg_tc_forward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_pa
         scale = c.dropout_p >= 1.f ? 0.f : 1.f / (1.f - c.dropout_p);
     }
     const int64_t P = ck.Sc * c.nw;
-    LstmTcArgs a{w.T, seq_node, seq_type, Wh, w.bp, reinterpret_cast<__half *>(w.acts), w.hfin, P, c.L, thr, scale, c.dropout_seed,
+    LstmTcArgs a{tc_legacy_gemm() ? nullptr : reinterpret_cast<const __half *>(w.t16), w.T, seq_node, seq_type, Wh, w.bp,
+                 reinterpret_cast<__half *>(w.acts), w.hfin, P, c.L, thr, scale, c.dropout_seed,
                  c.dropout_seed_dev, ck.s0 * c.nw, reinterpret_cast<unsigned char *>(w.XH), ck.save ? 1 : 0, nullptr, 0};
     long long *d_trace = nullptr;
     const char *trace_env = getenv("PN_TRACE_FWD");
@@ -1058,13 +1095,30 @@ __global__ void k_absmax_scale(float *slot)
 }
 
 // K0: Z = act(X W0^T + b0) (:175 / :242-243);  K1: T[n, d*H + j] = act(Z nets_w[d]^T + nets_b[d]) (:185-191 / :249-257, hoisted)
+// Default: the TMA-fed GEMM of gemm_tma.cu on fp16 copies (X: the caller's cached cfg.x16 or converted here; Z: written
+// by the fc0 epilogue; weights: converted here, 0.3 MB), which also writes the fp16 table the LSTM kernel gathers.
+// PN_TC_GEMM=legacy: the round-1 kernel that converts fp32 operands while staging them (kept for A/B runs).
 int pagg_tc_project(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_params &prm, const float *X, cudaStream_t st)
 {
     const int64_t N = c.N, F = c.F, H = c.H, L = c.L;
     const bool homo = c.variant == PN_VARIANT_HOMO;
-    int rc = launch_gemm_tc(st, X, F, prm.fc0_w, F, w.Z, H, N, H, F, prm.fc0_b, homo, false, false, false, false, 1, nullptr);
-    if (rc) return rc;
-    return launch_gemm_tc(st, w.Z, H, prm.nets_w, H, w.T, L * H, N, L * H, H, prm.nets_b, homo, false, false, false, false, 1, nullptr);
+    if (tc_legacy_gemm()) {
+        int rc = launch_gemm_tc(st, X, F, prm.fc0_w, F, w.Z, H, N, H, F, prm.fc0_b, homo, false, false, false, false, 1, nullptr);
+        if (rc) return rc;
+        return launch_gemm_tc(st, w.Z, H, prm.nets_w, H, w.T, L * H, N, L * H, H, prm.nets_b, homo, false, false, false, false, 1, nullptr);
+    }
+    const int64_t F16 = (F + 7) / 8 * 8;
+    __half *x16 = reinterpret_cast<__half *>(w.x16), *z16 = reinterpret_cast<__half *>(w.z16);
+    __half *w0 = reinterpret_cast<__half *>(w.w16), *wn = w0 + H * F16, *t16 = reinterpret_cast<__half *>(w.t16);
+    int rc;
+    if (c.x16) x16 = const_cast<__half *>(reinterpret_cast<const __half *>(c.x16));
+    else if ((rc = launch_f32_to_f16_rows(st, X, N, F, F, x16, F16))) return rc;
+    if ((rc = launch_f32_to_f16_rows(st, prm.fc0_w, H, F, F, w0, F16))) return rc;
+    if ((rc = launch_f32_to_f16_rows(st, prm.nets_w, L * H, H, H, wn, H))) return rc;
+    if ((rc = launch_gemm_tma(st, x16, w0, N, H, F16, prm.fc0_b, homo, w.Z, H, z16, H, 1.f))) return rc;
+    float tscale = 1.f;   // the LSTM kernel's dropout keeps x * 1/(1-p): folded into the fp16 table it gathers
+    if (c.training && c.dropout_p > 0.f) tscale = c.dropout_p >= 1.f ? 0.f : 1.f / (1.f - c.dropout_p);
+    return launch_gemm_tma(st, z16, wn, N, L * H, H, prm.nets_b, homo, w.T, L * H, t16, L * H, tscale);
 }
 
 // backward of the two projections: nets_w/nets_b, fc0_w/fc0_b from dT, dZ (w.dT / w.dZ hold the scattered gradients).

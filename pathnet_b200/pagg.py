@@ -134,6 +134,25 @@ def canonicalize(variant: str, neis: torch.Tensor, layer_type: torch.Tensor, num
     return seq_node, seq_type, partner
 
 
+class X16Cache:
+    """fp16 copy of X for the tensor-core mode's TMA loads (pn_pagg_pack_x16), kept while the same tensor object is
+    passed with an unchanged in-place version — X is constant over a training run (PathNet_run.py:300)."""
+
+    def __init__(self):
+        self.ent = None
+
+    def get(self, X):
+        e = self.ent
+        if e is not None and e[0] is X and e[1] == X._version and e[2] == X.data_ptr():
+            return e[3]
+        N, F = X.shape
+        buf = torch.empty(lib().pn_pagg_x16_bytes(N, F), dtype=torch.uint8, device=X.device)
+        with torch.cuda.device(X.device):
+            check(lib().pn_pagg_pack_x16(N, F, X.data_ptr(), buf.data_ptr(), _stream_ptr()))
+        self.ent = (X, X._version, X.data_ptr(), buf)
+        return buf
+
+
 class GradSink:
     """Where the latest backward put the parameter gradients: ONE flat fp32 buffer (the order of PARAM_NAMES) whose
     slices are returned to autograd, so `p.grad` of every parameter aliases it.  pathnet_b200.dist all-reduces
@@ -162,6 +181,10 @@ class _PaggFunction(torch.autograd.Function):
                       training=int(meta["training"]), dropout_p=float(meta["dropout"]),
                       dropout_seed=int(meta["seed"]), no_backward=int(not meta.get("need_backward", True)),
                       row_chunk=int(meta.get("row_chunk", 0) or 0), dropout_seed_dev=None, x16=None)
+        x16 = None
+        if cfg.math_mode == MATH["tc"] and meta.get("x16_cache") is not None and X.dtype == torch.float32 and X.is_contiguous():
+            x16 = meta["x16_cache"].get(X)     # keyed on the caller's tensor object: valid while X is not modified in place
+            cfg.x16 = x16.data_ptr()
         with torch.cuda.device(dev):
             ws_bytes = lib().pn_pagg_workspace_bytes(C.byref(cfg))
             if ws_bytes == 0:
@@ -175,7 +198,7 @@ class _PaggFunction(torch.autograd.Function):
         # the tensors backward re-reads go through save_for_backward, so an in-place update of a parameter (or of X)
         # between forward and backward trips autograd's version check instead of silently changing the gradients
         ctx.save_for_backward(X, *raw)
-        ctx.cfg, ctx.ws = cfg, ws
+        ctx.cfg, ctx.ws, ctx.x16 = cfg, ws, x16
         ctx.idx = (seq_node, seq_type, partner, rows)
         ctx.sink = meta.get("grad_sink")
         return logits
@@ -213,14 +236,14 @@ class _PaggFunction(torch.autograd.Function):
 
 
 def pagg_forward(variant, X, params: dict, seq_node, seq_type, partner, rows, *, dropout=0.0,
-                 training=False, seed=0, math_mode="auto", row_chunk=0, grad_sink=None):
+                 training=False, seed=0, math_mode="auto", row_chunk=0, grad_sink=None, x16_cache=None):
     """Functional form over a dict with the reference's state_dict keys."""
     L = seq_node.shape[2]
     nets_w = torch.stack([params[f"nets.{d}.weight"] for d in range(L)])
     nets_b = torch.stack([params[f"nets.{d}.bias"] for d in range(L)])
     need_bwd = torch.is_grad_enabled() and any(t.requires_grad for t in params.values() if torch.is_tensor(t))
     meta = dict(variant=variant, math_mode=math_mode, training=training, dropout=dropout, seed=seed,
-                need_backward=need_bwd, row_chunk=row_chunk, grad_sink=grad_sink)
+                need_backward=need_bwd, row_chunk=row_chunk, grad_sink=grad_sink, x16_cache=x16_cache)
     return _PaggFunction.apply(X, params["fc0.weight"], params["fc0.bias"], nets_w, nets_b,
                                params["LSTM.weight_ih_l0"], params["LSTM.weight_hh_l0"],
                                params["LSTM.bias_ih_l0"], params["LSTM.bias_hh_l0"],
@@ -261,7 +284,7 @@ class RowsCache:
 
 
 def fused_forward(self, variant, X, neis, num_w, walk_len, indices, layer_type, *, dropout, math_mode, row_chunk=0,
-                  rows_cache=None, guard=None, grad_sink=None):
+                  rows_cache=None, guard=None, grad_sink=None, x16_cache=None):
     """The 7-argument forward of both reference classes on the fused operator; shared by the drop-in modules below
     and by the launcher that rebinds the forward of the reference's own classes (pathnet_b200/run.py)."""
     dev = X.device
@@ -291,7 +314,7 @@ def fused_forward(self, variant, X, neis, num_w, walk_len, indices, layer_type, 
         seed = int(torch.randint(0, 2 ** 62, (1,)).item())  # follows torch.manual_seed (host generator: no device sync)
     sd = {k: v for k, v in self.named_parameters()}
     return pagg_forward(variant, X, sd, seq_node, seq_type, partner, rows, dropout=dropout, training=self.training,
-                        seed=seed, math_mode=math_mode, row_chunk=row_chunk, grad_sink=grad_sink)
+                        seed=seed, math_mode=math_mode, row_chunk=row_chunk, grad_sink=grad_sink, x16_cache=x16_cache)
 
 
 class _PathNetBase(nn.Module):
@@ -307,6 +330,7 @@ class _PathNetBase(nn.Module):
         self._rows_cache = RowsCache()
         self._guard = None
         self.grad_sink = GradSink()
+        self._x16 = X16Cache()
         self.feature_length, self.hidden_size, self.out_size = feature_length, hidden_size, out_size
         # construction order = the reference's (:162-170), so a given torch seed
         # yields the same initial weights
@@ -329,7 +353,7 @@ class _PathNetBase(nn.Module):
             self._guard = IndexGuard(X.device)
         return fused_forward(self, self._variant, X, neis, num_w, walk_len, indices, layer_type, dropout=self.dropout,
                              math_mode=self.math_mode, row_chunk=self.row_chunk, rows_cache=self._rows_cache,
-                             guard=self._guard, grad_sink=self.grad_sink)
+                             guard=self._guard, grad_sink=self.grad_sink, x16_cache=self._x16)
 
 
 class PathNet(_PathNetBase):

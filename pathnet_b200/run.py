@@ -30,10 +30,10 @@ def _fused_forward(variant):
         drop = float(getattr(mod, "dropout", 0.0)) if mod is not None else 0.0   # the script's module global (:71)
         st = self.__dict__.get("_pn_state")
         if st is None:   # per-module state of the fused path: mask -> rows cache (no per-call nonzero sync), index guard
-            st = self.__dict__["_pn_state"] = dict(rows=pagg.RowsCache(), guard=pagg.IndexGuard(X.device), sink=pagg.GradSink())
+            st = self.__dict__["_pn_state"] = dict(rows=pagg.RowsCache(), guard=pagg.IndexGuard(X.device), sink=pagg.GradSink(), x16=pagg.X16Cache())
         return pagg.fused_forward(self, variant, X, neis, num_w, walk_len, indices, layer_type, dropout=drop,
                                   math_mode=os.environ.get("PN_MATH_MODE", "auto"), rows_cache=st["rows"],
-                                  guard=st["guard"], grad_sink=st["sink"])
+                                  guard=st["guard"], grad_sink=st["sink"], x16_cache=st["x16"])
     return forward
 
 

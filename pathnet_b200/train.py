@@ -136,6 +136,12 @@ class TrainStep:
                            math_mode=pagg.MATH[mode], training=1, dropout_p=self.dropout, dropout_seed=base_seed,
                            no_backward=0, row_chunk=int(getattr(model, "row_chunk", 0) if row_chunk is None else row_chunk),
                            dropout_seed_dev=self.state.data_ptr(), x16=None)
+        self.x16 = None
+        if mode == "tc":   # X is constant over the run: its fp16 copy for the TMA-loaded fc0 GEMM is made once
+            self.x16 = torch.empty(lib().pn_pagg_x16_bytes(self.cfg.N, F), dtype=torch.uint8, device=self.dev)
+            with torch.cuda.device(self.dev):
+                check(lib().pn_pagg_pack_x16(self.cfg.N, F, self.X.data_ptr(), self.x16.data_ptr(), torch.cuda.current_stream().cuda_stream))
+            self.cfg.x16 = self.x16.data_ptr()
         with torch.cuda.device(self.dev):
             ws_bytes = lib().pn_pagg_workspace_bytes(C.byref(self.cfg))
             if ws_bytes == 0:

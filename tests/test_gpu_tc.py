@@ -4,8 +4,8 @@ Tolerance: operands are rounded to fp16 (11-bit significand, the same width
 as TF32), products accumulate in fp32 in TMEM, gate non-linearities use
 tanh.approx (2^-11 relative).  In the backward pass gradients
 travel as scaled fp16 too.  Against the fp64 oracle the logits are held to
-rtol 1e-2 / atol 3e-3, and every parameter gradient to a Frobenius-relative
-error of 2 %, with at most 0.5 % of the entries off by more than 2 % of that
+1e-3 of the largest logit (observed 1-3e-4), and every parameter gradient to a Frobenius-relative
+error of 0.5 % (observed <= 0.13 %), with at most 0.5 % of the entries off by more than 2 % of that
 gradient's largest entry (single rows can move by several % when a ReLU input of
 the homo variant sits within rounding distance of zero and flips its mask) — the 'stated fp32 tolerance' of
 BASELINE.json's north_star for this mode (the strict fp32 mode is tested in
@@ -19,10 +19,19 @@ from tests.test_gpu_pagg import _oracle_run, _random_case
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
-TC_FWD = dict(rtol=1e-2, atol=3e-3)
-TC_GRAD_REL_FRO = 2e-2
+TC_FWD_REL_TO_MAX = 1e-3         # max |logit error| <= 1e-3 * max(1, max |logit|); observed 0.9-3.1e-4 (profiles/r02/pytest_gpu_run1.txt)
+TC_GRAD_REL_FRO = 5e-3           # relative Frobenius error of every parameter gradient; observed <= 1.3e-3
 TC_GRAD_OUTLIER = (2e-2, 5e-3)   # entries off by > 2 % of max|g| may be at most 0.5 % of all entries
-TC_GRAD_LOOSE = (5e-2, 3e-2)     # natural homo weights (ReLU-mask flips): Frobenius 5 %, outliers 3 %
+TC_GRAD_LOOSE = (5e-2, 3e-2)     # natural homo weights (ReLU-mask flips): Frobenius 5 % (observed 1.1-3.3 %), outliers 3 %
+
+
+def assert_tc_logits(got, want, what="tc logits"):
+    """Tensor-core mode forward tolerance: fp16 operand rounding + tanh.approx give errors proportional to the
+    magnitude of the terms summed, so the bound is relative to the largest logit, not per entry."""
+    err = (got.double() - want.double()).abs().max().item()
+    lim = TC_FWD_REL_TO_MAX * max(1.0, want.abs().max().item())
+    assert torch.isfinite(got).all() and err <= lim, f"{what}: max abs error {err:.3e} > {lim:.3e}"
+    return err
 
 
 def assert_grad_close(got, want, name, fro_tol=None, outlier_frac=None):
@@ -97,7 +106,7 @@ def test_tc_mode_forward_backward_match_oracle(variant, N, Fd, Cc, nw, L, S):
     y = m(X.to(DEV), neis, nw, L, mask, lt, None)
     err = (y.cpu() - y_ref).abs().max().item()
     print(f"tc fwd max abs err {err:.3e} (ref max {y_ref.abs().max().item():.3f})")
-    torch.testing.assert_close(y.cpu(), y_ref, **TC_FWD)
+    assert_tc_logits(y.cpu(), y_ref)
     (y * G.to(DEV)).sum().backward()
     worst = max(assert_grad_close(p.grad.cpu(), g_ref[k], k) for k, p in m.named_parameters())
     print(f"tc grad worst relative Frobenius err {worst:.3e}")
@@ -113,7 +122,7 @@ def test_tc_mode_homo_natural_weights_statistical():
     m = m.to(DEV).eval()
     m.math_mode = "tc"
     y = m(X.to(DEV), neis, nw, L, mask, lt, None)
-    torch.testing.assert_close(y.cpu(), y_ref, **TC_FWD)
+    assert_tc_logits(y.cpu(), y_ref)
     (y * G.to(DEV)).sum().backward()
     worst = max(assert_grad_close(p.grad.cpu(), g_ref[k], k, *TC_GRAD_LOOSE) for k, p in m.named_parameters())
     print(f"tc homo natural-weights worst relative Frobenius err {worst:.3e}")
@@ -129,7 +138,7 @@ def test_tc_mode_matches_fp32_mode_at_pubmed_scale():
     m.math_mode = "tc"
     ytc = m(Xd, neis, nw, L, mask, lt, None)
     print("tc vs fp32 max abs diff", (ytc - y32).abs().max().item())
-    torch.testing.assert_close(ytc, y32, **TC_FWD)
+    assert_tc_logits(ytc, y32)
     G = torch.randn(S, Cc, device=DEV) / S
     (ytc * G).sum().backward()
     gtc = {k: p.grad.clone() for k, p in m.named_parameters()}
@@ -162,8 +171,56 @@ def test_tc_mode_training_dropout_matches_oracle_with_same_masks(variant):
     y = pagg.pagg_forward(variant, X.to(DEV), dict(m.named_parameters()), dev(sn, torch.int32), dev(st, torch.uint8),
                           dev(pt, torch.int32), dev(rows, torch.int32), dropout=p, training=True, seed=seed,
                           math_mode="tc")
-    torch.testing.assert_close(y.cpu(), y_ref.detach().float(), **TC_FWD)
+    assert_tc_logits(y.cpu(), y_ref.detach().float())
     (y * G.to(DEV)).sum().backward()
     tol = TC_GRAD_LOOSE if variant == "homo" else (None, None)
     for k, pr in m.named_parameters():
         assert_grad_close(pr.grad.cpu(), params[k].grad.float(), k, *tol)
+
+
+@pytest.mark.parametrize("M,N,K,relu,scale", [(128, 128, 64, False, 1.0), (300, 200, 500, True, 3.0), (1000, 512, 128, True, 1.0),
+                                              (77, 5, 24, False, 0.5), (19717, 128, 500, True, 1.0), (19717, 512, 128, True, 1.0 / 0.3)])
+def test_tma_gemm_matches_fp64(M, N, K, relu, scale):
+    """The TMA-fed, 128-byte-swizzled tcgen05 GEMM of the forward projections (fp32 and scaled-fp16 outputs)."""
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).half().float()      # fp16-representable: products exact in fp32
+    B = (torch.randn(N, K, generator=g) * 0.1).half().float()
+    bias = torch.randn(N, generator=g)
+    want = A.double() @ B.double().t() + bias.double()
+    if relu:
+        want = want.clamp_min(0)
+    Ad, Bd, bd = A.to(DEV), B.to(DEV), bias.to(DEV)
+    K16 = (K + 7) // 8 * 8
+    C = torch.full((M, N), float("nan"), device=DEV)
+    C16 = torch.full((M, N), float("nan"), device=DEV, dtype=torch.float16)
+    scratch = torch.empty((M + N) * K16, dtype=torch.float16, device=DEV)
+    _lib.check(_lib.lib().pn_debug_gemm_tma(Ad.data_ptr(), Bd.data_ptr(), C.data_ptr(), C16.data_ptr(), bd.data_ptr(), M, N, K,
+                                            int(relu), float(scale), scratch.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    torch.testing.assert_close(C.cpu().double(), want, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(C16.cpu().double(), want * scale, rtol=2e-3, atol=2e-3)
+
+
+def test_tma_and_legacy_projection_paths_agree():
+    """PN_TC_GEMM=legacy (fp32 operands converted while staged, fp32 table gather) and the default TMA path (fp16 copies, fp16
+    pre-scaled table gather) are the same arithmetic: identical operand rounding, so logits agree to fp32 summation order."""
+    import os
+    import subprocess
+    import sys
+    code = ("import torch, sys; sys.path.insert(0, '.');"
+            "from tests.test_gpu_pagg import _random_case;"
+            "m, X, mask, neis, lt = _random_case('homo', 500, 70, 128, 4, 9, 4, 210, seed=3);"
+            "m = m.to('cuda:0').train(); m.dropout = 0.6; m.math_mode = 'tc'; torch.manual_seed(5);"
+            "y = m(X.to('cuda:0'), neis, 9, 4, mask, lt, None); y.square().sum().backward();"
+            "torch.save((y.detach().cpu(), {k: p.grad.cpu() for k, p in m.named_parameters()}), sys.argv[1])")
+    outs = []
+    for mode in ("tma", "legacy"):
+        f = f"/tmp/pn_proj_{mode}_{os.getpid()}.pt"
+        r = subprocess.run([sys.executable, "-c", code, f], env=dict(os.environ, PN_TC_GEMM=mode), capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(torch.load(f))
+        os.unlink(f)
+    (y0, g0), (y1, g1) = outs
+    torch.testing.assert_close(y0, y1, rtol=1e-4, atol=1e-5)
+    for k in g0:
+        assert_grad_close(g0[k], g1[k], k, 2e-3, 1e-3)
