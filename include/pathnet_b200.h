@@ -137,7 +137,16 @@ int64_t pn_edges_parse_txt(const char *txt, int64_t bytes, int32_t cols, int64_t
  * ------------------------------------------------------------------ */
 
 typedef enum { PN_VARIANT_HETERO = 0, /* class PathNet      (:150) */
-               PN_VARIANT_HOMO = 1    /* class PathNet_homo (:214) */ } pn_variant;
+               PN_VARIANT_HOMO = 1,   /* class PathNet_homo (:214) */
+               PN_VARIANT_PLAIN = 2   /* natural path order, no ReLUs, no attention partner: the older `PAGG` class
+                                         (baseline/GPRGNN/src/copy.py:299-359) and the pooling ablations */ } pn_variant;
+
+/* SURVEY 8f-4 variants (fp32 math mode; the tensor-core kernels implement the LSTM cell only):
+ *   cell: LSTM (PathNet_run.py:164) or the tanh RNN of copy.py:307 (then w_ih / w_hh are [H,H], b_ih / b_hh [H])
+ *   pool: the variant's own attention (:199-204 / :269-273), or mean (copy.py:350) / sum / max over the path_num
+ *         final hidden states (attw_* are then unused and their gradients zero) */
+typedef enum { PN_CELL_LSTM = 0, PN_CELL_RNN = 1 } pn_cell;
+typedef enum { PN_POOL_ATTENTION = 0, PN_POOL_MEAN = 1, PN_POOL_SUM = 2, PN_POOL_MAX = 3 } pn_pool;
 
 typedef enum { PN_MATH_FP32 = 0, /* CUDA-core fp32 FMA, strict parity         */
                PN_MATH_TC = 1    /* tcgen05 tensor cores, fp16 operands/fp32 acc */ } pn_math;
@@ -163,6 +172,8 @@ typedef struct {
                                 padded), e.g. made once by pn_pagg_pack_x16: the tensor-core mode then TMA-loads it
                                 instead of re-reading and re-converting the fp32 X on every call (X is constant over
                                 a training run, PathNet_run.py:300).  NULL = convert per call.                       */
+    int32_t cell;            /* pn_cell  (0 = LSTM, the reference's)                                                  */
+    int32_t pool;            /* pn_pool  (0 = the variant's attention, the reference's)                               */
 } pn_pagg_cfg;
 
 /* Parameter (or gradient) block, fp32 device pointers, PyTorch layouts

@@ -177,3 +177,72 @@ def load_reference_classes(dropout=0.0, device="cpu"):
     ns = dict(torch=torch, nn=nn, F=F, MessagePassing=MessagePassing, device=device, dropout=dropout)
     exec(compile(ast.Module(body=keep, type_ignores=[]), "PathNet_run.py", "exec"), ns)
     return ns
+
+
+# --------------------------------------------------------------------------- SURVEY 8f-4 variants
+def rnn_last_hidden(x, w_ih, w_hh, b_ih, b_hh):
+    """x [L, B, H] -> h_L [B, H]; nn.RNN(hidden, hidden), tanh, single layer (baseline/GPRGNN/src/copy.py:307,348)."""
+    L, B, H = x.shape
+    h = x.new_zeros(B, H)
+    for t in range(L):
+        h = torch.tanh(x[t] @ w_ih.t() + b_ih + h @ w_hh.t() + b_hh)
+    return h
+
+
+def pagg_rnn_forward(params, X, neis, num_w, walk_len, indices, layer_type, mask_seq=None, mask_cat=None):
+    """Restatement of the reference's OLDER aggregator, `class PAGG` (baseline/GPRGNN/src/copy.py:331-359): fc0, gather,
+    all four nei{d} Linears then select by label, dropout, tanh RNN, mean over the paths, concat, dropout, fc2.
+    params: that class's state_dict keys (fc0.*, RNN.*_l0, fc2.*, nei0..nei3.*).  mask_seq [L, P, H], mask_cat [S, 2H]."""
+    H = params["fc0.weight"].shape[0]
+    indices = torch.as_tensor(np.asarray(indices)) if not torch.is_tensor(indices) else indices
+    split = int(indices.sum())
+    Z = X @ params["fc0.weight"].t() + params["fc0.bias"]                                   # :333
+    nei = Z[neis].view(split * num_w * walk_len, H)                                          # :337
+    lt = layer_type.reshape(split * num_w * walk_len)                                        # :340
+    proj = torch.stack([nei @ params[f"nei{d}.weight"].t() + params[f"nei{d}.bias"] for d in range(4)], dim=1)   # :342-346
+    seq = proj[torch.arange(nei.shape[0]), lt].view(split * num_w, walk_len, H).transpose(0, 1)                 # :348-349
+    if mask_seq is not None:
+        seq = seq * mask_seq                                                                 # :351
+    h_n = rnn_last_hidden(seq, params["RNN.weight_ih_l0"], params["RNN.weight_hh_l0"], params["RNN.bias_ih_l0"],
+                          params["RNN.bias_hh_l0"]).view(split, num_w, H)                    # :352-354
+    layer1 = torch.cat((Z[indices], h_n.mean(dim=1)), dim=1)                                # :356-358
+    if mask_cat is not None:
+        layer1 = layer1 * mask_cat                                                           # :360
+    return layer1 @ params["fc2.weight"].t() + params["fc2.bias"]                            # :361
+
+
+def pagg_forward_pool_variant(variant, params, X, neis, num_w, walk_len, indices, layer_type, pool):
+    """PathNet / PathNet_homo with the attention replaced by mean / sum / max over the paths (the pooling ablations
+    of performance.jpg): everything up to h_n as in pagg_forward(), then the plain reduction."""
+    H = params["fc0.weight"].shape[0]
+    S = int(torch.as_tensor(np.asarray(indices)).sum()) if not torch.is_tensor(indices) else int(indices.sum())
+    sn, st, pt = canonicalize(variant, neis.numpy(), layer_type.numpy(), num_w, walk_len)
+    homo = variant == "homo"
+    Z = X @ params["fc0.weight"].t() + params["fc0.bias"]
+    if homo:
+        Z = F.relu(Z)
+    T = torch.stack([Z @ w.t() + b for (w, b) in _nets(params, walk_len)], dim=0)
+    if homo:
+        T = F.relu(T)
+    seq = T[torch.as_tensor(st.astype(np.int64)), torch.as_tensor(sn.astype(np.int64))]       # [S, nw, L, H]
+    h = lstm_last_hidden(seq.reshape(S * num_w, walk_len, H).transpose(0, 1), params["LSTM.weight_ih_l0"],
+                         params["LSTM.weight_hh_l0"], params["LSTM.bias_ih_l0"], params["LSTM.bias_hh_l0"]).view(S, num_w, H)
+    pooled = h.mean(dim=1) if pool == "mean" else h.sum(dim=1) if pool == "sum" else h.max(dim=1).values
+    idx = torch.as_tensor(np.asarray(indices)) if not torch.is_tensor(indices) else indices
+    return torch.cat((Z[idx], pooled), dim=1) @ params["fc2.weight"].t() + params["fc2.bias"]
+
+
+def load_reference_pagg_rnn_class(device="cpu"):
+    """The reference's own `class PAGG`, AST-extracted from baseline/GPRGNN/src/copy.py (authoring container only)."""
+    import ast
+    import torch.nn as nn
+    tree = ast.parse(open("/root/reference/baseline/GPRGNN/src/copy.py").read())
+    keep = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "PAGG"]
+
+    class MessagePassing(nn.Module):
+        def __init__(self, *a, **k):
+            super().__init__()
+
+    ns = dict(torch=torch, nn=nn, F=F, MessagePassing=MessagePassing, device=device)
+    exec(compile(ast.Module(body=keep, type_ignores=[]), "copy.py", "exec"), ns)
+    return ns["PAGG"]

@@ -4,6 +4,6 @@ from .sampler import (MerwGraph, gen_merw, read_edge_input, write_paths_txt, for
                       parse_paths_txt, read_paths_txt)
 
 try:  # PAGG needs the same library; keep the sampler importable on its own
-    from .pagg import PathNet, PathNet_homo, PAGG, pagg_forward  # noqa: F401
+    from .pagg import PathNet, PathNet_homo, PAGG, PAGG_RNN, pagg_forward  # noqa: F401
 except ImportError:  # pragma: no cover
     pass

@@ -23,7 +23,7 @@ class PaggCfg(C.Structure):
                 ("S", C.c_int32), ("nw", C.c_int32), ("L", C.c_int32), ("variant", C.c_int32),
                 ("math_mode", C.c_int32), ("training", C.c_int32), ("dropout_p", C.c_float),
                 ("dropout_seed", C.c_uint64), ("no_backward", C.c_int32), ("row_chunk", C.c_int32),
-                ("dropout_seed_dev", C.c_void_p), ("x16", C.c_void_p)]
+                ("dropout_seed_dev", C.c_void_p), ("x16", C.c_void_p), ("cell", C.c_int32), ("pool", C.c_int32)]
 
 
 PARAM_NAMES = ("fc0_w", "fc0_b", "nets_w", "nets_b", "w_ih", "w_hh", "b_ih", "b_hh", "attw_w",

@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(192) k_gemm_tma(const __grid_constant__ CUtens
     __shared__ uint64_t full_bar[GT_STAGES], empty_bar[GT_STAGES], acc_full;
     __shared__ uint32_t s_taddr;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int64_t m0 = (int64_t)blockIdx.y * 128, n0 = (int64_t)blockIdx.x * 128;
+    const int64_t m0 = (int64_t)blockIdx.x * 128, n0 = (int64_t)blockIdx.y * 128;   // row tiles on grid.x: 10^7-row operands exceed grid.y's 65 535
     const int nk = (int)((g.K + 63) / 64);
     if (tid == 0) {
         for (int s = 0; s < GT_STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -223,7 +223,7 @@ int launch_gemm_tma(cudaStream_t st, const __half *A16, const __half *B16, int64
     if (rc) return rc;
     GemmTmaArgs g{M, N, K16, bias, relu ? 1 : 0, C, ldc, C16, ldc16, c16_scale};
     PN_CUDA(cudaFuncSetAttribute(k_gemm_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM));
-    dim3 grid((unsigned)ceil_div(N, 128), (unsigned)ceil_div(M, 128));
+    dim3 grid((unsigned)ceil_div(M, 128), (unsigned)ceil_div(N, 128));
     k_gemm_tma<<<grid, 192, GT_SMEM, st>>>(tmA, tmB, g);
     PN_LAUNCH_CHECK();
     return PN_OK;

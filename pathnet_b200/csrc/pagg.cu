@@ -38,8 +38,8 @@ __global__ void k_canonicalize(int variant, int64_t N, int64_t S, int nw, int L,
     const int t = (int)(i % L);
     const int64_t sw = i / L;  // s*nw + w
     int64_t node, type, pnode = 0;
-    if (variant == PN_VARIANT_HOMO) {
-        // sequence (s,w) = path p = s*nw+w in natural order (:246-265)
+    if (variant != PN_VARIANT_HETERO) {
+        // sequence (s,w) = path p = s*nw+w in natural order (:246-265; also baseline/GPRGNN/src/copy.py:335-349)
         node = (int64_t)neis[i];
         type = (int64_t)ltype[i];
         if (t == 0) pnode = (int64_t)neis[sw * L];  // step-0 entry of the same path (:259-260)
@@ -67,7 +67,9 @@ __global__ void k_canonicalize(int variant, int64_t N, int64_t S, int nw, int L,
 // ---------------------------------------------------------------------------
 // LSTM weight packing: Wp[k][unit*4+gate] (k < H: W_ih^T, k >= H: W_hh^T)
 // ---------------------------------------------------------------------------
-__global__ void k_pack_lstm(int H, const float *__restrict__ w_ih, const float *__restrict__ w_hh,
+// cell = PN_CELL_RNN (tanh RNN, baseline/GPRGNN/src/copy.py:307): w_ih / w_hh are [H,H]; they occupy the "g" slot
+// (gate 2, the tanh gate) of the packed layout and the other three slots are zero, so the same kernels serve both cells.
+__global__ void k_pack_lstm(int H, int cell, const float *__restrict__ w_ih, const float *__restrict__ w_hh,
                             const float *__restrict__ b_ih, const float *__restrict__ b_hh,
                             float *__restrict__ Wp, float *__restrict__ WpT, float *__restrict__ bp)
 {
@@ -75,22 +77,34 @@ __global__ void k_pack_lstm(int H, const float *__restrict__ w_ih, const float *
     const int G4 = 4 * H, K2 = 2 * H;
     if (i < K2 * G4) {
         int k = i / G4, col = i % G4, unit = col >> 2, gate = col & 3;
-        float v = k < H ? w_ih[(gate * H + unit) * H + k] : w_hh[(gate * H + unit) * H + (k - H)];
+        float v;
+        if (cell == PN_CELL_RNN) v = gate != 2 ? 0.f : (k < H ? w_ih[unit * H + k] : w_hh[unit * H + (k - H)]);
+        else v = k < H ? w_ih[(gate * H + unit) * H + k] : w_hh[(gate * H + unit) * H + (k - H)];
         Wp[i] = v;
         WpT[col * K2 + k] = v;
     }
     if (i < G4) {
         int unit = i >> 2, gate = i & 3;
-        bp[i] = b_ih[gate * H + unit] + b_hh[gate * H + unit];
+        if (cell == PN_CELL_RNN) bp[i] = gate != 2 ? 0.f : b_ih[unit] + b_hh[unit];
+        else bp[i] = b_ih[gate * H + unit] + b_hh[gate * H + unit];
     }
 }
 
-__global__ void k_unpack_lstm_grads(int H, const float *__restrict__ dWp, const float *__restrict__ dbp,
+__global__ void k_unpack_lstm_grads(int H, int cell, const float *__restrict__ dWp, const float *__restrict__ dbp,
                                     float *__restrict__ dw_ih, float *__restrict__ dw_hh,
                                     float *__restrict__ db_ih, float *__restrict__ db_hh)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int G4 = 4 * H;
+    if (cell == PN_CELL_RNN) {
+        if (i < H * H) {
+            const int unit = i / H, k = i % H, col = unit * 4 + 2;
+            dw_ih[i] = dWp[k * G4 + col];
+            dw_hh[i] = dWp[(H + k) * G4 + col];
+        }
+        if (i < H) { const float v = dbp[i * 4 + 2]; db_ih[i] = v; db_hh[i] = v; }
+        return;
+    }
     if (i < G4 * H) {
         int row = i / H, k = i % H, gate = row / H, unit = row % H;
         int col = unit * 4 + gate;
@@ -125,6 +139,7 @@ struct LstmArgs {
     uint64_t drop_seed;
     const uint64_t *seed_dev; // optional device word added to drop_seed (CUDA-graph replay)
     int64_t p_base;          // global index of this chunk's first sequence (row-chunked calls): mask indices are global
+    int cell;                // PN_CELL_LSTM | PN_CELL_RNN (h_t = tanh of the "g" slot; the saved "g" activation is h_t)
     // backward only
     const float *dhfin;      // [P,H]
     float *dT;               // [N,L,H]
@@ -228,11 +243,18 @@ __global__ void __launch_bounds__(256) k_lstm_fwd_f32(LstmArgs a)
 #pragma unroll
             for (int u = 0; u < UPT; u++) {
                 const int unit = u * 32 + tx;
-                const float ig = sigmoidf_(acc[pp][u][0]), fg = sigmoidf_(acc[pp][u][1]);
-                const float gg = tanhf(acc[pp][u][2]), og = sigmoidf_(acc[pp][u][3]);
-                const float cn = fg * c[pp][u] + ig * gg;
-                c[pp][u] = cn;
-                const float h = og * tanhf(cn);
+                float ig, fg, gg, og, cn, h;
+                if (a.cell == PN_CELL_RNN) {   // h_t = tanh(W_ih x_t + b_ih + W_hh h_{t-1} + b_hh)  (torch nn.RNN)
+                    gg = tanhf(acc[pp][u][2]);
+                    ig = fg = og = cn = 0.f;
+                    h = gg;
+                } else {
+                    ig = sigmoidf_(acc[pp][u][0]); fg = sigmoidf_(acc[pp][u][1]);
+                    gg = tanhf(acc[pp][u][2]); og = sigmoidf_(acc[pp][u][3]);
+                    cn = fg * c[pp][u] + ig * gg;
+                    c[pp][u] = cn;
+                    h = og * tanhf(cn);
+                }
                 As[row * AP + H + unit] = h;
                 if (p < a.P) {
                     if (a.acts) {
@@ -291,15 +313,19 @@ __global__ void __launch_bounds__(256) k_lstm_bwd_f32(LstmArgs a)
                     if (t > 0) {
                         const float *actp = a.acts + (((int64_t)(t - 1) * a.P + p) * 5) * H + unit;
                         cprev = actp[4 * H];
-                        hprev = actp[3 * H] * tanhf(cprev);
+                        hprev = a.cell == PN_CELL_RNN ? actp[2 * H] : actp[3 * H] * tanhf(cprev);
                     }
-                    const float tc = tanhf(cn);
-                    const float dcn = dc[pp][u] + dh[pp][u] * og * (1.f - tc * tc);
-                    da.x = dcn * gg * ig * (1.f - ig);          // i
-                    da.y = dcn * cprev * fg * (1.f - fg);       // f
-                    da.z = dcn * ig * (1.f - gg * gg);          // g
-                    da.w = dh[pp][u] * tc * og * (1.f - og);    // o
-                    dc[pp][u] = dcn * fg;
+                    if (a.cell == PN_CELL_RNN) {
+                        da.z = dh[pp][u] * (1.f - gg * gg);     // h_t = gg = tanh(pre-activation)
+                    } else {
+                        const float tc = tanhf(cn);
+                        const float dcn = dc[pp][u] + dh[pp][u] * og * (1.f - tc * tc);
+                        da.x = dcn * gg * ig * (1.f - ig);          // i
+                        da.y = dcn * cprev * fg * (1.f - fg);       // f
+                        da.z = dcn * ig * (1.f - gg * gg);          // g
+                        da.w = dh[pp][u] * tc * og * (1.f - og);    // o
+                        dc[pp][u] = dcn * fg;
+                    }
                     const int64_t r = (int64_t)t * a.P + p;
                     *reinterpret_cast<float4 *>(a.dA + r * G4 + unit * 4) = da;
                     a.XH[r * K2 + H + unit] = hprev;
@@ -388,6 +414,7 @@ struct PoolArgs {
     uint32_t drop_thr; float drop_scale; uint64_t drop_seed;
     const uint64_t *seed_dev;   // optional device word added to drop_seed
     int64_t s_base;             // global index of this chunk's first output row (mask indices are global)
+    int pool;                   // PN_POOL_ATTENTION (the variant's own attention) | MEAN | SUM | MAX over the nw sequences
     // backward
     const float *dcat;   // [S,2H] grad wrt the dropped concat
     float *dhfin, *dZ, *dT, *dattw;
@@ -594,6 +621,71 @@ __global__ void __launch_bounds__(256) k_pool_bwd(PoolArgs a)
 }
 
 // ---------------------------------------------------------------------------
+// pooling without attention (SURVEY 8f-4 ablations; MEAN is what baseline/GPRGNN/src/copy.py:350 does):
+// pooled[s] = mean / sum / max over the nw final hidden states of row s, then the same concat + dropout.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pool_simple_fwd(PoolArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t s = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (s >= a.S) return;
+    const int H = a.H, nw = a.nw;
+    const int64_t node = a.rows[s];
+    for (int j = lane; j < H; j += 32) {
+        float acc = a.pool == PN_POOL_MAX ? -INFINITY : 0.f;
+        for (int w = 0; w < nw; w++) {
+            const float v = a.hfin[(s * nw + w) * H + j];
+            acc = a.pool == PN_POOL_MAX ? fmaxf(acc, v) : acc + v;
+        }
+        float pooled = a.pool == PN_POOL_MEAN ? acc / (float)nw : acc;
+        float ego = a.Z[node * H + j];
+        if (a.drop_thr) {
+            ego = dropout_hash(PN_SEED(a), 1, (uint64_t)(s + a.s_base) * 2 * H + j) < a.drop_thr ? 0.f : ego * a.drop_scale;
+            pooled = dropout_hash(PN_SEED(a), 1, (uint64_t)(s + a.s_base) * 2 * H + H + j) < a.drop_thr ? 0.f : pooled * a.drop_scale;
+        }
+        a.cat[s * 2 * H + j] = ego;
+        a.cat[s * 2 * H + H + j] = pooled;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_pool_simple_bwd(PoolArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t s = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    float amax = 0.f;
+    if (s < a.S) {
+        const int H = a.H, nw = a.nw;
+        const int64_t node = a.rows[s];
+        for (int j = lane; j < H; j += 32) {
+            float g = a.dcat[s * 2 * H + H + j], e = a.dcat[s * 2 * H + j];
+            if (a.drop_thr) {
+                g = dropout_hash(PN_SEED(a), 1, (uint64_t)(s + a.s_base) * 2 * H + H + j) < a.drop_thr ? 0.f : g * a.drop_scale;
+                e = dropout_hash(PN_SEED(a), 1, (uint64_t)(s + a.s_base) * 2 * H + j) < a.drop_thr ? 0.f : e * a.drop_scale;
+            }
+            atomicAdd(a.dZ + node * H + j, e);
+            int arg = 0;
+            if (a.pool == PN_POOL_MAX) {   // gradient goes to the first maximal entry
+                float m = -INFINITY;
+                for (int w = 0; w < nw; w++) {
+                    const float v = a.hfin[(s * nw + w) * H + j];
+                    if (v > m) { m = v; arg = w; }
+                }
+            }
+            const float gm = a.pool == PN_POOL_MEAN ? g / (float)nw : g;
+            for (int w = 0; w < nw; w++) {
+                const float d = a.pool == PN_POOL_MAX ? (w == arg ? g : 0.f) : gm;
+                a.dhfin[(s * nw + w) * H + j] = d;
+                amax = fmaxf(amax, fabsf(d));
+            }
+        }
+    }
+    if (a.absmax_bits) {
+        amax = warp_max(amax);
+        if (lane == 0 && amax > 0.f) atomicMax(a.absmax_bits, __float_as_uint(amax));
+    }
+}
+
+// ---------------------------------------------------------------------------
 // H = 128 versions of the two pooling kernels: a lane owns 4 CONSECUTIVE hidden units, so every row of hfin / T / Z /
 // dhfin moves as one 16-byte access per lane (512 B per warp instruction) instead of four 4-byte ones.  Same math.
 // The partner vector is looked up once per run of equal partner rows (homo: the row's own step-0 entry for all its paths).
@@ -791,7 +883,15 @@ static int check_cfg(const pn_pagg_cfg *c)
                "pagg: bad sizes N=%d F=%d C=%d S=%d nw=%d L=%d", c->N, c->F, c->C, c->S, c->nw, c->L);
     PN_REQUIRE(c->H % 32 == 0 && c->H >= 32 && c->H <= 128,
                "pagg: hidden size %d unsupported (multiples of 32 up to 128)", c->H);
-    PN_REQUIRE(c->variant == PN_VARIANT_HETERO || c->variant == PN_VARIANT_HOMO, "pagg: bad variant %d", c->variant);
+    PN_REQUIRE(c->variant == PN_VARIANT_HETERO || c->variant == PN_VARIANT_HOMO || c->variant == PN_VARIANT_PLAIN, "pagg: bad variant %d", c->variant);
+    PN_REQUIRE(c->cell == PN_CELL_LSTM || c->cell == PN_CELL_RNN, "pagg: bad cell %d", c->cell);
+    PN_REQUIRE(c->pool >= PN_POOL_ATTENTION && c->pool <= PN_POOL_MAX, "pagg: bad pool %d", c->pool);
+    PN_REQUIRE(!(c->variant == PN_VARIANT_PLAIN && c->pool == PN_POOL_ATTENTION),
+               "pagg: the plain variant (no ReLU, natural path order) has no attention of its own: choose pool mean / sum / max");
+    if (c->math_mode == PN_MATH_TC && c->cell != PN_CELL_LSTM) {
+        set_error("pagg: the tensor-core kernels implement the LSTM cell only (cell %d needs math_mode fp32)", c->cell);
+        return PN_ERR_UNSUPPORTED;
+    }
     PN_REQUIRE(c->math_mode == PN_MATH_FP32 || c->math_mode == PN_MATH_TC, "pagg: bad math_mode %d", c->math_mode);
     PN_REQUIRE(c->dropout_p >= 0.f && c->dropout_p <= 1.f, "pagg: dropout p=%f outside [0,1]", (double)c->dropout_p);
     PN_REQUIRE(c->row_chunk >= 0, "pagg: row_chunk %d < 0", c->row_chunk);
@@ -848,7 +948,7 @@ extern "C" int pn_pagg_canonicalize(int32_t variant, int32_t N, int32_t S, int32
                                     int32_t type_dtype, int32_t *seq_node, uint8_t *seq_type, int32_t *partner,
                                     int32_t *status, void *stream)
 {
-    PN_REQUIRE(variant == PN_VARIANT_HETERO || variant == PN_VARIANT_HOMO, "canonicalize: bad variant %d", variant);
+    PN_REQUIRE(variant == PN_VARIANT_HETERO || variant == PN_VARIANT_HOMO || variant == PN_VARIANT_PLAIN, "canonicalize: bad variant %d", variant);
     PN_REQUIRE(N > 0 && S >= 0 && nw > 0 && L > 0 && L <= 255, "canonicalize: bad sizes N=%d S=%d nw=%d L=%d", N, S, nw, L);
     PN_REQUIRE(neis_dtype == PN_IDX_I64 || neis_dtype == PN_IDX_I32, "canonicalize: node ids must be int64 or int32 (dtype code %d)", neis_dtype);
     PN_REQUIRE(type_dtype == PN_IDX_I64 || type_dtype == PN_IDX_I32 || type_dtype == PN_IDX_U8,
@@ -905,7 +1005,7 @@ int lstm_forward_chunk(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_para
     la.T = w.T; la.seq_node = ix.seq_node; la.seq_type = ix.seq_type; la.Wp = w.Wp; la.WpT = w.WpT; la.bp = w.bp;
     la.acts = ck.save ? w.acts : nullptr; la.hfin = w.hfin; la.P = ck.Sc * c.nw; la.L = c.L;
     la.drop_thr = thr; la.drop_scale = scale; la.drop_seed = c.dropout_seed; la.seed_dev = c.dropout_seed_dev;
-    la.p_base = ck.s0 * c.nw;
+    la.p_base = ck.s0 * c.nw; la.cell = c.cell;
     switch (c.H / 32) {
         case 1: return launch_lstm_fwd<1>(la, st);
         case 2: return launch_lstm_fwd<2>(la, st);
@@ -924,7 +1024,7 @@ PoolArgs pool_args(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_params &
     pa.seq_type = ix.seq_type; pa.attw_w = prm.attw_w; pa.attw_b = prm.attw_b;
     pa.score = w.score; pa.att = w.att; pa.cat = w.cat;
     pa.drop_thr = thr; pa.drop_scale = scale; pa.drop_seed = c.dropout_seed; pa.seed_dev = c.dropout_seed_dev;
-    pa.s_base = ck.s0;
+    pa.s_base = ck.s0; pa.pool = c.pool;
     return pa;
 }
 
@@ -940,6 +1040,12 @@ int pool_forward_chunk(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_para
                        const PaggChunk &ck, float *logits, cudaStream_t st)
 {
     PoolArgs pa = pool_args(c, w, prm, ix, ck);
+    if (c.pool != PN_POOL_ATTENTION) {
+        k_pool_simple_fwd<<<(unsigned)ceil_div(ck.Sc, 8), 256, 0, st>>>(pa);
+        PN_LAUNCH_CHECK();
+        if (logits == nullptr) return PN_OK;
+        return launch_gemm(st, w.cat, 2 * c.H, 1, prm.fc2_w, 1, 2 * c.H, logits, c.C, ck.Sc, c.C, 2 * c.H, prm.fc2_b, false, false);
+    }
     const bool pool128 = pool128_ok(c, prm);
     const bool fuse_fc2 = pool128 && c.C <= POOL_FUSE_MAX_C && logits != nullptr;
     if (fuse_fc2) { pa.C = c.C; pa.fc2_w = prm.fc2_w; pa.fc2_b = prm.fc2_b; pa.logits = logits; }
@@ -980,7 +1086,7 @@ extern "C" int pn_pagg_forward(const pn_pagg_cfg *cfg, const pn_pagg_params *prm
         rc = launch_gemm(st, w.Z, H, 1, prm->nets_w, 1, H, w.T, L * H, N, L * H, H, prm->nets_b, homo, false);
         if (rc) return rc;
     }
-    k_pack_lstm<<<(unsigned)ceil_div(2 * H * 4 * H, 256), 256, 0, st>>>((int)H, prm->w_ih, prm->w_hh, prm->b_ih,
+    k_pack_lstm<<<(unsigned)ceil_div(2 * H * 4 * H, 256), 256, 0, st>>>((int)H, c.cell, prm->w_ih, prm->w_hh, prm->b_ih,
                                                                       prm->b_hh, w.Wp, w.WpT, w.bp);
     PN_LAUNCH_CHECK();
     const int64_t rows_per = chunk_rows(c);
@@ -1016,12 +1122,14 @@ extern "C" int pn_pagg_backward(const pn_pagg_cfg *cfg, const pn_pagg_params *pr
 #define ZERO(ptr, n) PN_CUDA(cudaMemsetAsync((ptr), 0, sizeof(float) * (size_t)(n), st))
     if (S == 0) {  // no rows: every gradient is zero
         ZERO(g.fc0_w, H * F); ZERO(g.fc0_b, H); ZERO(g.nets_w, L * H * H); ZERO(g.nets_b, L * H);
-        ZERO(g.w_ih, 4 * H * H); ZERO(g.w_hh, 4 * H * H); ZERO(g.b_ih, 4 * H); ZERO(g.b_hh, 4 * H);
+        const int64_t ng = c.cell == PN_CELL_RNN ? 1 : 4;   // gates of the cell
+        ZERO(g.w_ih, ng * H * H); ZERO(g.w_hh, ng * H * H); ZERO(g.b_ih, ng * H); ZERO(g.b_hh, ng * H);
         ZERO(g.attw_w, 2 * H); ZERO(g.attw_b, 1); ZERO(g.fc2_w, C * 2 * H); ZERO(g.fc2_b, C);
         return PN_OK;
     }
     PN_REQUIRE(seq_node && seq_type && partner && rows && dlogits, "pagg_backward: NULL pointer");
-    const bool pool128 = pool128_ok(c, *prm);
+    const bool attention = c.pool == PN_POOL_ATTENTION;
+    const bool pool128 = attention && pool128_ok(c, *prm);
     const bool fuse_fc2 = pool128 && C <= POOL_FUSE_MAX_C;   // fc2 backward inside the pooling kernel (it holds every concat row anyway)
     // accumulators shared by all chunks (the chunk kernels add into them atomically)
     ZERO(w.dZ, N * H); ZERO(w.dT, N * L * H); ZERO(w.dattw, 2 * H + 1);
@@ -1061,7 +1169,8 @@ extern "C" int pn_pagg_backward(const pn_pagg_cfg *cfg, const pn_pagg_params *pr
             pa.absmax_bits = reinterpret_cast<unsigned int *>(w.gscale);
         }
         if (fuse_fc2) { pa.C = (int)C; pa.fc2_w = prm->fc2_w; pa.dlogits = dl; pa.dfc2_w = g.fc2_w; pa.dfc2_b = g.fc2_b; }
-        if (pool128) k_pool_bwd128<<<(unsigned)ceil_div(Sc, 8), 256, sizeof(float) * (2 * H + 1 + (fuse_fc2 ? C * (2 * H + 1) : 0)), st>>>(pa);
+        if (!attention) k_pool_simple_bwd<<<(unsigned)ceil_div(Sc, 8), 256, 0, st>>>(pa);
+        else if (pool128) k_pool_bwd128<<<(unsigned)ceil_div(Sc, 8), 256, sizeof(float) * (2 * H + 1 + (fuse_fc2 ? C * (2 * H + 1) : 0)), st>>>(pa);
         else k_pool_bwd<<<(unsigned)ceil_div(Sc, 8), 256, sizeof(float) * (2 * H + 1), st>>>(pa);
         PN_LAUNCH_CHECK();
         // ---- LSTM BPTT ----
@@ -1073,7 +1182,7 @@ extern "C" int pn_pagg_backward(const pn_pagg_cfg *cfg, const pn_pagg_params *pr
             la.T = w.T; la.seq_node = ix.seq_node; la.seq_type = ix.seq_type; la.Wp = w.Wp; la.WpT = w.WpT; la.bp = w.bp;
             la.acts = w.acts; la.hfin = w.hfin; la.P = Pc; la.L = (int)L;
             la.drop_thr = thr; la.drop_scale = scale; la.drop_seed = c.dropout_seed; la.seed_dev = c.dropout_seed_dev;
-            la.p_base = s0 * c.nw;
+            la.p_base = s0 * c.nw; la.cell = c.cell;
             la.dhfin = w.dhfin; la.dT = w.dT; la.dA = w.dA; la.XH = w.XH;
             switch (H / 32) {
                 case 1: rc = launch_lstm_bwd<1>(la, st); break;
@@ -1096,7 +1205,7 @@ extern "C" int pn_pagg_backward(const pn_pagg_cfg *cfg, const pn_pagg_params *pr
     }
     PN_CUDA(cudaMemcpyAsync(g.attw_w, w.dattw, sizeof(float) * 2 * H, cudaMemcpyDeviceToDevice, st));
     PN_CUDA(cudaMemcpyAsync(g.attw_b, w.dattw + 2 * H, sizeof(float), cudaMemcpyDeviceToDevice, st));
-    k_unpack_lstm_grads<<<(unsigned)ceil_div(4 * H * H, 256), 256, 0, st>>>((int)H, w.dWp, w.dbp, g.w_ih, g.w_hh, g.b_ih, g.b_hh);
+    k_unpack_lstm_grads<<<(unsigned)ceil_div(4 * H * H, 256), 256, 0, st>>>((int)H, c.cell, w.dWp, w.dbp, g.w_ih, g.w_hh, g.b_ih, g.b_hh);
     PN_LAUNCH_CHECK();
     if (tcm) return pagg_tc_project_backward(c, w, *prm, X, g, st);
     // ---- table projection: T = act(Z Wn^T + bn) ----

@@ -121,7 +121,7 @@ static __global__ void __launch_bounds__(256) k_gemm_f32(GemmArgs g)
     __shared__ float As[16][64 + 4];
     __shared__ float Bs[16][64 + 4];
     const int tid = threadIdx.x;
-    const int64_t m0 = (int64_t)blockIdx.y * 64, n0 = (int64_t)blockIdx.x * 64;
+    const int64_t m0 = (int64_t)blockIdx.x * 64, n0 = (int64_t)blockIdx.y * 64;   // row tiles on grid.x (no 65 535 limit)
     const int tm = (tid / 16) * 4, tn = (tid % 16) * 4;
     // split-K range
     const int64_t kchunks = (g.K + 15) / 16;
@@ -188,7 +188,7 @@ inline int launch_gemm(cudaStream_t st, const float *A, int64_t sAm, int64_t sAk
         // atomics accumulate: caller guarantees C holds zeros (or the addend); relu unsupported
         if (relu) { set_error("launch_gemm: split-K with ReLU"); return PN_ERR_INVALID; }
     }
-    dim3 grid((unsigned)ceil_div(N, 64), (unsigned)ceil_div(M, 64), (unsigned)splitk);
+    dim3 grid((unsigned)ceil_div(M, 64), (unsigned)ceil_div(N, 64), (unsigned)splitk);
     k_gemm_f32<<<grid, 256, 0, st>>>(g);
     PN_LAUNCH_CHECK();
     return PN_OK;

@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(128) k_gemm_tc(GemmTcArgs g)
     __shared__ uint64_t bar[2];
     __shared__ uint32_t s_taddr;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN;
+    const int64_t m0 = (int64_t)blockIdx.x * BM, n0 = (int64_t)blockIdx.y * BN;   // row tiles on grid.x (no 65 535 limit)
     // split-K range (multiples of BK)
     const int64_t kt = (g.K + BK - 1) / BK, per = (kt + gridDim.z - 1) / gridDim.z;
     const int64_t kbeg = (int64_t)blockIdx.z * per * BK, kend = min(g.K, kbeg + per * BK);
@@ -203,7 +203,7 @@ int launch_gemm_tc(cudaStream_t st, const float *A, int64_t lda, const float *B,
     GemmTcArgs g{A, B, C, bias, M, N, K, lda, ldb, ldc, relu ? 1 : 0, accumulate ? 1 : 0, a_scale};
     constexpr int BN = 128;
     const size_t smem = 2 * (128 + BN) * 64 * 2;
-    dim3 grid((unsigned)ceil_div(N, BN), (unsigned)ceil_div(M, 128), (unsigned)std::max(1, splitk));
+    dim3 grid((unsigned)ceil_div(M, 128), (unsigned)ceil_div(N, BN), (unsigned)std::max(1, splitk));
 #define PN_GEMM_CASE(AM, BM_, BF)                                                                              \
     do {                                                                                                       \
         PN_CUDA(cudaFuncSetAttribute(k_gemm_tc<BN, AM, BM_, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \

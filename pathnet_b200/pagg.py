@@ -26,8 +26,10 @@ import torch.nn as nn
 
 from ._lib import PARAM_NAMES, PaggCfg, PaggParams, check, lib
 
-VARIANT = {"hetero": 0, "homo": 1}
+VARIANT = {"hetero": 0, "homo": 1, "plain": 2}
 MATH = {"fp32": 0, "tc": 1}
+CELL = {"lstm": 0, "rnn": 1}
+POOL = {"attention": 0, "mean": 1, "sum": 2, "max": 3}
 IDX_DTYPE = {torch.int64: 0, torch.int32: 1, torch.uint8: 2}
 _warned_auto_tc = False
 
@@ -180,7 +182,8 @@ class _PaggFunction(torch.autograd.Function):
                       variant=VARIANT[meta["variant"]], math_mode=MATH[resolve_math_mode(meta["math_mode"], H, L)],
                       training=int(meta["training"]), dropout_p=float(meta["dropout"]),
                       dropout_seed=int(meta["seed"]), no_backward=int(not meta.get("need_backward", True)),
-                      row_chunk=int(meta.get("row_chunk", 0) or 0), dropout_seed_dev=None, x16=None)
+                      row_chunk=int(meta.get("row_chunk", 0) or 0), dropout_seed_dev=None, x16=None,
+                      cell=CELL[meta.get("cell", "lstm")], pool=POOL[meta.get("pool", "attention")])
         x16 = None
         if cfg.math_mode == MATH["tc"] and meta.get("x16_cache") is not None and X.dtype == torch.float32 and X.is_contiguous():
             x16 = meta["x16_cache"].get(X)     # keyed on the caller's tensor object: valid while X is not modified in place
@@ -236,14 +239,18 @@ class _PaggFunction(torch.autograd.Function):
 
 
 def pagg_forward(variant, X, params: dict, seq_node, seq_type, partner, rows, *, dropout=0.0,
-                 training=False, seed=0, math_mode="auto", row_chunk=0, grad_sink=None, x16_cache=None):
-    """Functional form over a dict with the reference's state_dict keys."""
+                 training=False, seed=0, math_mode="auto", row_chunk=0, grad_sink=None, x16_cache=None, cell="lstm",
+                 pool="attention"):
+    """Functional form over a dict with the reference's state_dict keys.  cell / pool: the SURVEY 8f-4 variants
+    ("rnn": LSTM.* keys then hold nn.RNN-shaped tensors [H,H] / [H]; "mean" | "sum" | "max": attw.* unused)."""
     L = seq_node.shape[2]
+    if cell != "lstm" and math_mode == "auto":
+        math_mode = "fp32"   # the tensor-core kernels implement the LSTM cell only
     nets_w = torch.stack([params[f"nets.{d}.weight"] for d in range(L)])
     nets_b = torch.stack([params[f"nets.{d}.bias"] for d in range(L)])
     need_bwd = torch.is_grad_enabled() and any(t.requires_grad for t in params.values() if torch.is_tensor(t))
     meta = dict(variant=variant, math_mode=math_mode, training=training, dropout=dropout, seed=seed,
-                need_backward=need_bwd, row_chunk=row_chunk, grad_sink=grad_sink, x16_cache=x16_cache)
+                need_backward=need_bwd, row_chunk=row_chunk, grad_sink=grad_sink, x16_cache=x16_cache, cell=cell, pool=pool)
     return _PaggFunction.apply(X, params["fc0.weight"], params["fc0.bias"], nets_w, nets_b,
                                params["LSTM.weight_ih_l0"], params["LSTM.weight_hh_l0"],
                                params["LSTM.bias_ih_l0"], params["LSTM.bias_hh_l0"],
@@ -284,7 +291,7 @@ class RowsCache:
 
 
 def fused_forward(self, variant, X, neis, num_w, walk_len, indices, layer_type, *, dropout, math_mode, row_chunk=0,
-                  rows_cache=None, guard=None, grad_sink=None, x16_cache=None):
+                  rows_cache=None, guard=None, grad_sink=None, x16_cache=None, cell="lstm", pool="attention", params=None):
     """The 7-argument forward of both reference classes on the fused operator; shared by the drop-in modules below
     and by the launcher that rebinds the forward of the reference's own classes (pathnet_b200/run.py)."""
     dev = X.device
@@ -312,9 +319,10 @@ def fused_forward(self, variant, X, neis, num_w, walk_len, indices, layer_type, 
     seed = 0
     if self.training and dropout > 0:
         seed = int(torch.randint(0, 2 ** 62, (1,)).item())  # follows torch.manual_seed (host generator: no device sync)
-    sd = {k: v for k, v in self.named_parameters()}
+    sd = params if params is not None else {k: v for k, v in self.named_parameters()}
     return pagg_forward(variant, X, sd, seq_node, seq_type, partner, rows, dropout=dropout, training=self.training,
-                        seed=seed, math_mode=math_mode, row_chunk=row_chunk, grad_sink=grad_sink, x16_cache=x16_cache)
+                        seed=seed, math_mode=math_mode, row_chunk=row_chunk, grad_sink=grad_sink, x16_cache=x16_cache,
+                        cell=cell, pool=pool)
 
 
 class _PathNetBase(nn.Module):
@@ -325,6 +333,9 @@ class _PathNetBase(nn.Module):
         self.dropout = float(kwargs.pop("dropout", 0.0))     # the reference reads a module global (:71); its CLI default is 0.7
         self.math_mode = kwargs.pop("math_mode", "auto")     # "auto" | "fp32" (strict parity) | "tc"
         self.row_chunk = int(kwargs.pop("row_chunk", 0))     # > 0: bounded workspace, see pn_pagg_cfg.row_chunk
+        self.pool = kwargs.pop("pool", "attention")          # ablations: "mean" | "sum" | "max" instead of the attention
+        if self.pool not in POOL:
+            raise ValueError(f"pool must be one of {sorted(POOL)} (got {self.pool!r})")
         kwargs.setdefault("aggr", "mean")
         super().__init__()
         self._rows_cache = RowsCache()
@@ -353,7 +364,7 @@ class _PathNetBase(nn.Module):
             self._guard = IndexGuard(X.device)
         return fused_forward(self, self._variant, X, neis, num_w, walk_len, indices, layer_type, dropout=self.dropout,
                              math_mode=self.math_mode, row_chunk=self.row_chunk, rows_cache=self._rows_cache,
-                             guard=self._guard, grad_sink=self.grad_sink, x16_cache=self._x16)
+                             guard=self._guard, grad_sink=self.grad_sink, x16_cache=self._x16, pool=self.pool)
 
 
 class PathNet(_PathNetBase):
@@ -371,4 +382,48 @@ class PathNet_homo(_PathNetBase):
         nn.init.xavier_uniform_(self.fc2.weight)
 
 
-PAGG = PathNet  # the name the README (:118) and baseline/GPRGNN/src/copy.py:299 use
+PAGG = PathNet  # the name the README (:118) uses for the aggregator
+
+
+class PAGG_RNN(nn.Module):
+    """Drop-in for the OLDER aggregator `class PAGG` of the reference (baseline/GPRGNN/src/copy.py:299-359; the
+    "RNN / mean" ablation named in performance.jpg): fc0 -> gather -> one of four Linear(H,H) by distance label ->
+    dropout -> tanh nn.RNN over the path -> plain mean over the paths -> concat with the ego embedding -> dropout ->
+    fc2.  Same constructor `(feature_length, hidden_size, out_size, node_num)`, same 7-argument forward, same
+    parameter names (fc0, RNN, fc2, nei0..nei3).  The reference hard-codes dropout p = 0.9 (:347,:354)."""
+
+    def __init__(self, feature_length, hidden_size, out_size, node_num, **kwargs):
+        self.dropout = float(kwargs.pop("dropout", 0.9))
+        self.math_mode = kwargs.pop("math_mode", "fp32")
+        super().__init__()
+        self.feature_length, self.hidden_size, self.out_size, self.node_num = feature_length, hidden_size, out_size, node_num
+        self.fc0 = nn.Linear(feature_length, hidden_size)
+        self.RNN = nn.RNN(hidden_size, hidden_size)
+        self.fc2 = nn.Linear(2 * hidden_size, out_size)
+        self.nei0 = nn.Linear(hidden_size, hidden_size)
+        self.nei1 = nn.Linear(hidden_size, hidden_size)
+        self.nei2 = nn.Linear(hidden_size, hidden_size)
+        self.nei3 = nn.Linear(hidden_size, hidden_size)
+        for lin in (self.fc0, self.fc2, self.nei0, self.nei1, self.nei2, self.nei3):   # :312-317
+            nn.init.xavier_uniform_(lin.weight)
+        self.nets = [self.nei0, self.nei1, self.nei2, self.nei3]    # plain list: no extra state_dict keys
+        self._rows_cache, self._guard, self.grad_sink, self._x16 = RowsCache(), None, GradSink(), X16Cache()
+
+    def forward(self, X, neis, num_w, walk_len, indices, layer_type, indxx=None):
+        if X.device.type != "cuda":
+            raise RuntimeError("pathnet_b200 PAGG runs on CUDA only (no CPU fallback); X is on %s" % X.device)
+        if walk_len != 4:
+            raise ValueError("the reference's PAGG class has exactly four per-distance layers (walk_len must be 4)")
+        if self._guard is None or self._guard.dev_word.device != X.device:
+            self._guard = IndexGuard(X.device)
+        H = self.hidden_size
+        zero = X.new_zeros(1)
+        params = {"fc0.weight": self.fc0.weight, "fc0.bias": self.fc0.bias, "fc2.weight": self.fc2.weight, "fc2.bias": self.fc2.bias,
+                  "LSTM.weight_ih_l0": self.RNN.weight_ih_l0, "LSTM.weight_hh_l0": self.RNN.weight_hh_l0,
+                  "LSTM.bias_ih_l0": self.RNN.bias_ih_l0, "LSTM.bias_hh_l0": self.RNN.bias_hh_l0,
+                  "attw.weight": X.new_zeros(1, 2 * H), "attw.bias": zero}     # no attention in this class
+        for d, lin in enumerate(self.nets):
+            params[f"nets.{d}.weight"], params[f"nets.{d}.bias"] = lin.weight, lin.bias
+        return fused_forward(self, "plain", X, neis, num_w, walk_len, indices, layer_type, dropout=self.dropout,
+                             math_mode=self.math_mode, rows_cache=self._rows_cache, guard=self._guard, grad_sink=self.grad_sink,
+                             x16_cache=self._x16, cell="rnn", pool="mean", params=params)

@@ -135,7 +135,8 @@ class TrainStep:
         self.cfg = PaggCfg(N=self.X.shape[0], F=F, H=H, C=Cc, S=S, nw=self.nw, L=self.L, variant=pagg.VARIANT[self.variant],
                            math_mode=pagg.MATH[mode], training=1, dropout_p=self.dropout, dropout_seed=base_seed,
                            no_backward=0, row_chunk=int(getattr(model, "row_chunk", 0) if row_chunk is None else row_chunk),
-                           dropout_seed_dev=self.state.data_ptr(), x16=None)
+                           dropout_seed_dev=self.state.data_ptr(), x16=None, cell=0,
+                           pool=pagg.POOL[getattr(model, "pool", "attention")])
         self.x16 = None
         if mode == "tc":   # X is constant over the run: its fp16 copy for the TMA-loaded fc0 GEMM is made once
             self.x16 = torch.empty(lib().pn_pagg_x16_bytes(self.cfg.N, F), dtype=torch.uint8, device=self.dev)

@@ -111,7 +111,7 @@ def test_row_chunk_bounds_the_workspace():
               dropout_seed=1, no_backward=0, dropout_seed_dev=None, x16=None)
     whole = _lib.lib().pn_pagg_workspace_bytes(C.byref(_lib.PaggCfg(row_chunk=0, **kw)))
     chunked = _lib.lib().pn_pagg_workspace_bytes(C.byref(_lib.PaggCfg(row_chunk=4096, **kw)))
-    assert whole > 10 ** 13 and chunked < 120 * 2 ** 30       # BASELINE configs[4]: TBs whole, fits one B200 chunked
+    assert whole > 10 ** 13 and chunked < 140 * 2 ** 30       # BASELINE configs[4]: TBs whole, fits one B200 (180 GB) chunked
 
 
 # ------------------------------------------------------------------ autograd robustness

@@ -206,3 +206,35 @@ def test_uniform_rw_oracle_matches_reference_gen_binary_fixture():
             f = f"{d}/u_nsl.in"
             open(f, "w").write(f"{int(z['n'])} {len(z['u'])}\n" + "".join(f"{a} {b}\n" for a, b in zip(z["u"], z["v"])))
             assert mo.run_reference_uniform(f, int(z["nw"]), int(z["L"]), int(z["seed"]), epochs=int(z["epochs"]), name="u") == txt
+
+
+# --------------------------------------------------------------------------- the older RNN / mean aggregator
+PAGGRNN_FIXTURES = sorted(GOLDEN.glob("paggrnn_*.npz"))
+
+
+@pytest.mark.parametrize("path", PAGGRNN_FIXTURES, ids=lambda p: p.stem)
+def test_pagg_rnn_oracle_matches_reference_fixture(path):
+    """oracle.pagg_rnn_forward against what the reference's own `class PAGG` (baseline/GPRGNN/src/copy.py:299-359) produced."""
+    z = np.load(path)
+    params = {k[6:]: torch.tensor(z[k]).requires_grad_(True) for k in z.files if k.startswith("param:")}
+    y = po.pagg_rnn_forward(params, torch.tensor(z["X"]), torch.tensor(z["neis"].astype(np.int64)), int(z["nw"]), int(z["L"]),
+                            torch.tensor(z["mask"]), torch.tensor(z["layer_type"].astype(np.int64)))
+    torch.testing.assert_close(y.detach(), torch.tensor(z["logits"]), rtol=1e-5, atol=1e-6)
+    (y * torch.tensor(z["G"])).sum().backward()
+    for k, p in params.items():
+        torch.testing.assert_close(p.grad, torch.tensor(z["grad:" + k]), rtol=1e-4, atol=1e-6, msg=lambda s: f"{k}: {s}")
+
+
+def test_pagg_rnn_oracle_matches_live_reference_class(have_reference):
+    if not have_reference:
+        pytest.skip("reference not mounted")
+    cls = po.load_reference_pagg_rnn_class()
+    torch.manual_seed(3)
+    N, Fd, H, C, nw, L, S = 50, 10, 16, 3, 4, 4, 11
+    m = cls(Fd, H, C, N).eval()
+    X = torch.randn(N, Fd)
+    mask = torch.zeros(N, dtype=torch.bool); mask[torch.randperm(N)[:S]] = True
+    neis, lt = torch.randint(0, N, (S, nw * L)), torch.randint(0, L, (S, nw, L))
+    want = m(X, neis, nw, L, mask, lt, torch.arange(S * nw * L))
+    got = po.pagg_rnn_forward(dict(m.state_dict()), X, neis, nw, L, mask, lt)
+    torch.testing.assert_close(got, want.detach(), rtol=1e-5, atol=1e-6)
