@@ -172,8 +172,8 @@ typedef struct {
                                 padded), e.g. made once by pn_pagg_pack_x16: the tensor-core mode then TMA-loads it
                                 instead of re-reading and re-converting the fp32 X on every call (X is constant over
                                 a training run, PathNet_run.py:300).  NULL = convert per call.                       */
-    int32_t cell;            /* pn_cell  (0 = LSTM, the reference's)                                                  */
-    int32_t pool;            /* pn_pool  (0 = the variant's attention, the reference's)                               */
+    int32_t cell;            /* a pn_cell value: 0 = LSTM, the reference's                                                   */
+    int32_t pool;            /* a pn_pool value: 0 = the variant's attention                               */
 } pn_pagg_cfg;
 
 /* Parameter (or gradient) block, fp32 device pointers, PyTorch layouts
