@@ -18,6 +18,13 @@ void set_error(const char *fmt, ...)
 }
 }  // namespace pn
 
+// ---- NVTX ---------------------------------------------------------------------
+#include <nvtx3/nvToolsExt.h>
+namespace pn {
+void nvtx_push(const char *name) { nvtxRangePushA(name); }
+void nvtx_pop() { nvtxRangePop(); }
+}  // namespace pn
+
 // ---- profiling slots --------------------------------------------------------
 #include <map>
 #include <mutex>

@@ -42,13 +42,22 @@ inline void count_launch(uint64_t k = 1) { g_launches.fetch_add(k, std::memory_o
         PN_CUDA(cudaGetLastError());          \
     } while (0)
 
+// NVTX ranges (header-only nvtx3: a no-op unless a profiler injects itself): one per C-ABI entry point
+// (sampler S1/S2, PAGG K0-K4) and one per dominant kernel, so nsys / ncu timelines carry the reference-side names.
+void nvtx_push(const char *name);
+void nvtx_pop();
+struct NvtxScope {
+    explicit NvtxScope(const char *name) { nvtx_push(name); }
+    ~NvtxScope() { nvtx_pop(); }
+};
+
 // in-stream timing of named kernels (pn_profile_enable / pn_profile_read)
 void prof_begin(const char *slot, cudaStream_t st);
 void prof_end(const char *slot, cudaStream_t st);
 struct ProfScope {
     const char *slot; cudaStream_t st;
-    ProfScope(const char *s, cudaStream_t t) : slot(s), st(t) { prof_begin(slot, st); }
-    ~ProfScope() { prof_end(slot, st); }
+    ProfScope(const char *s, cudaStream_t t) : slot(s), st(t) { nvtx_push(slot); prof_begin(slot, st); }
+    ~ProfScope() { prof_end(slot, st); nvtx_pop(); }
 };
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

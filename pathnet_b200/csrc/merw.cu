@@ -771,6 +771,7 @@ extern "C" int pn_merw_sample(pn_graph *g, int32_t nw, int32_t L, int64_t epoch_
                               int32_t rng_mode, uint64_t seed, int32_t *nodes, uint8_t *types,
                               void *stream_)
 {
+    NvtxScope nvtx("pn_merw_sample");
     PN_REQUIRE(g, "pn_merw_sample: NULL graph");
     PN_REQUIRE(nw >= 0 && L >= 1 && L <= 64, "pn_merw_sample: bad nw=%d / L=%d", nw, L);
     PN_REQUIRE(epoch_begin >= 0 && epoch_end >= epoch_begin, "pn_merw_sample: bad epoch range");

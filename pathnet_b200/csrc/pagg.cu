@@ -705,6 +705,8 @@ __global__ void __launch_bounds__(256) k_pool_fwd128(PoolArgs a)
     float mx = -INFINITY;
     const float *pv_last = nullptr;
     float pd_last = 0.f;
+    float4 pooled = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool homo = a.variant != PN_VARIANT_HETERO;   // weight = 1 + score: no normaliser, so ONE pass over the h_w rows
 #pragma unroll 4
     for (int w = 0; w < nw; w++) {
         const int64_t p = s * nw + w;
@@ -712,30 +714,33 @@ __global__ void __launch_bounds__(256) k_pool_fwd128(PoolArgs a)
         const float *pv = partner_vec(a, p);
         if (pv != pv_last) { pd_last = dot4(wp, ld4(pv + 4 * lane)); pv_last = pv; }
         const float d = warp_sum(dot4(wh, h4) + pd_last) + bias;
-        if (lane == 0) a.score[p] = d;
+        if (lane == 0) { a.score[p] = d; if (homo) a.att[p] = 1.f + d; }
         mx = fmaxf(mx, d > 0.f ? d : 0.01f * d);
+        if (homo) {
+            const float at = 1.f + d;
+            pooled.x += at * h4.x; pooled.y += at * h4.y; pooled.z += at * h4.z; pooled.w += at * h4.w;
+        }
     }
-    __syncwarp();
-    float denom = 0.f;
-    if (a.variant == PN_VARIANT_HETERO) {
+    if (!homo) {
+        __syncwarp();
+        float denom = 0.f;
         for (int w = lane; w < nw; w += 32) {
             const float d = a.score[s * nw + w];
             denom += expf((d > 0.f ? d : 0.01f * d) - mx);
         }
         denom = warp_sum(denom);
-    }
-    for (int w = lane; w < nw; w += 32) {
-        const int64_t p = s * nw + w;
-        const float d = a.score[p];
-        a.att[p] = a.variant == PN_VARIANT_HETERO ? expf((d > 0.f ? d : 0.01f * d) - mx) / denom : 1.f + d;
-    }
-    __syncwarp();
-    float4 pooled = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int w = lane; w < nw; w += 32) {
+            const int64_t p = s * nw + w;
+            const float d = a.score[p];
+            a.att[p] = expf((d > 0.f ? d : 0.01f * d) - mx) / denom;
+        }
+        __syncwarp();
 #pragma unroll 8
-    for (int w = 0; w < nw; w++) {
-        const float at = a.att[s * nw + w];
-        const float4 h4 = ld4(a.hfin + (s * nw + w) * H + 4 * lane);
-        pooled.x += at * h4.x; pooled.y += at * h4.y; pooled.z += at * h4.z; pooled.w += at * h4.w;
+        for (int w = 0; w < nw; w++) {
+            const float at = a.att[s * nw + w];
+            const float4 h4 = ld4(a.hfin + (s * nw + w) * H + 4 * lane);
+            pooled.x += at * h4.x; pooled.y += at * h4.y; pooled.z += at * h4.z; pooled.w += at * h4.w;
+        }
     }
     const float inv_nw = 1.f / (float)nw;
     float po[4] = {pooled.x * inv_nw, pooled.y * inv_nw, pooled.z * inv_nw, pooled.w * inv_nw};
@@ -808,15 +813,20 @@ __global__ void __launch_bounds__(256) k_pool_bwd128(PoolArgs a)
             }
         }
         atomicAdd(reinterpret_cast<float4 *>(a.dZ + node * H + 4 * lane), e4);
-        // da_w = inv_nw * <dpooled, h_w>, kept by lane (w mod 32) for w < 64, else recomputed
+        // da_w = inv_nw * <dpooled, h_w>, kept by lane (w mod 32) for w < 64, else recomputed.  Only the softmax backward of
+        // the hetero variant needs every da_w before the main loop (its dot_sum); homo's weight is 1 + score, so da_w is
+        // computed where it is used and h_w is read once.
+        const bool two_pass = a.variant == PN_VARIANT_HETERO;
         float da_keep0 = 0.f, da_keep1 = 0.f;
         float dot_sum = 0.f;  // sum_v att_v * da_v (softmax backward), hetero only
+        if (two_pass) {
 #pragma unroll 4
-        for (int w = 0; w < nw; w++) {
-            const int64_t p = s * nw + w;
-            const float d = warp_sum(dot4(g4, ld4(a.hfin + p * H + 4 * lane))) * inv_nw;
-            if ((w & 31) == lane) { if (w < 32) da_keep0 = d; else if (w < 64) da_keep1 = d; }
-            dot_sum += a.att[p] * d;
+            for (int w = 0; w < nw; w++) {
+                const int64_t p = s * nw + w;
+                const float d = warp_sum(dot4(g4, ld4(a.hfin + p * H + 4 * lane))) * inv_nw;
+                if ((w & 31) == lane) { if (w < 32) da_keep0 = d; else if (w < 64) da_keep1 = d; }
+                dot_sum += a.att[p] * d;
+            }
         }
         const float4 wh = ld4(a.attw_w + 4 * lane), wp = ld4(a.attw_w + H + 4 * lane);
         float dbias = 0.f, amax = 0.f;
@@ -831,11 +841,11 @@ __global__ void __launch_bounds__(256) k_pool_bwd128(PoolArgs a)
             const float *pv = partner_vec(a, p);
             if (pv != pv_last) { pv4 = ld4(pv + 4 * lane); pv_last = pv; }
             float da;
-            if (w < 64) da = __shfl_sync(0xffffffffu, w < 32 ? da_keep0 : da_keep1, w & 31);
+            if (two_pass && w < 64) da = __shfl_sync(0xffffffffu, w < 32 ? da_keep0 : da_keep1, w & 31);
             else da = warp_sum(dot4(g4, h4)) * inv_nw;
-            const float raw = a.score[p], att = a.att[p];
+            const float att = a.att[p];
             float dscore;
-            if (a.variant == PN_VARIANT_HETERO) dscore = att * (da - dot_sum) * (raw > 0.f ? 1.f : 0.01f);
+            if (two_pass) dscore = att * (da - dot_sum) * (a.score[p] > 0.f ? 1.f : 0.01f);
             else dscore = da;  // weight = 1 + score
             dbias += dscore;
             float *dpv = a.variant == PN_VARIANT_HOMO
@@ -1063,6 +1073,7 @@ extern "C" int pn_pagg_forward(const pn_pagg_cfg *cfg, const pn_pagg_params *prm
                                const int32_t *partner, const int32_t *rows, void *workspace,
                                float *logits, void *stream)
 {
+    NvtxScope nvtx("pn_pagg_forward");
     int rc = check_cfg(cfg);
     if (rc != PN_OK) return rc;
     const pn_pagg_cfg &c = *cfg;
@@ -1108,6 +1119,7 @@ extern "C" int pn_pagg_backward(const pn_pagg_cfg *cfg, const pn_pagg_params *pr
                                 const int32_t *partner, const int32_t *rows, void *workspace,
                                 const float *dlogits, const pn_pagg_params *grads, void *stream)
 {
+    NvtxScope nvtx("pn_pagg_backward");
     int rc = check_cfg(cfg);
     if (rc != PN_OK) return rc;
     const pn_pagg_cfg &c = *cfg;

@@ -781,15 +781,38 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
             __syncwarp();
         };
         const bool tr = a.trace && blockIdx.x == a.trace_block && tid == 0;
+        // The saved activations of a half-iteration (4 hidden units x {i, f, g, o, c_t, c_{t-1}}: six 8-byte loads, plus
+        // dh_final at the first step) are fetched one half-iteration AHEAD of the gate-gradient math that consumes them —
+        // across the K-quarter boundaries and across the step boundary (where the dx scatter sits in between) — so the
+        // L2 round trip that used to be exposed once per quarter (the top stall of this kernel in round 1's ncu source
+        // view: 24 % of the samples on the first unpack after the loads) overlaps arithmetic.
+        struct BwdRaw { uint2 gi, gf, gg, go, cn, cp; float4 dh0; };
+        auto load_raw = [&](int s_, int hi_, BwdRaw &x) {
+            const int t_ = L - 1 - s_;
+            const int cb_ = cq * 4 + (hi_ >> 1), sub = (hi_ & 1) * 4;
+            const __half *act_ = a.acts + ((int64_t)tile * L + t_) * ACT_BLOCK_HALFS + r * 8 + cb_ * 1024 + sub;
+            x.gi = x.gf = x.gg = x.go = x.cn = x.cp = make_uint2(0u, 0u);
+            x.dh0 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid) {
+                x.gi = __ldg(reinterpret_cast<const uint2 *>(act_ + 0 * 16384));
+                x.gf = __ldg(reinterpret_cast<const uint2 *>(act_ + 1 * 16384));
+                x.gg = __ldg(reinterpret_cast<const uint2 *>(act_ + 2 * 16384));
+                x.go = __ldg(reinterpret_cast<const uint2 *>(act_ + 3 * 16384));
+                x.cn = __ldg(reinterpret_cast<const uint2 *>(act_ + 4 * 16384));
+                if (t_ > 0) x.cp = __ldg(reinterpret_cast<const uint2 *>(act_ - ACT_BLOCK_HALFS + 4 * 16384));
+                if (s_ == 0) x.dh0 = __ldg(reinterpret_cast<const float4 *>(a.dhfin + p * TC_H + cb_ * 8 + sub));
+            }
+        };
+        BwdRaw nxt;
+        load_raw(0, 0, nxt);
         for (int s = 0; s < L; s++) {
             const int t = L - 1 - s;
             if (tr) a.trace[s * 8 + 0] = clock64();
             const int64_t blk = (int64_t)t * a.ntiles + tile;
             unsigned char *da_blk = a.da_img + blk * DA_BLOCK_BYTES;
-            const __half *act = a.acts + ((int64_t)tile * L + t) * ACT_BLOCK_HALFS + r * 8;
-            const __half *actp = act - ACT_BLOCK_HALFS;  // step t-1 (only read when t > 0)
             // ---- pull the next step's activations towards L2 (a whole step ahead) ----
             if (valid && t > 0) {
+                const __half *actp = a.acts + ((int64_t)tile * L + t - 1) * ACT_BLOCK_HALFS + r * 8;
 #pragma unroll
                 for (int cb = cq * 4; cb < cq * 4 + 4; cb++) {
 #pragma unroll
@@ -801,44 +824,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
             if (s > 0) scatter_dx(s - 1);
             if (tr) a.trace[s * 8 + 1] = clock64();
             const uint32_t dh_rd = 128u + (uint32_t)((s - 1) & 1) * 128u;
-            // ---- gate gradients, one K-quarter of the operand tile per iteration ----
-#pragma unroll 1
-            for (int cb = cq * 4; cb < cq * 4 + 4; cb++) {
-                const int u0 = cb * 8;
-                float dh[8], dc[8];
+            // ---- gate gradients: 8 half-iterations of 4 units; two of them complete one K-quarter of the operand tile ----
+#pragma unroll 2
+            for (int hi = 0; hi < 8; hi++) {
+                const BwdRaw cur = nxt;
+                if (hi < 7) load_raw(s, hi + 1, nxt);
+                else if (s + 1 < L) load_raw(s + 1, 0, nxt);
+                const int cb = cq * 4 + (hi >> 1), u0 = cb * 8 + (hi & 1) * 4;
+                float dh[4], dc[4];
                 if (s == 0) {
-#pragma unroll
-                    for (int j = 0; j < 8; j++) { dh[j] = 0.f; dc[j] = 0.f; }
-                    if (valid) {
-                        const float4 x0 = __ldg(reinterpret_cast<const float4 *>(a.dhfin + p * TC_H + u0));
-                        const float4 x1 = __ldg(reinterpret_cast<const float4 *>(a.dhfin + p * TC_H + u0 + 4));
-                        dh[0] = x0.x * scale; dh[1] = x0.y * scale; dh[2] = x0.z * scale; dh[3] = x0.w * scale;
-                        dh[4] = x1.x * scale; dh[5] = x1.y * scale; dh[6] = x1.z * scale; dh[7] = x1.w * scale;
-                    }
+                    dh[0] = cur.dh0.x * scale; dh[1] = cur.dh0.y * scale; dh[2] = cur.dh0.z * scale; dh[3] = cur.dh0.w * scale;
+                    dc[0] = dc[1] = dc[2] = dc[3] = 0.f;
                 } else {
-                    uint32_t v0[8], v1[8];
-                    tmem_ld8(lane_base + dh_rd + u0, v0);
-                    tmem_ld8(lane_base + 384 + u0, v1);
+                    uint32_t v0[4], v1[4];
+                    tmem_ld4(lane_base + dh_rd + u0, v0);
+                    tmem_ld4(lane_base + 384 + u0, v1);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 8; j++) { dh[j] = __uint_as_float(v0[j]); dc[j] = __uint_as_float(v1[j]); }
+                    for (int j = 0; j < 4; j++) { dh[j] = __uint_as_float(v0[j]); dc[j] = __uint_as_float(v1[j]); }
                 }
-                float gi[8], gf[8], gg[8], go[8], cn[8], cp[8];
+                float gi[4], gf[4], gg[4], go[4], cn[4], cp[4];
+                unpack4_f16(cur.gi, gi); unpack4_f16(cur.gf, gf); unpack4_f16(cur.gg, gg);
+                unpack4_f16(cur.go, go); unpack4_f16(cur.cn, cn); unpack4_f16(cur.cp, cp);
+                float da[2][8];  // [q][.]: packed columns (u0 + 2q + {0,1}) * 4 + gate
+                uint32_t dcn_bits[4];
 #pragma unroll
-                for (int j = 0; j < 8; j++) { gi[j] = gf[j] = gg[j] = go[j] = cn[j] = cp[j] = 0.f; }
-                if (valid) {
-                    const int ub = cb * 1024;
-                    unpack8_f16(__ldg(reinterpret_cast<const uint4 *>(act + 0 * 16384 + ub)), gi);
-                    unpack8_f16(__ldg(reinterpret_cast<const uint4 *>(act + 1 * 16384 + ub)), gf);
-                    unpack8_f16(__ldg(reinterpret_cast<const uint4 *>(act + 2 * 16384 + ub)), gg);
-                    unpack8_f16(__ldg(reinterpret_cast<const uint4 *>(act + 3 * 16384 + ub)), go);
-                    unpack8_f16(__ldg(reinterpret_cast<const uint4 *>(act + 4 * 16384 + ub)), cn);
-                    if (t > 0) unpack8_f16(__ldg(reinterpret_cast<const uint4 *>(actp + 4 * 16384 + ub)), cp);
-                }
-                float da[4][8];  // [q][.]: packed columns (u0 + 2q + {0,1}) * 4 + gate
-                uint32_t dcn_bits[8];
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
+                for (int j = 0; j < 4; j++) {
                     const float tcn = tanh_fast(cn[j]);
                     const float dcn = fmaf(dh[j] * go[j], 1.f - tcn * tcn, dc[j]);
                     const float d_i = dcn * gg[j] * gi[j] * (1.f - gi[j]);
@@ -849,17 +860,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
                     da[j >> 1][(j & 1) * 4 + 0] = d_i; da[j >> 1][(j & 1) * 4 + 1] = d_f;
                     da[j >> 1][(j & 1) * 4 + 2] = d_g; da[j >> 1][(j & 1) * 4 + 3] = d_o;
                 }
-                tmem_st8(lane_base + 384 + u0, dcn_bits);
+                tmem_st4(lane_base + 384 + u0, dcn_bits);
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
+                for (int q = 0; q < 2; q++) {
+                    const int chunk = cb * 4 + (hi & 1) * 2 + q;   // 8 packed gate columns = 16 bytes
                     const uint4 pk = pack8_f16(da[q]);
-                    *reinterpret_cast<uint4 *>(As + canon_off(r, cb * 32 + q * 8, TC_G4)) = pk;          // dgrad operand
-                    *reinterpret_cast<uint4 *>(da_blk + (size_t)(cb * 4 + q) * 2048 + r * 16) = pk;       // wgrad operand image
+                    *reinterpret_cast<uint4 *>(As + canon_off(r, chunk * 8, TC_G4)) = pk;          // dgrad operand
+                    *reinterpret_cast<uint4 *>(da_blk + (size_t)chunk * 2048 + r * 16) = pk;       // wgrad operand image
                 }
-                // this quarter of the operand tile is written: let the tensor core start on it
-                fence_proxy_async();
-                tc_fence_before();
-                mbar_arrive(&a_ready[cb - cq * 4]);
+                if (hi & 1) {   // this quarter of the operand tile is written: let the tensor core start on it
+                    fence_proxy_async();
+                    tc_fence_before();
+                    mbar_arrive(&a_ready[hi >> 1]);
+                }
             }
             tmem_st_wait();
             if (tr) a.trace[s * 8 + 2] = clock64();

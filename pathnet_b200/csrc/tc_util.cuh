@@ -171,6 +171,15 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8])
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                  : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&v)[4])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
+}
 // registers -> TMEM (thread i writes its lane's 8 consecutive columns)
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8])
 {
@@ -195,6 +204,13 @@ __device__ __forceinline__ void unpack8_f16(const uint4 &pk, float (&f)[8])
     const __half2 *h = reinterpret_cast<const __half2 *>(&pk);
 #pragma unroll
     for (int i = 0; i < 4; i++) { const float2 t = __half22float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+
+__device__ __forceinline__ void unpack4_f16(const uint2 &pk, float (&f)[4])
+{
+    const __half2 *h = reinterpret_cast<const __half2 *>(&pk);
+    const float2 a = __half22float2(h[0]), b = __half22float2(h[1]);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
 }
 
 // byte offset of element (r, k) in the canonical layout of a [rows][K] fp16 operand

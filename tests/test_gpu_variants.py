@@ -97,13 +97,14 @@ def test_pooling_ablations_match_oracle(variant, pool, mode, H):
     else:
         assert_tc_logits(y.cpu(), y_ref.detach().float())
     for k, q in m.named_parameters():
-        want = params[k].grad.float()
         if k.startswith("attw"):
-            assert float(q.grad.abs().max()) == 0.0      # no attention: its parameters get zero gradient
-        elif mode == "fp32":
+            assert params[k].grad is None and float(q.grad.abs().max()) == 0.0      # no attention: its parameters get zero gradient
+            continue
+        want = params[k].grad.float()
+        if mode == "fp32":
             torch.testing.assert_close(q.grad.cpu(), want, **GRAD_TOL, msg=lambda s: f"{k}: {s}")
-        else:
-            assert_grad_close(q.grad.cpu(), want, k, 1e-2, 1e-2)
+        else:   # max pooling routes each gradient to ONE path: an argmax that flips under fp16 rounding moves whole rows
+            assert_grad_close(q.grad.cpu(), want, k, *((5e-2, 3e-2) if pool == "max" else (1e-2, 1e-2)))
 
 
 def test_variant_argument_errors():
