@@ -417,7 +417,12 @@ struct PoolArgs {
     int pool;                   // PN_POOL_ATTENTION (the variant's own attention) | MEAN | SUM | MAX over the nw sequences
     // backward
     const float *dcat;   // [S,2H] grad wrt the dropped concat
-    float *dhfin, *dZ, *dT, *dattw;
+    float *dhfin, *dZ, *dT, *dattw;   // dhfin may be null when the factored form below is written instead
+    // factored dh_final for the tensor-core LSTM backward: dh_final[p] = dh_k[p] * gdrop[row(p)] + dh_s[p] * attw_w[0:H]
+    // (dh_k = att/nw, dh_s = dscore; gdrop = the row's pooled-half gradient after dropout, leading dimension gdrop_ld),
+    // 2 scalars per path + one vector per ROW instead of a [P,H] tensor written here and read back there
+    float *dh_k, *dh_s, *gdrop;
+    int64_t gdrop_ld;
     unsigned int *absmax_bits;  // max |dhfin| as float bits (tensor-core backward's gradient scale), may be null
     // classifier fused into the H = 128 kernels (few classes: each warp already holds its whole concat row)
     int C;
@@ -813,6 +818,7 @@ __global__ void __launch_bounds__(256) k_pool_bwd128(PoolArgs a)
             }
         }
         atomicAdd(reinterpret_cast<float4 *>(a.dZ + node * H + 4 * lane), e4);
+        if (a.gdrop) *reinterpret_cast<float4 *>(a.gdrop + s * a.gdrop_ld + 4 * lane) = g4;
         // da_w = inv_nw * <dpooled, h_w>, kept by lane (w mod 32) for w < 64, else recomputed.  Only the softmax backward of
         // the hetero variant needs every da_w before the main loop (its dot_sum); homo's weight is 1 + score, so da_w is
         // computed where it is used and h_w is read once.
@@ -858,7 +864,8 @@ __global__ void __launch_bounds__(256) k_pool_bwd128(PoolArgs a)
             }
             const float k = inv_nw * att;
             const float4 dh = make_float4(k * g4.x + dscore * wh.x, k * g4.y + dscore * wh.y, k * g4.z + dscore * wh.z, k * g4.w + dscore * wh.w);
-            *reinterpret_cast<float4 *>(a.dhfin + p * H + 4 * lane) = dh;
+            if (a.dhfin) *reinterpret_cast<float4 *>(a.dhfin + p * H + 4 * lane) = dh;
+            if (a.dh_k && lane == 0) { a.dh_k[p] = k; a.dh_s[p] = dscore; }   // (may alias att / score: both were read above)
             amax = fmaxf(amax, fmaxf(fmaxf(fabsf(dh.x), fabsf(dh.y)), fmaxf(fabsf(dh.z), fabsf(dh.w))));
             dw_h.x += dscore * h4.x; dw_h.y += dscore * h4.y; dw_h.z += dscore * h4.z; dw_h.w += dscore * h4.w;
             dw_p.x += dscore * pv4.x; dw_p.y += dscore * pv4.y; dw_p.z += dscore * pv4.z; dw_p.w += dscore * pv4.w;
@@ -944,7 +951,7 @@ static int launch_lstm_bwd(const LstmArgs &a, cudaStream_t st)
 int pagg_tc_forward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_params &prm, const int32_t *seq_node,
                          const uint8_t *seq_type, const PaggChunk &ck, cudaStream_t st);   // pagg_tc.cu
 int pagg_tc_backward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_params &prm, const int32_t *seq_node,
-                          const uint8_t *seq_type, const PaggChunk &ck, cudaStream_t st);  // pagg_tc.cu
+                          const uint8_t *seq_type, const PaggChunk &ck, bool factored_dh, cudaStream_t st);  // pagg_tc.cu
 int pagg_tc_project(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_params &prm, const float *X, cudaStream_t st);          // pagg_tc.cu
 int pagg_tc_project_backward(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_params &prm, const float *X,
                              const pn_pagg_params &g, cudaStream_t st);                                                          // pagg_tc.cu
@@ -1097,9 +1104,11 @@ extern "C" int pn_pagg_forward(const pn_pagg_cfg *cfg, const pn_pagg_params *prm
         rc = launch_gemm(st, w.Z, H, 1, prm->nets_w, 1, H, w.T, L * H, N, L * H, H, prm->nets_b, homo, false);
         if (rc) return rc;
     }
-    k_pack_lstm<<<(unsigned)ceil_div(2 * H * 4 * H, 256), 256, 0, st>>>((int)H, c.cell, prm->w_ih, prm->w_hh, prm->b_ih,
-                                                                      prm->b_hh, w.Wp, w.WpT, w.bp);
-    PN_LAUNCH_CHECK();
+    if (!tcm) {   // (the tensor-core mode packs its own fp16 images of the weights into the same regions)
+        k_pack_lstm<<<(unsigned)ceil_div(2 * H * 4 * H, 256), 256, 0, st>>>((int)H, c.cell, prm->w_ih, prm->w_hh, prm->b_ih,
+                                                                          prm->b_hh, w.Wp, w.WpT, w.bp);
+        PN_LAUNCH_CHECK();
+    }
     const int64_t rows_per = chunk_rows(c);
     const bool single = rows_per >= c.S;
     for (int64_t s0 = 0; s0 < c.S; s0 += rows_per) {
@@ -1181,13 +1190,19 @@ extern "C" int pn_pagg_backward(const pn_pagg_cfg *cfg, const pn_pagg_params *pr
             pa.absmax_bits = reinterpret_cast<unsigned int *>(w.gscale);
         }
         if (fuse_fc2) { pa.C = (int)C; pa.fc2_w = prm->fc2_w; pa.dlogits = dl; pa.dfc2_w = g.fc2_w; pa.dfc2_b = g.fc2_b; }
+        const bool factored = tcm && pool128;   // k_pool_bwd128 -> k_lstm_bwd_tc: dh_final travels as (k, dscore) per path + one vector per row
+        if (factored) {
+            pa.dhfin = nullptr;
+            pa.dh_k = w.att; pa.dh_s = w.score;          // in place: a path's att / score are read before they are overwritten
+            pa.gdrop = w.dcat + H; pa.gdrop_ld = 2 * H;  // in place of the row's pooled-half gradient (unused when fc2 is fused)
+        }
         if (!attention) k_pool_simple_bwd<<<(unsigned)ceil_div(Sc, 8), 256, 0, st>>>(pa);
         else if (pool128) k_pool_bwd128<<<(unsigned)ceil_div(Sc, 8), 256, sizeof(float) * (2 * H + 1 + (fuse_fc2 ? C * (2 * H + 1) : 0)), st>>>(pa);
         else k_pool_bwd<<<(unsigned)ceil_div(Sc, 8), 256, sizeof(float) * (2 * H + 1), st>>>(pa);
         PN_LAUNCH_CHECK();
         // ---- LSTM BPTT ----
         if (tcm) {
-            rc = pagg_tc_backward_lstm(c, w, *prm, ix.seq_node, ix.seq_type, ck, st);
+            rc = pagg_tc_backward_lstm(c, w, *prm, ix.seq_node, ix.seq_type, ck, factored, st);
             if (rc) return rc;
         } else {
             LstmArgs la{};

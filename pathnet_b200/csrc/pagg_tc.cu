@@ -632,7 +632,10 @@ struct LstmBwdTcArgs {
     const uint8_t *seq_type;
     const unsigned char *WhT;  // 16 chunks x 16 KB
     const __half *acts;        // tile images (see LstmTcArgs)
-    const float *dhfin;        // [P,H]
+    const float *dhfin;        // [P,H], or null: dh_final[p] = dh_k[p] * gdrop[p / nw] + dh_s[p] * attw_h (see PoolArgs)
+    const float *dh_k, *dh_s, *gdrop, *attw_h;
+    int64_t gdrop_ld;
+    int nw;
     const float *gscale;       // {scale, 1/scale}
     float *dT;                 // [N,L,H]
     unsigned char *da_img;     // block b = t*ntiles + tile: [64 col8][128 r][8] fp16   (128 KB)
@@ -654,6 +657,9 @@ __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefe
 
 // (Measured and dropped: pairing neighbouring tiles in a cluster that multicasts the W' stream halves its L2 traffic but
 // couples the two CTAs chunk by chunk -- 5 % slower.  The stream is latency-, not bandwidth-limited: depth helps.)
+// PF = true: the variant that fetches activations one half-iteration ahead (measured: +4 % kernel time — the removed L2
+// waits are paid back as 8 % more instructions and twice as many TMEM round trips; kept for A/B runs, PN_BWD_PF=1)
+template <bool PF>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
 {
     extern __shared__ unsigned char smem_dyn[];
@@ -781,6 +787,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
             __syncwarp();
         };
         const bool tr = a.trace && blockIdx.x == a.trace_block && tid == 0;
+        // factored dh_final: this sequence's two scalars and its output row
+        float dh_kk = 1.f, dh_ds = 0.f;
+        int64_t grow = 0;
+        if (!a.dhfin && valid) { dh_kk = a.dh_k[p]; dh_ds = a.dh_s[p]; grow = p / a.nw; }
+        if constexpr (PF) {
         // The saved activations of a half-iteration (4 hidden units x {i, f, g, o, c_t, c_{t-1}}: six 8-byte loads, plus
         // dh_final at the first step) are fetched one half-iteration AHEAD of the gate-gradient math that consumes them —
         // across the K-quarter boundaries and across the step boundary (where the dx scatter sits in between) — so the
@@ -800,7 +811,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
                 x.go = __ldg(reinterpret_cast<const uint2 *>(act_ + 3 * 16384));
                 x.cn = __ldg(reinterpret_cast<const uint2 *>(act_ + 4 * 16384));
                 if (t_ > 0) x.cp = __ldg(reinterpret_cast<const uint2 *>(act_ - ACT_BLOCK_HALFS + 4 * 16384));
-                if (s_ == 0) x.dh0 = __ldg(reinterpret_cast<const float4 *>(a.dhfin + p * TC_H + cb_ * 8 + sub));
+                if (s_ == 0) x.dh0 = a.dhfin ? __ldg(reinterpret_cast<const float4 *>(a.dhfin + p * TC_H + cb_ * 8 + sub))
+                                             : __ldg(reinterpret_cast<const float4 *>(a.gdrop + grow * a.gdrop_ld + cb_ * 8 + sub));
             }
         };
         BwdRaw nxt;
@@ -833,7 +845,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
                 const int cb = cq * 4 + (hi >> 1), u0 = cb * 8 + (hi & 1) * 4;
                 float dh[4], dc[4];
                 if (s == 0) {
-                    dh[0] = cur.dh0.x * scale; dh[1] = cur.dh0.y * scale; dh[2] = cur.dh0.z * scale; dh[3] = cur.dh0.w * scale;
+                    float4 d0 = cur.dh0;
+                    if (!a.dhfin) {
+                        const float4 wh = __ldg(reinterpret_cast<const float4 *>(a.attw_h + u0));   // same address across the warp
+                        d0 = make_float4(fmaf(dh_kk, d0.x, dh_ds * wh.x), fmaf(dh_kk, d0.y, dh_ds * wh.y), fmaf(dh_kk, d0.z, dh_ds * wh.z),
+                                         fmaf(dh_kk, d0.w, dh_ds * wh.w));
+                        if (!valid) d0 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    dh[0] = d0.x * scale; dh[1] = d0.y * scale; dh[2] = d0.z * scale; dh[3] = d0.w * scale;
                     dc[0] = dc[1] = dc[2] = dc[3] = 0.f;
                 } else {
                     uint32_t v0[4], v1[4];
@@ -880,6 +899,105 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
             tc_fence_after();
             if (tr) a.trace[s * 8 + 3] = clock64();
             if (tr) a.trace[s * 8 + 4] = clock64();
+        }
+        } else {
+        for (int s = 0; s < L; s++) {
+            const int t = L - 1 - s;
+            if (tr) a.trace[s * 8 + 0] = clock64();
+            const int64_t blk = (int64_t)t * a.ntiles + tile;
+            unsigned char *da_blk = a.da_img + blk * DA_BLOCK_BYTES;
+            const __half *act = a.acts + ((int64_t)tile * L + t) * ACT_BLOCK_HALFS + r * 8;
+            const __half *actp = act - ACT_BLOCK_HALFS;  // step t-1 (only read when t > 0)
+            // ---- pull the next step's activations towards L2 (a whole step ahead) ----
+            if (valid && t > 0) {
+#pragma unroll
+                for (int cb = cq * 4; cb < cq * 4 + 4; cb++) {
+#pragma unroll
+                    for (int q = 0; q < 5; q++) prefetch_l2(actp + q * 16384 + cb * 1024);
+                    if (t > 1) prefetch_l2(actp - ACT_BLOCK_HALFS + 4 * 16384 + cb * 1024);
+                }
+            }
+            // ---- the previous step's dx (complete since acc_full) -> dT, before this step's MMAs overwrite the region ----
+            if (s > 0) scatter_dx(s - 1);
+            if (tr) a.trace[s * 8 + 1] = clock64();
+            const uint32_t dh_rd = 128u + (uint32_t)((s - 1) & 1) * 128u;
+            // ---- gate gradients, one K-quarter of the operand tile per iteration ----
+#pragma unroll 1
+            for (int cb = cq * 4; cb < cq * 4 + 4; cb++) {
+                const int u0 = cb * 8;
+                float dh[8], dc[8];
+                if (s == 0) {
+#pragma unroll
+                    for (int j = 0; j < 8; j++) { dh[j] = 0.f; dc[j] = 0.f; }
+                    if (valid) {
+                        float4 x0, x1;
+                        if (a.dhfin) {
+                            x0 = __ldg(reinterpret_cast<const float4 *>(a.dhfin + p * TC_H + u0));
+                            x1 = __ldg(reinterpret_cast<const float4 *>(a.dhfin + p * TC_H + u0 + 4));
+                        } else {   // dh_final = k * (row's pooled-half gradient) + dscore * attw_w[0:H]  (see PoolArgs)
+                            const float4 g0 = __ldg(reinterpret_cast<const float4 *>(a.gdrop + grow * a.gdrop_ld + u0));
+                            const float4 g1 = __ldg(reinterpret_cast<const float4 *>(a.gdrop + grow * a.gdrop_ld + u0 + 4));
+                            const float4 w0 = __ldg(reinterpret_cast<const float4 *>(a.attw_h + u0));
+                            const float4 w1 = __ldg(reinterpret_cast<const float4 *>(a.attw_h + u0 + 4));
+                            x0 = make_float4(fmaf(dh_kk, g0.x, dh_ds * w0.x), fmaf(dh_kk, g0.y, dh_ds * w0.y), fmaf(dh_kk, g0.z, dh_ds * w0.z), fmaf(dh_kk, g0.w, dh_ds * w0.w));
+                            x1 = make_float4(fmaf(dh_kk, g1.x, dh_ds * w1.x), fmaf(dh_kk, g1.y, dh_ds * w1.y), fmaf(dh_kk, g1.z, dh_ds * w1.z), fmaf(dh_kk, g1.w, dh_ds * w1.w));
+                        }
+                        dh[0] = x0.x * scale; dh[1] = x0.y * scale; dh[2] = x0.z * scale; dh[3] = x0.w * scale;
+                        dh[4] = x1.x * scale; dh[5] = x1.y * scale; dh[6] = x1.z * scale; dh[7] = x1.w * scale;
+                    }
+                } else {
+                    uint32_t v0[8], v1[8];
+                    tmem_ld8(lane_base + dh_rd + u0, v0);
+                    tmem_ld8(lane_base + 384 + u0, v1);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 8; j++) { dh[j] = __uint_as_float(v0[j]); dc[j] = __uint_as_float(v1[j]); }
+                }
+                float gi[8], gf[8], gg[8], go[8], cn[8], cp[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) { gi[j] = gf[j] = gg[j] = go[j] = cn[j] = cp[j] = 0.f; }
+                if (valid) {
+                    const int ub = cb * 1024;
+                    unpack8_f16(__ldg(reinterpret_cast<const uint4 *>(act + 0 * 16384 + ub)), gi);
+                    unpack8_f16(__ldg(reinterpret_cast<const uint4 *>(act + 1 * 16384 + ub)), gf);
+                    unpack8_f16(__ldg(reinterpret_cast<const uint4 *>(act + 2 * 16384 + ub)), gg);
+                    unpack8_f16(__ldg(reinterpret_cast<const uint4 *>(act + 3 * 16384 + ub)), go);
+                    unpack8_f16(__ldg(reinterpret_cast<const uint4 *>(act + 4 * 16384 + ub)), cn);
+                    if (t > 0) unpack8_f16(__ldg(reinterpret_cast<const uint4 *>(actp + 4 * 16384 + ub)), cp);
+                }
+                float da[4][8];  // [q][.]: packed columns (u0 + 2q + {0,1}) * 4 + gate
+                uint32_t dcn_bits[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const float tcn = tanh_fast(cn[j]);
+                    const float dcn = fmaf(dh[j] * go[j], 1.f - tcn * tcn, dc[j]);
+                    const float d_i = dcn * gg[j] * gi[j] * (1.f - gi[j]);
+                    const float d_f = dcn * cp[j] * gf[j] * (1.f - gf[j]);
+                    const float d_g = dcn * gi[j] * (1.f - gg[j] * gg[j]);
+                    const float d_o = dh[j] * tcn * go[j] * (1.f - go[j]);
+                    dcn_bits[j] = __float_as_uint(dcn * gf[j]);
+                    da[j >> 1][(j & 1) * 4 + 0] = d_i; da[j >> 1][(j & 1) * 4 + 1] = d_f;
+                    da[j >> 1][(j & 1) * 4 + 2] = d_g; da[j >> 1][(j & 1) * 4 + 3] = d_o;
+                }
+                tmem_st8(lane_base + 384 + u0, dcn_bits);
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const uint4 pk = pack8_f16(da[q]);
+                    *reinterpret_cast<uint4 *>(As + canon_off(r, cb * 32 + q * 8, TC_G4)) = pk;          // dgrad operand
+                    *reinterpret_cast<uint4 *>(da_blk + (size_t)(cb * 4 + q) * 2048 + r * 16) = pk;       // wgrad operand image
+                }
+                // this quarter of the operand tile is written: let the tensor core start on it
+                fence_proxy_async();
+                tc_fence_before();
+                mbar_arrive(&a_ready[cb - cq * 4]);
+            }
+            tmem_st_wait();
+            if (tr) a.trace[s * 8 + 2] = clock64();
+            mbar_wait(&acc_full, s & 1);
+            tc_fence_after();
+            if (tr) a.trace[s * 8 + 3] = clock64();
+            if (tr) a.trace[s * 8 + 4] = clock64();
+        }
         }
         scatter_dx(L - 1);   // the last step's dx (nothing left to overlap it with)
     }
@@ -1017,7 +1135,7 @@ __global__ void __launch_bounds__(192, 1) k_wgrad_tc(WgradTcArgs a)
 // LSTM backward in tensor-core mode: fills w.dWp [2H][4H] and w.dbp [4H] (packed
 // layouts, same as the fp32 path) and scatters dx into w.dT.
 int pagg_tc_backward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_params &prm,
-                          const int32_t *seq_node, const uint8_t *seq_type, const PaggChunk &ck, cudaStream_t st)
+                          const int32_t *seq_node, const uint8_t *seq_type, const PaggChunk &ck, bool factored_dh, cudaStream_t st)
 {
     if (c.H != TC_H) {
         set_error("PN_MATH_TC: the tensor-core LSTM is built for hidden size 128 (got %d)", c.H);
@@ -1038,7 +1156,8 @@ int pagg_tc_backward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_p
         scale = c.dropout_p >= 1.f ? 0.f : 1.f / (1.f - c.dropout_p);
     }
     unsigned char *da_img = reinterpret_cast<unsigned char *>(w.dA), *xh_img = reinterpret_cast<unsigned char *>(w.XH);
-    LstmBwdTcArgs a{w.T, seq_node, seq_type, WhT, reinterpret_cast<const __half *>(w.acts), w.dhfin, w.gscale, w.dT,
+    LstmBwdTcArgs a{w.T, seq_node, seq_type, WhT, reinterpret_cast<const __half *>(w.acts), factored_dh ? nullptr : w.dhfin,
+                    w.att, w.score, w.dcat + c.H, prm.attw_w, 2 * (int64_t)c.H, c.nw, w.gscale, w.dT,
                     da_img, xh_img, P, ntiles, c.L, thr, scale, c.dropout_seed, c.dropout_seed_dev, ck.s0 * c.nw, nullptr, 0};
     long long *d_trace = nullptr;
     const char *trace_env = getenv("PN_TRACE_BWD");
@@ -1049,10 +1168,13 @@ int pagg_tc_backward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_p
         a.trace_block = atoi(trace_env);
     }
     const int bwd_smem = TCB_SMEM_FIXED + 128 * c.L * (int)sizeof(int32_t);
-    PN_CUDA(cudaFuncSetAttribute(k_lstm_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TCB_SMEM_FIXED + 128 * TC_MAX_L * (int)sizeof(int32_t)));
+    static const bool bwd_pf = [] { const char *e = getenv("PN_BWD_PF"); return e && e[0] == '1'; }();
+    PN_CUDA(cudaFuncSetAttribute(k_lstm_bwd_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCB_SMEM_FIXED + 128 * TC_MAX_L * (int)sizeof(int32_t)));
+    PN_CUDA(cudaFuncSetAttribute(k_lstm_bwd_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCB_SMEM_FIXED + 128 * TC_MAX_L * (int)sizeof(int32_t)));
     {
         ProfScope prof("lstm_bwd", st);
-        k_lstm_bwd_tc<<<(unsigned)ntiles, TC_THREADS, bwd_smem, st>>>(a);
+        if (bwd_pf) k_lstm_bwd_tc<true><<<(unsigned)ntiles, TC_THREADS, bwd_smem, st>>>(a);
+        else k_lstm_bwd_tc<false><<<(unsigned)ntiles, TC_THREADS, bwd_smem, st>>>(a);
     }
     PN_LAUNCH_CHECK();
     if (d_trace) {  // debug only

@@ -103,8 +103,12 @@ def test_pooling_ablations_match_oracle(variant, pool, mode, H):
         want = params[k].grad.float()
         if mode == "fp32":
             torch.testing.assert_close(q.grad.cpu(), want, **GRAD_TOL, msg=lambda s: f"{k}: {s}")
-        else:   # max pooling routes each gradient to ONE path: an argmax that flips under fp16 rounding moves whole rows
-            assert_grad_close(q.grad.cpu(), want, k, *((5e-2, 3e-2) if pool == "max" else (1e-2, 1e-2)))
+        elif pool == "max":   # max pooling routes each gradient to ONE path: an argmax that flips under fp16 rounding moves a
+            g = q.grad.cpu().double().flatten()   # whole row's worth of gradient, so hold the direction, not the entries
+            cos = torch.dot(g, want.double().flatten()) / (g.norm() * want.double().norm() + 1e-30)
+            assert torch.isfinite(g).all() and cos > 0.99, f"{k}: cosine to the oracle gradient {cos:.4f}"
+        else:
+            assert_grad_close(q.grad.cpu(), want, k, 1e-2, 1e-2)
 
 
 def test_variant_argument_errors():
