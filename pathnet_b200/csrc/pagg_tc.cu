@@ -657,8 +657,9 @@ __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefe
 
 // (Measured and dropped: pairing neighbouring tiles in a cluster that multicasts the W' stream halves its L2 traffic but
 // couples the two CTAs chunk by chunk -- 5 % slower.  The stream is latency-, not bandwidth-limited: depth helps.)
-// PF = true: the variant that fetches activations one half-iteration ahead (measured: +4 % kernel time — the removed L2
-// waits are paid back as 8 % more instructions and twice as many TMEM round trips; kept for A/B runs, PN_BWD_PF=1)
+// PF = true (default): activations are fetched one half-iteration (4 units, six 8-byte loads) ahead of the gate-gradient
+// math; PF = false (PN_BWD_PF=0): the round-1 loop (8 units per iteration, loads consumed where issued).  Same-box A/B,
+// pubmed step (profiles/r02/bench_tc_bwd_pf{0,1}_run5.json): 1.072 vs 1.111 ms per launch.
 template <bool PF>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
 {
@@ -1168,7 +1169,7 @@ int pagg_tc_backward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_p
         a.trace_block = atoi(trace_env);
     }
     const int bwd_smem = TCB_SMEM_FIXED + 128 * c.L * (int)sizeof(int32_t);
-    static const bool bwd_pf = [] { const char *e = getenv("PN_BWD_PF"); return e && e[0] == '1'; }();
+    static const bool bwd_pf = [] { const char *e = getenv("PN_BWD_PF"); return !(e && e[0] == '0'); }();
     PN_CUDA(cudaFuncSetAttribute(k_lstm_bwd_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCB_SMEM_FIXED + 128 * TC_MAX_L * (int)sizeof(int32_t)));
     PN_CUDA(cudaFuncSetAttribute(k_lstm_bwd_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCB_SMEM_FIXED + 128 * TC_MAX_L * (int)sizeof(int32_t)));
     {
