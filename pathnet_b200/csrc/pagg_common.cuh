@@ -39,6 +39,7 @@ struct PaggWs {
     float *z16;      // [N][H]   fp16 copy of Z written by the fc0 epilogue
     float *w16;      // fc0_w [H][F16] then nets_w [L*H][H], fp16
     float *t16;      // [N][L*H] fp16 copy of T times the dropout scale (what the LSTM kernel gathers)
+    float *dmask;    // [tile][L][4][128] uint32 dropout-mask words of the LSTM input (forward -> backward)
     size_t bytes;
 };
 
@@ -95,6 +96,7 @@ inline PaggWs carve_workspace(const pn_pagg_cfg &c, void *base)
     take(w.z16, c.math_mode == PN_MATH_TC ? (N * H + 1) / 2 : 0);
     take(w.w16, c.math_mode == PN_MATH_TC ? (H * F16 + L * H * H + 1) / 2 : 0);
     take(w.t16, c.math_mode == PN_MATH_TC ? (N * L * H + 1) / 2 : 0);
+    take(w.dmask, c.math_mode == PN_MATH_TC ? L * P128 * 4 : 0);
     w.bytes = off;
     return w;
 }

@@ -108,8 +108,10 @@ __device__ __forceinline__ void stage_tile(unsigned char *dst, const float *__re
     }
 }
 
+// 256 threads: all eight warps stage operand tiles (the kernel is bound by the latency of those loads), warps 0-3 own the
+// four TMEM lane quarters in the epilogue.
 template <int BN, bool A_MN, bool B_MN, bool BF16>
-__global__ void __launch_bounds__(128) k_gemm_tc(GemmTcArgs g)
+__global__ void __launch_bounds__(256) k_gemm_tc(GemmTcArgs g)
 {
     constexpr int BM = 128, BK = 64;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -138,8 +140,8 @@ __global__ void __launch_bounds__(128) k_gemm_tc(GemmTcArgs g)
         const int b = it & 1;
         unsigned char *As = smem_raw + b * STAGE, *Bs = As + BM * BK * 2;
         if (it >= 2) { mbar_wait(&bar[b], phase[b]); phase[b] ^= 1; }
-        stage_tile<BM, 128, A_MN, BF16>(As, g.A, g.lda, m0, g.M, k0, kend, tid, a_mul);
-        stage_tile<BN, 128, B_MN, BF16>(Bs, g.B, g.ldb, n0, g.N, k0, kend, tid);
+        stage_tile<BM, 256, A_MN, BF16>(As, g.A, g.lda, m0, g.M, k0, kend, tid, a_mul);
+        stage_tile<BN, 256, B_MN, BF16>(Bs, g.B, g.ldb, n0, g.N, k0, kend, tid);
         fence_proxy_async();
         __syncthreads();
         if (tid == 0) {
@@ -160,7 +162,7 @@ __global__ void __launch_bounds__(128) k_gemm_tc(GemmTcArgs g)
     // that every store instruction would touch 32 different lines, so each 32 x 32 block is transposed through shared memory
     // (the operand stages are idle: every MMA has committed) and leaves as whole 128-byte row segments.
     const bool atomic = gridDim.z > 1 || g.accumulate;
-    if (kbeg < kend) {
+    if (kbeg < kend && warp < 4) {
         float *stg = reinterpret_cast<float *>(smem_raw) + warp * (32 * 33);
         for (int c0 = 0; c0 < BN; c0 += 32) {
             uint32_t v[32];
@@ -207,7 +209,7 @@ int launch_gemm_tc(cudaStream_t st, const float *A, int64_t lda, const float *B,
 #define PN_GEMM_CASE(AM, BM_, BF)                                                                              \
     do {                                                                                                       \
         PN_CUDA(cudaFuncSetAttribute(k_gemm_tc<BN, AM, BM_, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        k_gemm_tc<BN, AM, BM_, BF><<<grid, 128, smem, st>>>(g);                                                \
+        k_gemm_tc<BN, AM, BM_, BF><<<grid, 256, smem, st>>>(g);                                                \
     } while (0)
     if (!a_mn && !b_mn && !bf16) PN_GEMM_CASE(false, false, false);
     else if (!a_mn && b_mn && bf16) PN_GEMM_CASE(false, true, true);
@@ -273,6 +275,8 @@ struct LstmTcArgs {
     const uint64_t *seed_dev; // optional device word added to drop_seed (CUDA-graph replay)
     int64_t p_base;           // global index of this call's first sequence (row-chunked calls)
     unsigned char *xh_img;    // wgrad operand images [x_t | h_{t-1}] (see LstmBwdTcArgs), written here
+    uint32_t *dmask;          // [tile][t][cq][128 rows]: bit u of a word = "x_t[32 cq + u] was kept" — the backward's dx scatter
+                              // reads 4 bytes instead of recomputing 16 hashes (null: no dropout, or nothing saved)
     int save;                 // 0: inference only, skip activations and operand images
     long long *trace;         // optional clock64() trace of CTA `trace_block` (debug)
     int trace_block;
@@ -300,7 +304,7 @@ constexpr int TC_THREADS = (TC_CWARPS + 2) * 32;  // + MMA warp + weight-produce
 // With the fp16 table (written by the projection GEMM's epilogue, already times 1/(1-p)) the row is 4 x 16 bytes and
 // dropout is a bit mask on the packed halves; the fp32 table costs 8 loads, the scale multiply and the conversion.
 __device__ __forceinline__ void tc_gather_quarter(const LstmTcArgs &a, unsigned char *Xs, int r, int cq, int32_t row_off,
-                                                   uint64_t elem0 /* (p*L + t) * H */, unsigned char *xh_blk)
+                                                   uint64_t elem0 /* (p*L + t) * H */, unsigned char *xh_blk, uint32_t *mask_out)
 {
     const bool valid = row_off >= 0;
     const uint32_t key = dropout_key(a.seed_dev ? a.drop_seed + *a.seed_dev : a.drop_seed, 0);
@@ -309,6 +313,7 @@ __device__ __forceinline__ void tc_gather_quarter(const LstmTcArgs &a, unsigned 
         uint4 ld[4];
 #pragma unroll
         for (int i = 0; i < 4; i++) ld[i] = valid ? __ldg(src + i) : make_uint4(0, 0, 0, 0);
+        uint32_t mbits = 0;
 #pragma unroll
         for (int kk = 0; kk < 4; kk++) {
             const int k8 = cq * 4 + kk;
@@ -318,14 +323,16 @@ __device__ __forceinline__ void tc_gather_quarter(const LstmTcArgs &a, unsigned 
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
                     const uint32_t h = dropout_hash_pair_k(key, pair + q);
-                    const uint32_t keep = ((h & 0xFFFFu) < a.drop_thr ? 0u : 0x0000FFFFu) | ((h >> 16) < a.drop_thr ? 0u : 0xFFFF0000u);
-                    wv[q] &= keep;
+                    const uint32_t k0 = (h & 0xFFFFu) < a.drop_thr ? 0u : 1u, k1 = (h >> 16) < a.drop_thr ? 0u : 1u;
+                    wv[q] &= (0u - k0) & 0x0000FFFFu | (0u - k1) & 0xFFFF0000u;
+                    mbits |= (k0 | (k1 << 1)) << (kk * 8 + q * 2);
                 }
             }
             const uint4 pk = make_uint4(wv[0], wv[1], wv[2], wv[3]);
             *reinterpret_cast<uint4 *>(Xs + canon_off(r, k8 * 8, TC_H)) = pk;
             if (a.save) *reinterpret_cast<uint4 *>(xh_blk + (size_t)k8 * 2048 + r * 16) = pk;   // x half of the wgrad operand image
         }
+        if (mask_out) *mask_out = mbits;
         return;
     }
     const float *src = a.T + (int64_t)(valid ? row_off : 0) * TC_H;
@@ -445,8 +452,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_fwd_tc(LstmTcArgs a)
         const bool tr = a.trace && blockIdx.x == a.trace_block && tid == 0;
         if (tr) a.trace[6] = clock64();
         const int64_t ntiles = gridDim.x;
+        // dropout-mask word of (tile, t, cq, row): written only when the backward will need it
+        auto mask_slot = [&](int t_) { return (a.dmask && a.save && a.drop_thr) ? a.dmask + (((int64_t)blockIdx.x * L + t_) * 4 + cq) * 128 + r : nullptr; };
         tc_gather_quarter(a, Xs, r, cq, rowoff_s[r * TC_MAX_L + 0], (uint64_t)((p + a.p_base) * L + 0) * TC_H,
-                          a.xh_img + ((int64_t)0 * ntiles + blockIdx.x) * XH_BLOCK_BYTES);
+                          a.xh_img + ((int64_t)0 * ntiles + blockIdx.x) * XH_BLOCK_BYTES, mask_slot(0));
         // h_{-1} = 0: h half of step 0's image
 #pragma unroll
         for (int k8 = 16 + cq * 4; k8 < 16 + cq * 4 + 4; k8++)
@@ -460,7 +469,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_fwd_tc(LstmTcArgs a)
             // reader of that buffer, completed before acc_full(t-1) was observed)
             if (t + 1 < L)
                 tc_gather_quarter(a, Xs + ((t + 1) & 1) * TC_XBYTES, r, cq, rowoff_s[r * TC_MAX_L + t + 1],
-                                  (uint64_t)((p + a.p_base) * L + t + 1) * TC_H, a.xh_img + ((int64_t)(t + 1) * ntiles + blockIdx.x) * XH_BLOCK_BYTES);
+                                  (uint64_t)((p + a.p_base) * L + t + 1) * TC_H, a.xh_img + ((int64_t)(t + 1) * ntiles + blockIdx.x) * XH_BLOCK_BYTES,
+                                  mask_slot(t + 1));
             if (tr) a.trace[t * 8 + 1] = clock64();
             // ---- wait for the gate pre-activations ----
             mbar_wait(&acc_full, t & 1);
@@ -567,7 +577,8 @@ int pagg_tc_forward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_pa
     const int64_t P = ck.Sc * c.nw;
     LstmTcArgs a{tc_legacy_gemm() ? nullptr : reinterpret_cast<const __half *>(w.t16), w.T, seq_node, seq_type, Wh, w.bp,
                  reinterpret_cast<__half *>(w.acts), w.hfin, P, c.L, thr, scale, c.dropout_seed,
-                 c.dropout_seed_dev, ck.s0 * c.nw, reinterpret_cast<unsigned char *>(w.XH), ck.save ? 1 : 0, nullptr, 0};
+                 c.dropout_seed_dev, ck.s0 * c.nw, reinterpret_cast<unsigned char *>(w.XH),
+                 tc_legacy_gemm() ? nullptr : reinterpret_cast<uint32_t *>(w.dmask), ck.save ? 1 : 0, nullptr, 0};
     long long *d_trace = nullptr;
     const char *trace_env = getenv("PN_TRACE_FWD");
     if (trace_env) {
@@ -640,6 +651,7 @@ struct LstmBwdTcArgs {
     float *dT;                 // [N,L,H]
     unsigned char *da_img;     // block b = t*ntiles + tile: [64 col8][128 r][8] fp16   (128 KB)
     const unsigned char *xh_img;  // block b: [32 k8][128 r][8] fp16 (64 KB): k8 < 16 x_t, k8 >= 16 h_{t-1}; written by the FORWARD kernel
+    const uint32_t *dmask;        // the forward's dropout-mask words (see LstmTcArgs), or null: recompute the hashes
     int64_t P, ntiles;
     int L;
     uint32_t drop_thr; float drop_scale; uint64_t drop_seed;
@@ -753,6 +765,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
         // dx of step `ss` (time tt = L-1-ss) -> dT with the forward's dropout mask
         auto scatter_dx = [&](int ss) {
             const int tt = L - 1 - ss;
+            // the forward's mask word of (tile, tt, cq, row): issued before the TMEM load so both latencies overlap
+            uint32_t mbits = 0xFFFFFFFFu;
+            const bool have_mask = a.dmask != nullptr && a.drop_thr != 0;
+            if (have_mask) mbits = __ldg(a.dmask + (((int64_t)tile * L + tt) * 4 + cq) * 128 + r);
             // tcgen05.ld is warp-collective (.sync.aligned): every lane loads, only valid rows scatter
             uint32_t v[32];
             tmem_ld32(lane_base + cq * 32, v);   // dx region = columns [0,128)
@@ -760,28 +776,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
             if (valid) {
                 const int64_t e = p * L + tt;
                 float *dst = a.dT + (int64_t)rowoff_s[r * L + tt] * TC_H + cq * 32;
+                const float mul = inv_scale * (a.drop_thr ? a.drop_scale : 1.f);
 #pragma unroll
                 for (int c8 = 0; c8 < 4; c8++) {
-                    float f[8];
-#pragma unroll
-                    for (int j = 0; j < 8; j++) f[j] = __uint_as_float(v[c8 * 8 + j]) * inv_scale;
-                    if (a.drop_thr) {
+                    if (a.drop_thr && !have_mask) {   // no saved mask (legacy gather path): recompute this chunk's 8 bits
                         const uint64_t pair = ((uint64_t)(e + a.p_base * L) * TC_H + cq * 32 + c8 * 8) >> 1;
+                        uint32_t b = 0;
 #pragma unroll
                         for (int q = 0; q < 4; q++) {
                             const uint32_t h = dropout_hash_pair_k(dkey, pair + q);
-                            f[2 * q] = (h & 0xFFFFu) < a.drop_thr ? 0.f : f[2 * q] * a.drop_scale;
-                            f[2 * q + 1] = (h >> 16) < a.drop_thr ? 0.f : f[2 * q + 1] * a.drop_scale;
+                            b |= (((h & 0xFFFFu) < a.drop_thr ? 0u : 1u) | ((h >> 16) < a.drop_thr ? 0u : 2u)) << (2 * q);
                         }
+                        mbits = (mbits & ~(0xFFu << (c8 * 8))) | (b << (c8 * 8));
                     }
                     if (a.drop_thr) {   // most elements are dropped (p = 0.7 upstream): only touch the pairs that carry anything
 #pragma unroll
-                        for (int q = 0; q < 4; q++)
-                            if (f[2 * q] != 0.f || f[2 * q + 1] != 0.f)
-                                atomicAdd(reinterpret_cast<float2 *>(dst + c8 * 8 + 2 * q), make_float2(f[2 * q], f[2 * q + 1]));
+                        for (int q = 0; q < 4; q++) {
+                            const uint32_t b = (mbits >> (c8 * 8 + 2 * q)) & 3u;
+                            if (b) atomicAdd(reinterpret_cast<float2 *>(dst + c8 * 8 + 2 * q),
+                                             make_float2((b & 1u) ? __uint_as_float(v[c8 * 8 + 2 * q]) * mul : 0.f,
+                                                         (b & 2u) ? __uint_as_float(v[c8 * 8 + 2 * q + 1]) * mul : 0.f));
+                        }
                     } else {
-                        atomicAdd(reinterpret_cast<float4 *>(dst + c8 * 8), make_float4(f[0], f[1], f[2], f[3]));
-                        atomicAdd(reinterpret_cast<float4 *>(dst + c8 * 8 + 4), make_float4(f[4], f[5], f[6], f[7]));
+                        atomicAdd(reinterpret_cast<float4 *>(dst + c8 * 8), make_float4(__uint_as_float(v[c8 * 8]) * mul, __uint_as_float(v[c8 * 8 + 1]) * mul,
+                                                                                     __uint_as_float(v[c8 * 8 + 2]) * mul, __uint_as_float(v[c8 * 8 + 3]) * mul));
+                        atomicAdd(reinterpret_cast<float4 *>(dst + c8 * 8 + 4), make_float4(__uint_as_float(v[c8 * 8 + 4]) * mul, __uint_as_float(v[c8 * 8 + 5]) * mul,
+                                                                                         __uint_as_float(v[c8 * 8 + 6]) * mul, __uint_as_float(v[c8 * 8 + 7]) * mul));
                     }
                 }
             }
@@ -1159,7 +1179,8 @@ int pagg_tc_backward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_p
     unsigned char *da_img = reinterpret_cast<unsigned char *>(w.dA), *xh_img = reinterpret_cast<unsigned char *>(w.XH);
     LstmBwdTcArgs a{w.T, seq_node, seq_type, WhT, reinterpret_cast<const __half *>(w.acts), factored_dh ? nullptr : w.dhfin,
                     w.att, w.score, w.dcat + c.H, prm.attw_w, 2 * (int64_t)c.H, c.nw, w.gscale, w.dT,
-                    da_img, xh_img, P, ntiles, c.L, thr, scale, c.dropout_seed, c.dropout_seed_dev, ck.s0 * c.nw, nullptr, 0};
+                    da_img, xh_img, tc_legacy_gemm() ? nullptr : reinterpret_cast<const uint32_t *>(w.dmask), P, ntiles, c.L, thr, scale,
+                    c.dropout_seed, c.dropout_seed_dev, ck.s0 * c.nw, nullptr, 0};
     long long *d_trace = nullptr;
     const char *trace_env = getenv("PN_TRACE_BWD");
     if (trace_env) {

@@ -95,7 +95,7 @@ class TrainStep:
 
     def __init__(self, model, X, indices, y_rows, num_w, walk_len, *, lr=0.005, weight_decay=0.0005, betas=(0.9, 0.999),
                  eps=1e-8, dropout=None, math_mode=None, row_chunk=None, seed=None, graph=True, s_global=None, group=None,
-                 shard=None):
+                 shard=None, graph_collective=None):
         if X.device.type != "cuda":
             raise RuntimeError("pathnet_b200 TrainStep runs on CUDA only (no CPU fallback); X is on %s" % X.device)
         self.model, self.dev = model, X.device
@@ -123,9 +123,12 @@ class TrainStep:
         Cc = model.fc2.weight.shape[0]
         self.params = FlatParams(model)
         n = self.params.numel
-        self.grad = torch.zeros(n, dtype=torch.float32, device=self.dev)
-        self.exp_avg = torch.zeros_like(self.grad)
-        self.exp_avg_sq = torch.zeros_like(self.grad)
+        # gradients: one flat buffer in the parameters' layout, + one 16-byte slot at the end where the CE kernel accumulates
+        # the loss — so the data-parallel exchange (gradients AND the loss value) is ONE all-reduce
+        self.grad_all = torch.zeros(n + 4, dtype=torch.float32, device=self.dev)
+        self.grad = self.grad_all[:n]
+        self.exp_avg = torch.zeros(n, dtype=torch.float32, device=self.dev)
+        self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=self.dev)
         # p.grad = views of the flat gradient buffer (so code that inspects .grad keeps working)
         for k, p in model.named_parameters():
             p.grad = None
@@ -153,10 +156,14 @@ class TrainStep:
         self.partner = torch.empty((S_all, self.nw), dtype=torch.int32, device=self.dev)
         self.logits = torch.empty((S, Cc), dtype=torch.float32, device=self.dev)
         self.dlogits = torch.empty_like(self.logits)
-        self.loss = torch.zeros(1, dtype=torch.float32, device=self.dev)
+        self.loss = self.grad_all[n:n + 1]
         self.guard = pagg.IndexGuard(self.dev)
         self.neis_buf = self.lt_buf = None
         self.use_graph, self.graph = bool(graph), None
+        # multi-GPU: capture the gradient all-reduce and the Adam kernel in the same graph as forward / backward (one launch per
+        # step and no host gap before the collective); PN_GRAPH_NCCL=0 keeps the collective outside the graph
+        import os
+        self.graph_collective = (os.environ.get("PN_GRAPH_NCCL", "1") != "0") if graph_collective is None else bool(graph_collective)
         self._copy_stream = None
         self.steps = 0
         self.launches_per_step = 0
@@ -191,6 +198,8 @@ class TrainStep:
         self._enqueue_fwd_bwd()
         if single:
             self._enqueue_adam()
+        elif self.graph_collective:   # the all-reduce and the optimiser step belong to the same graph (NCCL supports capture)
+            self._reduce_and_update()
         self.launches_per_step = int(lib().pn_launch_count() - n0)   # kernels of this library per step (a replayed graph launches the same nodes)
 
     # ------------------------------------------------------------------ public
@@ -247,7 +256,9 @@ class TrainStep:
                 self._stage(neis, layer_type)
             single = _world(self.group) == 1
             if not self.use_graph:
-                self._enqueue(single)
+                self._enqueue_fwd_bwd()
+                if single:
+                    self._enqueue_adam()
             else:
                 if self.graph is None:
                     # one eager step first (function attributes, lazy one-time queries), on a side stream as capture requires
@@ -257,7 +268,7 @@ class TrainStep:
                         self._enqueue(single)
                     torch.cuda.current_stream().wait_stream(s)
                     self.steps += 1
-                    if not single:
+                    if not single and not self.graph_collective:
                         self._reduce_and_update()
                     self.guard.arm()
                     self.graph = torch.cuda.CUDAGraph()
@@ -265,15 +276,14 @@ class TrainStep:
                         self._enqueue(single)
                     return self.loss
                 self.graph.replay()
-            if not single:
+            if not single and not (self.use_graph and self.graph_collective):
                 self._reduce_and_update()
             self.guard.arm()
         self.steps += 1
         return self.loss
 
     def _reduce_and_update(self):
-        dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=self.group)
-        dist.all_reduce(self.loss, op=dist.ReduceOp.SUM, group=self.group)
+        dist.all_reduce(self.grad_all, op=dist.ReduceOp.SUM, group=self.group)   # gradients + the loss slot, in place
         self._enqueue_adam()
 
     def grads(self):
