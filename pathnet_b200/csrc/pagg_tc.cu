@@ -668,7 +668,11 @@ constexpr int TCB_SMEM_FIXED = TCB_A_BYTES + TCB_NSTAGE * TCB_CHUNK_BYTES + 128 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // (Measured and dropped: pairing neighbouring tiles in a cluster that multicasts the W' stream halves its L2 traffic but
-// couples the two CTAs chunk by chunk -- 5 % slower.  The stream is latency-, not bandwidth-limited: depth helps.)
+// couples the two CTAs chunk by chunk -- 5 % slower.
+//  Round 2, also measured and dropped: two 32 KB quarter buffers for da instead of the whole tile + an 8-stage W' ring
+//  (same 192 KB): 1.144 vs 1.072 ms.  In-kernel traces put the wait for acc_full after the last quarter at ~3 k cycles per
+//  step with EITHER ring depth -- it is the 16 MMAs of the last quarter plus commit / wake-up latency, not the stream --
+//  while the extra "buffer free" waits slowed the gate-gradient loop from 10.5 k to 12.9 k cycles per step.)
 // PF = true (default): activations are fetched one half-iteration (4 units, six 8-byte loads) ahead of the gate-gradient
 // math; PF = false (PN_BWD_PF=0): the round-1 loop (8 units per iteration, loads consumed where issued).  Same-box A/B,
 // pubmed step (profiles/r02/bench_tc_bwd_pf{0,1}_run5.json): 1.072 vs 1.111 ms per launch.
