@@ -47,6 +47,7 @@ def main(rep, out):
     traffic = json.load(open(tpath)) if os.path.exists(tpath) else {}
     for r in rows[2:]:
         name = re.sub(r"\(.*", "", r[idx["Kernel Name"]]).split("::")[-1]
+        name = re.sub(r"<.*", "", name).replace("void ", "").strip()     # template instances: k_lstm_bwd_tc<1>
         if name in slot:
             rd = float(r[idx["dram__bytes_read.sum"]].replace(",", "")) * mult.get(units[idx["dram__bytes_read.sum"]], 1)
             wr = float(r[idx["dram__bytes_write.sum"]].replace(",", "")) * mult.get(units[idx["dram__bytes_write.sum"]], 1)
