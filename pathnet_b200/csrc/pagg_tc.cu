@@ -298,7 +298,19 @@ __device__ __forceinline__ float tanh_fast(float x)
 __device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
 
 constexpr int TC_CWARPS = 16;                    // compute warps: 4 TMEM lane quarters x 4 column quarters
-constexpr int TC_THREADS = (TC_CWARPS + 2) * 32;  // + MMA warp + weight-producer warp
+constexpr int TC_THREADS = (TC_CWARPS + 2) * 32;  // forward: + MMA warp + weight-producer warp
+// backward: + a whole service warpgroup (MMA warp, W' producer, two idle warps) so that setmaxnreg -- which works on warpgroups
+// of 4 consecutive warps, inside the register pool the CTA was given at launch -- can move registers: 20 warps = 5 per SM
+// sub-partition -> 96 per thread at launch; the service warpgroup shrinks to 32 and the 16 compute warps grow to 112.
+constexpr int TCB_THREADS = (TC_CWARPS + 4) * 32;
+__device__ __forceinline__ bool elect_one()   // true in exactly one lane of a converged warp
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
 // this thread's quarter (32 values) of table row `row_off` -> dropout -> fp16 -> x tile (canonical, K extent 128).
 // With the fp16 table (written by the projection GEMM's epilogue, already times 1/(1-p)) the row is 4 x 16 bytes and
@@ -410,33 +422,38 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_fwd_tc(LstmTcArgs a)
             }
         }
     } else if (warp == TC_CWARPS) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
+        // ===== MMA issuer: the whole warp runs the loop (uniform control flow keeps the descriptors in uniform registers: no
+        //       R2UR / election loop per MMA, tools/probe/ring_probe.cu), one elected lane issues =====
+        {
             constexpr uint32_t idesc = make_idesc_f16(128, 256);
             uint32_t stage = 0, phase = 0;
+            const bool trm = a.trace && blockIdx.x == a.trace_block && lane == 0;
             for (int t = 0; t < L; t++) {
                 mbar_wait(&a_ready, t & 1);  // x_t (and h_{t-1}) staged, TMEM drained
                 tc_fence_after();
-                if (a.trace && blockIdx.x == a.trace_block) a.trace[t * 8 + 4] = clock64();
+                if (trm) a.trace[t * 8 + 4] = clock64();
                 const int nch = t == 0 ? TC_NCHUNK / 2 : TC_NCHUNK;  // h_0 = 0: skip the W_hh half
                 const uint32_t xbase = smem_u32(Xs + (t & 1) * TC_XBYTES), hbase = smem_u32(Hs);
                 for (int c = 0; c < nch; c++) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t wbase = smem_u32(Ws + stage * TC_CHUNK_BYTES);
-                    // chunk c = 16 consecutive k: two core matrices (256 B) of the x half (c < 8) or the h half
-                    const uint32_t abase = (c < TC_NCHUNK / 2 ? xbase + (uint32_t)c * 256 : hbase + (uint32_t)(c - TC_NCHUNK / 2) * 256);
-                    const uint64_t ad = make_smem_desc(abase, 128, (TC_H / 8) * 128);
+                    if (elect_one()) {
+                        // chunk c = 16 consecutive k: two core matrices (256 B) of the x half (c < 8) or the h half
+                        const uint32_t abase = (c < TC_NCHUNK / 2 ? xbase + (uint32_t)c * 256 : hbase + (uint32_t)(c - TC_NCHUNK / 2) * 256);
+                        const uint64_t ad = make_smem_desc(abase, 128, (TC_H / 8) * 128);
 #pragma unroll
-                    for (int nh = 0; nh < 2; nh++) {
-                        const uint64_t bd = make_smem_desc(wbase + (uint32_t)nh * (256 / 8) * ((TC_KC / 8) * 128), 128, (TC_KC / 8) * 128);
-                        mma_f16(taddr + (uint32_t)nh * 256, ad, bd, idesc, c > 0);
+                        for (int nh = 0; nh < 2; nh++) {
+                            const uint64_t bd = make_smem_desc(wbase + (uint32_t)nh * (256 / 8) * ((TC_KC / 8) * 128), 128, (TC_KC / 8) * 128);
+                            mma_f16(taddr + (uint32_t)nh * 256, ad, bd, idesc, c > 0);
+                        }
+                        mma_commit(&empty_bar[stage]);  // slot reusable once these MMAs have read it
+                        if (c == nch - 1) mma_commit(&acc_full);
                     }
-                    mma_commit(&empty_bar[stage]);  // slot reusable once these MMAs have read it
+                    __syncwarp();
                     if (++stage == TC_NSTAGE) { stage = 0; phase ^= 1; }
                 }
-                mma_commit(&acc_full);
-                if (a.trace && blockIdx.x == a.trace_block) a.trace[t * 8 + 5] = clock64();
+                if (trm) a.trace[t * 8 + 5] = clock64();
             }
         }
     } else {
@@ -677,7 +694,7 @@ __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefe
 // math; PF = false (PN_BWD_PF=0): the round-1 loop (8 units per iteration, loads consumed where issued).  Same-box A/B,
 // pubmed step (profiles/r02/bench_tc_bwd_pf{0,1}_run5.json): 1.072 vs 1.111 ms per launch.
 template <bool PF>
-__global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
+__global__ void __launch_bounds__(TCB_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
 {
     extern __shared__ unsigned char smem_dyn[];
     // no-swizzle UMMA operands and bulk copies need 16-byte alignment only; 128 keeps the tiles on line boundaries
@@ -690,7 +707,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t tile = blockIdx.x, p0 = tile * 128;
     const int L = a.L;
-    for (int i = tid; i < 128 * L; i += TC_THREADS) {
+    for (int i = tid; i < 128 * L; i += TCB_THREADS) {
         const int rr = i / L, tt = i % L;
         const int64_t pp = p0 + rr;
         int32_t off = -1;
@@ -715,6 +732,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
     // the weight streaming and the tensor-core time hide under the remaining gate-gradient work.
     const uint32_t taddr = s_taddr;
 
+    if (warp >= TC_CWARPS) {
+    reg_dec<32>();   // all four warps of the service warpgroup (two of them have nothing else to do)
     if (warp == TC_CWARPS + 1) {
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
@@ -728,18 +747,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
                 }
         }
     } else if (warp == TC_CWARPS) {
-        if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
-            for (int s = 0; s < L; s++) {
-                const int t = L - 1 - s;
-                constexpr uint32_t idesc = make_idesc_f16(128, 128);
-                const uint32_t dh_col = 128u + (uint32_t)(s & 1) * 128u;
-                for (int j = 0; j < TCB_NCHUNK; j++) {
-                    const int c = 4 * (j & 3) + (j >> 2);
-                    if ((j & 3) == 0) { mbar_wait(&a_ready[j >> 2], s & 1); tc_fence_after(); }
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    const uint32_t wbase = smem_u32(Ws + stage * TCB_CHUNK_BYTES);
+        // the whole warp runs the loop (uniform control flow: descriptors stay in uniform registers, no R2UR / election loop
+        // per MMA -- tools/probe/ring_probe.cu: ~15 % less issue overhead per stage), one elected lane issues
+        uint32_t stage = 0, phase = 0;
+        constexpr uint32_t idesc = make_idesc_f16(128, 128);
+        for (int s = 0; s < L; s++) {
+            const int t = L - 1 - s;
+            const uint32_t dh_col = 128u + (uint32_t)(s & 1) * 128u;
+            for (int j = 0; j < TCB_NCHUNK; j++) {
+                const int c = 4 * (j & 3) + (j >> 2);
+                if ((j & 3) == 0) { mbar_wait(&a_ready[j >> 2], s & 1); tc_fence_after(); }
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                const uint32_t wbase = smem_u32(Ws + stage * TCB_CHUNK_BYTES);
+                if (elect_one()) {
 #pragma unroll
                     for (int ks = 0; ks < TCB_KC / 16; ks++) {
                         const uint64_t ad = make_smem_desc(smem_u32(As) + (uint32_t)(c * (TCB_KC / 8) + ks * 2) * 128, 128, (TC_G4 / 8) * 128);
@@ -752,12 +773,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
                         }
                     }
                     mma_commit(&empty_bar[stage]);
-                    if (++stage == TCB_NSTAGE) { stage = 0; phase ^= 1; }
+                    if (j == TCB_NCHUNK - 1) mma_commit(&acc_full);
                 }
-                mma_commit(&acc_full);
+                __syncwarp();
+                if (++stage == TCB_NSTAGE) { stage = 0; phase ^= 1; }
             }
         }
+    }
     } else {
+        reg_inc<112>();
         // warp = (TMEM lane quarter lq, column quarter cq): sequence p0 + 32 lq + lane, units [32 cq, 32 cq + 32)
         const int lq = warp & 3, cq = warp >> 2;
         const int r = lq * 32 + lane;
@@ -845,8 +869,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
                                              : __ldg(reinterpret_cast<const float4 *>(a.gdrop + grow * a.gdrop_ld + cb_ * 8 + sub));
             }
         };
-        BwdRaw nxt;
-        load_raw(0, 0, nxt);
+        // two half-iterations of activations in flight (n1: the next one, n2: the one after it)
+        BwdRaw n1, n2;
+        load_raw(0, 0, n1);
+        load_raw(0, 1, n2);
         for (int s = 0; s < L; s++) {
             const int t = L - 1 - s;
             if (tr) a.trace[s * 8 + 0] = clock64();
@@ -866,12 +892,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
             if (s > 0) scatter_dx(s - 1);
             if (tr) a.trace[s * 8 + 1] = clock64();
             const uint32_t dh_rd = 128u + (uint32_t)((s - 1) & 1) * 128u;
+            // dh / dc of a half-iteration are fetched from TMEM during the previous one (inside a step: the next step's dh
+            // is complete only at acc_full), so one TMEM round trip per step is exposed instead of eight
+            uint32_t v0n[4] = {0u, 0u, 0u, 0u}, v1n[4] = {0u, 0u, 0u, 0u};
+            if (s > 0) {
+                tmem_ld4(lane_base + dh_rd + cq * 32, v0n);
+                tmem_ld4(lane_base + 384 + cq * 32, v1n);
+            }
             // ---- gate gradients: 8 half-iterations of 4 units; two of them complete one K-quarter of the operand tile ----
 #pragma unroll 2
             for (int hi = 0; hi < 8; hi++) {
-                const BwdRaw cur = nxt;
-                if (hi < 7) load_raw(s, hi + 1, nxt);
-                else if (s + 1 < L) load_raw(s + 1, 0, nxt);
+                const BwdRaw cur = n1;
+                n1 = n2;
+                if (hi < 6) load_raw(s, hi + 2, n2);
+                else if (s + 1 < L) load_raw(s + 1, hi - 6, n2);
                 const int cb = cq * 4 + (hi >> 1), u0 = cb * 8 + (hi & 1) * 4;
                 float dh[4], dc[4];
                 if (s == 0) {
@@ -885,12 +919,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
                     dh[0] = d0.x * scale; dh[1] = d0.y * scale; dh[2] = d0.z * scale; dh[3] = d0.w * scale;
                     dc[0] = dc[1] = dc[2] = dc[3] = 0.f;
                 } else {
-                    uint32_t v0[4], v1[4];
-                    tmem_ld4(lane_base + dh_rd + u0, v0);
-                    tmem_ld4(lane_base + 384 + u0, v1);
-                    tmem_ld_wait();
+                    tmem_ld_wait_dep(v0n, v1n);
 #pragma unroll
-                    for (int j = 0; j < 4; j++) { dh[j] = __uint_as_float(v0[j]); dc[j] = __uint_as_float(v1[j]); }
+                    for (int j = 0; j < 4; j++) { dh[j] = __uint_as_float(v0n[j]); dc[j] = __uint_as_float(v1n[j]); }
+                    if (hi < 7) {
+                        const int u1 = (cq * 4 + ((hi + 1) >> 1)) * 8 + ((hi + 1) & 1) * 4;
+                        tmem_ld4(lane_base + dh_rd + u1, v0n);
+                        tmem_ld4(lane_base + 384 + u1, v1n);
+                    }
                 }
                 float gi[4], gf[4], gg[4], go[4], cn[4], cp[4];
                 unpack4_f16(cur.gi, gi); unpack4_f16(cur.gf, gf); unpack4_f16(cur.gg, gg);
@@ -1204,8 +1240,8 @@ int pagg_tc_backward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_p
     PN_CUDA(cudaFuncSetAttribute(k_lstm_bwd_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCB_SMEM_FIXED + 128 * TC_MAX_L * (int)sizeof(int32_t)));
     {
         ProfScope prof("lstm_bwd", st);
-        if (bwd_pf) k_lstm_bwd_tc<true><<<(unsigned)ntiles, TC_THREADS, bwd_smem, st>>>(a);
-        else k_lstm_bwd_tc<false><<<(unsigned)ntiles, TC_THREADS, bwd_smem, st>>>(a);
+        if (bwd_pf) k_lstm_bwd_tc<true><<<(unsigned)ntiles, TCB_THREADS, bwd_smem, st>>>(a);
+        else k_lstm_bwd_tc<false><<<(unsigned)ntiles, TCB_THREADS, bwd_smem, st>>>(a);
     }
     PN_LAUNCH_CHECK();
     if (d_trace) {  // debug only

@@ -188,6 +188,14 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8])
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// the same wait, tied to the destination registers of loads that were issued EARLIER than the statement before it: the
+// hardware writes them asynchronously until the wait, so the compiler must not read (copy) them before it
+__device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&a)[4], uint32_t (&b)[4])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(b[0]), "+r"(b[1]), "+r"(b[2]), "+r"(b[3])
+                 :: "memory");
+}
 
 // pack 8 floats into 8 halves (16 bytes)
 __device__ __forceinline__ uint4 pack8_f16(const float (&f)[8])
