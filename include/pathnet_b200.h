@@ -84,7 +84,12 @@ int pn_graph_cells_host(const pn_graph *g, int64_t *off, int32_t *A, int32_t *B,
 int pn_graph_prepare_labels(pn_graph *g, int32_t L, size_t max_bytes, void *stream);
 
 typedef enum {
-    PN_RNG_GLIBC = 0 /* bit-exact srand(seed)/rand() stream of the reference */
+    PN_RNG_GLIBC = 0, /* bit-exact srand(seed)/rand() stream of the reference (seed: low 32 bits) */
+    PN_RNG_PHILOX = 1 /* counter-based Philox4x32-10, one stream per walk: counter {lo32(g), hi32(g), t/2, 0}, key = the 64-bit
+                       * seed, g = (epoch*n + st)*nw + i; roll t uses words 2(t&1), 2(t&1)+1 of its block, each >> 1.  Not the
+                       * reference's stream (nothing but rand() can be), but the same walk law, order-free and shard-invariant:
+                       * the mode for multi-GPU / per-epoch on-device resampling where bit-compatibility with a reference
+                       * path file is not needed.  CPU restatement: oracle/merw_oracle.c:merw_oracle_sample_philox. */
 } pn_rng_mode;
 
 /* Replaces the walk loop (gen_merw.cpp:182-209 / gen_epoch_merw.cpp:164-206).
@@ -142,10 +147,12 @@ typedef enum { PN_VARIANT_HETERO = 0, /* class PathNet      (:150) */
                                          (baseline/GPRGNN/src/copy.py:299-359) and the pooling ablations */ } pn_variant;
 
 /* SURVEY 8f-4 variants (fp32 math mode; the tensor-core kernels implement the LSTM cell only):
- *   cell: LSTM (PathNet_run.py:164) or the tanh RNN of copy.py:307 (then w_ih / w_hh are [H,H], b_ih / b_hh [H])
+ *   cell: LSTM (PathNet_run.py:164), the tanh RNN of copy.py:307 (then w_ih / w_hh are [H,H], b_ih / b_hh [H]), or a GRU
+ *         (the "GRU" ablation of performance.jpg; torch nn.GRU semantics and layout: w_ih / w_hh [3H,H] in r, z, n order,
+ *         b_ih / b_hh [3H]; n = tanh(W_in x + b_in + r * (W_hn h + b_hn)), h' = (1 - z) * n + z * h)
  *   pool: the variant's own attention (:199-204 / :269-273), or mean (copy.py:350) / sum / max over the path_num
  *         final hidden states (attw_* are then unused and their gradients zero) */
-typedef enum { PN_CELL_LSTM = 0, PN_CELL_RNN = 1 } pn_cell;
+typedef enum { PN_CELL_LSTM = 0, PN_CELL_RNN = 1, PN_CELL_GRU = 2 } pn_cell;
 typedef enum { PN_POOL_ATTENTION = 0, PN_POOL_MEAN = 1, PN_POOL_SUM = 2, PN_POOL_MAX = 3 } pn_pool;
 
 typedef enum { PN_MATH_FP32 = 0, /* CUDA-core fp32 FMA, strict parity         */

@@ -313,6 +313,79 @@ int merw_oracle_sample(const merw_graph *g, int nw, int L, unsigned int seed,
     return merw_oracle_sample_range(g, nw, L, seed, epoch_begin, epoch_end, 0, g->n, nodes, types);
 }
 
+/* ---------------------------------------------------------------------------
+ * rng_mode = philox (an extension of this repo, SURVEY 8b: `rng_mode{glibc_compat, philox}`; the reference has only
+ * the sequential rand() stream).  Philox4x32-10, Salmon et al., "Parallel random numbers: as easy as 1, 2, 3" (SC'11),
+ * restated from the paper; pinned by the Random123 known-answer vectors in tests/test_oracle_pinning.py.
+ * Walk g = (epoch * n + st) * nw + i (the reference's walk order) owns the counter stream {lo32(g), hi32(g), b, 0}
+ * under key {lo32(seed), hi32(seed)}; roll t (t = 0 .. L-2, the wasted L-th roll of the reference is not drawn) takes
+ * words 2(t & 1), 2(t & 1) + 1 of block b = t / 2, each >> 1 (31 bits, like rand()):
+ *     x = r1 % cells(u);  next = r2 > thr[x] ? A[x] : B[x]   with  r2 > thr  <=>  1.0 * r2 / RAND_MAX > S  (gen_merw.cpp:88-90)
+ * Every walk is independent of every other: any sharding of epochs / start nodes / walks gives the same walks. */
+void merw_oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
+{
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
+    for (int r = 0; r < 10; r++) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+int merw_oracle_sample_philox(const merw_graph *g, int nw, int L, unsigned long long seed,
+                              long epoch_begin, long epoch_end, int node_begin, int node_end,
+                              int32_t *nodes, uint8_t *types)
+{
+    const int n = g->n;
+    const long np = node_end - node_begin;
+    const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    for (long epoch = epoch_begin; epoch < epoch_end; epoch++)
+        for (int st = node_begin; st < node_end; st++)
+            for (int i = 0; i < nw; i++) {
+                int32_t *o = nodes + ((((epoch - epoch_begin) * np + (st - node_begin)) * nw + i) * L);
+                const uint64_t gw = ((uint64_t)epoch * (uint64_t)n + (uint64_t)st) * (uint64_t)nw + (uint64_t)i;
+                uint32_t blk[4] = {0, 0, 0, 0};
+                int u = st;
+                for (int t = 0; t < L; t++) {
+                    o[t] = u;
+                    if (t + 1 == L) break;
+                    if ((t & 1) == 0) {
+                        const uint32_t ctr[4] = {(uint32_t)gw, (uint32_t)(gw >> 32), (uint32_t)(t >> 1), 0u};
+                        merw_oracle_philox4x32_10(ctr, key, blk);
+                    }
+                    const uint32_t r1 = blk[2 * (t & 1)] >> 1, r2 = blk[2 * (t & 1) + 1] >> 1;
+                    const long off = g->off[u];
+                    const int cells = (int)(g->off[u + 1] - off);
+                    if (cells == 0) return -1;
+                    const int x = (int)(r1 % (uint32_t)cells);
+                    if (g->uniform) u = g->adj[off + x];
+                    else {
+                        const double p = 1.0 * (double)r2 / 2147483647;
+                        u = p > g->S[off + x] ? g->A[off + x] : g->B[off + x];
+                    }
+                }
+            }
+    if (!types) return 0;
+    unsigned char *dis = (unsigned char *)calloc((size_t)(n ? n : 1), 1);
+    int *queue = (int *)malloc(sizeof(int) * (size_t)(n ? n : 1));
+    long E = epoch_end - epoch_begin;
+    for (int st = node_begin; st < node_end; st++) {
+        long touched = bfs_row(g, st, L, dis, queue);
+        for (long e = 0; e < E; e++)
+            for (int i = 0; i < nw; i++) {
+                long base = ((e * np + (st - node_begin)) * nw + i) * L;
+                for (int t = 0; t < L; t++)
+                    types[base + t] = (uint8_t)(dis[nodes[base + t]] - 1);
+            }
+        for (long k = 0; k < touched; k++) dis[queue[k]] = 0;
+    }
+    free(dis); free(queue);
+    return 0;
+}
+
 /* Text sink, gen_merw.cpp:188-206: "[n0, n1, ..., o0, o1, ...]\n" per walk.
  * Returns bytes written (or needed, when buf is NULL). */
 long merw_oracle_format(const int32_t *nodes, const uint8_t *types, long walks,

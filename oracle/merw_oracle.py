@@ -154,6 +154,32 @@ class OracleGraph:
         return nodes, types
 
 
+    def sample_philox(self, nw, L, seed, epoch_begin=0, epoch_end=1, labels=True, node_begin=0, node_end=None):
+        """rng_mode = philox (see merw_oracle.c): every walk draws from its own Philox4x32-10 counter stream."""
+        node_end = self.n if node_end is None else node_end
+        E = epoch_end - epoch_begin
+        nodes = np.zeros((E, node_end - node_begin, nw, L), dtype=np.int32)
+        types = np.zeros((E, node_end - node_begin, nw, L), dtype=np.uint8) if labels else None
+        fn = lib().merw_oracle_sample_philox
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_ulonglong, C.c_long, C.c_long, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        rc = fn(self._h, nw, L, seed, epoch_begin, epoch_end, node_begin, node_end,
+                nodes.ctypes.data, types.ctypes.data if labels else None)
+        if rc != 0:
+            raise RuntimeError("dead-end node rolled")
+        return nodes, types
+
+
+def philox4x32_10(ctr, key) -> list[int]:
+    """One Philox4x32-10 block through the C restatement (known-answer tests)."""
+    c = (C.c_uint32 * 4)(*ctr); k = (C.c_uint32 * 2)(*key); o = (C.c_uint32 * 4)()
+    fn = lib().merw_oracle_philox4x32_10
+    fn.restype = None
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    fn(c, k, o)
+    return [int(x) for x in o]
+
+
 def format_txt(nodes: np.ndarray, types: np.ndarray) -> bytes:
     L = nodes.shape[-1]
     nodes = np.ascontiguousarray(nodes.reshape(-1, L), dtype=np.int32)

@@ -211,6 +211,52 @@ def pagg_rnn_forward(params, X, neis, num_w, walk_len, indices, layer_type, mask
     return layer1 @ params["fc2.weight"].t() + params["fc2.bias"]                            # :361
 
 
+def gru_last_hidden(x, w_ih, w_hh, b_ih, b_hh):
+    """x [L, B, H] -> h_L [B, H]; torch nn.GRU(hidden, hidden), single layer, h_0 = 0, written out step by step (the "GRU"
+    aggregator ablation of performance.jpg; the reference ships no code for it, so the definition is torch's):
+        r = sigmoid(W_ir x + b_ir + W_hr h + b_hr);  z = sigmoid(W_iz x + b_iz + W_hz h + b_hz)
+        n = tanh(W_in x + b_in + r * (W_hn h + b_hn));  h' = (1 - z) * n + z * h
+    Pinned against torch.nn.GRU itself in tests/test_oracle_pinning.py."""
+    L, B, H = x.shape
+    h = x.new_zeros(B, H)
+    for t in range(L):
+        gi = x[t] @ w_ih.t() + b_ih
+        gh = h @ w_hh.t() + b_hh
+        r = torch.sigmoid(gi[:, :H] + gh[:, :H])
+        z = torch.sigmoid(gi[:, H:2 * H] + gh[:, H:2 * H])
+        n = torch.tanh(gi[:, 2 * H:] + r * gh[:, 2 * H:])
+        h = (1 - z) * n + z * h
+    return h
+
+
+def pagg_forward_cell_variant(variant, params, X, neis, num_w, walk_len, indices, layer_type, cell="gru"):
+    """PathNet / PathNet_homo with the LSTM replaced by another sequence encoder under the same `LSTM.*` keys (cell = "gru"):
+    everything else -- projections, the variant's attention, pooling, classifier -- as in pagg_forward_canonical()."""
+    assert cell == "gru"
+    sn, st, pt = canonicalize(variant, neis.numpy(), layer_type.numpy(), num_w, walk_len)
+    idx = torch.as_tensor(np.asarray(indices)) if not torch.is_tensor(indices) else indices
+    rows = torch.nonzero(idx).reshape(-1).numpy()
+    H = params["fc0.weight"].shape[0]
+    S, nw, L = sn.shape
+    homo = variant == "homo"
+    Z = X @ params["fc0.weight"].t() + params["fc0.bias"]
+    if homo:
+        Z = F.relu(Z)
+    T = torch.stack([Z @ w.t() + b for (w, b) in _nets(params, L)], dim=0)
+    if homo:
+        T = F.relu(T)
+    seq = T[torch.as_tensor(st.astype(np.int64)), torch.as_tensor(sn.astype(np.int64))]
+    part = seq[:, :, 0, :] if homo else Z[torch.as_tensor(pt.astype(np.int64))]
+    h = gru_last_hidden(seq.reshape(S * nw, L, H).transpose(0, 1), params["LSTM.weight_ih_l0"], params["LSTM.weight_hh_l0"],
+                        params["LSTM.bias_ih_l0"], params["LSTM.bias_hh_l0"]).view(S, nw, H)
+    score = torch.cat((h, part), dim=-1) @ params["attw.weight"].t() + params["attw.bias"]
+    if homo:
+        pooled = ((1 + score) * h).mean(dim=1)
+    else:
+        pooled = (F.softmax(F.leaky_relu(score, 0.01), dim=1) * h).mean(dim=1)
+    return torch.cat((Z[torch.as_tensor(rows.astype(np.int64))], pooled), dim=1) @ params["fc2.weight"].t() + params["fc2.bias"]
+
+
 def pagg_forward_pool_variant(variant, params, X, neis, num_w, walk_len, indices, layer_type, pool):
     """PathNet / PathNet_homo with the attention replaced by mean / sum / max over the paths (the pooling ablations
     of performance.jpg): everything up to h_n as in pagg_forward(), then the plain reduction."""

@@ -177,6 +177,10 @@ struct WalkParams {
     const int32_t *adj;      // [m]
     int64_t epochs;          // E
     int *overflow;           // set to 1 when a start node's radius-(L-2) ball exceeds the shared-memory table
+    // rng_mode = PN_RNG_PHILOX: walk g = ((epoch_begin + e) * n + st) * nw + i draws from its own counter stream
+    int32_t rng;             // a pn_rng_mode value
+    uint32_t key0, key1;     // lo / hi word of the 64-bit seed
+    int64_t epoch_begin;
     // jump-ahead tables (host-computed per call); chunk stride = 2L*wpt draws
     uint32_t base[lfg::DEG];               // window whose first generated word is the
                                            // first rand() of (epoch_begin, node_begin, walk 0)
@@ -377,6 +381,69 @@ k_merw_walk(const __grid_constant__ WalkParams P)
 //      31-term dot product of the lane's jump polynomial with the warp's window;
 //   3. labels by hash lookup: found -> distance, not found -> position (= L-1).
 // ----------------------------------------------------------------------------
+// ----------------------------------------------------------------------------
+// rng_mode = PN_RNG_PHILOX (SURVEY 8b lists it beside glibc_compat; the reference itself has only rand()):
+// Philox4x32-10 (Salmon et al., SC'11), one counter stream per walk -- counter {lo32(g), hi32(g), block, 0}, key = seed;
+// roll t takes words 2(t & 1), 2(t & 1) + 1 of block t / 2, each >> 1 (31 bits like rand()); the reference's wasted
+// L-th roll is not drawn.  No jump-ahead, no ordering between walks: any split of epochs / start nodes / walks over
+// calls, streams or GPUs reproduces the same walks.  Restated on the CPU in oracle/merw_oracle.c (pinned by the Random123
+// known-answer vectors).
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t (&out)[4])
+{
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// one thread per walk; labels from the dense distance table (P.dist) or none
+__global__ void __launch_bounds__(256)
+k_merw_walk_philox(const __grid_constant__ WalkParams P)
+{
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // walk index within this call
+    if (w >= P.epochs * P.wpe) return;
+    const int L = P.L;
+    const int64_t e = w / P.wpe, r = w % P.wpe;
+    const int32_t st = P.node_begin + (int32_t)(r / P.nw);
+    const uint64_t g = ((uint64_t)(P.epoch_begin + e) * (uint64_t)P.n + (uint64_t)st) * (uint64_t)P.nw + (uint64_t)(r % P.nw);
+    int32_t *out_n = P.nodes + w * L;
+    uint8_t *out_t = P.types ? P.types + w * L : nullptr;
+    const uint2 rec = __ldg(&P.noderec[st]);
+    uint32_t off = rec.x, deg = rec.y;
+    int32_t u = st;
+    uint32_t blk[4] = {0u, 0u, 0u, 0u};
+    for (int t = 0; t < L; t++) {
+        out_n[t] = u;
+        if (out_t) {
+            uint32_t lab = 0;
+            if (t == 1) lab = (u != st);
+            else if (t >= 2) {
+                const uint32_t d = __ldg(P.dist + (int64_t)st * P.dist_pitch + u);
+                lab = d < (uint32_t)t ? d : (uint32_t)t;
+            }
+            out_t[t] = (uint8_t)lab;
+        }
+        if (t + 1 == L) break;
+        if ((t & 1) == 0) philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)(t >> 1), 0u, P.key0, P.key1, blk);
+        const uint32_t r1 = ((t & 1) ? blk[2] : blk[0]) >> 1, r2 = ((t & 1) ? blk[3] : blk[1]) >> 1;
+        const uint32_t x = r1 % deg;
+        uint32_t c0, c1, c2, c3, c4, c5, c6, c7;   // one 32-byte sector = one 256-bit load
+        asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(c0), "=r"(c1), "=r"(c2), "=r"(c3), "=r"(c4), "=r"(c5), "=r"(c6), "=r"(c7)
+                     : "l"(P.cells + (off + x)));
+        const bool takeA = (int32_t)r2 > (int32_t)c2;
+        u = takeA ? (int32_t)c0 : (int32_t)c1;
+        off = takeA ? c3 : c5;
+        deg = takeA ? c4 : c6;
+    }
+}
+
 constexpr int ROOT_THREADS = 128;
 constexpr int ROOT_HASH = 8192;    // slots (power of two); ball capacity = ROOT_QCAP
 constexpr int ROOT_QCAP = 4096;
@@ -439,10 +506,11 @@ k_merw_walk_root(const __grid_constant__ WalkParams P)
     // ---- 2./3. walks: group g = 32 consecutive walks of this start node, lane = walk ----
     const uint2 rec0 = __ldg(&P.noderec[st]);
     const int64_t c_root = (int64_t)(st - P.node_begin) * P.nw;          // chunk (= walk) index of the node's first walk
+    const bool philox = P.rng == PN_RNG_PHILOX;
     for (int g = warp; g * 32 < P.nw; g += ROOT_THREADS / 32) {
         // warp window at (epoch 0, walk c_root + 32 g)
         uint32_t w = lane < lfg::DEG ? P.base[lane] : 0u;
-        {
+        if (!philox) {
             uint64_t cb = (uint64_t)(c_root + g * 32);
             for (int i = 0; cb; i++, cb >>= 4)
                 if (cb & 15) w = warp_window_apply(P.jchunk16[i][(cb & 15) - 1], w, scratch[warp], lane);
@@ -453,16 +521,18 @@ k_merw_walk_root(const __grid_constant__ WalkParams P)
 #pragma unroll
         for (int i = 0; i < lfg::DEG; i++) cf[i] = lane_poly[lane][i];
         for (int64_t ep = 0; ep < P.epochs; ep++) {
-            if (ep > 0) w = warp_window_apply(P.jepoch[0], w, scratch[warp], lane);   // + one epoch
+            if (ep > 0 && !philox) w = warp_window_apply(P.jepoch[0], w, scratch[warp], lane);   // + one epoch
             // extended window e_0..e_60 in shared memory
             uint32_t *ext = scratch[warp];
             __syncwarp();
             if (lane < lfg::DEG) ext[lane] = w;
             __syncwarp();
-            for (int d0 = 0; d0 < 30; d0 += 3) {
+            for (int d0 = 0; d0 < 30 && !philox; d0 += 3) {
                 if (lane < 3) ext[31 + d0 + lane] = ext[d0 + lane] + ext[28 + d0 + lane];
                 __syncwarp();
             }
+            const uint64_t gw = ((uint64_t)(P.epoch_begin + ep) * (uint64_t)P.n + (uint64_t)st) * (uint64_t)P.nw + (uint64_t)wi;
+            uint32_t blk[4] = {0u, 0u, 0u, 0u};
             int32_t *out_n = P.nodes + ((ep * P.wpe) + c_root + wi) * L;
             uint8_t *out_t = P.types ? P.types + ((ep * P.wpe) + c_root + wi) * L : nullptr;
             int32_t u = st;
@@ -470,9 +540,14 @@ k_merw_walk_root(const __grid_constant__ WalkParams P)
             for (int t = 0; t < L; t++) {
                 // the walk's draws 2t and 2t+1: words 2t, 2t+1 of the lane's window = dot(cf, ext[i .. i+30])
                 uint32_t r1 = 0, r2 = 0;
-                const int i1 = P.dpr * t, i2 = P.dpr == 2 ? i1 + 1 : i1;
+                if (philox) {
+                    if ((t & 1) == 0) philox4x32_10((uint32_t)gw, (uint32_t)(gw >> 32), (uint32_t)(t >> 1), 0u, P.key0, P.key1, blk);
+                    r1 = (t & 1) ? blk[2] : blk[0]; r2 = (t & 1) ? blk[3] : blk[1];
+                } else {
+                    const int i1 = P.dpr * t, i2 = P.dpr == 2 ? i1 + 1 : i1;
 #pragma unroll
-                for (int j = 0; j < lfg::DEG; j++) { r1 += cf[j] * ext[i1 + j]; r2 += cf[j] * ext[i2 + j]; }
+                    for (int j = 0; j < lfg::DEG; j++) { r1 += cf[j] * ext[i1 + j]; r2 += cf[j] * ext[i2 + j]; }
+                }
                 r1 >>= 1; r2 >>= 1;
                 if (active) {
                     out_n[t] = u;
@@ -777,7 +852,7 @@ extern "C" int pn_merw_sample(pn_graph *g, int32_t nw, int32_t L, int64_t epoch_
     PN_REQUIRE(epoch_begin >= 0 && epoch_end >= epoch_begin, "pn_merw_sample: bad epoch range");
     PN_REQUIRE(node_begin >= 0 && node_end >= node_begin && node_end <= g->n,
                "pn_merw_sample: bad node range [%d,%d) for n=%d", node_begin, node_end, g->n);
-    PN_REQUIRE(rng_mode == PN_RNG_GLIBC, "pn_merw_sample: unknown rng_mode %d", rng_mode);
+    PN_REQUIRE(rng_mode == PN_RNG_GLIBC || rng_mode == PN_RNG_PHILOX, "pn_merw_sample: unknown rng_mode %d", rng_mode);
     if (g->dead_end >= 0) {
         set_error("pn_merw_sample: node %d has no out-rows (the reference prints "
                   "'A.size() == 0 in Alias Table' and exits)", g->dead_end);
@@ -808,6 +883,7 @@ extern "C" int pn_merw_sample(pn_graph *g, int32_t nw, int32_t L, int64_t epoch_
         if (rc != PN_OK) return rc;
     }
     P.noderec = g->d_noderec; P.cells = g->d_cells;
+    P.rng = rng_mode; P.key0 = (uint32_t)seed; P.key1 = (uint32_t)(seed >> 32); P.epoch_begin = epoch_begin; P.epochs = E;
     P.dist = (types && L > 2 && !sparse) ? g->d_dist : nullptr;
     P.dist_pitch = ceil_div(g->n, 16) * 16;
     P.nodes = nodes; P.types = types;
@@ -831,6 +907,14 @@ extern "C" int pn_merw_sample(pn_graph *g, int32_t nw, int32_t L, int64_t epoch_
                       "path keeps it in shared memory (dense table needs n*n bytes <= 24 GiB)", L - 2, ROOT_QCAP);
             return PN_ERR_UNSUPPORTED;
         }
+        return PN_OK;
+    }
+    if (rng_mode == PN_RNG_PHILOX) {
+        const int64_t pblocks = ceil_div(E * wpe, 256);
+        PN_REQUIRE(pblocks < ((int64_t)1 << 31), "pn_merw_sample: grid too large; split the epoch range");
+        ProfScope prof("merw_walk", stream);
+        k_merw_walk_philox<<<(unsigned)pblocks, 256, 0, stream>>>(P);
+        PN_LAUNCH_CHECK();
         return PN_OK;
     }
     const int64_t blocks = ceil_div(P.total_chunks, WALK_THREADS);

@@ -69,6 +69,9 @@ __global__ void k_canonicalize(int variant, int64_t N, int64_t S, int nw, int L,
 // ---------------------------------------------------------------------------
 // cell = PN_CELL_RNN (tanh RNN, baseline/GPRGNN/src/copy.py:307): w_ih / w_hh are [H,H]; they occupy the "g" slot
 // (gate 2, the tanh gate) of the packed layout and the other three slots are zero, so the same kernels serve both cells.
+// cell = PN_CELL_GRU (torch nn.GRU: w_ih / w_hh [3H,H] in r, z, n order): slot 0 = r, slot 1 = z (x and h rows summed by the
+// GEMM, as the LSTM gates are), slot 2 = the x part of n (W_in, b_in; its h rows are zero), slot 3 = the h part of n
+// (W_hn, b_hn; its x rows are zero) -- n = tanh(slot2 + r * slot3) needs the two parts separately.
 __global__ void k_pack_lstm(int H, int cell, const float *__restrict__ w_ih, const float *__restrict__ w_hh,
                             const float *__restrict__ b_ih, const float *__restrict__ b_hh,
                             float *__restrict__ Wp, float *__restrict__ WpT, float *__restrict__ bp)
@@ -79,6 +82,11 @@ __global__ void k_pack_lstm(int H, int cell, const float *__restrict__ w_ih, con
         int k = i / G4, col = i % G4, unit = col >> 2, gate = col & 3;
         float v;
         if (cell == PN_CELL_RNN) v = gate != 2 ? 0.f : (k < H ? w_ih[unit * H + k] : w_hh[unit * H + (k - H)]);
+        else if (cell == PN_CELL_GRU) {
+            if (gate < 2) v = k < H ? w_ih[(gate * H + unit) * H + k] : w_hh[(gate * H + unit) * H + (k - H)];
+            else if (gate == 2) v = k < H ? w_ih[(2 * H + unit) * H + k] : 0.f;
+            else v = k < H ? 0.f : w_hh[(2 * H + unit) * H + (k - H)];
+        }
         else v = k < H ? w_ih[(gate * H + unit) * H + k] : w_hh[(gate * H + unit) * H + (k - H)];
         Wp[i] = v;
         WpT[col * K2 + k] = v;
@@ -86,6 +94,7 @@ __global__ void k_pack_lstm(int H, int cell, const float *__restrict__ w_ih, con
     if (i < G4) {
         int unit = i >> 2, gate = i & 3;
         if (cell == PN_CELL_RNN) bp[i] = gate != 2 ? 0.f : b_ih[unit] + b_hh[unit];
+        else if (cell == PN_CELL_GRU) bp[i] = gate < 2 ? b_ih[gate * H + unit] + b_hh[gate * H + unit] : gate == 2 ? b_ih[2 * H + unit] : b_hh[2 * H + unit];
         else bp[i] = b_ih[gate * H + unit] + b_hh[gate * H + unit];
     }
 }
@@ -103,6 +112,19 @@ __global__ void k_unpack_lstm_grads(int H, int cell, const float *__restrict__ d
             dw_hh[i] = dWp[(H + k) * G4 + col];
         }
         if (i < H) { const float v = dbp[i * 4 + 2]; db_ih[i] = v; db_hh[i] = v; }
+        return;
+    }
+    if (cell == PN_CELL_GRU) {
+        if (i < 3 * H * H) {
+            const int row = i / H, k = i % H, gate = row / H, unit = row % H;
+            dw_ih[i] = dWp[k * G4 + unit * 4 + (gate < 2 ? gate : 2)];
+            dw_hh[i] = dWp[(H + k) * G4 + unit * 4 + (gate < 2 ? gate : 3)];
+        }
+        if (i < 3 * H) {
+            const int gate = i / H, unit = i % H;
+            db_ih[i] = dbp[unit * 4 + (gate < 2 ? gate : 2)];
+            db_hh[i] = dbp[unit * 4 + (gate < 2 ? gate : 3)];
+        }
         return;
     }
     if (i < G4 * H) {
@@ -139,7 +161,8 @@ struct LstmArgs {
     uint64_t drop_seed;
     const uint64_t *seed_dev; // optional device word added to drop_seed (CUDA-graph replay)
     int64_t p_base;          // global index of this chunk's first sequence (row-chunked calls): mask indices are global
-    int cell;                // PN_CELL_LSTM | PN_CELL_RNN (h_t = tanh of the "g" slot; the saved "g" activation is h_t)
+    int cell;                // PN_CELL_LSTM | PN_CELL_RNN (h_t = tanh of the "g" slot; the saved "g" activation is h_t) |
+                             // PN_CELL_GRU (saved: r, z, n, the h part of n's pre-activation, h_t)
     // backward only
     const float *dhfin;      // [P,H]
     float *dT;               // [N,L,H]
@@ -248,6 +271,14 @@ __global__ void __launch_bounds__(256) k_lstm_fwd_f32(LstmArgs a)
                     gg = tanhf(acc[pp][u][2]);
                     ig = fg = og = cn = 0.f;
                     h = gg;
+                } else if (a.cell == PN_CELL_GRU) {   // torch nn.GRU; this thread is the only reader / writer of its h element
+                    const float hprev = As[row * AP + H + unit];
+                    ig = sigmoidf_(acc[pp][u][0]);                      // r
+                    fg = sigmoidf_(acc[pp][u][1]);                      // z
+                    og = acc[pp][u][3];                                 // W_hn h + b_hn
+                    gg = tanhf(acc[pp][u][2] + ig * og);                // n
+                    h = (1.f - fg) * gg + fg * hprev;
+                    cn = h;
                 } else {
                     ig = sigmoidf_(acc[pp][u][0]); fg = sigmoidf_(acc[pp][u][1]);
                     gg = tanhf(acc[pp][u][2]); og = sigmoidf_(acc[pp][u][3]);
@@ -313,10 +344,18 @@ __global__ void __launch_bounds__(256) k_lstm_bwd_f32(LstmArgs a)
                     if (t > 0) {
                         const float *actp = a.acts + (((int64_t)(t - 1) * a.P + p) * 5) * H + unit;
                         cprev = actp[4 * H];
-                        hprev = a.cell == PN_CELL_RNN ? actp[2 * H] : actp[3 * H] * tanhf(cprev);
+                        hprev = a.cell == PN_CELL_RNN ? actp[2 * H] : a.cell == PN_CELL_GRU ? cprev : actp[3 * H] * tanhf(cprev);
                     }
                     if (a.cell == PN_CELL_RNN) {
                         da.z = dh[pp][u] * (1.f - gg * gg);     // h_t = gg = tanh(pre-activation)
+                    } else if (a.cell == PN_CELL_GRU) {         // ig = r, fg = z, gg = n, og = W_hn h + b_hn
+                        const float d = dh[pp][u];
+                        const float dn = d * (1.f - fg), dz = d * (hprev - gg);
+                        da.z = dn * (1.f - gg * gg);            // x part of n's pre-activation
+                        da.w = da.z * ig;                       // h part of it
+                        da.x = da.z * og * ig * (1.f - ig);     // r
+                        da.y = dz * fg * (1.f - fg);            // z
+                        dc[pp][u] = d * fg;                     // the direct path h_{t-1} -> h_t, added to dh_{t-1} below
                     } else {
                         const float tc = tanhf(cn);
                         const float dcn = dc[pp][u] + dh[pp][u] * og * (1.f - tc * tc);
@@ -384,7 +423,7 @@ __global__ void __launch_bounds__(256) k_lstm_bwd_f32(LstmArgs a)
         for (int pp = 0; pp < 8; pp++) {
             const int64_t p = p0 + ty * 8 + pp;
 #pragma unroll
-            for (int u = 0; u < UPT; u++) dh[pp][u] = acc[pp][UPT + u];
+            for (int u = 0; u < UPT; u++) dh[pp][u] = acc[pp][UPT + u] + (a.cell == PN_CELL_GRU ? dc[pp][u] : 0.f);
             if (p < a.P) {
                 const int64_t e = p * a.L + t;
                 float *dst = a.dT + ((int64_t)a.seq_node[e] * a.L + a.seq_type[e]) * H;
@@ -901,7 +940,7 @@ static int check_cfg(const pn_pagg_cfg *c)
     PN_REQUIRE(c->H % 32 == 0 && c->H >= 32 && c->H <= 128,
                "pagg: hidden size %d unsupported (multiples of 32 up to 128)", c->H);
     PN_REQUIRE(c->variant == PN_VARIANT_HETERO || c->variant == PN_VARIANT_HOMO || c->variant == PN_VARIANT_PLAIN, "pagg: bad variant %d", c->variant);
-    PN_REQUIRE(c->cell == PN_CELL_LSTM || c->cell == PN_CELL_RNN, "pagg: bad cell %d", c->cell);
+    PN_REQUIRE(c->cell == PN_CELL_LSTM || c->cell == PN_CELL_RNN || c->cell == PN_CELL_GRU, "pagg: bad cell %d", c->cell);
     PN_REQUIRE(c->pool >= PN_POOL_ATTENTION && c->pool <= PN_POOL_MAX, "pagg: bad pool %d", c->pool);
     PN_REQUIRE(!(c->variant == PN_VARIANT_PLAIN && c->pool == PN_POOL_ATTENTION),
                "pagg: the plain variant (no ReLU, natural path order) has no attention of its own: choose pool mean / sum / max");
@@ -1143,7 +1182,7 @@ extern "C" int pn_pagg_backward(const pn_pagg_cfg *cfg, const pn_pagg_params *pr
 #define ZERO(ptr, n) PN_CUDA(cudaMemsetAsync((ptr), 0, sizeof(float) * (size_t)(n), st))
     if (S == 0) {  // no rows: every gradient is zero
         ZERO(g.fc0_w, H * F); ZERO(g.fc0_b, H); ZERO(g.nets_w, L * H * H); ZERO(g.nets_b, L * H);
-        const int64_t ng = c.cell == PN_CELL_RNN ? 1 : 4;   // gates of the cell
+        const int64_t ng = c.cell == PN_CELL_RNN ? 1 : c.cell == PN_CELL_GRU ? 3 : 4;   // gate blocks of the cell's parameters
         ZERO(g.w_ih, ng * H * H); ZERO(g.w_hh, ng * H * H); ZERO(g.b_ih, ng * H); ZERO(g.b_hh, ng * H);
         ZERO(g.attw_w, 2 * H); ZERO(g.attw_b, 1); ZERO(g.fc2_w, C * 2 * H); ZERO(g.fc2_b, C);
         return PN_OK;

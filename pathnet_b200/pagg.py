@@ -28,7 +28,7 @@ from ._lib import PARAM_NAMES, PaggCfg, PaggParams, check, lib
 
 VARIANT = {"hetero": 0, "homo": 1, "plain": 2}
 MATH = {"fp32": 0, "tc": 1}
-CELL = {"lstm": 0, "rnn": 1}
+CELL = {"lstm": 0, "rnn": 1, "gru": 2}
 POOL = {"attention": 0, "mean": 1, "sum": 2, "max": 3}
 IDX_DTYPE = {torch.int64: 0, torch.int32: 1, torch.uint8: 2}
 _warned_auto_tc = False
@@ -242,7 +242,8 @@ def pagg_forward(variant, X, params: dict, seq_node, seq_type, partner, rows, *,
                  training=False, seed=0, math_mode="auto", row_chunk=0, grad_sink=None, x16_cache=None, cell="lstm",
                  pool="attention"):
     """Functional form over a dict with the reference's state_dict keys.  cell / pool: the SURVEY 8f-4 variants
-    ("rnn": LSTM.* keys then hold nn.RNN-shaped tensors [H,H] / [H]; "mean" | "sum" | "max": attw.* unused)."""
+    ("rnn": LSTM.* keys then hold nn.RNN-shaped tensors [H,H] / [H]; "gru": nn.GRU-shaped [3H,H] / [3H];
+    "mean" | "sum" | "max": attw.* unused)."""
     L = seq_node.shape[2]
     if cell != "lstm" and math_mode == "auto":
         math_mode = "fp32"   # the tensor-core kernels implement the LSTM cell only
@@ -336,6 +337,9 @@ class _PathNetBase(nn.Module):
         self.pool = kwargs.pop("pool", "attention")          # ablations: "mean" | "sum" | "max" instead of the attention
         if self.pool not in POOL:
             raise ValueError(f"pool must be one of {sorted(POOL)} (got {self.pool!r})")
+        self.cell = kwargs.pop("cell", "lstm")               # sequence-encoder ablation: "gru" = nn.GRU under the same `LSTM.*` keys
+        if self.cell not in ("lstm", "gru"):
+            raise ValueError(f"cell must be 'lstm' or 'gru' (got {self.cell!r}); the tanh-RNN variant is class PAGG_RNN")
         kwargs.setdefault("aggr", "mean")
         super().__init__()
         self._rows_cache = RowsCache()
@@ -346,7 +350,7 @@ class _PathNetBase(nn.Module):
         # construction order = the reference's (:162-170), so a given torch seed
         # yields the same initial weights
         self.fc0 = nn.Linear(feature_length, hidden_size)
-        self.LSTM = nn.LSTM(hidden_size, hidden_size)
+        self.LSTM = nn.LSTM(hidden_size, hidden_size) if self.cell == "lstm" else nn.GRU(hidden_size, hidden_size)
         self.fc2 = nn.Linear(2 * hidden_size, out_size)
         self.nets = nn.ModuleList([nn.Linear(hidden_size, hidden_size) for _ in range(wl)])
         self.attw = nn.Linear(2 * hidden_size, 1)
@@ -364,7 +368,7 @@ class _PathNetBase(nn.Module):
             self._guard = IndexGuard(X.device)
         return fused_forward(self, self._variant, X, neis, num_w, walk_len, indices, layer_type, dropout=self.dropout,
                              math_mode=self.math_mode, row_chunk=self.row_chunk, rows_cache=self._rows_cache,
-                             guard=self._guard, grad_sink=self.grad_sink, x16_cache=self._x16, pool=self.pool)
+                             guard=self._guard, grad_sink=self.grad_sink, x16_cache=self._x16, pool=self.pool, cell=self.cell)
 
 
 class PathNet(_PathNetBase):

@@ -107,9 +107,12 @@ class MerwGraph:
                                                 torch.cuda.current_stream().cuda_stream))
 
     def sample(self, path_num, path_len, epochs=1, seed=12345, epoch_begin=0, node_begin=0,
-               node_end=None, labels=True, out=None):
-        """-> (nodes int32 [E, n', nw, L], types uint8 [E, n', nw, L]) on the GPU,
-        bit-identical to what the reference prints for srand(seed)."""
+               node_end=None, labels=True, out=None, rng="glibc"):
+        """-> (nodes int32 [E, n', nw, L], types uint8 [E, n', nw, L]) on the GPU.
+        rng="glibc" (default): bit-identical to what the reference prints for srand(seed).
+        rng="philox": counter-based Philox4x32-10, one stream per walk (include/pathnet_b200.h: PN_RNG_PHILOX) -- the same
+        walk law, independent of how epochs / start nodes are split over calls or GPUs; 64-bit seed."""
+        mode = {"glibc": 0, "philox": 1}[rng]
         if self.device is None:
             raise RuntimeError("host-only graph: no device to sample on")
         node_end = self.n if node_end is None else node_end
@@ -122,7 +125,7 @@ class MerwGraph:
             else:
                 nodes, types = out
             check(lib().pn_merw_sample(self._h, path_num, path_len, epoch_begin, epoch_begin + E,
-                                       node_begin, node_end, 0, int(seed) & 0xFFFFFFFF,
+                                       node_begin, node_end, mode, int(seed) & (0xFFFFFFFF if mode == 0 else 0xFFFFFFFFFFFFFFFF),
                                        nodes.data_ptr(), types.data_ptr() if types is not None else None,
                                        torch.cuda.current_stream().cuda_stream))
         return nodes, types
@@ -132,7 +135,7 @@ _GRAPH_CACHE: dict = {}
 
 
 def gen_merw(name_or_edges, path_num, path_len, epochs=1000, seed=None, device="cuda:0",
-             edge_root="../edge_input", epoch_begin=0):
+             edge_root="../edge_input", epoch_begin=0, rng="glibc"):
     """Drop-in for `./gen_merw <name> <path_num> <path_len>` that hands tensors over.
 
     name_or_edges: dataset name (reads `<edge_root>/<name>.in` like
@@ -155,7 +158,7 @@ def gen_merw(name_or_edges, path_num, path_len, epochs=1000, seed=None, device="
         g = _GRAPH_CACHE.get(key)
         if g is None:
             g = _GRAPH_CACHE[key] = MerwGraph.from_file(p, device=device)
-    nodes, types = g.sample(path_num, path_len, epochs=epochs, seed=seed, epoch_begin=epoch_begin)
+    nodes, types = g.sample(path_num, path_len, epochs=epochs, seed=seed, epoch_begin=epoch_begin, rng=rng)
     E, n = nodes.shape[0], nodes.shape[1]
     return nodes.view(E, n, path_num * path_len).long(), types.long()
 

@@ -202,3 +202,53 @@ def test_uniform_rw_on_a_larger_graph_matches_oracle():
     want_n, want_t = mo.OracleGraph(n, u, v).sample(40, 4, 321, 0, 2)
     got_n, got_t = _gpu_sample(sampler.MerwGraph(n, u, v, None), 40, 4, 321, epochs=2)
     assert (got_n == want_n).all() and (got_t == want_t).all()
+
+
+# ---------------------------------------------------------------- rng_mode = philox (PN_RNG_PHILOX) --
+@pytest.mark.parametrize("n,deg,nw,L,E,seed", [(300, 8, 5, 3, 3, 1), (300, 8, 40, 4, 2, 2), (500, 6, 9, 5, 2, 3),
+                                              (257, 4, 1, 8, 3, 5), (64, 3, 33, 2, 2, 6), (100, 5, 3, 1, 2, 7)])
+def test_philox_mode_matches_oracle_on_messy_graphs(n, deg, nw, L, E, seed):
+    gr = messy_graph(n, deg, seed)
+    big_seed = (0x1234ABCD << 32) | (5000 + seed)          # exercises both key words
+    want_n, want_t = mo.OracleGraph(*gr).sample_philox(nw, L, big_seed, 0, E)
+    got_n, got_t = _gpu_sample(sampler.MerwGraph(*gr), nw, L, big_seed, epochs=E, rng="philox")
+    assert (got_n == want_n).all()
+    assert (got_t == want_t).all()
+
+
+def test_philox_mode_is_invariant_under_epoch_and_node_splits_and_label_paths(monkeypatch):
+    gr = messy_graph(350, 6, 9)
+    g = sampler.MerwGraph(*gr)
+    full_n, full_t = _gpu_sample(g, 6, 4, 77, epochs=5, rng="philox")
+    n1, t1 = _gpu_sample(g, 6, 4, 77, epochs=2, epoch_begin=3, rng="philox")
+    assert (n1 == full_n[3:]).all() and (t1 == full_t[3:]).all()
+    a_n, a_t = _gpu_sample(g, 6, 4, 77, epochs=5, node_begin=0, node_end=123, rng="philox")
+    b_n, b_t = _gpu_sample(g, 6, 4, 77, epochs=5, node_begin=123, node_end=350, rng="philox")
+    assert (np.concatenate([a_n, b_n], axis=1) == full_n).all()
+    assert (np.concatenate([a_t, b_t], axis=1) == full_t).all()
+    # a far epoch (the 64-bit walk index reaches the counter's high word only beyond 2^32 walks; check the oracle there)
+    far = (1 << 32) // (350 * 6) + 5
+    o_n, o_t = mo.OracleGraph(*gr).sample_philox(6, 4, 77, far, far + 2)
+    l_n, l_t = _gpu_sample(g, 6, 4, 77, epochs=2, epoch_begin=far, rng="philox")
+    assert (l_n == o_n).all() and (l_t == o_t).all()
+    # the root-centric (sparse label) kernel draws the same walks
+    monkeypatch.setenv("PN_MERW_SPARSE", "1")
+    s_n, s_t = _gpu_sample(sampler.MerwGraph(*gr), 6, 4, 77, epochs=5, rng="philox")
+    assert (s_n == full_n).all() and (s_t == full_t).all()
+    # and it is a different stream from the reference-compatible one, with the same invariants
+    gl_n, _ = _gpu_sample(g, 6, 4, 77, epochs=5)
+    assert (gl_n != full_n).any()
+    assert (full_n[..., 0] == np.arange(350)[None, :, None]).all() and (full_t[..., 0] == 0).all()
+
+
+def test_philox_mode_walks_follow_the_transition_law():
+    """Same law as the reference's roll (x uniform over the cells, A with probability 1 - S): the empirical next-node
+    frequencies from one start node agree between the two rng modes (and with the cells) to sampling error."""
+    gr = messy_graph(120, 6, 17, neg_frac=0.0, zero_frac=0.0)
+    g = sampler.MerwGraph(*gr)
+    ph, _ = _gpu_sample(g, 64, 2, 5, epochs=400, rng="philox")
+    gl, _ = _gpu_sample(g, 64, 2, 5, epochs=400)
+    for st in (0, 7, 63):
+        a = np.bincount(ph[:, st, :, 1].ravel(), minlength=120) / (400 * 64)
+        b = np.bincount(gl[:, st, :, 1].ravel(), minlength=120) / (400 * 64)
+        assert np.abs(a - b).max() < 0.02

@@ -120,4 +120,40 @@ def test_variant_argument_errors():
     assert bytes_(variant=2, math_mode=0, cell=1, pool=1) > 0
     assert bytes_(variant=2, math_mode=0, cell=1, pool=0) == 0        # plain variant has no attention
     assert bytes_(variant=1, math_mode=1, cell=1, pool=0) == 0        # tensor-core kernels: LSTM only
-    assert bytes_(variant=1, math_mode=0, cell=2, pool=0) == 0
+    assert bytes_(variant=1, math_mode=0, cell=2, pool=0) > 0         # GRU (fp32 math mode)
+    assert bytes_(variant=1, math_mode=1, cell=2, pool=0) == 0        # tensor-core kernels: LSTM only
+    assert bytes_(variant=1, math_mode=0, cell=3, pool=0) == 0
+
+
+@pytest.mark.parametrize("variant", ["hetero", "homo"])
+@pytest.mark.parametrize("H", [32, 64, 128])
+def test_gru_cell_matches_oracle(variant, H):
+    """cell="gru" (nn.GRU under the `LSTM.*` keys): logits and every parameter gradient against the fp64 oracle, in
+    training mode with the kernels' own dropout masks handed to nobody -- dropout off, like the pooling ablations."""
+    N, Fd, Cc, nw, L, S = 130, 18, 5, 6, 4, 47
+    cls = pagg.PathNet if variant == "hetero" else pagg.PathNet_homo
+    torch.manual_seed(9)
+    m = cls(Fd, H, Cc, L, cell="gru")                 # math_mode "auto" -> fp32 for a non-LSTM cell
+    assert m.LSTM.weight_ih_l0.shape == (3 * H, H)
+    g = torch.Generator().manual_seed(13)
+    X = torch.randn(N, Fd, generator=g)
+    mask = torch.zeros(N, dtype=torch.bool); mask[torch.randperm(N, generator=g)[:S]] = True
+    neis, lt = torch.randint(0, N, (S, nw * L), generator=g), torch.randint(0, L, (S, nw, L), generator=g)
+    params = {k: v.detach().clone().double().requires_grad_(True) for k, v in m.state_dict().items()}
+    y_ref = po.pagg_forward_cell_variant(variant, params, X.double(), neis, nw, L, mask, lt, "gru")
+    G = torch.randn(S, Cc)
+    (y_ref * G.double()).sum().backward()
+    m = m.to(DEV).eval()
+    y = m(X.to(DEV), neis, nw, L, mask, lt, None)
+    (y * G.to(DEV)).sum().backward()
+    torch.testing.assert_close(y.cpu(), y_ref.detach().float(), **FWD_TOL)
+    for k, q in m.named_parameters():
+        torch.testing.assert_close(q.grad.cpu(), params[k].grad.float(), **GRAD_TOL, msg=lambda s: f"{k}: {s}")
+
+
+def test_gru_cell_is_refused_by_the_tensor_core_mode():
+    m = pagg.PathNet(18, 128, 5, 4, cell="gru", math_mode="tc").to(DEV)
+    X = torch.randn(50, 18, device=DEV)
+    mask = torch.zeros(50, dtype=torch.bool); mask[:7] = True
+    with pytest.raises(Exception, match="LSTM cell only"):
+        m(X, torch.randint(0, 50, (7, 12)), 3, 4, mask, torch.randint(0, 4, (7, 3, 4)), None)

@@ -238,3 +238,38 @@ def test_pagg_rnn_oracle_matches_live_reference_class(have_reference):
     want = m(X, neis, nw, L, mask, lt, torch.arange(S * nw * L))
     got = po.pagg_rnn_forward(dict(m.state_dict()), X, neis, nw, L, mask, lt)
     torch.testing.assert_close(got, want.detach(), rtol=1e-5, atol=1e-6)
+
+
+def test_philox_restatement_matches_random123_known_answers():
+    """Philox4x32-10 of oracle/merw_oracle.c against the known-answer vectors shipped with Random123 (kat_vectors)."""
+    from oracle import merw_oracle as mo
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8)),
+           ((0xFFFFFFFF,) * 4, (0xFFFFFFFF,) * 2, (0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD)),
+           ((0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344), (0xA4093822, 0x299F31D0),
+            (0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1))]
+    for ctr, key, want in kat:
+        assert tuple(mo.philox4x32_10(ctr, key)) == want
+
+
+def test_philox_oracle_is_split_invariant_and_labels_are_hop_distances():
+    from oracle import merw_oracle as mo
+    from tests.helpers import messy_graph
+    gr = messy_graph(90, 5, 3)
+    og = mo.OracleGraph(*gr)
+    full_n, full_t = og.sample_philox(4, 5, 99, 0, 3)
+    part_n, part_t = og.sample_philox(4, 5, 99, 1, 3, node_begin=20, node_end=50)
+    assert (part_n == full_n[1:, 20:50]).all() and (part_t == full_t[1:, 20:50]).all()
+    assert (full_t[..., 0] == 0).all() and (full_t <= np.arange(5)).all()
+    assert (full_n[..., 0] == np.arange(90)[None, :, None]).all()
+
+
+def test_gru_restatement_matches_torch_nn_gru():
+    """The GRU ablation has no reference code; its oracle is pinned to torch.nn.GRU (the layer a PathNet author would use)."""
+    from oracle import pagg_oracle as po
+    torch.manual_seed(3)
+    H, L, B = 24, 5, 17
+    gru = torch.nn.GRU(H, H).double()
+    x = torch.randn(L, B, H, dtype=torch.float64)
+    want = gru(x)[1][0]
+    got = po.gru_last_hidden(x, gru.weight_ih_l0, gru.weight_hh_l0, gru.bias_ih_l0, gru.bias_hh_l0)
+    torch.testing.assert_close(got, want, rtol=1e-12, atol=1e-12)
