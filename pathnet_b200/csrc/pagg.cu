@@ -15,6 +15,8 @@
 //   logits = fc2(dropout([Z[rows[s]] ; pooled[s]]))
 #include <algorithm>
 
+#include <mutex>
+
 #include "pagg_common.cuh"
 
 namespace pn {
@@ -990,7 +992,7 @@ static int launch_lstm_bwd(const LstmArgs &a, cudaStream_t st)
 int pagg_tc_forward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_params &prm, const int32_t *seq_node,
                          const uint8_t *seq_type, const PaggChunk &ck, cudaStream_t st);   // pagg_tc.cu
 int pagg_tc_backward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_params &prm, const int32_t *seq_node,
-                          const uint8_t *seq_type, const PaggChunk &ck, bool factored_dh, cudaStream_t st);  // pagg_tc.cu
+                          const uint8_t *seq_type, const PaggChunk &ck, bool factored_dh, cudaStream_t st, cudaEvent_t after_bptt = nullptr);  // pagg_tc.cu
 int pagg_tc_project(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_params &prm, const float *X, cudaStream_t st);          // pagg_tc.cu
 int pagg_tc_project_backward(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_params &prm, const float *X,
                              const pn_pagg_params &g, cudaStream_t st);                                                          // pagg_tc.cu
@@ -1162,6 +1164,32 @@ extern "C" int pn_pagg_forward(const pn_pagg_cfg *cfg, const pn_pagg_params *prm
     return PN_OK;
 }
 
+// side stream + fork / join events of the tensor-core backward (one set per device, created on first use)
+namespace pn {
+struct BwdFork { cudaStream_t side; cudaEvent_t ev_fork, ev_join; };
+static int bwd_fork_get(BwdFork &f)
+{
+    static BwdFork slots[64] = {};
+    static bool made[64] = {};
+    static std::mutex mu;
+    f = BwdFork{};
+    const char *e = getenv("PN_BWD_FORK");
+    if (e && e[0] == '0') return PN_OK;
+    int dev = 0;
+    PN_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return PN_OK;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!made[dev]) {
+        PN_CUDA(cudaStreamCreateWithFlags(&slots[dev].side, cudaStreamNonBlocking));
+        PN_CUDA(cudaEventCreateWithFlags(&slots[dev].ev_fork, cudaEventDisableTiming));
+        PN_CUDA(cudaEventCreateWithFlags(&slots[dev].ev_join, cudaEventDisableTiming));
+        made[dev] = true;
+    }
+    f = slots[dev];
+    return PN_OK;
+}
+}  // namespace pn
+
 extern "C" int pn_pagg_backward(const pn_pagg_cfg *cfg, const pn_pagg_params *prm, const float *X,
                                 const int32_t *seq_node, const uint8_t *seq_type,
                                 const int32_t *partner, const int32_t *rows, void *workspace,
@@ -1199,6 +1227,13 @@ extern "C" int pn_pagg_backward(const pn_pagg_cfg *cfg, const pn_pagg_params *pr
     drop_params(c, thr, scale);
     const int64_t rows_per = chunk_rows(c);
     const bool single = rows_per >= S;
+    // Tensor-core mode: after the last chunk's BPTT kernel the step forks.  The weight-gradient GEMM of the LSTM (0.45 ms on 132
+    // SMs, one 230 KB CTA each) and the backward of the two projections (five small kernels, 0.2 ms, that need only dT / dZ) are
+    // independent, so the projections run on a side stream -- the column sweeps beside the wgrad CTAs, the GEMMs on the 16 SMs
+    // the wgrad clusters leave free -- and join before the call returns.  Works the same under stream capture (the graph gets
+    // two branches).  PN_BWD_FORK=0 keeps everything on the caller's stream.
+    BwdFork fork{};
+    if (tcm) { rc = bwd_fork_get(fork); if (rc) return rc; }
     for (int64_t s0 = 0; s0 < S; s0 += rows_per) {
         const PaggChunk ck{s0, std::min<int64_t>(rows_per, S - s0), true, s0 == 0};
         const ChunkPtrs ix = chunk_ptrs(c, ck, seq_node, seq_type, partner, rows);
@@ -1241,7 +1276,7 @@ extern "C" int pn_pagg_backward(const pn_pagg_cfg *cfg, const pn_pagg_params *pr
         PN_LAUNCH_CHECK();
         // ---- LSTM BPTT ----
         if (tcm) {
-            rc = pagg_tc_backward_lstm(c, w, *prm, ix.seq_node, ix.seq_type, ck, factored, st);
+            rc = pagg_tc_backward_lstm(c, w, *prm, ix.seq_node, ix.seq_type, ck, factored, st, (s0 + rows_per >= S) ? fork.ev_fork : nullptr);
             if (rc) return rc;
         } else {
             LstmArgs la{};
@@ -1269,10 +1304,17 @@ extern "C" int pn_pagg_backward(const pn_pagg_cfg *cfg, const pn_pagg_params *pr
             if (rc) return rc;
         }
     }
+    if (tcm && fork.ev_fork) {   // the projections' backward on the side stream, from the point where dT / dZ were complete
+        PN_CUDA(cudaStreamWaitEvent(fork.side, fork.ev_fork, 0));
+        rc = pagg_tc_project_backward(c, w, *prm, X, g, fork.side);
+        if (rc) return rc;
+        PN_CUDA(cudaEventRecord(fork.ev_join, fork.side));
+    }
     PN_CUDA(cudaMemcpyAsync(g.attw_w, w.dattw, sizeof(float) * 2 * H, cudaMemcpyDeviceToDevice, st));
     PN_CUDA(cudaMemcpyAsync(g.attw_b, w.dattw + 2 * H, sizeof(float), cudaMemcpyDeviceToDevice, st));
     k_unpack_lstm_grads<<<(unsigned)ceil_div(4 * H * H, 256), 256, 0, st>>>((int)H, c.cell, w.dWp, w.dbp, g.w_ih, g.w_hh, g.b_ih, g.b_hh);
     PN_LAUNCH_CHECK();
+    if (tcm && fork.ev_fork) { PN_CUDA(cudaStreamWaitEvent(st, fork.ev_join, 0)); return PN_OK; }
     if (tcm) return pagg_tc_project_backward(c, w, *prm, X, g, st);
     // ---- table projection: T = act(Z Wn^T + bn) ----
     // homo: ReLU backward fused with the bias gradient (column sums) of the table projection

@@ -1201,7 +1201,8 @@ __global__ void __launch_bounds__(192, 1) k_wgrad_tc(WgradTcArgs a)
 // LSTM backward in tensor-core mode: fills w.dWp [2H][4H] and w.dbp [4H] (packed
 // layouts, same as the fp32 path) and scatters dx into w.dT.
 int pagg_tc_backward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_params &prm,
-                          const int32_t *seq_node, const uint8_t *seq_type, const PaggChunk &ck, bool factored_dh, cudaStream_t st)
+                          const int32_t *seq_node, const uint8_t *seq_type, const PaggChunk &ck, bool factored_dh, cudaStream_t st,
+                          cudaEvent_t after_bptt)
 {
     if (c.H != TC_H) {
         set_error("PN_MATH_TC: the tensor-core LSTM is built for hidden size 128 (got %d)", c.H);
@@ -1254,6 +1255,7 @@ int pagg_tc_backward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_p
             fprintf(stderr, "[trace bwd cta %d] s=%d  begin %lld | prev dx scattered %lld | 4 da quarters arrived %lld | acc_full seen %lld | %lld\n",
                     a.trace_block, q, h[q * 8 + 0] - t00, h[q * 8 + 1] - t00, h[q * 8 + 2] - t00, h[q * 8 + 3] - t00, h[q * 8 + 4] - t00);
     }
+    if (after_bptt) PN_CUDA(cudaEventRecord(after_bptt, st));   // dT is complete: the caller forks the projections' backward here
     // dWp / dbp are zeroed once per call by pn_pagg_backward: every chunk adds into them
     WgradTcArgs wa{xh_img, da_img, nblocks, w.gscale, w.dWp, w.dbp};
     PN_CUDA(cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
@@ -1274,7 +1276,13 @@ int pagg_tc_backward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_p
             max_clusters = std::max(1, std::min(mc, 64));
             if (getenv("PN_TRACE_BWD")) fprintf(stderr, "[wgrad] max active clusters of 4 = %d\n", mc);
         }
-        const unsigned nsplit = (unsigned)std::max<int64_t>(1, std::min<int64_t>(max_clusters, nblocks));
+        // When the projections' backward runs beside this kernel (after_bptt: the caller forked it onto a side stream), leave it
+        // 6 clusters = 24 more SMs: its GEMM CTAs (64 KB of shared memory) cannot share an SM with a 230 KB wgrad CTA.  Same-box
+        // sweep on the pubmed step, clusters -> ms/step: 33 2.689, 31 2.698, 29 2.675, 27 2.647, 25 2.674 (this kernel alone slows
+        // from 0.465 to 0.534 ms at 27, the step gains).  PN_WGRAD_CLUSTERS overrides.
+        int cap = after_bptt ? std::max(1, max_clusters - 6) : max_clusters;
+        if (const char *e = getenv("PN_WGRAD_CLUSTERS")) { const int v = atoi(e); if (v >= 1) cap = std::min(max_clusters, v); }
+        const unsigned nsplit = (unsigned)std::max<int64_t>(1, std::min<int64_t>(cap, nblocks));
         lc.gridDim = dim3(nsplit, 4);
         PN_CUDA(cudaLaunchKernelEx(&lc, k_wgrad_tc, wa));
     }
