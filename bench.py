@@ -339,7 +339,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--math", default=os.environ.get("PN_BENCH_MATH", "tc"), choices=["fp32", "tc"])
+    ap.add_argument("--math", default=os.environ.get("PN_BENCH_MATH", "tc"), choices=["fp32", "tc", "tc3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the strict / module-API / status-quo / MERW legs")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
@@ -533,6 +533,28 @@ def main():
                                 "note": "same step in the strict-parity math mode (CUDA-core fp32 FMA; logits within 1e-4 of the reference's fp32 math)"}
             del ts32
 
+            # ---- split-precision tensor-core mode: the strict mode's parity bar on tcgen05 (three fp16 passes per product) ----
+            _, ts3 = make_step("tc3")
+            for _ in range(3):
+                ts3.step(neis_dev, ltype_dev)
+            n3 = max(5, args.steps)
+            ms3 = timed(lambda: ts3.step(neis_dev, ltype_dev), n3) / n3
+            ts3.prefetch(neis_host, ltype_host)
+
+            def e2e3():
+                ts3.step()
+                ts3.prefetch(neis_host, ltype_host)
+                return float(ts3.loss.item())
+            e2e3()
+            ms3e = timed(e2e3, n3) / n3
+            extras["strict_tc3"] = {"math_mode": "tc3", "dtype": "2xf16 split operands x 3 passes, f32 accumulate (fp32-grade)",
+                                    "value": P_job / (ms3 * 1e-3), "ms_per_step": ms3, "e2e": P_job / (ms3e * 1e-3),
+                                    "e2e_ms_per_step": ms3e, "unit": "paths/s", "steps": n3,
+                                    "note": "same step in the split-precision tensor-core mode: LSTM operands as hi + lo fp16 terms, "
+                                            "A W = A_hi W_hi + A_lo W_hi + A_hi W_lo on tcgen05, ex2/rcp gates, projections on the fp32 "
+                                            "kernels; held to the fp32 mode's parity bar (tests/test_gpu_tc3.py)"}
+            del ts3
+
         # ---- MERW walks/sec (labels included), same graph ----
         E = MERW_EPOCHS_PER_STEP
         out_n = torch.empty((E, w["n"], nw, L_), dtype=torch.int32, device=dev)
@@ -577,7 +599,7 @@ def main():
         "metric": "pagg_paths_per_sec_fwd_bwd", "value": value, "unit": "paths/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": args.scaling if world > 1 else "weak", "vs_baseline": None,
-        "dtype": "f32" if args.math == "fp32" else "f16xf32acc", "data": "synthetic",
+        "dtype": {"fp32": "f32", "tc": "f16xf32acc", "tc3": "2xf16-split x3 passes, f32acc"}[args.math], "data": "synthetic",
         "config": config_of(world, args.scaling),
         "math_mode": args.math,
         "l2": "per-step working set ~9 GB >> 126 MB L2 (no explicit flush for PAGG); MERW leg flushes L2 with a 256 MiB write between launches",
@@ -592,6 +614,8 @@ def main():
         roofline["merw"] = {"value": merw["value"], "unit": "walks/s", "frac_of_hbm_roof": merw["roofline"]["frac"]}
     if "strict" in extras:
         e2e["strict"] = extras["strict"]
+    if "strict_tc3" in extras:
+        e2e["strict_tc3"] = extras["strict_tc3"]
     if world > 1:
         dist.barrier()
     if rank == 0:

@@ -156,7 +156,11 @@ typedef enum { PN_CELL_LSTM = 0, PN_CELL_RNN = 1, PN_CELL_GRU = 2 } pn_cell;
 typedef enum { PN_POOL_ATTENTION = 0, PN_POOL_MEAN = 1, PN_POOL_SUM = 2, PN_POOL_MAX = 3 } pn_pool;
 
 typedef enum { PN_MATH_FP32 = 0, /* CUDA-core fp32 FMA, strict parity         */
-               PN_MATH_TC = 1    /* tcgen05 tensor cores, fp16 operands/fp32 acc */ } pn_math;
+               PN_MATH_TC = 1,   /* tcgen05 tensor cores, fp16 operands/fp32 acc */
+               PN_MATH_TC3 = 2   /* tcgen05 tensor cores at fp32-grade accuracy: the LSTM's operands travel as two fp16
+                                    terms (hi + lo, 22 bits) and every product is three tensor-core passes into one fp32
+                                    accumulator; ex2/rcp gates; projections on the fp32 kernels.  Same parity bar as
+                                    PN_MATH_FP32 (hidden 128, path_len <= 8, LSTM cell)                               */ } pn_math;
 
 typedef struct {
     int32_t N, F, H, C;      /* nodes, input features, hidden, classes       */

@@ -946,11 +946,11 @@ static int check_cfg(const pn_pagg_cfg *c)
     PN_REQUIRE(c->pool >= PN_POOL_ATTENTION && c->pool <= PN_POOL_MAX, "pagg: bad pool %d", c->pool);
     PN_REQUIRE(!(c->variant == PN_VARIANT_PLAIN && c->pool == PN_POOL_ATTENTION),
                "pagg: the plain variant (no ReLU, natural path order) has no attention of its own: choose pool mean / sum / max");
-    if (c->math_mode == PN_MATH_TC && c->cell != PN_CELL_LSTM) {
+    if ((c->math_mode == PN_MATH_TC || c->math_mode == PN_MATH_TC3) && c->cell != PN_CELL_LSTM) {
         set_error("pagg: the tensor-core kernels implement the LSTM cell only (cell %d needs math_mode fp32)", c->cell);
         return PN_ERR_UNSUPPORTED;
     }
-    PN_REQUIRE(c->math_mode == PN_MATH_FP32 || c->math_mode == PN_MATH_TC, "pagg: bad math_mode %d", c->math_mode);
+    PN_REQUIRE(c->math_mode == PN_MATH_FP32 || c->math_mode == PN_MATH_TC || c->math_mode == PN_MATH_TC3, "pagg: bad math_mode %d", c->math_mode);
     PN_REQUIRE(c->dropout_p >= 0.f && c->dropout_p <= 1.f, "pagg: dropout p=%f outside [0,1]", (double)c->dropout_p);
     PN_REQUIRE(c->row_chunk >= 0, "pagg: row_chunk %d < 0", c->row_chunk);
     PN_REQUIRE((int64_t)c->N * c->L < ((int64_t)1 << 31), "pagg: N*L = %lld table rows exceed int32 row offsets", (long long)c->N * c->L);
@@ -994,6 +994,9 @@ int pagg_tc_forward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_pa
 int pagg_tc_backward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_params &prm, const int32_t *seq_node,
                           const uint8_t *seq_type, const PaggChunk &ck, bool factored_dh, cudaStream_t st, cudaEvent_t after_bptt = nullptr);  // pagg_tc.cu
 int pagg_tc_project(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_params &prm, const float *X, cudaStream_t st);          // pagg_tc.cu
+int pagg_tc3_forward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_params &prm, const int32_t *seq_node,
+                          const uint8_t *seq_type, const PaggChunk &ck, cudaStream_t st);   // pagg_tc3.cu
+int launch_split_table(cudaStream_t st, const float *T, float scale, void *hi, void *lo, int64_t n);   // pagg_tc3.cu
 int pagg_tc_project_backward(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_params &prm, const float *X,
                              const pn_pagg_params &g, cudaStream_t st);                                                          // pagg_tc.cu
 
@@ -1057,6 +1060,7 @@ int lstm_forward_chunk(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_para
                        const PaggChunk &ck, cudaStream_t st)
 {
     if (c.math_mode == PN_MATH_TC) return pagg_tc_forward_lstm(c, w, prm, ix.seq_node, ix.seq_type, ck, st);
+    if (c.math_mode == PN_MATH_TC3) return pagg_tc3_forward_lstm(c, w, prm, ix.seq_node, ix.seq_type, ck, st);
     uint32_t thr; float scale;
     drop_params(c, thr, scale);
     LstmArgs la{};
@@ -1145,7 +1149,12 @@ extern "C" int pn_pagg_forward(const pn_pagg_cfg *cfg, const pn_pagg_params *prm
         rc = launch_gemm(st, w.Z, H, 1, prm->nets_w, 1, H, w.T, L * H, N, L * H, H, prm->nets_b, homo, false);
         if (rc) return rc;
     }
-    if (!tcm) {   // (the tensor-core mode packs its own fp16 images of the weights into the same regions)
+    if (c.math_mode == PN_MATH_TC3) {   // split-precision LSTM: it gathers the table as two fp16 terms, times the dropout scale
+        uint32_t thr; float tscale;
+        drop_params(c, thr, tscale);
+        rc = launch_split_table(st, w.T, tscale, w.t16, reinterpret_cast<unsigned char *>(w.t16) + 2 * (N * L * H), N * L * H);
+        if (rc) return rc;
+    } else if (!tcm) {   // (the tensor-core modes pack their own fp16 images of the weights into the same regions)
         k_pack_lstm<<<(unsigned)ceil_div(2 * H * 4 * H, 256), 256, 0, st>>>((int)H, c.cell, prm->w_ih, prm->w_hh, prm->b_ih,
                                                                           prm->b_hh, w.Wp, w.WpT, w.bp);
         PN_LAUNCH_CHECK();
@@ -1205,7 +1214,8 @@ extern "C" int pn_pagg_backward(const pn_pagg_cfg *cfg, const pn_pagg_params *pr
     const PaggWs w = carve_workspace(c, (void *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255));
     const int64_t N = c.N, F = c.F, H = c.H, L = c.L, S = c.S, C = c.C;
     const bool homo = c.variant == PN_VARIANT_HOMO;
-    const bool tcm = c.math_mode == PN_MATH_TC;
+    const bool tcm = c.math_mode == PN_MATH_TC;                    // projections on tensor cores
+    const bool tcl = tcm || c.math_mode == PN_MATH_TC3;            // LSTM on tensor cores
     const pn_pagg_params &g = *grads;
 #define ZERO(ptr, n) PN_CUDA(cudaMemsetAsync((ptr), 0, sizeof(float) * (size_t)(n), st))
     if (S == 0) {  // no rows: every gradient is zero
@@ -1259,12 +1269,12 @@ extern "C" int pn_pagg_backward(const pn_pagg_cfg *cfg, const pn_pagg_params *pr
         PoolArgs pa = pool_args(c, w, *prm, ix, ck);
         pa.dcat = w.dcat; pa.dhfin = w.dhfin; pa.dZ = w.dZ; pa.dT = w.dT; pa.dattw = w.dattw;
         pa.absmax_bits = nullptr;
-        if (tcm) {
+        if (tcl) {
             ZERO(w.gscale, 2);
             pa.absmax_bits = reinterpret_cast<unsigned int *>(w.gscale);
         }
         if (fuse_fc2) { pa.C = (int)C; pa.fc2_w = prm->fc2_w; pa.dlogits = dl; pa.dfc2_w = g.fc2_w; pa.dfc2_b = g.fc2_b; }
-        const bool factored = tcm && pool128;   // k_pool_bwd128 -> k_lstm_bwd_tc: dh_final travels as (k, dscore) per path + one vector per row
+        const bool factored = tcl && pool128;   // k_pool_bwd128 -> k_lstm_bwd_tc: dh_final travels as (k, dscore) per path + one vector per row
         if (factored) {
             pa.dhfin = nullptr;
             pa.dh_k = w.att; pa.dh_s = w.score;          // in place: a path's att / score are read before they are overwritten
@@ -1275,7 +1285,7 @@ extern "C" int pn_pagg_backward(const pn_pagg_cfg *cfg, const pn_pagg_params *pr
         else k_pool_bwd<<<(unsigned)ceil_div(Sc, 8), 256, sizeof(float) * (2 * H + 1), st>>>(pa);
         PN_LAUNCH_CHECK();
         // ---- LSTM BPTT ----
-        if (tcm) {
+        if (tcl) {
             rc = pagg_tc_backward_lstm(c, w, *prm, ix.seq_node, ix.seq_type, ck, factored, st, (s0 + rows_per >= S) ? fork.ev_fork : nullptr);
             if (rc) return rc;
         } else {

@@ -38,7 +38,8 @@ struct PaggWs {
     float *x16;      // [N][F16] fp16 copy of X (unless the caller supplied cfg.x16)
     float *z16;      // [N][H]   fp16 copy of Z written by the fc0 epilogue
     float *w16;      // fc0_w [H][F16] then nets_w [L*H][H], fp16
-    float *t16;      // [N][L*H] fp16 copy of T times the dropout scale (what the LSTM kernel gathers)
+    float *t16;      // [N][L*H] fp16 copy of T times the dropout scale (what the LSTM kernel gathers); split-precision mode: two
+                     // such arrays, fp16(T s) then fp16(T s - hi)
     float *dmask;    // [tile][L][4][128] uint32 dropout-mask words of the LSTM input (forward -> backward)
     size_t bytes;
 };
@@ -95,8 +96,8 @@ inline PaggWs carve_workspace(const pn_pagg_cfg &c, void *base)
     take(w.x16, c.math_mode == PN_MATH_TC && !c.x16 ? (N * F16 + 1) / 2 : 0);
     take(w.z16, c.math_mode == PN_MATH_TC ? (N * H + 1) / 2 : 0);
     take(w.w16, c.math_mode == PN_MATH_TC ? (H * F16 + L * H * H + 1) / 2 : 0);
-    take(w.t16, c.math_mode == PN_MATH_TC ? (N * L * H + 1) / 2 : 0);
-    take(w.dmask, c.math_mode == PN_MATH_TC ? L * P128 * 4 : 0);
+    take(w.t16, c.math_mode == PN_MATH_TC ? (N * L * H + 1) / 2 : c.math_mode == PN_MATH_TC3 ? N * L * H : 0);   // TC3: hi then lo term
+    take(w.dmask, c.math_mode == PN_MATH_TC || c.math_mode == PN_MATH_TC3 ? L * P128 * 4 : 0);
     w.bytes = off;
     return w;
 }

@@ -21,6 +21,7 @@
 #include <cstdlib>
 
 #include "tc_util.cuh"
+#include "pagg_tc.cuh"
 
 namespace pn {
 using namespace tc;
@@ -224,6 +225,7 @@ int launch_gemm_tc(cudaStream_t st, const float *A, int64_t lda, const float *B,
 }
 
 int launch_f32_to_f16_rows(cudaStream_t st, const float *src, int64_t rows, int64_t K, int64_t ld_src, __half *dst, int64_t K16);   // gemm_tma.cu
+int launch_pack_lstm_tc3_bwd(cudaStream_t st, const float *w_ih, const float *w_hh, unsigned char *WhT);   // pagg_tc3.cu
 int launch_gemm_tma(cudaStream_t st, const __half *A16, const __half *B16, int64_t M, int64_t N, int64_t K16, const float *bias,
                     bool relu, float *C, int64_t ldc, __half *C16, int64_t ldc16, float c16_scale);                                  // gemm_tma.cu
 static bool tc_legacy_gemm()
@@ -237,8 +239,6 @@ static bool tc_legacy_gemm()
 // chunk ([512 cols][16 k], 16 KB) is one contiguous bulk copy.
 //   column = unit*4 + gate (i,f,g,o), k < H: W_ih, k >= H: W_hh      (H = 128)
 // ---------------------------------------------------------------------------
-constexpr int TC_H = 128, TC_G4 = 512, TC_K2 = 256, TC_KC = 16, TC_NCHUNK = TC_K2 / TC_KC;
-constexpr int TC_CHUNK_BYTES = TC_G4 * TC_KC * 2;  // 16 KB
 
 __global__ void k_pack_lstm_tc(const float *__restrict__ w_ih, const float *__restrict__ w_hh,
                                const float *__restrict__ b_ih, const float *__restrict__ b_hh,
@@ -260,57 +260,6 @@ __global__ void k_pack_lstm_tc(const float *__restrict__ w_ih, const float *__re
     }
 }
 
-struct LstmTcArgs {
-    const __half *T16;        // [N,L,H] fp16 table, pre-multiplied by the dropout scale (null: gather the fp32 table below)
-    const float *T;           // [N,L,H] fp32 table
-    const int32_t *seq_node;  // [P,L]
-    const uint8_t *seq_type;  // [P,L]
-    const unsigned char *Wh;  // packed fp16 weights (16 chunks x 16 KB)
-    const float *bp;          // [512]
-    __half *acts;             // tile images: block (tile, t) = [5 (i,f,g,o,c)][16 unit8][128 rows][8] fp16
-    float *hfin;              // [P,H]
-    int64_t P;
-    int L;
-    uint32_t drop_thr; float drop_scale; uint64_t drop_seed;
-    const uint64_t *seed_dev; // optional device word added to drop_seed (CUDA-graph replay)
-    int64_t p_base;           // global index of this call's first sequence (row-chunked calls)
-    unsigned char *xh_img;    // wgrad operand images [x_t | h_{t-1}] (see LstmBwdTcArgs), written here
-    uint32_t *dmask;          // [tile][t][cq][128 rows]: bit u of a word = "x_t[32 cq + u] was kept" — the backward's dx scatter
-                              // reads 4 bytes instead of recomputing 16 hashes (null: no dropout, or nothing saved)
-    int save;                 // 0: inference only, skip activations and operand images
-    long long *trace;         // optional clock64() trace of CTA `trace_block` (debug)
-    int trace_block;
-};
-
-constexpr int ACT_BLOCK_HALFS = 5 * 16 * 128 * 8;  // 160 KB per (tile, step)
-constexpr int DA_BLOCK_BYTES = 64 * 128 * 16, XH_BLOCK_BYTES = 32 * 128 * 16;  // wgrad operand images per (tile, step)
-constexpr int TC_NSTAGE = 7;                        // 112 KB weight ring (largest that fits beside the operand tiles)
-constexpr int TC_XBYTES = 128 * TC_H * 2;           // 32 KB: one [128][128] fp16 operand half (x_t or h_{t-1})
-constexpr int TC_SMEM = 3 * TC_XBYTES + TC_NSTAGE * TC_CHUNK_BYTES + 2048 /*bias*/ + 128 * 8 * 4 /*row offsets*/ + 1024 /*align*/;
-constexpr int TC_MAX_L = 8;
-
-__device__ __forceinline__ float tanh_fast(float x)
-{
-    float y;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
-
-constexpr int TC_CWARPS = 16;                    // compute warps: 4 TMEM lane quarters x 4 column quarters
-constexpr int TC_THREADS = (TC_CWARPS + 2) * 32;  // forward: + MMA warp + weight-producer warp
-// backward: + a whole service warpgroup (MMA warp, W' producer, two idle warps) so that setmaxnreg -- which works on warpgroups
-// of 4 consecutive warps, inside the register pool the CTA was given at launch -- can move registers: 20 warps = 5 per SM
-// sub-partition -> 96 per thread at launch; the service warpgroup shrinks to 32 and the 16 compute warps grow to 112.
-constexpr int TCB_THREADS = (TC_CWARPS + 4) * 32;
-__device__ __forceinline__ bool elect_one()   // true in exactly one lane of a converged warp
-{
-    uint32_t pred;
-    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-    return pred != 0;
-}
-template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
-template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
 // this thread's quarter (32 values) of table row `row_off` -> dropout -> fp16 -> x tile (canonical, K extent 128).
 // With the fp16 table (written by the projection GEMM's epilogue, already times 1/(1-p)) the row is 4 x 16 bytes and
@@ -693,7 +642,11 @@ __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefe
 // PF = true (default): activations are fetched one half-iteration (4 units, six 8-byte loads) ahead of the gate-gradient
 // math; PF = false (PN_BWD_PF=0): the round-1 loop (8 units per iteration, loads consumed where issued).  Same-box A/B,
 // pubmed step (profiles/r02/bench_tc_bwd_pf{0,1}_run5.json): 1.072 vs 1.111 ms per launch.
-template <bool PF>
+// SPLITW = true (split-precision mode, pagg_tc3.cu): W' is streamed as two fp16 terms per chunk (a.WhT holds 32 chunks, hi / lo
+// interleaved) and every K-chunk of da meets both, da W' ~= da W'_hi + da W'_lo -- the fixed rounding of the weights, the one
+// error of this GEMM that does not average out over sequences, is gone; tanh(c_t) is evaluated with ex2 / rcp instead of
+// tanh.approx.  The da operand stays one fp16 term (its rounding is unbiased and independent per element).
+template <bool PF, bool SPLITW>
 __global__ void __launch_bounds__(TCB_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
 {
     extern __shared__ unsigned char smem_dyn[];
@@ -740,10 +693,13 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
             for (int s = 0; s < L; s++)
                 for (int j = 0; j < TCB_NCHUNK; j++) {
                     const int c = 4 * (j & 3) + (j >> 2);   // quarter-major order, the order the MMA warp consumes them in
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&full_bar[stage], TCB_CHUNK_BYTES);
-                    bulk_g2s(Ws + stage * TCB_CHUNK_BYTES, a.WhT + (size_t)c * TCB_CHUNK_BYTES, TCB_CHUNK_BYTES, &full_bar[stage]);
-                    if (++stage == TCB_NSTAGE) { stage = 0; phase ^= 1; }
+#pragma unroll
+                    for (int part = 0; part < (SPLITW ? 2 : 1); part++) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        mbar_arrive_expect_tx(&full_bar[stage], TCB_CHUNK_BYTES);
+                        bulk_g2s(Ws + stage * TCB_CHUNK_BYTES, a.WhT + (size_t)(SPLITW ? 2 * c + part : c) * TCB_CHUNK_BYTES, TCB_CHUNK_BYTES, &full_bar[stage]);
+                        if (++stage == TCB_NSTAGE) { stage = 0; phase ^= 1; }
+                    }
                 }
         }
     } else if (warp == TC_CWARPS) {
@@ -757,26 +713,29 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
             for (int j = 0; j < TCB_NCHUNK; j++) {
                 const int c = 4 * (j & 3) + (j >> 2);
                 if ((j & 3) == 0) { mbar_wait(&a_ready[j >> 2], s & 1); tc_fence_after(); }
-                mbar_wait(&full_bar[stage], phase);
-                tc_fence_after();
-                const uint32_t wbase = smem_u32(Ws + stage * TCB_CHUNK_BYTES);
-                if (elect_one()) {
 #pragma unroll
-                    for (int ks = 0; ks < TCB_KC / 16; ks++) {
-                        const uint64_t ad = make_smem_desc(smem_u32(As) + (uint32_t)(c * (TCB_KC / 8) + ks * 2) * 128, 128, (TC_G4 / 8) * 128);
-                        // rows 0..127 of W' give dx, rows 128..255 (16 row groups further) give dh_{t-1} (unused at t = 0)
-                        const uint64_t bd_x = make_smem_desc(wbase + (uint32_t)ks * 256, 128, (TCB_KC / 8) * 128);
-                        mma_f16(taddr, ad, bd_x, idesc, (j > 0) || (ks > 0));
-                        if (t > 0) {
-                            const uint64_t bd_h = make_smem_desc(wbase + 16u * ((TCB_KC / 8) * 128) + (uint32_t)ks * 256, 128, (TCB_KC / 8) * 128);
-                            mma_f16(taddr + dh_col, ad, bd_h, idesc, (j > 0) || (ks > 0));
+                for (int part = 0; part < (SPLITW ? 2 : 1); part++) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t wbase = smem_u32(Ws + stage * TCB_CHUNK_BYTES);
+                    if (elect_one()) {
+#pragma unroll
+                        for (int ks = 0; ks < TCB_KC / 16; ks++) {
+                            const uint64_t ad = make_smem_desc(smem_u32(As) + (uint32_t)(c * (TCB_KC / 8) + ks * 2) * 128, 128, (TC_G4 / 8) * 128);
+                            // rows 0..127 of W' give dx, rows 128..255 (16 row groups further) give dh_{t-1} (unused at t = 0)
+                            const uint64_t bd_x = make_smem_desc(wbase + (uint32_t)ks * 256, 128, (TCB_KC / 8) * 128);
+                            mma_f16(taddr, ad, bd_x, idesc, (j > 0) || (ks > 0) || (part > 0));
+                            if (t > 0) {
+                                const uint64_t bd_h = make_smem_desc(wbase + 16u * ((TCB_KC / 8) * 128) + (uint32_t)ks * 256, 128, (TCB_KC / 8) * 128);
+                                mma_f16(taddr + dh_col, ad, bd_h, idesc, (j > 0) || (ks > 0) || (part > 0));
+                            }
                         }
+                        mma_commit(&empty_bar[stage]);
+                        if (j == TCB_NCHUNK - 1 && part == (SPLITW ? 1 : 0)) mma_commit(&acc_full);
                     }
-                    mma_commit(&empty_bar[stage]);
-                    if (j == TCB_NCHUNK - 1) mma_commit(&acc_full);
+                    __syncwarp();
+                    if (++stage == TCB_NSTAGE) { stage = 0; phase ^= 1; }
                 }
-                __syncwarp();
-                if (++stage == TCB_NSTAGE) { stage = 0; phase ^= 1; }
             }
         }
     }
@@ -935,7 +894,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
                 uint32_t dcn_bits[4];
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    const float tcn = tanh_fast(cn[j]);
+                    const float tcn = SPLITW ? tanh_acc(cn[j]) : tanh_fast(cn[j]);
                     const float dcn = fmaf(dh[j] * go[j], 1.f - tcn * tcn, dc[j]);
                     const float d_i = dcn * gg[j] * gi[j] * (1.f - gi[j]);
                     const float d_f = dcn * cp[j] * gf[j] * (1.f - gf[j]);
@@ -1035,7 +994,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
                 uint32_t dcn_bits[8];
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
-                    const float tcn = tanh_fast(cn[j]);
+                    const float tcn = SPLITW ? tanh_acc(cn[j]) : tanh_fast(cn[j]);
                     const float dcn = fmaf(dh[j] * go[j], 1.f - tcn * tcn, dc[j]);
                     const float d_i = dcn * gg[j] * gi[j] * (1.f - gi[j]);
                     const float d_f = dcn * cp[j] * gf[j] * (1.f - gf[j]);
@@ -1205,7 +1164,7 @@ int pagg_tc_backward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_p
                           cudaEvent_t after_bptt)
 {
     if (c.H != TC_H) {
-        set_error("PN_MATH_TC: the tensor-core LSTM is built for hidden size 128 (got %d)", c.H);
+        set_error("PN_MATH_TC / TC3: the tensor-core LSTM is built for hidden size 128 (got %d)", c.H);
         return PN_ERR_UNSUPPORTED;
     }
     const int64_t P = ck.Sc * c.nw, ntiles = ceil_div(P, 128), nblocks = ntiles * c.L;
@@ -1213,9 +1172,13 @@ int pagg_tc_backward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_p
     k_make_scale<<<1, 1, 0, st>>>(w.gscale);
     PN_LAUNCH_CHECK();
     unsigned char *WhT = reinterpret_cast<unsigned char *>(w.WpT);  // 256 KB of the 512 KB fp32 region
+    const bool split = c.math_mode == PN_MATH_TC3;   // split-precision mode: two fp16 terms of W' (all 512 KB of the region)
     if (ck.first) {
-        k_pack_lstm_tc_bwd<<<(unsigned)ceil_div(TC_G4 * TC_K2, 256), 256, 0, st>>>(prm.w_ih, prm.w_hh, WhT);
-        PN_LAUNCH_CHECK();
+        if (split) { const int rc = launch_pack_lstm_tc3_bwd(st, prm.w_ih, prm.w_hh, WhT); if (rc) return rc; }
+        else {
+            k_pack_lstm_tc_bwd<<<(unsigned)ceil_div(TC_G4 * TC_K2, 256), 256, 0, st>>>(prm.w_ih, prm.w_hh, WhT);
+            PN_LAUNCH_CHECK();
+        }
     }
     uint32_t thr = 0; float scale = 1.f;
     if (c.training && c.dropout_p > 0.f) {
@@ -1225,7 +1188,7 @@ int pagg_tc_backward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_p
     unsigned char *da_img = reinterpret_cast<unsigned char *>(w.dA), *xh_img = reinterpret_cast<unsigned char *>(w.XH);
     LstmBwdTcArgs a{w.T, seq_node, seq_type, WhT, reinterpret_cast<const __half *>(w.acts), factored_dh ? nullptr : w.dhfin,
                     w.att, w.score, w.dcat + c.H, prm.attw_w, 2 * (int64_t)c.H, c.nw, w.gscale, w.dT,
-                    da_img, xh_img, tc_legacy_gemm() ? nullptr : reinterpret_cast<const uint32_t *>(w.dmask), P, ntiles, c.L, thr, scale,
+                    da_img, xh_img, (tc_legacy_gemm() && !split) ? nullptr : reinterpret_cast<const uint32_t *>(w.dmask), P, ntiles, c.L, thr, scale,
                     c.dropout_seed, c.dropout_seed_dev, ck.s0 * c.nw, nullptr, 0};
     long long *d_trace = nullptr;
     const char *trace_env = getenv("PN_TRACE_BWD");
@@ -1237,12 +1200,15 @@ int pagg_tc_backward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_p
     }
     const int bwd_smem = TCB_SMEM_FIXED + 128 * c.L * (int)sizeof(int32_t);
     static const bool bwd_pf = [] { const char *e = getenv("PN_BWD_PF"); return !(e && e[0] == '0'); }();
-    PN_CUDA(cudaFuncSetAttribute(k_lstm_bwd_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCB_SMEM_FIXED + 128 * TC_MAX_L * (int)sizeof(int32_t)));
-    PN_CUDA(cudaFuncSetAttribute(k_lstm_bwd_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCB_SMEM_FIXED + 128 * TC_MAX_L * (int)sizeof(int32_t)));
+    constexpr int bwd_smem_max = TCB_SMEM_FIXED + 128 * TC_MAX_L * (int)sizeof(int32_t);
+    PN_CUDA(cudaFuncSetAttribute(k_lstm_bwd_tc<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem_max));
+    PN_CUDA(cudaFuncSetAttribute(k_lstm_bwd_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem_max));
+    PN_CUDA(cudaFuncSetAttribute(k_lstm_bwd_tc<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem_max));
     {
         ProfScope prof("lstm_bwd", st);
-        if (bwd_pf) k_lstm_bwd_tc<true><<<(unsigned)ntiles, TCB_THREADS, bwd_smem, st>>>(a);
-        else k_lstm_bwd_tc<false><<<(unsigned)ntiles, TCB_THREADS, bwd_smem, st>>>(a);
+        if (split) k_lstm_bwd_tc<true, true><<<(unsigned)ntiles, TCB_THREADS, bwd_smem, st>>>(a);
+        else if (bwd_pf) k_lstm_bwd_tc<true, false><<<(unsigned)ntiles, TCB_THREADS, bwd_smem, st>>>(a);
+        else k_lstm_bwd_tc<false, false><<<(unsigned)ntiles, TCB_THREADS, bwd_smem, st>>>(a);
     }
     PN_LAUNCH_CHECK();
     if (d_trace) {  // debug only

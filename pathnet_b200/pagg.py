@@ -27,7 +27,7 @@ import torch.nn as nn
 from ._lib import PARAM_NAMES, PaggCfg, PaggParams, check, lib
 
 VARIANT = {"hetero": 0, "homo": 1, "plain": 2}
-MATH = {"fp32": 0, "tc": 1}
+MATH = {"fp32": 0, "tc": 1, "tc3": 2}
 CELL = {"lstm": 0, "rnn": 1, "gru": 2}
 POOL = {"attention": 0, "mean": 1, "sum": 2, "max": 3}
 IDX_DTYPE = {torch.int64: 0, torch.int32: 1, torch.uint8: 2}
@@ -38,7 +38,10 @@ def resolve_math_mode(mode: str, H: int, L: int) -> str:
     """"fp32": strict-parity mode (1e-4 against the reference's CPU fp32 math), any hidden size up to 128.
     "tc": tcgen05 tensor cores — fp16 operands (11-bit significand, the width of TF32, which is what the reference
     itself runs on under cuDNN/cuBLAS on a current GPU), fp32 accumulation; needs hidden 128 and path_len <= 8 and
-    raises otherwise.  "auto" (the modules' default, overridable with env PN_MATH_MODE): "tc" where it exists, else
+    raises otherwise.  "tc3": the same tensor-core LSTM at fp32-grade accuracy — every operand travels as two fp16 terms
+    (hi + lo) and every product is three tensor-core passes into one fp32 accumulator, gates on ex2 / rcp, projections on
+    the fp32 kernels: held to the SAME parity bar as "fp32" at roughly a tenth of its step time (hidden 128, path_len <= 8).
+    "auto" (the modules' default, overridable with env PN_MATH_MODE): "tc" where it exists, else
     "fp32"; the first time it resolves to "tc" a one-line notice names the tolerance class."""
     global _warned_auto_tc
     if mode == "auto":
@@ -53,7 +56,7 @@ def resolve_math_mode(mode: str, H: int, L: int) -> str:
             return "tc"
         return "fp32"
     if mode not in MATH:
-        raise ValueError(f"math_mode must be 'auto', 'fp32' or 'tc' (got {mode!r})")
+        raise ValueError(f"math_mode must be 'auto', 'fp32', 'tc' or 'tc3' (got {mode!r})")
     return mode
 
 

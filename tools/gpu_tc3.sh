@@ -1,0 +1,10 @@
+#!/bin/bash
+# split-precision mode: its parity tests (verbose: the observed errors are printed), then a short bench in that mode
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+echo "== tc3 tests"; timeout 600 python -m pytest tests/test_gpu_tc3.py -q -s --timeout 240 > gpurun_out/pytest_tc3.log 2>&1; rc=$?; echo "rc=$rc"
+grep -E "^\[tc3|passed|failed|Error|error|tc3 vs" gpurun_out/pytest_tc3.log | head -60
+if [ $rc -eq 124 ]; then echo "tests hung -- stopping"; exit 1; fi
+echo "== bench tc3"; timeout 300 python bench.py --math tc3 --steps 10 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/bench_tc3.json 2> gpurun_out/bench_tc3.err; echo "rc=$?"
+python -c "
+import json; d=json.load(open('gpurun_out/bench_tc3.json')); print('tc3 ms/step', d['ms_per_step'], 'e2e', d['e2e']['ms_per_step'])"; tail -3 gpurun_out/bench_tc3.err
