@@ -226,6 +226,7 @@ int launch_gemm_tc(cudaStream_t st, const float *A, int64_t lda, const float *B,
 
 int launch_f32_to_f16_rows(cudaStream_t st, const float *src, int64_t rows, int64_t K, int64_t ld_src, __half *dst, int64_t K16);   // gemm_tma.cu
 int launch_pack_lstm_tc3_bwd(cudaStream_t st, const float *w_ih, const float *w_hh, unsigned char *WhT);   // pagg_tc3.cu
+int launch_lstm_bwd_tc3(const LstmBwdTcArgs &a, int64_t ntiles, int smem, int smem_max, cudaStream_t st);    // pagg_tc3.cu
 int launch_gemm_tma(cudaStream_t st, const __half *A16, const __half *B16, int64_t M, int64_t N, int64_t K16, const float *bias,
                     bool relu, float *C, int64_t ldc, __half *C16, int64_t ldc16, float c16_scale);                                  // gemm_tma.cu
 static bool tc_legacy_gemm()
@@ -590,9 +591,6 @@ __global__ void k_make_scale(float *gscale)
     gscale[1] = 1.f / sc;
 }
 
-// W' = [W_ih | W_hh] as B operand of the dgrad GEMM: [256 rows = input index k][K = 512 gate columns],
-// fp16 canonical, cut into 16 chunks of 32 columns (16 KB each).
-constexpr int TCB_KC = 32, TCB_NCHUNK = TC_G4 / TCB_KC, TCB_CHUNK_BYTES = TC_K2 * TCB_KC * 2;
 __global__ void k_pack_lstm_tc_bwd(const float *__restrict__ w_ih, const float *__restrict__ w_hh, unsigned char *__restrict__ WhT)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -603,35 +601,6 @@ __global__ void k_pack_lstm_tc_bwd(const float *__restrict__ w_ih, const float *
     *reinterpret_cast<__half *>(WhT + (size_t)chunk * TCB_CHUNK_BYTES + canon_off(k, kk, TCB_KC)) = __float2half_rn(v);
 }
 
-struct LstmBwdTcArgs {
-    const float *T;
-    const int32_t *seq_node;
-    const uint8_t *seq_type;
-    const unsigned char *WhT;  // 16 chunks x 16 KB
-    const __half *acts;        // tile images (see LstmTcArgs)
-    const float *dhfin;        // [P,H], or null: dh_final[p] = dh_k[p] * gdrop[p / nw] + dh_s[p] * attw_h (see PoolArgs)
-    const float *dh_k, *dh_s, *gdrop, *attw_h;
-    int64_t gdrop_ld;
-    int nw;
-    const float *gscale;       // {scale, 1/scale}
-    float *dT;                 // [N,L,H]
-    unsigned char *da_img;     // block b = t*ntiles + tile: [64 col8][128 r][8] fp16   (128 KB)
-    const unsigned char *xh_img;  // block b: [32 k8][128 r][8] fp16 (64 KB): k8 < 16 x_t, k8 >= 16 h_{t-1}; written by the FORWARD kernel
-    const uint32_t *dmask;        // the forward's dropout-mask words (see LstmTcArgs), or null: recompute the hashes
-    int64_t P, ntiles;
-    int L;
-    uint32_t drop_thr; float drop_scale; uint64_t drop_seed;
-    const uint64_t *seed_dev;
-    int64_t p_base;
-    long long *trace;
-    int trace_block;
-};
-constexpr int TCB_NSTAGE = 4;   // 64 KB of W' in flight beside the 128 KB operand tile: the deepest ring that stays inside the 196 KB
-                                // shared-memory carve-out (6 stages -> 228 KB carve-out, the smaller L1 costs more than the depth wins)
-constexpr int TCB_A_BYTES = 128 * TC_G4 * 2;  // 128 KB: da tile [128][512] fp16 canonical
-constexpr int TCB_SMEM_FIXED = TCB_A_BYTES + TCB_NSTAGE * TCB_CHUNK_BYTES + 128 /*align*/;   // + 128 * L * 4 bytes of row offsets
-
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // (Measured and dropped: pairing neighbouring tiles in a cluster that multicasts the W' stream halves its L2 traffic but
 // couples the two CTAs chunk by chunk -- 5 % slower.
@@ -642,11 +611,7 @@ __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefe
 // PF = true (default): activations are fetched one half-iteration (4 units, six 8-byte loads) ahead of the gate-gradient
 // math; PF = false (PN_BWD_PF=0): the round-1 loop (8 units per iteration, loads consumed where issued).  Same-box A/B,
 // pubmed step (profiles/r02/bench_tc_bwd_pf{0,1}_run5.json): 1.072 vs 1.111 ms per launch.
-// SPLITW = true (split-precision mode, pagg_tc3.cu): W' is streamed as two fp16 terms per chunk (a.WhT holds 32 chunks, hi / lo
-// interleaved) and every K-chunk of da meets both, da W' ~= da W'_hi + da W'_lo -- the fixed rounding of the weights, the one
-// error of this GEMM that does not average out over sequences, is gone; tanh(c_t) is evaluated with ex2 / rcp instead of
-// tanh.approx.  The da operand stays one fp16 term (its rounding is unbiased and independent per element).
-template <bool PF, bool SPLITW>
+template <bool PF>
 __global__ void __launch_bounds__(TCB_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
 {
     extern __shared__ unsigned char smem_dyn[];
@@ -693,13 +658,10 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
             for (int s = 0; s < L; s++)
                 for (int j = 0; j < TCB_NCHUNK; j++) {
                     const int c = 4 * (j & 3) + (j >> 2);   // quarter-major order, the order the MMA warp consumes them in
-#pragma unroll
-                    for (int part = 0; part < (SPLITW ? 2 : 1); part++) {
-                        mbar_wait(&empty_bar[stage], phase ^ 1);
-                        mbar_arrive_expect_tx(&full_bar[stage], TCB_CHUNK_BYTES);
-                        bulk_g2s(Ws + stage * TCB_CHUNK_BYTES, a.WhT + (size_t)(SPLITW ? 2 * c + part : c) * TCB_CHUNK_BYTES, TCB_CHUNK_BYTES, &full_bar[stage]);
-                        if (++stage == TCB_NSTAGE) { stage = 0; phase ^= 1; }
-                    }
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[stage], TCB_CHUNK_BYTES);
+                    bulk_g2s(Ws + stage * TCB_CHUNK_BYTES, a.WhT + (size_t)c * TCB_CHUNK_BYTES, TCB_CHUNK_BYTES, &full_bar[stage]);
+                    if (++stage == TCB_NSTAGE) { stage = 0; phase ^= 1; }
                 }
         }
     } else if (warp == TC_CWARPS) {
@@ -713,29 +675,26 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
             for (int j = 0; j < TCB_NCHUNK; j++) {
                 const int c = 4 * (j & 3) + (j >> 2);
                 if ((j & 3) == 0) { mbar_wait(&a_ready[j >> 2], s & 1); tc_fence_after(); }
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                const uint32_t wbase = smem_u32(Ws + stage * TCB_CHUNK_BYTES);
+                if (elect_one()) {
 #pragma unroll
-                for (int part = 0; part < (SPLITW ? 2 : 1); part++) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    const uint32_t wbase = smem_u32(Ws + stage * TCB_CHUNK_BYTES);
-                    if (elect_one()) {
-#pragma unroll
-                        for (int ks = 0; ks < TCB_KC / 16; ks++) {
-                            const uint64_t ad = make_smem_desc(smem_u32(As) + (uint32_t)(c * (TCB_KC / 8) + ks * 2) * 128, 128, (TC_G4 / 8) * 128);
-                            // rows 0..127 of W' give dx, rows 128..255 (16 row groups further) give dh_{t-1} (unused at t = 0)
-                            const uint64_t bd_x = make_smem_desc(wbase + (uint32_t)ks * 256, 128, (TCB_KC / 8) * 128);
-                            mma_f16(taddr, ad, bd_x, idesc, (j > 0) || (ks > 0) || (part > 0));
-                            if (t > 0) {
-                                const uint64_t bd_h = make_smem_desc(wbase + 16u * ((TCB_KC / 8) * 128) + (uint32_t)ks * 256, 128, (TCB_KC / 8) * 128);
-                                mma_f16(taddr + dh_col, ad, bd_h, idesc, (j > 0) || (ks > 0) || (part > 0));
-                            }
+                    for (int ks = 0; ks < TCB_KC / 16; ks++) {
+                        const uint64_t ad = make_smem_desc(smem_u32(As) + (uint32_t)(c * (TCB_KC / 8) + ks * 2) * 128, 128, (TC_G4 / 8) * 128);
+                        // rows 0..127 of W' give dx, rows 128..255 (16 row groups further) give dh_{t-1} (unused at t = 0)
+                        const uint64_t bd_x = make_smem_desc(wbase + (uint32_t)ks * 256, 128, (TCB_KC / 8) * 128);
+                        mma_f16(taddr, ad, bd_x, idesc, (j > 0) || (ks > 0));
+                        if (t > 0) {
+                            const uint64_t bd_h = make_smem_desc(wbase + 16u * ((TCB_KC / 8) * 128) + (uint32_t)ks * 256, 128, (TCB_KC / 8) * 128);
+                            mma_f16(taddr + dh_col, ad, bd_h, idesc, (j > 0) || (ks > 0));
                         }
-                        mma_commit(&empty_bar[stage]);
-                        if (j == TCB_NCHUNK - 1 && part == (SPLITW ? 1 : 0)) mma_commit(&acc_full);
                     }
-                    __syncwarp();
-                    if (++stage == TCB_NSTAGE) { stage = 0; phase ^= 1; }
+                    mma_commit(&empty_bar[stage]);
+                    if (j == TCB_NCHUNK - 1) mma_commit(&acc_full);
                 }
+                __syncwarp();
+                if (++stage == TCB_NSTAGE) { stage = 0; phase ^= 1; }
             }
         }
     }
@@ -894,7 +853,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
                 uint32_t dcn_bits[4];
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    const float tcn = SPLITW ? tanh_acc(cn[j]) : tanh_fast(cn[j]);
+                    const float tcn = tanh_fast(cn[j]);
                     const float dcn = fmaf(dh[j] * go[j], 1.f - tcn * tcn, dc[j]);
                     const float d_i = dcn * gg[j] * gi[j] * (1.f - gi[j]);
                     const float d_f = dcn * cp[j] * gf[j] * (1.f - gf[j]);
@@ -994,7 +953,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
                 uint32_t dcn_bits[8];
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
-                    const float tcn = SPLITW ? tanh_acc(cn[j]) : tanh_fast(cn[j]);
+                    const float tcn = tanh_fast(cn[j]);
                     const float dcn = fmaf(dh[j] * go[j], 1.f - tcn * tcn, dc[j]);
                     const float d_i = dcn * gg[j] * gi[j] * (1.f - gi[j]);
                     const float d_f = dcn * cp[j] * gf[j] * (1.f - gf[j]);
@@ -1046,6 +1005,7 @@ struct WgradTcArgs {
     const float *gscale;
     float *dWp;  // [256][512] fp32, atomically accumulated
     float *dbp;  // [512]      fp32, atomically accumulated (bias gradient = column sums of da)
+    int do_bias; // 0: skip the bias rows (split-precision mode: the pass that pairs the lo term of [x|h] with da again)
 };
 constexpr int WG_STAGE_BYTES = 32768 + 65536;
 constexpr int WG_ONES_BYTES = 32768;   // constant A operand [128 (m)][128 (r)] with row m = 0 all ones
@@ -1114,8 +1074,9 @@ __global__ void __launch_bounds__(192, 1) k_wgrad_tc(WgradTcArgs a)
                     const uint64_t bd = make_smem_desc(bbase + ks * 256, 128, 2048);
                     mma_f16(taddr, ad, bd, idesc, !first_blk || ks > 0);
                     // bias: ones . dA over this CTA's share of the columns (mt picks which 128 of the 256)
-                    mma_f16(taddr + 256, make_smem_desc(obase + ks * 256, 128, 2048),
-                            make_smem_desc(bbase + mt * 32768 + ks * 256, 128, 2048), idesc_b, !first_blk || ks > 0);
+                    if (a.do_bias)
+                        mma_f16(taddr + 256, make_smem_desc(obase + ks * 256, 128, 2048),
+                                make_smem_desc(bbase + mt * 32768 + ks * 256, 128, 2048), idesc_b, !first_blk || ks > 0);
                 }
                 first_blk = false;
                 mma_commit_mc(&empty_bar[stage], peers);
@@ -1139,7 +1100,7 @@ __global__ void __launch_bounds__(192, 1) k_wgrad_tc(WgradTcArgs a)
                               make_float4(__uint_as_float(v[j]) * inv_scale, __uint_as_float(v[j + 1]) * inv_scale,
                                           __uint_as_float(v[j + 2]) * inv_scale, __uint_as_float(v[j + 3]) * inv_scale));
             }
-            if (warp == 0) {   // TMEM lane 0 of the second accumulator = sum over rows of da[:, col]
+            if (warp == 0 && a.do_bias) {   // TMEM lane 0 of the second accumulator = sum over rows of da[:, col]
                 for (int c0 = 0; c0 < 128; c0 += 32) {
                     uint32_t v[32];
                     tmem_ld32(taddr + 256 + (uint32_t)c0, v);
@@ -1189,7 +1150,8 @@ int pagg_tc_backward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_p
     LstmBwdTcArgs a{w.T, seq_node, seq_type, WhT, reinterpret_cast<const __half *>(w.acts), factored_dh ? nullptr : w.dhfin,
                     w.att, w.score, w.dcat + c.H, prm.attw_w, 2 * (int64_t)c.H, c.nw, w.gscale, w.dT,
                     da_img, xh_img, (tc_legacy_gemm() && !split) ? nullptr : reinterpret_cast<const uint32_t *>(w.dmask), P, ntiles, c.L, thr, scale,
-                    c.dropout_seed, c.dropout_seed_dev, ck.s0 * c.nw, nullptr, 0};
+                    c.dropout_seed, c.dropout_seed_dev, ck.s0 * c.nw, nullptr, 0,
+                    w.acts, da_img + nblocks * DA_BLOCK_BYTES};   // split-precision mode: fp32 activations, second term of the da images
     long long *d_trace = nullptr;
     const char *trace_env = getenv("PN_TRACE_BWD");
     if (trace_env) {
@@ -1201,14 +1163,13 @@ int pagg_tc_backward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_p
     const int bwd_smem = TCB_SMEM_FIXED + 128 * c.L * (int)sizeof(int32_t);
     static const bool bwd_pf = [] { const char *e = getenv("PN_BWD_PF"); return !(e && e[0] == '0'); }();
     constexpr int bwd_smem_max = TCB_SMEM_FIXED + 128 * TC_MAX_L * (int)sizeof(int32_t);
-    PN_CUDA(cudaFuncSetAttribute(k_lstm_bwd_tc<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem_max));
-    PN_CUDA(cudaFuncSetAttribute(k_lstm_bwd_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem_max));
-    PN_CUDA(cudaFuncSetAttribute(k_lstm_bwd_tc<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem_max));
+    PN_CUDA(cudaFuncSetAttribute(k_lstm_bwd_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem_max));
+    PN_CUDA(cudaFuncSetAttribute(k_lstm_bwd_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem_max));
     {
         ProfScope prof("lstm_bwd", st);
-        if (split) k_lstm_bwd_tc<true, true><<<(unsigned)ntiles, TCB_THREADS, bwd_smem, st>>>(a);
-        else if (bwd_pf) k_lstm_bwd_tc<true, false><<<(unsigned)ntiles, TCB_THREADS, bwd_smem, st>>>(a);
-        else k_lstm_bwd_tc<false, false><<<(unsigned)ntiles, TCB_THREADS, bwd_smem, st>>>(a);
+        if (split) { const int rc = launch_lstm_bwd_tc3(a, ntiles, bwd_smem, bwd_smem_max, st); if (rc) return rc; }
+        else if (bwd_pf) k_lstm_bwd_tc<true><<<(unsigned)ntiles, TCB_THREADS, bwd_smem, st>>>(a);
+        else k_lstm_bwd_tc<false><<<(unsigned)ntiles, TCB_THREADS, bwd_smem, st>>>(a);
     }
     PN_LAUNCH_CHECK();
     if (d_trace) {  // debug only
@@ -1223,7 +1184,7 @@ int pagg_tc_backward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_p
     }
     if (after_bptt) PN_CUDA(cudaEventRecord(after_bptt, st));   // dT is complete: the caller forks the projections' backward here
     // dWp / dbp are zeroed once per call by pn_pagg_backward: every chunk adds into them
-    WgradTcArgs wa{xh_img, da_img, nblocks, w.gscale, w.dWp, w.dbp};
+    WgradTcArgs wa{xh_img, da_img, nblocks, w.gscale, w.dWp, w.dbp, 1};
     PN_CUDA(cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
     {
         ProfScope prof("wgrad", st);
@@ -1251,6 +1212,14 @@ int pagg_tc_backward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_p
         const unsigned nsplit = (unsigned)std::max<int64_t>(1, std::min<int64_t>(cap, nblocks));
         lc.gridDim = dim3(nsplit, 4);
         PN_CUDA(cudaLaunchKernelEx(&lc, k_wgrad_tc, wa));
+        if (split) {
+            // split-precision mode: dW = [x|h]_hi^T da_hi (above) + [x|h]_lo^T da_hi + [x|h]_hi^T da_lo, all accumulated into dWp; the
+            // bias gradient is the column sums of da_hi (above) + da_lo
+            WgradTcArgs w2{xh_img + nblocks * XH_BLOCK_BYTES, da_img, nblocks, w.gscale, w.dWp, w.dbp, 0};
+            PN_CUDA(cudaLaunchKernelEx(&lc, k_wgrad_tc, w2));
+            WgradTcArgs w3{xh_img, da_img + nblocks * DA_BLOCK_BYTES, nblocks, w.gscale, w.dWp, w.dbp, 1};
+            PN_CUDA(cudaLaunchKernelEx(&lc, k_wgrad_tc, w3));
+        }
     }
     PN_LAUNCH_CHECK();
     return PN_OK;

@@ -31,6 +31,8 @@ struct LstmTcArgs {
     long long *trace;         // optional clock64() trace of CTA `trace_block` (debug)
     int trace_block;
     const __half *T16lo;      // split-precision mode (pagg_tc3.cu): fp16(T * scale - T16), the second term of the table
+    unsigned char *xh_img_lo; // split-precision mode: second fp16 term of the [x_t | h_{t-1}] images
+    float *acts32;            // split-precision mode: activations saved as fp32, block (tile, t) = [5][32 unit4][128 rows][4]
 };
 
 constexpr int ACT_BLOCK_HALFS = 5 * 16 * 128 * 8;  // 160 KB per (tile, step)
@@ -83,5 +85,41 @@ __device__ __forceinline__ bool elect_one()   // true in exactly one lane of a c
 }
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
+// W' = [W_ih | W_hh] as B operand of the dgrad GEMM: [256 rows = input index k][K = 512 gate columns],
+// fp16 canonical, cut into 16 chunks of 32 columns (16 KB each).
+constexpr int TCB_KC = 32, TCB_NCHUNK = TC_G4 / TCB_KC, TCB_CHUNK_BYTES = TC_K2 * TCB_KC * 2;
+
+struct LstmBwdTcArgs {
+    const float *T;
+    const int32_t *seq_node;
+    const uint8_t *seq_type;
+    const unsigned char *WhT;  // 16 chunks x 16 KB
+    const __half *acts;        // tile images (see LstmTcArgs)
+    const float *dhfin;        // [P,H], or null: dh_final[p] = dh_k[p] * gdrop[p / nw] + dh_s[p] * attw_h (see PoolArgs)
+    const float *dh_k, *dh_s, *gdrop, *attw_h;
+    int64_t gdrop_ld;
+    int nw;
+    const float *gscale;       // {scale, 1/scale}
+    float *dT;                 // [N,L,H]
+    unsigned char *da_img;     // block b = t*ntiles + tile: [64 col8][128 r][8] fp16   (128 KB)
+    const unsigned char *xh_img;  // block b: [32 k8][128 r][8] fp16 (64 KB): k8 < 16 x_t, k8 >= 16 h_{t-1}; written by the FORWARD kernel
+    const uint32_t *dmask;        // the forward's dropout-mask words (see LstmTcArgs), or null: recompute the hashes
+    int64_t P, ntiles;
+    int L;
+    uint32_t drop_thr; float drop_scale; uint64_t drop_seed;
+    const uint64_t *seed_dev;
+    int64_t p_base;
+    long long *trace;
+    int trace_block;
+    const float *acts32;       // split-precision mode: activations as fp32 tile images (see k_lstm_fwd_tc3)
+    unsigned char *da_img_lo;  // split-precision mode: second fp16 term of the da images (same block layout as da_img)
+};
+constexpr int TCB_NSTAGE = 4;   // 64 KB of W' in flight beside the 128 KB operand tile: the deepest ring that stays inside the 196 KB
+                                // shared-memory carve-out (6 stages -> 228 KB carve-out, the smaller L1 costs more than the depth wins)
+constexpr int TCB_A_BYTES = 128 * TC_G4 * 2;  // 128 KB: da tile [128][512] fp16 canonical
+constexpr int TCB_SMEM_FIXED = TCB_A_BYTES + TCB_NSTAGE * TCB_CHUNK_BYTES + 128 /*align*/;   // + 128 * L * 4 bytes of row offsets
+
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 }  // namespace pn

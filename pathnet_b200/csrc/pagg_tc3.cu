@@ -3,7 +3,7 @@
 // (22 significant bits together), and a product is three tensor-core passes into the same fp32 TMEM accumulator,
 //     A W  ~=  A_hi W_hi + A_lo W_hi + A_hi W_lo            (the dropped A_lo W_lo term is 2^-22 relative),
 // the gates use ex2.approx / rcp.approx (1-2 ulp) instead of tanh.approx (2^-11).  The projections around the LSTM run
-// on the strict fp32 kernels of pagg.cu in this mode; the backward is k_lstm_bwd_tc<.., SPLITW = true> (pagg_tc.cu).
+// on the strict fp32 kernels of pagg.cu in this mode; the backward is k_lstm_bwd_tc3 below plus three passes of k_wgrad_tc.
 //
 //   k_lstm_fwd_tc3  same tiling as k_lstm_fwd_tc (CTA = 128 sequences = 128 TMEM lanes, 16 compute warps + MMA warp +
 //                   weight-producer warp), but four operand tiles (x_hi, x_lo, h_hi, h_lo) and a 5-stage weight ring
@@ -19,6 +19,7 @@
 namespace pn {
 using namespace tc;
 
+constexpr int ACT3_BLOCK_FLOATS = 5 * 32 * 128 * 4;   // saved activations of one (tile, step) as fp32: [5 (i,f,g,o,c)][32 unit4][128 rows][4]
 constexpr int TC3_NSTAGE = 5;   // 80 KB ring beside 128 KB of operand tiles
 constexpr int TC3_SMEM = 4 * TC_XBYTES + TC3_NSTAGE * TC_CHUNK_BYTES + 2048 /*bias*/ + 128 * TC_MAX_L * 4 /*row offsets*/ + 1024 /*align*/;
 static_assert(TC3_SMEM <= 232448, "k_lstm_fwd_tc3: shared memory over the 227 KB limit");
@@ -218,7 +219,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_fwd_tc3(LstmTcArgs a)
                 const int k8 = cq * 4 + kk;
                 *reinterpret_cast<uint4 *>(Xhi + canon_off(r, k8 * 8, TC_H)) = gh[kk];
                 *reinterpret_cast<uint4 *>(Xlo + canon_off(r, k8 * 8, TC_H)) = gl[kk];
-                if (a.save) *reinterpret_cast<uint4 *>(xh_blk + (size_t)k8 * 2048 + r * 16) = gh[kk];
+                if (a.save) {
+                    *reinterpret_cast<uint4 *>(xh_blk + (size_t)k8 * 2048 + r * 16) = gh[kk];
+                    *reinterpret_cast<uint4 *>(a.xh_img_lo + (xh_blk - a.xh_img) + (size_t)k8 * 2048 + r * 16) = gl[kk];
+                }
             }
             if (a.dmask && a.save && a.drop_thr) a.dmask[(((int64_t)blockIdx.x * L + t_) * 4 + cq) * 128 + r] = gmask;
         };
@@ -227,7 +231,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_fwd_tc3(LstmTcArgs a)
         // h_{-1} = 0: h half of step 0's image
 #pragma unroll
         for (int k8 = 16 + cq * 4; k8 < 16 + cq * 4 + 4; k8++)
-            if (a.save) *reinterpret_cast<uint4 *>(a.xh_img + (int64_t)blockIdx.x * XH_BLOCK_BYTES + (size_t)k8 * 2048 + r * 16) = make_uint4(0, 0, 0, 0);
+            if (a.save) {
+                *reinterpret_cast<uint4 *>(a.xh_img + (int64_t)blockIdx.x * XH_BLOCK_BYTES + (size_t)k8 * 2048 + r * 16) = make_uint4(0, 0, 0, 0);
+                *reinterpret_cast<uint4 *>(a.xh_img_lo + (int64_t)blockIdx.x * XH_BLOCK_BYTES + (size_t)k8 * 2048 + r * 16) = make_uint4(0, 0, 0, 0);
+            }
         for (int t = 0; t < L; t++) {
             fence_proxy_async();   // generic-proxy smem writes (x_t, h_{t-1}) -> async proxy (tcgen05.mma)
             tc_fence_before();     // order this thread's earlier tcgen05.ld before the MMA that overwrites TMEM
@@ -236,13 +243,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_fwd_tc3(LstmTcArgs a)
             mbar_wait(&acc_full, t & 1);
             tc_fence_after();
             if (t + 1 < L) gather_store(t + 1);  // every MMA of step t has completed: the x tiles are free
-            __half *act = a.acts + ((int64_t)blockIdx.x * L + t) * ACT_BLOCK_HALFS + r * 8;
+            float *act = a.acts32 + ((int64_t)blockIdx.x * L + t) * ACT3_BLOCK_FLOATS + r * 4;   // fp32: [5][32 unit4][128 rows][4]
             const bool t_is_last = t == L - 1;
 #pragma unroll
             for (int jj = 0; jj < 4; jj++) {
                 const int c0 = cq * 128 + jj * 32;   // packed gate columns of units [c0/4, c0/4 + 8)
-                uint32_t pi[4], pf[4], pg[4], po[4], pc[4], ph[4], pl[4];
-                float hq[4];
+                uint32_t ph[4], pl[4];
+                float hq[4], fi[4], ff[4], fg[4], fo[4], fc[4];
                 uint32_t v[16];
 #pragma unroll
                 for (int u2 = 0; u2 < 4; u2++) {
@@ -276,15 +283,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_fwd_tc3(LstmTcArgs a)
                         hh2[e] = go2[e] * ((1.f - ec) * (r2 * dov));
                     }
                     __half2 t2;
-                    t2 = __floats2half2_rn(gi2[0], gi2[1]); pi[u2] = *reinterpret_cast<uint32_t *>(&t2);
-                    t2 = __floats2half2_rn(gf2[0], gf2[1]); pf[u2] = *reinterpret_cast<uint32_t *>(&t2);
-                    t2 = __floats2half2_rn(gg2[0], gg2[1]); pg[u2] = *reinterpret_cast<uint32_t *>(&t2);
-                    t2 = __floats2half2_rn(go2[0], go2[1]); po[u2] = *reinterpret_cast<uint32_t *>(&t2);
-                    t2 = __floats2half2_rn(cn2[0], cn2[1]); pc[u2] = *reinterpret_cast<uint32_t *>(&t2);
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        const int q4 = (u2 & 1) * 2 + e;
+                        fi[q4] = gi2[e]; ff[q4] = gf2[e]; fg[q4] = gg2[e]; fo[q4] = go2[e]; fc[q4] = cn2[e];
+                    }
                     t2 = __floats2half2_rn(hh2[0], hh2[1]); ph[u2] = *reinterpret_cast<uint32_t *>(&t2);
                     const float2 back = __half22float2(t2);
                     t2 = __floats2half2_rn(hh2[0] - back.x, hh2[1] - back.y); pl[u2] = *reinterpret_cast<uint32_t *>(&t2);
                     hq[(u2 & 1) * 2] = hh2[0]; hq[(u2 & 1) * 2 + 1] = hh2[1];
+                    if ((u2 & 1) && valid && a.save) {   // four units complete: their activations leave as one float4 per tensor
+                        float *ap = act + (c0 / 16 + (u2 >> 1)) * 512;
+                        *reinterpret_cast<float4 *>(ap + 0 * 16384) = make_float4(fi[0], fi[1], fi[2], fi[3]);
+                        *reinterpret_cast<float4 *>(ap + 1 * 16384) = make_float4(ff[0], ff[1], ff[2], ff[3]);
+                        *reinterpret_cast<float4 *>(ap + 2 * 16384) = make_float4(fg[0], fg[1], fg[2], fg[3]);
+                        *reinterpret_cast<float4 *>(ap + 3 * 16384) = make_float4(fo[0], fo[1], fo[2], fo[3]);
+                        *reinterpret_cast<float4 *>(ap + 4 * 16384) = make_float4(fc[0], fc[1], fc[2], fc[3]);
+                    }
                     if (t_is_last && (u2 & 1)) {
                         // final h (fp32) -> staging tile in the (now idle) x tiles, 16-byte slots XOR-swizzled by the row
                         const int j4 = c0 / 16 + (u2 >> 1);
@@ -295,15 +310,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_fwd_tc3(LstmTcArgs a)
                     const uint4 hpk = make_uint4(ph[0], ph[1], ph[2], ph[3]);
                     *reinterpret_cast<uint4 *>(Hhi + canon_off(r, c0 / 4, TC_H)) = hpk;
                     *reinterpret_cast<uint4 *>(Hlo + canon_off(r, c0 / 4, TC_H)) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
-                    if (a.save) *reinterpret_cast<uint4 *>(a.xh_img + ((int64_t)(t + 1) * ntiles + blockIdx.x) * XH_BLOCK_BYTES + (size_t)(16 + c0 / 32) * 2048 + r * 16) = hpk;
-                }
-                if (valid && a.save) {
-                    const int ub = (c0 / 32) * 1024;
-                    *reinterpret_cast<uint4 *>(act + 0 * 16384 + ub) = make_uint4(pi[0], pi[1], pi[2], pi[3]);
-                    *reinterpret_cast<uint4 *>(act + 1 * 16384 + ub) = make_uint4(pf[0], pf[1], pf[2], pf[3]);
-                    *reinterpret_cast<uint4 *>(act + 2 * 16384 + ub) = make_uint4(pg[0], pg[1], pg[2], pg[3]);
-                    *reinterpret_cast<uint4 *>(act + 3 * 16384 + ub) = make_uint4(po[0], po[1], po[2], po[3]);
-                    *reinterpret_cast<uint4 *>(act + 4 * 16384 + ub) = make_uint4(pc[0], pc[1], pc[2], pc[3]);
+                    if (a.save) {
+                        const size_t ho = ((int64_t)(t + 1) * ntiles + blockIdx.x) * XH_BLOCK_BYTES + (size_t)(16 + c0 / 32) * 2048 + r * 16;
+                        *reinterpret_cast<uint4 *>(a.xh_img + ho) = hpk;
+                        *reinterpret_cast<uint4 *>(a.xh_img_lo + ho) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+                    }
                 }
             }
         }
@@ -320,6 +331,263 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_fwd_tc3(LstmTcArgs a)
     tc_fence_before();
     __syncthreads();
     if (warp == TC_CWARPS) { __syncwarp(); tmem_dealloc<512>(taddr); }
+}
+
+// ---------------------------------------------------------------------------
+// k_lstm_bwd_tc3: BPTT at fp32-grade accuracy.  Same tiling and TMEM map as k_lstm_bwd_tc ([0,128) dx, [128,384) dh ping-pong,
+// [384,512) running dc; 16 compute warps, MMA warp, W' producer, setmaxnreg), but
+//   * the saved activations are fp32 (written by k_lstm_fwd_tc3), tanh(c_t) goes through ex2 / rcp;
+//   * the gate gradients da leave as TWO fp16 terms, into the dgrad operand and into the wgrad operand images;
+//   * [dx | dh] = da W' is three passes per K-chunk: da_hi W'_hi + da_lo W'_hi + da_hi W'_lo (192 N=128 MMAs per step);
+//   * the 128 KB operand region holds two K-QUARTER buffers (hi 32 KB + lo 32 KB each) instead of the whole tile: quarter
+//     Q = 4 s + i goes to buffer Q & 1 once the MMAs of quarter Q - 2 have committed (q_free).
+// ---------------------------------------------------------------------------
+constexpr int TCB3_QBYTES = 128 * 128 * 2;   // one term of one K-quarter of da: [128 rows][128 gate columns] fp16 canonical
+
+__global__ void __launch_bounds__(TCB_THREADS, 1) k_lstm_bwd_tc3(LstmBwdTcArgs a)
+{
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 127) & ~(uintptr_t)127);
+    unsigned char *As = base;                 // buffer b at As + b * 2 * TCB3_QBYTES: hi term, then lo term
+    unsigned char *Ws = base + TCB_A_BYTES;   // ring of W' chunks
+    int32_t *rowoff_s = reinterpret_cast<int32_t *>(Ws + TCB_NSTAGE * TCB_CHUNK_BYTES);   // [128][L]: dT row of (sequence, step)
+    __shared__ uint64_t full_bar[TCB_NSTAGE], empty_bar[TCB_NSTAGE], a_ready[4], q_free[2], acc_full;
+    __shared__ uint32_t s_taddr;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t tile = blockIdx.x, p0 = tile * 128;
+    const int L = a.L;
+    for (int i = tid; i < 128 * L; i += TCB_THREADS) {
+        const int rr = i / L, tt = i % L;
+        const int64_t pp = p0 + rr;
+        int32_t off = -1;
+        if (pp < a.P) { const int64_t e = pp * L + tt; off = a.seq_node[e] * L + a.seq_type[e]; }
+        rowoff_s[rr * L + tt] = off;
+    }
+    if (tid == 0) {
+        for (int s = 0; s < TCB_NSTAGE; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int i = 0; i < 4; i++) mbar_init(&a_ready[i], TC_CWARPS * 32);
+        mbar_init(&q_free[0], 1); mbar_init(&q_free[1], 1);
+        mbar_init(&acc_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == TC_CWARPS) tmem_alloc<512>(&s_taddr);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t taddr = s_taddr;
+
+    if (warp >= TC_CWARPS) {
+        reg_dec<32>();
+        if (warp == TC_CWARPS + 1) {
+            // ===== W' producer: quarter-major chunk order, hi image then lo image of each chunk =====
+            if (lane == 0) {
+                uint32_t stage = 0, phase = 0;
+                for (int s = 0; s < L; s++)
+                    for (int j = 0; j < 2 * TCB_NCHUNK; j++) {
+                        const int jj = j >> 1, c = 4 * (jj & 3) + (jj >> 2);
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        mbar_arrive_expect_tx(&full_bar[stage], TCB_CHUNK_BYTES);
+                        bulk_g2s(Ws + stage * TCB_CHUNK_BYTES, a.WhT + (size_t)(2 * c + (j & 1)) * TCB_CHUNK_BYTES, TCB_CHUNK_BYTES, &full_bar[stage]);
+                        if (++stage == TCB_NSTAGE) { stage = 0; phase ^= 1; }
+                    }
+            }
+        } else if (warp == TC_CWARPS) {
+            // ===== MMA issuer (converged warp, one elected lane) =====
+            uint32_t stage = 0, phase = 0;
+            constexpr uint32_t idesc = make_idesc_f16(128, 128);
+            for (int s = 0; s < L; s++) {
+                const int t = L - 1 - s;
+                const uint32_t dh_col = 128u + (uint32_t)(s & 1) * 128u;
+                for (int j = 0; j < TCB_NCHUNK; j++) {
+                    const int i = j >> 2, cqj = j & 3;   // K-quarter i, chunk 4 cqj + i of W' = 32 gate columns of column quarter cqj
+                    if (cqj == 0) { mbar_wait(&a_ready[i], s & 1); tc_fence_after(); }
+                    const int Q = 4 * s + i;
+                    const uint32_t a_hi = smem_u32(As) + (uint32_t)(Q & 1) * (2 * TCB3_QBYTES) + (uint32_t)cqj * 4 * 128, a_lo = a_hi + TCB3_QBYTES;
+#pragma unroll
+                    for (int part = 0; part < 2; part++) {   // part 0: W'_hi against da_hi and da_lo; part 1: W'_lo against da_hi
+                        mbar_wait(&full_bar[stage], phase);
+                        tc_fence_after();
+                        const uint32_t wbase = smem_u32(Ws + stage * TCB_CHUNK_BYTES);
+                        if (elect_one()) {
+#pragma unroll
+                            for (int ks = 0; ks < TCB_KC / 16; ks++) {
+                                const uint64_t ad_hi = make_smem_desc(a_hi + (uint32_t)ks * 256, 128, (128 / 8) * 128);
+                                const uint64_t ad_lo = make_smem_desc(a_lo + (uint32_t)ks * 256, 128, (128 / 8) * 128);
+                                // rows 0..127 of W' give dx, rows 128..255 (16 row groups further) give dh_{t-1} (unused at t = 0)
+                                const uint64_t bd_x = make_smem_desc(wbase + (uint32_t)ks * 256, 128, (TCB_KC / 8) * 128);
+                                const uint64_t bd_h = make_smem_desc(wbase + 16u * ((TCB_KC / 8) * 128) + (uint32_t)ks * 256, 128, (TCB_KC / 8) * 128);
+                                const bool acc = (j > 0) || (ks > 0) || (part > 0);
+                                mma_f16(taddr, ad_hi, bd_x, idesc, acc);
+                                if (part == 0) mma_f16(taddr, ad_lo, bd_x, idesc, true);
+                                if (t > 0) {
+                                    mma_f16(taddr + dh_col, ad_hi, bd_h, idesc, acc);
+                                    if (part == 0) mma_f16(taddr + dh_col, ad_lo, bd_h, idesc, true);
+                                }
+                            }
+                            mma_commit(&empty_bar[stage]);
+                            if (part == 1 && cqj == 3) mma_commit(&q_free[Q & 1]);
+                            if (part == 1 && j == TCB_NCHUNK - 1) mma_commit(&acc_full);
+                        }
+                        __syncwarp();
+                        if (++stage == TCB_NSTAGE) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else {
+        reg_inc<112>();
+        // warp = (TMEM lane quarter lq, column quarter cq): sequence p0 + 32 lq + lane, units [32 cq, 32 cq + 32)
+        const int lq = warp & 3, cq = warp >> 2;
+        const int r = lq * 32 + lane;
+        const int64_t p = p0 + r;
+        const bool valid = p < a.P;
+        const uint32_t lane_base = taddr + ((uint32_t)(lq * 32) << 16);
+        const float scale = a.gscale[0], inv_scale = a.gscale[1];
+        const uint32_t dkey = dropout_key(a.seed_dev ? a.drop_seed + *a.seed_dev : a.drop_seed, 0);
+        // dx of step `ss` (time tt = L-1-ss) -> dT with the forward's dropout mask (same scatter as k_lstm_bwd_tc)
+        auto scatter_dx = [&](int ss) {
+            const int tt = L - 1 - ss;
+            uint32_t mbits = 0xFFFFFFFFu;
+            const bool have_mask = a.dmask != nullptr && a.drop_thr != 0;
+            if (have_mask) mbits = __ldg(a.dmask + (((int64_t)tile * L + tt) * 4 + cq) * 128 + r);
+            uint32_t v[32];
+            tmem_ld32(lane_base + cq * 32, v);   // warp-collective: every lane loads, only valid rows scatter
+            tmem_ld_wait();
+            if (valid) {
+                const int64_t e = p * L + tt;
+                float *dst = a.dT + (int64_t)rowoff_s[r * L + tt] * TC_H + cq * 32;
+                const float mul = inv_scale * (a.drop_thr ? a.drop_scale : 1.f);
+#pragma unroll
+                for (int c8 = 0; c8 < 4; c8++) {
+                    if (a.drop_thr && !have_mask) {
+                        const uint64_t pair = ((uint64_t)(e + a.p_base * L) * TC_H + cq * 32 + c8 * 8) >> 1;
+                        uint32_t b = 0;
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const uint32_t h = dropout_hash_pair_k(dkey, pair + q);
+                            b |= (((h & 0xFFFFu) < a.drop_thr ? 0u : 1u) | ((h >> 16) < a.drop_thr ? 0u : 2u)) << (2 * q);
+                        }
+                        mbits = (mbits & ~(0xFFu << (c8 * 8))) | (b << (c8 * 8));
+                    }
+#pragma unroll
+                    for (int q = 0; q < 2; q++) {
+                        const uint32_t b = a.drop_thr ? (mbits >> (c8 * 8 + 4 * q)) & 15u : 15u;
+                        if (b) atomicAdd(reinterpret_cast<float4 *>(dst + c8 * 8 + 4 * q),
+                                         make_float4((b & 1u) ? __uint_as_float(v[c8 * 8 + 4 * q]) * mul : 0.f,
+                                                     (b & 2u) ? __uint_as_float(v[c8 * 8 + 4 * q + 1]) * mul : 0.f,
+                                                     (b & 4u) ? __uint_as_float(v[c8 * 8 + 4 * q + 2]) * mul : 0.f,
+                                                     (b & 8u) ? __uint_as_float(v[c8 * 8 + 4 * q + 3]) * mul : 0.f));
+                    }
+                }
+            }
+            __syncwarp();
+        };
+        // factored dh_final: this sequence's two scalars and its output row
+        float dh_kk = 1.f, dh_ds = 0.f;
+        int64_t grow = 0;
+        if (!a.dhfin && valid) { dh_kk = a.dh_k[p]; dh_ds = a.dh_s[p]; grow = p / a.nw; }
+        for (int s = 0; s < L; s++) {
+            const int t = L - 1 - s;
+            const int64_t blk = (int64_t)t * a.ntiles + tile;
+            unsigned char *da_blk = a.da_img + blk * DA_BLOCK_BYTES, *da_blk_lo = a.da_img_lo + blk * DA_BLOCK_BYTES;
+            const float *act = a.acts32 + ((int64_t)tile * L + t) * ACT3_BLOCK_FLOATS + r * 4;
+            // ---- the previous step's dx (complete since acc_full) -> dT, before this step's MMAs overwrite the region ----
+            if (s > 0) scatter_dx(s - 1);
+            const uint32_t dh_rd = 128u + (uint32_t)((s - 1) & 1) * 128u;
+#pragma unroll 1
+            for (int hi = 0; hi < 8; hi++) {   // half-iterations of 4 units; two of them fill one K-quarter of this warp's columns
+                const int i = hi >> 1;
+                const int u4 = cq * 8 + hi, u0 = u4 * 4;   // units [u0, u0 + 4)
+                float4 gi = make_float4(0.f, 0.f, 0.f, 0.f), gf = gi, gg = gi, go = gi, cn = gi, cp = gi, d0 = gi;
+                if (valid) {
+                    const float *ap = act + u4 * 512;
+                    gi = __ldg(reinterpret_cast<const float4 *>(ap + 0 * 16384));
+                    gf = __ldg(reinterpret_cast<const float4 *>(ap + 1 * 16384));
+                    gg = __ldg(reinterpret_cast<const float4 *>(ap + 2 * 16384));
+                    go = __ldg(reinterpret_cast<const float4 *>(ap + 3 * 16384));
+                    cn = __ldg(reinterpret_cast<const float4 *>(ap + 4 * 16384));
+                    if (t > 0) cp = __ldg(reinterpret_cast<const float4 *>(ap - ACT3_BLOCK_FLOATS + 4 * 16384));
+                    if (s == 0) d0 = a.dhfin ? __ldg(reinterpret_cast<const float4 *>(a.dhfin + p * TC_H + u0))
+                                             : __ldg(reinterpret_cast<const float4 *>(a.gdrop + grow * a.gdrop_ld + u0));
+                }
+                float dh[4], dc[4];
+                if (s == 0) {
+                    if (!a.dhfin) {
+                        const float4 wh = __ldg(reinterpret_cast<const float4 *>(a.attw_h + u0));
+                        d0 = make_float4(fmaf(dh_kk, d0.x, dh_ds * wh.x), fmaf(dh_kk, d0.y, dh_ds * wh.y), fmaf(dh_kk, d0.z, dh_ds * wh.z),
+                                         fmaf(dh_kk, d0.w, dh_ds * wh.w));
+                        if (!valid) d0 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    dh[0] = d0.x * scale; dh[1] = d0.y * scale; dh[2] = d0.z * scale; dh[3] = d0.w * scale;
+                    dc[0] = dc[1] = dc[2] = dc[3] = 0.f;
+                } else {
+                    uint32_t v0[4], v1[4];
+                    tmem_ld4(lane_base + dh_rd + u0, v0);
+                    tmem_ld4(lane_base + 384 + u0, v1);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 4; j++) { dh[j] = __uint_as_float(v0[j]); dc[j] = __uint_as_float(v1[j]); }
+                }
+                const float gi_[4] = {gi.x, gi.y, gi.z, gi.w}, gf_[4] = {gf.x, gf.y, gf.z, gf.w}, gg_[4] = {gg.x, gg.y, gg.z, gg.w};
+                const float go_[4] = {go.x, go.y, go.z, go.w}, cn_[4] = {cn.x, cn.y, cn.z, cn.w}, cp_[4] = {cp.x, cp.y, cp.z, cp.w};
+                float da[2][8];  // [q][.]: packed columns (u0 + 2q + {0,1}) * 4 + gate
+                uint32_t dcn_bits[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const float tcn = tanh_acc(cn_[j]);
+                    const float dcn = fmaf(dh[j] * go_[j], 1.f - tcn * tcn, dc[j]);
+                    da[j >> 1][(j & 1) * 4 + 0] = dcn * gg_[j] * gi_[j] * (1.f - gi_[j]);
+                    da[j >> 1][(j & 1) * 4 + 1] = dcn * cp_[j] * gf_[j] * (1.f - gf_[j]);
+                    da[j >> 1][(j & 1) * 4 + 2] = dcn * gi_[j] * (1.f - gg_[j] * gg_[j]);
+                    da[j >> 1][(j & 1) * 4 + 3] = dh[j] * tcn * go_[j] * (1.f - go_[j]);
+                    dcn_bits[j] = __float_as_uint(dcn * gf_[j]);
+                }
+                tmem_st4(lane_base + 384 + u0, dcn_bits);
+                if ((hi & 1) == 0) {   // first write into quarter Q's buffer: the MMAs of quarter Q - 2 (same buffer) must have completed
+                    const int Q = 4 * s + i;
+                    if (Q >= 2) mbar_wait(&q_free[Q & 1], (uint32_t)(((Q >> 1) - 1) & 1));
+                }
+                unsigned char *buf = As + (size_t)((4 * s + i) & 1) * (2 * TCB3_QBYTES);
+#pragma unroll
+                for (int q = 0; q < 2; q++) {
+                    float lo[8];
+                    const uint4 pk = pack8_f16(da[q]);
+                    {
+                        float back[8];
+                        unpack8_f16(pk, back);
+#pragma unroll
+                        for (int e = 0; e < 8; e++) lo[e] = da[q][e] - back[e];
+                    }
+                    const uint4 pl = pack8_f16(lo);
+                    const int kq = cq * 32 + (hi & 1) * 16 + q * 8;             // column inside the quarter buffer
+                    const int chunk = (cq * 4 + i) * 4 + (hi & 1) * 2 + q;      // 8 packed gate columns of the whole tile = 16 bytes
+                    *reinterpret_cast<uint4 *>(buf + canon_off(r, kq, 128)) = pk;
+                    *reinterpret_cast<uint4 *>(buf + TCB3_QBYTES + canon_off(r, kq, 128)) = pl;
+                    *reinterpret_cast<uint4 *>(da_blk + (size_t)chunk * 2048 + r * 16) = pk;
+                    *reinterpret_cast<uint4 *>(da_blk_lo + (size_t)chunk * 2048 + r * 16) = pl;
+                }
+                if (hi & 1) {   // this quarter is written: let the tensor core start on it
+                    fence_proxy_async();
+                    tc_fence_before();
+                    mbar_arrive(&a_ready[i]);
+                }
+            }
+            tmem_st_wait();
+            mbar_wait(&acc_full, s & 1);
+            tc_fence_after();
+        }
+        scatter_dx(L - 1);   // the last step's dx
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == TC_CWARPS) { __syncwarp(); tmem_dealloc<512>(taddr); }
+}
+
+int launch_lstm_bwd_tc3(const LstmBwdTcArgs &a, int64_t ntiles, int smem, int smem_max, cudaStream_t st)
+{
+    PN_CUDA(cudaFuncSetAttribute(k_lstm_bwd_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+    k_lstm_bwd_tc3<<<(unsigned)ntiles, TCB_THREADS, smem, st>>>(a);
+    return PN_OK;
 }
 
 int launch_split_table(cudaStream_t st, const float *T, float scale, void *hi, void *lo, int64_t n)
@@ -361,7 +629,8 @@ int pagg_tc3_forward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_p
     const __half *t16hi = reinterpret_cast<const __half *>(w.t16), *t16lo = t16hi + (int64_t)c.N * c.L * c.H;
     LstmTcArgs a{t16hi, w.T, seq_node, seq_type, Wh, w.bp, reinterpret_cast<__half *>(w.acts), w.hfin, P, c.L, thr, scale,
                  c.dropout_seed, c.dropout_seed_dev, ck.s0 * c.nw, reinterpret_cast<unsigned char *>(w.XH),
-                 reinterpret_cast<uint32_t *>(w.dmask), ck.save ? 1 : 0, nullptr, 0, t16lo};
+                 reinterpret_cast<uint32_t *>(w.dmask), ck.save ? 1 : 0, nullptr, 0, t16lo,
+                 reinterpret_cast<unsigned char *>(w.XH) + ceil_div(P, 128) * c.L * (int64_t)XH_BLOCK_BYTES, w.acts};
     PN_CUDA(cudaFuncSetAttribute(k_lstm_fwd_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, TC3_SMEM));
     {
         ProfScope prof("lstm_fwd", st);

@@ -17,7 +17,6 @@ from tests.test_gpu_pagg import FWD_TOL, GRAD_TOL, _fixture, _module_for, _oracl
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 H128_FIXTURES = sorted(GOLDEN.glob("pagg_*_h128.npz"))
-TC3_GRAD_TOL = dict(rtol=5e-3, atol=2e-4)   # interim: the backward still rounds saved activations / da / [x|h] images to one fp16 term
 
 
 def _report(tag, y, y_ref, grads, g_ref):
@@ -39,7 +38,7 @@ def test_tc3_matches_reference_fixture_at_the_fp32_bar(path):
     _report(path.stem, y.detach().cpu(), torch.tensor(z["logits"]), {k: p.grad.cpu() for k, p in m.named_parameters()}, grads)
     torch.testing.assert_close(y.detach().cpu(), torch.tensor(z["logits"]), **FWD_TOL)
     for k, p in m.named_parameters():
-        torch.testing.assert_close(p.grad.cpu(), grads[k], **TC3_GRAD_TOL, msg=lambda s: f"{k}: {s}")
+        torch.testing.assert_close(p.grad.cpu(), grads[k], **GRAD_TOL, msg=lambda s: f"{k}: {s}")
 
 
 @pytest.mark.parametrize("variant", ["homo", "hetero"])
@@ -57,7 +56,7 @@ def test_tc3_forward_backward_match_oracle(variant, N, Fd, Cc, nw, L, S):
     _report(f"{variant} N={N} L={L}", y.detach().cpu(), y_ref, {k: p.grad.cpu() for k, p in m.named_parameters()}, g_ref)
     torch.testing.assert_close(y.detach().cpu(), y_ref, **FWD_TOL)
     for k, p in m.named_parameters():
-        torch.testing.assert_close(p.grad.cpu(), g_ref[k], **TC3_GRAD_TOL, msg=lambda s: f"{k}: {s}")
+        torch.testing.assert_close(p.grad.cpu(), g_ref[k], **GRAD_TOL, msg=lambda s: f"{k}: {s}")
 
 
 @pytest.mark.parametrize("variant", ["homo", "hetero"])
@@ -84,7 +83,7 @@ def test_tc3_training_dropout_matches_oracle_with_same_masks(variant):
             {k: params[k].grad.float() for k in params})
     torch.testing.assert_close(y.detach().cpu(), y_ref.detach().float(), **FWD_TOL)
     for k, pr in m.named_parameters():
-        torch.testing.assert_close(pr.grad.cpu(), params[k].grad.float(), **TC3_GRAD_TOL, msg=lambda s: f"{k}: {s}")
+        torch.testing.assert_close(pr.grad.cpu(), params[k].grad.float(), **GRAD_TOL, msg=lambda s: f"{k}: {s}")
 
 
 def test_tc3_is_deterministic_in_the_forward_and_close_to_fp32_mode_at_pubmed_scale():
