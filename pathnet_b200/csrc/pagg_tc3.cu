@@ -81,7 +81,10 @@ __global__ void k_split_table(const float *__restrict__ T, float scale, __half *
     reinterpret_cast<uint4 *>(lo)[i] = pack8_f16(l);
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_fwd_tc3(LstmTcArgs a)
+// 20 warps like the backward kernels: 16 compute warps + a service warpgroup (MMA issuer, weight producer, two idle warps) so that
+// setmaxnreg can move registers (96 per thread at launch -> service warps 32, compute warps 112: no spills around the 32 gather
+// registers that stay live across the wait for the accumulators)
+__global__ void __launch_bounds__(TCB_THREADS, 1) k_lstm_fwd_tc3(LstmTcArgs a)
 {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
@@ -103,8 +106,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_fwd_tc3(LstmTcArgs a)
         fence_mbar_init();
     }
     if (warp == TC_CWARPS) tmem_alloc<512>(&s_taddr);
-    for (int i = tid; i < TC_G4; i += TC_THREADS) bias_s[i] = a.bp[i];
-    for (int i = tid; i < 128 * L; i += TC_THREADS) {
+    for (int i = tid; i < TC_G4; i += TCB_THREADS) bias_s[i] = a.bp[i];
+    for (int i = tid; i < 128 * L; i += TCB_THREADS) {
         const int r = i / L, t = i % L;
         const int64_t p = p0 + r;
         int32_t off = -1;
@@ -116,7 +119,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_fwd_tc3(LstmTcArgs a)
     tc_fence_after();
     const uint32_t taddr = s_taddr;
 
-    if (warp == TC_CWARPS + 1) {
+    if (warp > TC_CWARPS + 1) {
+        reg_dec<32>();   // (idle warps of the service warpgroup)
+    } else if (warp == TC_CWARPS + 1) {
+        reg_dec<32>();
         // ===== weight producer: per step and K-chunk the hi image, then the lo image (step 0: x half only, h_0 = 0) =====
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
@@ -131,14 +137,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_fwd_tc3(LstmTcArgs a)
             }
         }
     } else if (warp == TC_CWARPS) {
+        reg_dec<32>();
         // ===== MMA issuer (whole warp converged, one elected lane issues; see k_lstm_fwd_tc) =====
         constexpr uint32_t idesc = make_idesc_f16(128, 256);
         uint32_t stage = 0, phase = 0;
+        const bool trm = a.trace && blockIdx.x == a.trace_block && lane == 0;
         for (int t = 0; t < L; t++) {
             mbar_wait(&a_ready, t & 1);  // x_t (and h_{t-1}) staged, TMEM drained
             tc_fence_after();
+            if (trm) a.trace[t * 8 + 4] = clock64();
             const int nch = t == 0 ? TC_NCHUNK / 2 : TC_NCHUNK;
             for (int c = 0; c < nch; c++) {
+                if (trm && c == nch - 1) a.trace[t * 8 + 5] = clock64();
                 // chunk c = 16 consecutive k: two core matrices (256 B) of the x half (c < 8) or the h half
                 const uint32_t off = (uint32_t)(c < TC_NCHUNK / 2 ? c : c - TC_NCHUNK / 2) * 256;
                 const uint32_t a_hi = smem_u32(c < TC_NCHUNK / 2 ? Xhi : Hhi) + off, a_lo = smem_u32(c < TC_NCHUNK / 2 ? Xlo : Hlo) + off;
@@ -170,6 +180,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_fwd_tc3(LstmTcArgs a)
     } else {
         // ===== gather + gate math: warp = (TMEM lane quarter lq, column quarter cq); the thread owns sequence
         //       p0 + 32 lq + lane (= its TMEM lane) and hidden units [32 cq, 32 cq + 32) =====
+        reg_inc<112>();
         const int lq = warp & 3, cq = warp >> 2;
         const int r = lq * 32 + lane;
         const int64_t p = p0 + r;
@@ -235,14 +246,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_fwd_tc3(LstmTcArgs a)
                 *reinterpret_cast<uint4 *>(a.xh_img + (int64_t)blockIdx.x * XH_BLOCK_BYTES + (size_t)k8 * 2048 + r * 16) = make_uint4(0, 0, 0, 0);
                 *reinterpret_cast<uint4 *>(a.xh_img_lo + (int64_t)blockIdx.x * XH_BLOCK_BYTES + (size_t)k8 * 2048 + r * 16) = make_uint4(0, 0, 0, 0);
             }
+        const bool tr = a.trace && blockIdx.x == a.trace_block && tid == 0;
         for (int t = 0; t < L; t++) {
+            if (tr) a.trace[t * 8 + 0] = clock64();
             fence_proxy_async();   // generic-proxy smem writes (x_t, h_{t-1}) -> async proxy (tcgen05.mma)
             tc_fence_before();     // order this thread's earlier tcgen05.ld before the MMA that overwrites TMEM
             mbar_arrive(&a_ready);
             if (t + 1 < L) gather_load(t + 1);   // in flight while the tensor core works on step t
+            if (tr) a.trace[t * 8 + 1] = clock64();
             mbar_wait(&acc_full, t & 1);
             tc_fence_after();
+            if (tr) a.trace[t * 8 + 2] = clock64();
             if (t + 1 < L) gather_store(t + 1);  // every MMA of step t has completed: the x tiles are free
+            if (tr) a.trace[t * 8 + 6] = clock64();
             float *act = a.acts32 + ((int64_t)blockIdx.x * L + t) * ACT3_BLOCK_FLOATS + r * 4;   // fp32: [5][32 unit4][128 rows][4]
             const bool t_is_last = t == L - 1;
 #pragma unroll
@@ -317,6 +333,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lstm_fwd_tc3(LstmTcArgs a)
                     }
                 }
             }
+            if (tr) a.trace[t * 8 + 3] = clock64();
         }
         // ---- final h: staging tile -> hfin[P][H], whole 512-byte rows per warp ----
         asm volatile("bar.sync 1, %0;" ::"n"(TC_CWARPS * 32) : "memory");
@@ -631,12 +648,30 @@ int pagg_tc3_forward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_p
                  c.dropout_seed, c.dropout_seed_dev, ck.s0 * c.nw, reinterpret_cast<unsigned char *>(w.XH),
                  reinterpret_cast<uint32_t *>(w.dmask), ck.save ? 1 : 0, nullptr, 0, t16lo,
                  reinterpret_cast<unsigned char *>(w.XH) + ceil_div(P, 128) * c.L * (int64_t)XH_BLOCK_BYTES, w.acts};
+    long long *d_trace = nullptr;
+    const char *trace_env = getenv("PN_TRACE_FWD");   // debug: phase timestamps (clock64) of one CTA
+    if (trace_env) {
+        PN_CUDA(cudaMalloc(&d_trace, sizeof(long long) * 8 * 64));
+        PN_CUDA(cudaMemsetAsync(d_trace, 0, sizeof(long long) * 8 * 64, st));
+        a.trace = d_trace;
+        a.trace_block = atoi(trace_env);
+    }
     PN_CUDA(cudaFuncSetAttribute(k_lstm_fwd_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, TC3_SMEM));
     {
         ProfScope prof("lstm_fwd", st);
-        k_lstm_fwd_tc3<<<(unsigned)ceil_div(P, 128), TC_THREADS, TC3_SMEM, st>>>(a);
+        k_lstm_fwd_tc3<<<(unsigned)ceil_div(P, 128), TCB_THREADS, TC3_SMEM, st>>>(a);
     }
     PN_LAUNCH_CHECK();
+    if (d_trace) {
+        long long h[8 * 64];
+        PN_CUDA(cudaStreamSynchronize(st));
+        PN_CUDA(cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost));
+        cudaFree(d_trace);
+        const long long t00 = h[0];
+        for (int t = 0; t < c.L && t < 8; t++)
+            fprintf(stderr, "[trace fwd3 cta %d] t=%d  begin %lld | gather loads issued %lld | mma saw a_ready %lld | last chunk reached %lld | acc_full seen %lld | x stored %lld | gate math done %lld\n",
+                    a.trace_block, t, h[t * 8 + 0] - t00, h[t * 8 + 1] - t00, h[t * 8 + 4] - t00, h[t * 8 + 5] - t00, h[t * 8 + 2] - t00, h[t * 8 + 6] - t00, h[t * 8 + 3] - t00);
+    }
     return PN_OK;
 }
 

@@ -35,14 +35,15 @@ _warned_auto_tc = False
 
 
 def resolve_math_mode(mode: str, H: int, L: int) -> str:
-    """"fp32": strict-parity mode (1e-4 against the reference's CPU fp32 math), any hidden size up to 128.
-    "tc": tcgen05 tensor cores — fp16 operands (11-bit significand, the width of TF32, which is what the reference
-    itself runs on under cuDNN/cuBLAS on a current GPU), fp32 accumulation; needs hidden 128 and path_len <= 8 and
-    raises otherwise.  "tc3": the same tensor-core LSTM at fp32-grade accuracy — every operand travels as two fp16 terms
-    (hi + lo) and every product is three tensor-core passes into one fp32 accumulator, gates on ex2 / rcp, projections on
-    the fp32 kernels: held to the SAME parity bar as "fp32" at roughly a tenth of its step time (hidden 128, path_len <= 8).
-    "auto" (the modules' default, overridable with env PN_MATH_MODE): "tc" where it exists, else
-    "fp32"; the first time it resolves to "tc" a one-line notice names the tolerance class."""
+    """"fp32": strict-parity CUDA-core mode (1e-4 against the reference's fp32 math), any hidden size up to 128.
+    "tc3": the LSTM on tcgen05 tensor cores at fp32-grade accuracy — every operand travels as two fp16 terms (hi + lo) and
+    every product is three tensor-core passes into one fp32 accumulator, gates on ex2 / rcp, projections on the fp32
+    kernels: held to the SAME parity bar as "fp32" at about a ninth of its step time (hidden 128, path_len <= 8).
+    "tc": the fast mode — single-pass fp16 operands (11-bit significand, the width of TF32, which is what the reference itself
+    runs on under cuDNN / cuBLAS on a current GPU), fp32 accumulation, tanh.approx: logits within ~1e-3 of fp32 math;
+    half the step time of "tc3".  Both tensor-core modes need hidden 128 and path_len <= 8 and raise otherwise.
+    "auto" (the modules' default, overridable with env PN_MATH_MODE): parity first — "tc3" where it exists, else "fp32";
+    the first time it resolves to "tc3" a one-line notice names the faster opt-in mode."""
     global _warned_auto_tc
     if mode == "auto":
         mode = os.environ.get("PN_MATH_MODE", "auto")
@@ -50,10 +51,10 @@ def resolve_math_mode(mode: str, H: int, L: int) -> str:
         if H == 128 and L <= 8:
             if not _warned_auto_tc:
                 _warned_auto_tc = True
-                warnings.warn("pathnet_b200: math_mode='auto' selected the tensor-core kernels (fp16 operands, fp32 "
-                              "accumulate: logits within ~1e-3 of fp32 math); pass math_mode='fp32' or set "
-                              "PN_MATH_MODE=fp32 for strict 1e-4 parity", stacklevel=3)
-            return "tc"
+                warnings.warn("pathnet_b200: math_mode='auto' selected 'tc3' (split-precision tensor-core kernels, the fp32 "
+                              "mode's 1e-4 parity bar); pass math_mode='tc' or set PN_MATH_MODE=tc for the single-pass fp16 "
+                              "kernels (2x faster, logits within ~1e-3 of fp32 math)", stacklevel=3)
+            return "tc3"
         return "fp32"
     if mode not in MATH:
         raise ValueError(f"math_mode must be 'auto', 'fp32', 'tc' or 'tc3' (got {mode!r})")
@@ -335,7 +336,7 @@ class _PathNetBase(nn.Module):
     def __init__(self, feature_length, hidden_size, out_size, wl, **kwargs):
         # kwargs mirrors the reference signature (`aggr` is set and ignored there, :156-157)
         self.dropout = float(kwargs.pop("dropout", 0.0))     # the reference reads a module global (:71); its CLI default is 0.7
-        self.math_mode = kwargs.pop("math_mode", "auto")     # "auto" | "fp32" (strict parity) | "tc"
+        self.math_mode = kwargs.pop("math_mode", "auto")     # "auto" (= "tc3" where it exists, else "fp32") | "fp32" | "tc3" | "tc" (fast)
         self.row_chunk = int(kwargs.pop("row_chunk", 0))     # > 0: bounded workspace, see pn_pagg_cfg.row_chunk
         self.pool = kwargs.pop("pool", "attention")          # ablations: "mean" | "sum" | "max" instead of the attention
         if self.pool not in POOL:

@@ -118,8 +118,9 @@ def test_math_mode_resolution(monkeypatch):
     pagg._warned_auto_tc = False
     with warnings.catch_warnings(record=True) as w:
         warnings.simplefilter("always")
-        assert pagg.resolve_math_mode("auto", 128, 4) == "tc"
-        assert pagg.resolve_math_mode("auto", 128, 4) == "tc"
-    assert len(w) == 1 and "fp32" in str(w[0].message)            # one notice naming the strict mode
+        assert pagg.resolve_math_mode("auto", 128, 4) == "tc3"      # parity first: the split-precision tensor-core mode
+        assert pagg.resolve_math_mode("auto", 128, 4) == "tc3"
+    assert len(w) == 1 and "'tc'" in str(w[0].message)            # one notice naming the faster opt-in mode
+    assert pagg.resolve_math_mode("tc3", 128, 4) == "tc3"
     with pytest.raises(ValueError):
         pagg.resolve_math_mode("bf16", 128, 4)
