@@ -284,7 +284,7 @@ uint32_t pn_dropout_hash(uint64_t seed, uint32_t stream_id, uint64_t idx);
  * path (fp16 operands, fp32 accumulate); device pointers, fp32, row-major. */
 int pn_debug_gemm_tc(const float *A, const float *B, float *C, const float *bias, int64_t M,
                      int64_t N, int64_t K, int relu, void *stream);
-/* same with operand-layout flags: bit0 A is [K][M], bit1 B is [K][N], bit2 bf16 operands,
+/* same with operand-layout flags: bit0 A is [K][M], bit1 B is [K][N], bit2 bf16 operands, bit4 split precision (hi + lo fp16 terms, 3 passes),
  * bit3 accumulate into C (atomics); splitk >= 1 splits K across CTAs (C pre-zeroed). */
 int pn_debug_gemm_tc2(const float *A, const float *B, float *C, int64_t M, int64_t N, int64_t K,
                       int flags, int splitk, void *stream);

@@ -1140,7 +1140,7 @@ extern "C" int pn_pagg_forward(const pn_pagg_cfg *cfg, const pn_pagg_params *prm
 
     // K0: Z = act(X W0^T + b0)                                     (:175 / :242-243)
     // K1: T[n, d*H + j] = act(Z nets_w[d]^T + nets_b[d])           (:185-191 / :249-257, hoisted)
-    if (tcm) {
+    if (tcm || c.math_mode == PN_MATH_TC3) {   // (TC3: the same projections as three fp16 passes per product, fp32 in and out)
         rc = pagg_tc_project(c, w, *prm, X, st);
         if (rc) return rc;
     } else {
@@ -1243,7 +1243,7 @@ extern "C" int pn_pagg_backward(const pn_pagg_cfg *cfg, const pn_pagg_params *pr
     // the wgrad clusters leave free -- and join before the call returns.  Works the same under stream capture (the graph gets
     // two branches).  PN_BWD_FORK=0 keeps everything on the caller's stream.
     BwdFork fork{};
-    if (tcm) { rc = bwd_fork_get(fork); if (rc) return rc; }
+    if (tcl) { rc = bwd_fork_get(fork); if (rc) return rc; }
     for (int64_t s0 = 0; s0 < S; s0 += rows_per) {
         const PaggChunk ck{s0, std::min<int64_t>(rows_per, S - s0), true, s0 == 0};
         const ChunkPtrs ix = chunk_ptrs(c, ck, seq_node, seq_type, partner, rows);
@@ -1314,7 +1314,7 @@ extern "C" int pn_pagg_backward(const pn_pagg_cfg *cfg, const pn_pagg_params *pr
             if (rc) return rc;
         }
     }
-    if (tcm && fork.ev_fork) {   // the projections' backward on the side stream, from the point where dT / dZ were complete
+    if (tcl && fork.ev_fork) {   // the projections' backward on the side stream, from the point where dT / dZ were complete
         PN_CUDA(cudaStreamWaitEvent(fork.side, fork.ev_fork, 0));
         rc = pagg_tc_project_backward(c, w, *prm, X, g, fork.side);
         if (rc) return rc;
@@ -1324,8 +1324,8 @@ extern "C" int pn_pagg_backward(const pn_pagg_cfg *cfg, const pn_pagg_params *pr
     PN_CUDA(cudaMemcpyAsync(g.attw_b, w.dattw + 2 * H, sizeof(float), cudaMemcpyDeviceToDevice, st));
     k_unpack_lstm_grads<<<(unsigned)ceil_div(4 * H * H, 256), 256, 0, st>>>((int)H, c.cell, w.dWp, w.dbp, g.w_ih, g.w_hh, g.b_ih, g.b_hh);
     PN_LAUNCH_CHECK();
-    if (tcm && fork.ev_fork) { PN_CUDA(cudaStreamWaitEvent(st, fork.ev_join, 0)); return PN_OK; }
-    if (tcm) return pagg_tc_project_backward(c, w, *prm, X, g, st);
+    if (tcl && fork.ev_fork) { PN_CUDA(cudaStreamWaitEvent(st, fork.ev_join, 0)); return PN_OK; }
+    if (tcl) return pagg_tc_project_backward(c, w, *prm, X, g, st);
     // ---- table projection: T = act(Z Wn^T + bn) ----
     // homo: ReLU backward fused with the bias gradient (column sums) of the table projection
     if (homo) {

@@ -60,11 +60,13 @@ __device__ __forceinline__ uint4 pack8_half_or_bf16(const float (&f)[8])
 
 // stage a [ROWS x 64] operand tile.  MN = false: src[row][k]; MN = true: src[k][row].
 // Two phases so that all of a thread's global loads are in flight together.
-template <int ROWS, int NTHREADS, bool MN, bool BF16>
+// BK: depth of the K tile (64, or 32 for the split-precision variant); SPLIT: also write the second fp16 term of every value
+// (lo = fp16(v - hi)) as a second tile image at dst_lo.
+template <int ROWS, int NTHREADS, bool MN, bool BF16, int BK = 64, bool SPLIT = false>
 __device__ __forceinline__ void stage_tile(unsigned char *dst, const float *__restrict__ src, int64_t ld, int64_t row0,
-                                           int64_t nrows, int64_t k0, int64_t kend, int tid, float mul = 1.f)
+                                           int64_t nrows, int64_t k0, int64_t kend, int tid, float mul = 1.f, unsigned char *dst_lo = nullptr)
 {
-    constexpr int CHUNKS = ROWS * 8;  // 16-byte chunks (8 elements)
+    constexpr int CHUNKS = ROWS * BK / 8;  // 16-byte chunks (8 elements)
     constexpr int PER = CHUNKS / NTHREADS;
     static_assert(CHUNKS % NTHREADS == 0, "tile must divide evenly among the threads");
     const bool vec_ok = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
@@ -81,7 +83,7 @@ __device__ __forceinline__ void stage_tile(unsigned char *dst, const float *__re
             any = gr < nrows && gk < kend;
             full = gr < nrows && gk + 8 <= kend;
         } else {
-            const int k = c % 64, r8 = c / 64;
+            const int k = c % BK, r8 = c / BK;
             const int64_t gk = k0 + k, gr = row0 + r8 * 8;
             base = gk * ld + gr;
             any = gk < kend && gr < nrows;
@@ -92,7 +94,7 @@ __device__ __forceinline__ void stage_tile(unsigned char *dst, const float *__re
             hi[i] = __ldg(reinterpret_cast<const float4 *>(src + base + 4));
         } else {
             float f[8];
-            const int64_t lim = !MN ? (kend - (k0 + (c / ROWS) * 8)) : (nrows - (row0 + (c / 64) * 8));
+            const int64_t lim = !MN ? (kend - (k0 + (c / ROWS) * 8)) : (nrows - (row0 + (c / BK) * 8));
 #pragma unroll
             for (int j = 0; j < 8; j++) f[j] = (any && j < lim) ? __ldg(src + base + j) : 0.f;
             lo[i] = make_float4(f[0], f[1], f[2], f[3]);
@@ -102,21 +104,34 @@ __device__ __forceinline__ void stage_tile(unsigned char *dst, const float *__re
 #pragma unroll
     for (int i = 0; i < PER; i++) {
         const int c = tid + i * NTHREADS;
-        const uint32_t off = !MN ? canon_off(c % ROWS, (c / ROWS) * 8, 64)
-                                 : (uint32_t)((c / 64) * 1024 + ((c % 64) >> 3) * 128 + ((c % 64) & 7) * 16);
+        const uint32_t off = !MN ? canon_off(c % ROWS, (c / ROWS) * 8, BK)
+                                 : (uint32_t)((c / BK) * (BK / 8 * 128) + ((c % BK) >> 3) * 128 + ((c % BK) & 7) * 16);
         const float f[8] = {lo[i].x * mul, lo[i].y * mul, lo[i].z * mul, lo[i].w * mul, hi[i].x * mul, hi[i].y * mul, hi[i].z * mul, hi[i].w * mul};
-        *reinterpret_cast<uint4 *>(dst + off) = pack8_half_or_bf16<BF16>(f);
+        const uint4 pk = pack8_half_or_bf16<BF16>(f);
+        *reinterpret_cast<uint4 *>(dst + off) = pk;
+        if constexpr (SPLIT) {
+            float back[8], rest[8];
+            unpack8_f16(pk, back);
+#pragma unroll
+            for (int j = 0; j < 8; j++) rest[j] = f[j] - back[j];
+            *reinterpret_cast<uint4 *>(dst_lo + off) = pack8_f16(rest);
+        }
     }
 }
 
 // 256 threads: all eight warps stage operand tiles (the kernel is bound by the latency of those loads), warps 0-3 own the
 // four TMEM lane quarters in the epilogue.
-template <int BN, bool A_MN, bool B_MN, bool BF16>
+// SPLIT (split-precision mode "tc3"): both operands are staged as two fp16 terms and every K step is three MMAs,
+// A B ~= A_hi B_hi + A_lo B_hi + A_hi B_lo, into the same fp32 accumulator: fp32-grade products on the tensor core.  Its K tile is
+// 32 deep so that a stage (four tile images) stays at 32 KB and three CTAs still fit on an SM.
+template <int BN, bool A_MN, bool B_MN, bool BF16, int BK = 64, bool SPLIT = false>
 __global__ void __launch_bounds__(256) k_gemm_tc(GemmTcArgs g)
 {
-    constexpr int BM = 128, BK = 64;
+    constexpr int BM = 128;
+    static_assert(!(SPLIT && BF16), "split precision uses fp16 terms");
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr int STAGE = (BM + BN) * BK * 2;     // A tile then B tile, 16-bit; two stages (double buffer)
+    constexpr int TERM = (BM + BN) * BK * 2;      // A tile then B tile, 16-bit: one term
+    constexpr int STAGE = TERM * (SPLIT ? 2 : 1); // hi term, then lo term; two stages (double buffer)
     __shared__ uint64_t bar[2];
     __shared__ uint32_t s_taddr;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -141,8 +156,8 @@ __global__ void __launch_bounds__(256) k_gemm_tc(GemmTcArgs g)
         const int b = it & 1;
         unsigned char *As = smem_raw + b * STAGE, *Bs = As + BM * BK * 2;
         if (it >= 2) { mbar_wait(&bar[b], phase[b]); phase[b] ^= 1; }
-        stage_tile<BM, 256, A_MN, BF16>(As, g.A, g.lda, m0, g.M, k0, kend, tid, a_mul);
-        stage_tile<BN, 256, B_MN, BF16>(Bs, g.B, g.ldb, n0, g.N, k0, kend, tid);
+        stage_tile<BM, 256, A_MN, BF16, BK, SPLIT>(As, g.A, g.lda, m0, g.M, k0, kend, tid, a_mul, As + TERM);
+        stage_tile<BN, 256, B_MN, BF16, BK, SPLIT>(Bs, g.B, g.ldb, n0, g.N, k0, kend, tid, 1.f, Bs + TERM);
         fence_proxy_async();
         __syncthreads();
         if (tid == 0) {
@@ -150,8 +165,15 @@ __global__ void __launch_bounds__(256) k_gemm_tc(GemmTcArgs g)
             const uint64_t ad = make_smem_desc(smem_u32(As), 128, (BK / 8) * 128);
             const uint64_t bd = make_smem_desc(smem_u32(Bs), 128, (BK / 8) * 128);
 #pragma unroll
-            for (int kk = 0; kk < BK / 16; kk++)
+            for (int kk = 0; kk < BK / 16; kk++) {
                 mma_f16(taddr, ad + (uint64_t)(kk * 16), bd + (uint64_t)(kk * 16), idesc, (k0 > kbeg) || (kk > 0));
+                if constexpr (SPLIT) {
+                    const uint64_t ad_lo = make_smem_desc(smem_u32(As + TERM), 128, (BK / 8) * 128);
+                    const uint64_t bd_lo = make_smem_desc(smem_u32(Bs + TERM), 128, (BK / 8) * 128);
+                    mma_f16(taddr, ad_lo + (uint64_t)(kk * 16), bd + (uint64_t)(kk * 16), idesc, true);
+                    mma_f16(taddr, ad + (uint64_t)(kk * 16), bd_lo + (uint64_t)(kk * 16), idesc, true);
+                }
+            }
             mma_commit(&bar[b]);
         }
     }
@@ -199,7 +221,7 @@ __global__ void __launch_bounds__(256) k_gemm_tc(GemmTcArgs g)
 // splitk > 1 or accumulate: results are atomically added to C (no ReLU then).
 int launch_gemm_tc(cudaStream_t st, const float *A, int64_t lda, const float *B, int64_t ldb, float *C, int64_t ldc,
                    int64_t M, int64_t N, int64_t K, const float *bias, bool relu, bool a_mn, bool b_mn, bool bf16,
-                   bool accumulate, int splitk, const float *a_scale)
+                   bool accumulate, int splitk, const float *a_scale, bool split3 = false)
 {
     if (M <= 0 || N <= 0) return PN_OK;
     if ((splitk > 1 || accumulate) && relu) { set_error("launch_gemm_tc: ReLU with atomic accumulation"); return PN_ERR_INVALID; }
@@ -212,6 +234,22 @@ int launch_gemm_tc(cudaStream_t st, const float *A, int64_t lda, const float *B,
         PN_CUDA(cudaFuncSetAttribute(k_gemm_tc<BN, AM, BM_, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         k_gemm_tc<BN, AM, BM_, BF><<<grid, 256, smem, st>>>(g);                                                \
     } while (0)
+    if (split3) {   // split-precision variant: fp16 hi + lo terms of both operands, K tile 32
+        if (bf16) { set_error("launch_gemm_tc: split precision uses fp16 terms"); return PN_ERR_INVALID; }
+        const size_t smem3 = 2 * 2 * (128 + BN) * 32 * 2;
+#define PN_GEMM_CASE3(AM, BM_)                                                                                 \
+    do {                                                                                                       \
+        PN_CUDA(cudaFuncSetAttribute(k_gemm_tc<BN, AM, BM_, false, 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3)); \
+        k_gemm_tc<BN, AM, BM_, false, 32, true><<<grid, 256, smem3, st>>>(g);                                  \
+    } while (0)
+        if (!a_mn && !b_mn) PN_GEMM_CASE3(false, false);
+        else if (a_mn && b_mn) PN_GEMM_CASE3(true, true);
+        else if (!a_mn && b_mn) PN_GEMM_CASE3(false, true);
+        else { set_error("launch_gemm_tc: operand layout combination not instantiated (split precision)"); return PN_ERR_UNSUPPORTED; }
+#undef PN_GEMM_CASE3
+        PN_LAUNCH_CHECK();
+        return PN_OK;
+    }
     if (!a_mn && !b_mn && !bf16) PN_GEMM_CASE(false, false, false);
     else if (!a_mn && b_mn && bf16) PN_GEMM_CASE(false, true, true);
     else if (a_mn && b_mn && bf16) PN_GEMM_CASE(true, true, true);
@@ -1247,10 +1285,11 @@ int pagg_tc_project(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_params 
 {
     const int64_t N = c.N, F = c.F, H = c.H, L = c.L;
     const bool homo = c.variant == PN_VARIANT_HOMO;
-    if (tc_legacy_gemm()) {
-        int rc = launch_gemm_tc(st, X, F, prm.fc0_w, F, w.Z, H, N, H, F, prm.fc0_b, homo, false, false, false, false, 1, nullptr);
+    const bool split3 = c.math_mode == PN_MATH_TC3;   // split-precision mode: three fp16 passes per product, fp32 operands in and out
+    if (tc_legacy_gemm() || split3) {
+        int rc = launch_gemm_tc(st, X, F, prm.fc0_w, F, w.Z, H, N, H, F, prm.fc0_b, homo, false, false, false, false, 1, nullptr, split3);
         if (rc) return rc;
-        return launch_gemm_tc(st, w.Z, H, prm.nets_w, H, w.T, L * H, N, L * H, H, prm.nets_b, homo, false, false, false, false, 1, nullptr);
+        return launch_gemm_tc(st, w.Z, H, prm.nets_w, H, w.T, L * H, N, L * H, H, prm.nets_b, homo, false, false, false, false, 1, nullptr, split3);
     }
     const int64_t F16 = (F + 7) / 8 * 8;
     __half *x16 = reinterpret_cast<__half *>(w.x16), *z16 = reinterpret_cast<__half *>(w.z16);
@@ -1275,6 +1314,7 @@ int pagg_tc_project_backward(const pn_pagg_cfg &c, const PaggWs &w, const pn_pag
     const int64_t N = c.N, F = c.F, H = c.H, L = c.L;
     const bool homo = c.variant == PN_VARIANT_HOMO;
     float *sc_T = w.gscale + 2, *sc_Z = w.gscale + 4;
+    const bool split3 = c.math_mode == PN_MATH_TC3;   // split-precision mode: the scaled gradients travel as two fp16 terms
     PN_CUDA(cudaMemsetAsync(w.gscale + 2, 0, sizeof(float) * 4, st));
     int rc;
     // ---- table projection: T = act(Z Wn^T + bn) ----  (homo: ReLU backward fused with the bias gradient sweep)
@@ -1288,10 +1328,10 @@ int pagg_tc_project_backward(const pn_pagg_cfg &c, const PaggWs &w, const pn_pag
         const int splitk = (int)std::max<int64_t>(1, std::min<int64_t>(148 / std::max<int64_t>(1, ceil_div(L * H, 128) * ceil_div(H, 128)), N / 256));
         if (splitk > 1) PN_CUDA(cudaMemsetAsync(g.nets_w, 0, sizeof(float) * (size_t)(L * H * H), st));
         // dWn[m][i] = sum_n dT[n][m] Z[n][i]: both operands have the reduction index as their row (MN-major)
-        rc = launch_gemm_tc(st, w.dT, L * H, w.Z, H, g.nets_w, H, L * H, H, N, nullptr, false, true, true, false, false, splitk, sc_T);
+        rc = launch_gemm_tc(st, w.dT, L * H, w.Z, H, g.nets_w, H, L * H, H, N, nullptr, false, true, true, false, false, splitk, sc_T, split3);
         if (rc) return rc;
     }
-    rc = launch_gemm_tc(st, w.dT, L * H, prm.nets_w, H, w.dZ, H, N, H, L * H, nullptr, false, false, true, false, true, 1, sc_T);  // dZ += dT Wn
+    rc = launch_gemm_tc(st, w.dT, L * H, prm.nets_w, H, w.dZ, H, N, H, L * H, nullptr, false, false, true, false, true, 1, sc_T, split3);  // dZ += dT Wn
     if (rc) return rc;
     // ---- fc0: Z = act(X W0^T + b0) ----
     rc = homo ? launch_relu_mask_colsum(st, w.dZ, w.Z, N, H, g.fc0_b, reinterpret_cast<unsigned int *>(sc_Z))
@@ -1302,7 +1342,7 @@ int pagg_tc_project_backward(const pn_pagg_cfg &c, const PaggWs &w, const pn_pag
     {
         const int splitk = (int)std::max<int64_t>(1, std::min<int64_t>(148 / std::max<int64_t>(1, ceil_div(H, 128) * ceil_div(F, 128)), N / 256));
         if (splitk > 1) PN_CUDA(cudaMemsetAsync(g.fc0_w, 0, sizeof(float) * (size_t)(H * F), st));
-        rc = launch_gemm_tc(st, w.dZ, H, X, F, g.fc0_w, F, H, F, N, nullptr, false, true, true, false, false, splitk, sc_Z);  // dW0 = dZ^T X
+        rc = launch_gemm_tc(st, w.dZ, H, X, F, g.fc0_w, F, H, F, N, nullptr, false, true, true, false, false, splitk, sc_Z, split3);  // dW0 = dZ^T X
     }
     return rc;
 }
@@ -1310,7 +1350,7 @@ int pagg_tc_project_backward(const pn_pagg_cfg &c, const PaggWs &w, const pn_pag
 }  // namespace pn
 
 // stand-alone entry for the tcgen05 GEMM (unit-tested against fp64 math).  flags: bit0 A given as [K][M],
-// bit1 B given as [K][N], bit2 bf16 operands, bit3 accumulate into C; splitk >= 1.
+// bit1 B given as [K][N], bit2 bf16 operands, bit3 accumulate into C, bit4 split precision (three fp16 passes); splitk >= 1.
 extern "C" int pn_debug_gemm_tc(const float *A, const float *B, float *C, const float *bias, int64_t M, int64_t N,
                                 int64_t K, int relu, void *stream)
 {
@@ -1319,7 +1359,7 @@ extern "C" int pn_debug_gemm_tc(const float *A, const float *B, float *C, const 
 extern "C" int pn_debug_gemm_tc2(const float *A, const float *B, float *C, int64_t M, int64_t N, int64_t K, int flags,
                                  int splitk, void *stream)
 {
-    const bool a_mn = flags & 1, b_mn = flags & 2, bf16 = flags & 4, acc = flags & 8;
+    const bool a_mn = flags & 1, b_mn = flags & 2, bf16 = flags & 4, acc = flags & 8, split3 = flags & 16;
     return pn::launch_gemm_tc((cudaStream_t)stream, A, a_mn ? M : K, B, b_mn ? N : K, C, N, M, N, K, nullptr, false, a_mn,
-                              b_mn, bf16, acc, splitk, nullptr);
+                              b_mn, bf16, acc, splitk, nullptr, split3);
 }

@@ -101,3 +101,29 @@ def test_tc3_is_deterministic_in_the_forward_and_close_to_fp32_mode_at_pubmed_sc
     assert torch.equal(y3a, y3b)
     print("tc3 vs fp32 mode at pubmed scale: max abs diff", (y3a - y32).abs().max().item(), "max |logit|", y32.abs().max().item())
     torch.testing.assert_close(y3a, y32, rtol=2e-4, atol=5e-5)
+
+
+@pytest.mark.parametrize("flags,splitk", [(16, 1), (19, 1), (19, 5), (18, 1), (26, 1)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (512, 128, 1000), (300, 77, 130), (1000, 512, 500)])
+def test_split_precision_tcgen05_gemm_is_fp32_grade(M, N, K, flags, splitk):
+    """The projections' GEMM in this mode: arbitrary fp32 operands (NOT fp16-representable), every operand layout the
+    projections use, split-K and accumulate — against fp64.  Observed: 2-4x the error of a cuBLAS fp32 GEMM at K = 500 .. 1000
+    (the tensor core's fp32 accumulator truncates, so the error grows with the length of the accumulation chain; with
+    split-K 5 it equals cuBLAS'), i.e. ~4e-6 of max |C|: the bound below is 1e-5 relative + 1e-5 sqrt(K) absolute."""
+    from pathnet_b200 import _lib
+    g = torch.Generator().manual_seed(M + N + K + flags)
+    a_mn, b_mn, acc = bool(flags & 1), bool(flags & 2), bool(flags & 8)
+    A = torch.randn(M, K, generator=g) * 3.0
+    B = torch.randn(N, K, generator=g) * 0.1
+    C0 = torch.randn(M, N, generator=g) if acc else torch.zeros(M, N)
+    want = A.double() @ B.double().t() + C0.double()
+    Ad = (A.t().contiguous() if a_mn else A).to(DEV)
+    Bd = (B.t().contiguous() if b_mn else B).to(DEV)
+    C = C0.clone().to(DEV)
+    _lib.check(_lib.lib().pn_debug_gemm_tc2(Ad.data_ptr(), Bd.data_ptr(), C.data_ptr(), M, N, K, flags, splitk,
+                                            torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    err = (C.cpu().double() - want).abs().max().item()
+    ref32 = ((A.to(DEV) @ B.to(DEV).t()).cpu().double() + C0.double() - want).abs().max().item()   # what cuBLAS fp32 (no TF32) makes of it
+    print(f"[split gemm M={M} N={N} K={K} flags={flags} splitk={splitk}] max abs err {err:.3e} (cuBLAS fp32: {ref32:.3e}, max |C| {want.abs().max().item():.2f})")
+    torch.testing.assert_close(C.cpu().double(), want, rtol=1e-5, atol=1e-5 * float(K) ** 0.5)
