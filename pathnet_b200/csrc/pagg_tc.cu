@@ -834,8 +834,9 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) k_lstm_bwd_tc(LstmBwdTcArgs a)
             if (tr) a.trace[s * 8 + 0] = clock64();
             const int64_t blk = (int64_t)t * a.ntiles + tile;
             unsigned char *da_blk = a.da_img + blk * DA_BLOCK_BYTES;
-            // ---- pull the next step's activations towards L2 (a whole step ahead) ----
-            if (valid && t > 0) {
+            // ---- optionally pull the next step's activations towards L2 a whole step ahead (PN_BWD_L2PF=1).  Off by default since the
+            //      register prefetch below exists: same-box A/B on the pubmed step, on / off: 1.006 / 0.967 ms per launch, step 2.66 / 2.61 ms ----
+            if (valid && t > 0 && a.l2pf) {
                 const __half *actp = a.acts + ((int64_t)tile * L + t - 1) * ACT_BLOCK_HALFS + r * 8;
 #pragma unroll
                 for (int cb = cq * 4; cb < cq * 4 + 4; cb++) {
@@ -1189,7 +1190,8 @@ int pagg_tc_backward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_p
                     w.att, w.score, w.dcat + c.H, prm.attw_w, 2 * (int64_t)c.H, c.nw, w.gscale, w.dT,
                     da_img, xh_img, (tc_legacy_gemm() && !split) ? nullptr : reinterpret_cast<const uint32_t *>(w.dmask), P, ntiles, c.L, thr, scale,
                     c.dropout_seed, c.dropout_seed_dev, ck.s0 * c.nw, nullptr, 0,
-                    w.acts, da_img + nblocks * DA_BLOCK_BYTES};   // split-precision mode: fp32 activations, second term of the da images
+                    w.acts, da_img + nblocks * DA_BLOCK_BYTES,   // split-precision mode: fp32 activations, second term of the da images
+                    []{ const char *e = getenv("PN_BWD_L2PF"); return (e && e[0] == '1') ? 1 : 0; }()};
     long long *d_trace = nullptr;
     const char *trace_env = getenv("PN_TRACE_BWD");
     if (trace_env) {

@@ -114,6 +114,7 @@ struct LstmBwdTcArgs {
     int trace_block;
     const float *acts32;       // split-precision mode: activations as fp32 tile images (see k_lstm_fwd_tc3)
     unsigned char *da_img_lo;  // split-precision mode: second fp16 term of the da images (same block layout as da_img)
+    int l2pf;                  // k_lstm_bwd_tc<PF = true>: prefetch.global.L2 of the next step's activations (off by default; PN_BWD_L2PF=1 turns it on)
 };
 constexpr int TCB_NSTAGE = 4;   // 64 KB of W' in flight beside the 128 KB operand tile: the deepest ring that stays inside the 196 KB
                                 // shared-memory carve-out (6 stages -> 228 KB carve-out, the smaller L1 costs more than the depth wins)

@@ -361,6 +361,12 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) k_lstm_fwd_tc3(LstmTcArgs a)
 // ---------------------------------------------------------------------------
 constexpr int TCB3_QBYTES = 128 * 128 * 2;   // one term of one K-quarter of da: [128 rows][128 gate columns] fp16 canonical
 
+// PF bit 1: activations fetched into registers one half-iteration ahead; bit 0: prefetch.global.L2 of the next step's activations
+// a whole step ahead.  Same-box A/B (pubmed step, PN_BWD3_PF): 0 -> 5.28 / 5.32 ms, 1 -> 5.67 / 5.65, 3 -> 5.60 / 5.59: the L2
+// prefetch costs 0.35 ms here (this kernel runs at 0.7 of the HBM roof; the hints add traffic ahead of demand); second box,
+// 0 vs 2: 5.26 / 5.17 vs 5.28 / 5.38 ms -- the register prefetch does not pay either (loads of 4 warps per scheduler already
+// overlap), so the default is 0.
+template <int PF>
 __global__ void __launch_bounds__(TCB_THREADS, 1) k_lstm_bwd_tc3(LstmBwdTcArgs a)
 {
     extern __shared__ unsigned char smem_dyn[];
@@ -503,11 +509,40 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) k_lstm_bwd_tc3(LstmBwdTcArgs a
         float dh_kk = 1.f, dh_ds = 0.f;
         int64_t grow = 0;
         if (!a.dhfin && valid) { dh_kk = a.dh_k[p]; dh_ds = a.dh_s[p]; grow = p / a.nw; }
+        // the saved activations of a half-iteration (4 units x {i, f, g, o, c_t, c_{t-1}}: six 16-byte loads, plus dh_final at the
+        // first step) are fetched one half-iteration ahead of the math that consumes them, across quarter and step boundaries
+        struct Raw3 { float4 gi, gf, gg, go, cn, cp, d0; };
+        auto load_raw = [&](int s_, int hi_, Raw3 &x) {
+            const int t_ = L - 1 - s_, u4_ = cq * 8 + hi_;
+            x.gi = x.gf = x.gg = x.go = x.cn = x.cp = x.d0 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid) {
+                const float *ap = a.acts32 + ((int64_t)tile * L + t_) * ACT3_BLOCK_FLOATS + r * 4 + u4_ * 512;
+                x.gi = __ldg(reinterpret_cast<const float4 *>(ap + 0 * 16384));
+                x.gf = __ldg(reinterpret_cast<const float4 *>(ap + 1 * 16384));
+                x.gg = __ldg(reinterpret_cast<const float4 *>(ap + 2 * 16384));
+                x.go = __ldg(reinterpret_cast<const float4 *>(ap + 3 * 16384));
+                x.cn = __ldg(reinterpret_cast<const float4 *>(ap + 4 * 16384));
+                if (t_ > 0) x.cp = __ldg(reinterpret_cast<const float4 *>(ap - ACT3_BLOCK_FLOATS + 4 * 16384));
+                if (s_ == 0) x.d0 = a.dhfin ? __ldg(reinterpret_cast<const float4 *>(a.dhfin + p * TC_H + u4_ * 4))
+                                            : __ldg(reinterpret_cast<const float4 *>(a.gdrop + grow * a.gdrop_ld + u4_ * 4));
+            }
+        };
+        Raw3 nxt;
+        if (PF & 2) load_raw(0, 0, nxt);
         for (int s = 0; s < L; s++) {
             const int t = L - 1 - s;
             const int64_t blk = (int64_t)t * a.ntiles + tile;
             unsigned char *da_blk = a.da_img + blk * DA_BLOCK_BYTES, *da_blk_lo = a.da_img_lo + blk * DA_BLOCK_BYTES;
-            const float *act = a.acts32 + ((int64_t)tile * L + t) * ACT3_BLOCK_FLOATS + r * 4;
+            // ---- pull the next step's activations towards L2 (a whole step ahead; one lane per 128-byte line) ----
+            if ((PF & 1) && valid && t > 0 && (lane & 7) == 0) {
+                const float *actp = a.acts32 + ((int64_t)tile * L + t - 1) * ACT3_BLOCK_FLOATS + r * 4;
+#pragma unroll
+                for (int u = cq * 8; u < cq * 8 + 8; u++) {
+#pragma unroll
+                    for (int q = 0; q < 5; q++) prefetch_l2(actp + q * 16384 + u * 512);
+                    if (t > 1) prefetch_l2(actp - ACT3_BLOCK_FLOATS + 4 * 16384 + u * 512);
+                }
+            }
             // ---- the previous step's dx (complete since acc_full) -> dT, before this step's MMAs overwrite the region ----
             if (s > 0) scatter_dx(s - 1);
             const uint32_t dh_rd = 128u + (uint32_t)((s - 1) & 1) * 128u;
@@ -515,18 +550,16 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) k_lstm_bwd_tc3(LstmBwdTcArgs a
             for (int hi = 0; hi < 8; hi++) {   // half-iterations of 4 units; two of them fill one K-quarter of this warp's columns
                 const int i = hi >> 1;
                 const int u4 = cq * 8 + hi, u0 = u4 * 4;   // units [u0, u0 + 4)
-                float4 gi = make_float4(0.f, 0.f, 0.f, 0.f), gf = gi, gg = gi, go = gi, cn = gi, cp = gi, d0 = gi;
-                if (valid) {
-                    const float *ap = act + u4 * 512;
-                    gi = __ldg(reinterpret_cast<const float4 *>(ap + 0 * 16384));
-                    gf = __ldg(reinterpret_cast<const float4 *>(ap + 1 * 16384));
-                    gg = __ldg(reinterpret_cast<const float4 *>(ap + 2 * 16384));
-                    go = __ldg(reinterpret_cast<const float4 *>(ap + 3 * 16384));
-                    cn = __ldg(reinterpret_cast<const float4 *>(ap + 4 * 16384));
-                    if (t > 0) cp = __ldg(reinterpret_cast<const float4 *>(ap - ACT3_BLOCK_FLOATS + 4 * 16384));
-                    if (s == 0) d0 = a.dhfin ? __ldg(reinterpret_cast<const float4 *>(a.dhfin + p * TC_H + u0))
-                                             : __ldg(reinterpret_cast<const float4 *>(a.gdrop + grow * a.gdrop_ld + u0));
+                Raw3 cur;
+                if (PF & 2) {
+                    cur = nxt;
+                    if (hi < 7) load_raw(s, hi + 1, nxt);
+                    else if (s + 1 < L) load_raw(s + 1, 0, nxt);
+                } else {
+                    load_raw(s, hi, cur);
                 }
+                const float4 gi = cur.gi, gf = cur.gf, gg = cur.gg, go = cur.go, cn = cur.cn, cp = cur.cp;
+                float4 d0 = cur.d0;
                 float dh[4], dc[4];
                 if (s == 0) {
                     if (!a.dhfin) {
@@ -602,8 +635,15 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) k_lstm_bwd_tc3(LstmBwdTcArgs a
 
 int launch_lstm_bwd_tc3(const LstmBwdTcArgs &a, int64_t ntiles, int smem, int smem_max, cudaStream_t st)
 {
-    PN_CUDA(cudaFuncSetAttribute(k_lstm_bwd_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-    k_lstm_bwd_tc3<<<(unsigned)ntiles, TCB_THREADS, smem, st>>>(a);
+    static const int pf = [] { const char *e = getenv("PN_BWD3_PF"); return e ? atoi(e) : 0; }();
+    PN_CUDA(cudaFuncSetAttribute(k_lstm_bwd_tc3<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+    PN_CUDA(cudaFuncSetAttribute(k_lstm_bwd_tc3<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+    PN_CUDA(cudaFuncSetAttribute(k_lstm_bwd_tc3<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+    PN_CUDA(cudaFuncSetAttribute(k_lstm_bwd_tc3<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+    if (pf <= 0) k_lstm_bwd_tc3<0><<<(unsigned)ntiles, TCB_THREADS, smem, st>>>(a);
+    else if (pf == 1) k_lstm_bwd_tc3<1><<<(unsigned)ntiles, TCB_THREADS, smem, st>>>(a);
+    else if (pf == 2) k_lstm_bwd_tc3<2><<<(unsigned)ntiles, TCB_THREADS, smem, st>>>(a);
+    else k_lstm_bwd_tc3<3><<<(unsigned)ntiles, TCB_THREADS, smem, st>>>(a);
     return PN_OK;
 }
 

@@ -11,3 +11,7 @@ import json; d=json.load(open('gpurun_out/bench_tc3.json')); print('tc3 ms/step'
 if [ "$1" = "all" ]; then
 echo "== other suites"; timeout 900 python -m pytest tests/test_gpu_tc.py tests/test_gpu_v2.py tests/test_gpu_train.py -q -x --timeout 300 > gpurun_out/pytest_q.log 2>&1; echo "rc=$?"; tail -5 gpurun_out/pytest_q.log
 fi
+if [ "$1" = "sweep" ]; then
+for v in 33 30 24; do echo "== bench tc3 PN_WGRAD_CLUSTERS=$v"; PN_WGRAD_CLUSTERS=$v timeout 200 python bench.py --math tc3 --steps 10 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/bench_tc3_$v.json 2>/dev/null; python -c "
+import json; d=json.load(open('gpurun_out/bench_tc3_$v.json')); print('tc3 ms/step', d['ms_per_step'])"; done
+fi
