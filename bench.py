@@ -334,6 +334,9 @@ def run_reference_arm(args):
 
 # ------------------------------------------------------------------------ our arm
 def main():
+    if os.environ.get("PN_BENCH_DEADLINE"):   # debug: dump every thread's Python stack and exit instead of hanging past N seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["PN_BENCH_DEADLINE"]), exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -630,7 +633,9 @@ def main():
                 line["merw"]["cpu_baseline"] = cpu_merw_baseline(graph)
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        del ts, model          # the captured graphs (they hold NCCL kernels) go before the communicator
+        from pathnet_b200.dist import shutdown
+        shutdown()
 
 
 if __name__ == "__main__":

@@ -28,6 +28,29 @@ def shard_rows(mask: torch.Tensor, rank: int, world: int):
     return local, lo, hi
 
 
+def shutdown(timeout_s: float = 20.0) -> None:
+    """Tear the default process group down without ever blocking the exit of a finished job: `destroy_process_group()` runs in a
+    helper thread; if it has not returned after `timeout_s` (seen on a 2 x B200 box: every rank had finished its work and sat in
+    ncclCommDestroy with captured graphs still alive) the process flushes its streams and leaves with status 0.  Call it last."""
+    import os
+    import sys
+    import threading
+    if not (dist.is_available() and dist.is_initialized()):
+        return
+    try:
+        torch.cuda.synchronize()
+    except Exception:
+        pass
+    th = threading.Thread(target=dist.destroy_process_group, daemon=True)
+    th.start()
+    th.join(timeout_s)
+    if th.is_alive():
+        sys.stdout.flush()
+        sys.stderr.write("pathnet_b200.dist.shutdown: destroy_process_group() still blocked after %.0f s; exiting\n" % timeout_s)
+        sys.stderr.flush()
+        os._exit(0)
+
+
 def _world(group=None) -> int:
     return dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
 

@@ -47,7 +47,9 @@ def main():
     dist.barrier()
     if rank == 0:
         torch.save(res, out)
-    dist.destroy_process_group()
+    del ts                      # the captured graph (it holds an NCCL kernel) goes before the communicator
+    from pathnet_b200.dist import shutdown
+    shutdown()
 
 
 if __name__ == "__main__":

@@ -42,7 +42,8 @@ def main(rep, out):
     # per-kernel DRAM traffic (bytes per launch, last launch of each kernel) for bench.py's roofline.traffic
     import json, os
     mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
-    slot = {"k_lstm_fwd_tc": "lstm_fwd", "k_lstm_bwd_tc": "lstm_bwd", "k_wgrad_tc": "wgrad", "k_merw_walk": "merw_walk"}
+    slot = {"k_lstm_fwd_tc": "lstm_fwd", "k_lstm_bwd_tc": "lstm_bwd", "k_wgrad_tc": "wgrad", "k_merw_walk": "merw_walk",
+            "k_lstm_fwd_tc3": "lstm_fwd_tc3", "k_lstm_bwd_tc3": "lstm_bwd_tc3"}
     tpath = os.path.join(os.path.dirname(out), "ncu_traffic.json")
     traffic = json.load(open(tpath)) if os.path.exists(tpath) else {}
     for r in rows[2:]:
