@@ -6,7 +6,7 @@ import time
 from pathlib import Path
 
 faulthandler.dump_traceback_later(int(os.environ.get("DIAG_DEADLINE", "70")), exit=True)
-sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+sys.path.insert(0, str(Path(__file__).resolve().parents[2]))
 t0 = time.time()
 rank = int(os.environ.get("RANK", "0"))
 

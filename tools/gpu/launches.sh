@@ -1,6 +1,6 @@
 #!/bin/bash
 # launch lists (ncu gpu__time_duration) of one bench step, once per environment setting given as arguments
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 i=0
 for kv in "${@:-PN_X=1}"; do

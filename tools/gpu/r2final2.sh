@@ -1,7 +1,7 @@
 #!/bin/bash
 # round 2, final validation + evidence pass (1 GPU): smoke, every GPU test, both bench arms, the other workloads, launch lists and
 # ncu --set full captures of the tensor-core kernels in both tensor-core math modes
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > gpurun_out/nvsmi.txt 2>&1
 echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "rc=$?"; tail -1 gpurun_out/smoke.log

@@ -1,6 +1,6 @@
 #!/bin/bash
 # compute-sanitizer (memcheck, racecheck) over the split-precision mode: module forward/backward and a row-chunked TrainStep
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 cat > /tmp/san3.py <<'PY'
 import sys, torch

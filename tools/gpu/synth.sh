@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 free -g | head -2
 echo "== synthetic 1M"; timeout 600 python tools/bench_synthetic.py 1000 2 32 > gpurun_out/synth_1m.json 2> gpurun_out/synth_1m.err; echo "rc=$?"; cat gpurun_out/synth_1m.json; tail -3 gpurun_out/synth_1m.err

@@ -1,6 +1,6 @@
 #!/bin/bash
 # split-precision mode: its parity tests (verbose: the observed errors are printed), the other tensor-core suites, then a short bench
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 echo "== tc3 tests"; timeout 600 python -m pytest tests/test_gpu_tc3.py -q -s --timeout 240 > gpurun_out/pytest_tc3.log 2>&1; rc=$?; echo "rc=$rc"
 grep -E "^\[tc3|passed|failed|Mismatched|Greatest|AssertionError|tc3 vs" gpurun_out/pytest_tc3.log | head -80

@@ -1,6 +1,6 @@
 #!/bin/bash
 # where the split-precision step spends its time: ncu launch list of one step + the library's in-stream kernel timers
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_tc3.csv python bench.py --math tc3 --steps 1 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/bench_ncu_tc3.log 2>&1; echo "ncu rc=$?"
 python - <<'PY'

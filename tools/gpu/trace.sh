@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 PN_TRACE_FWD=700 PN_TRACE_BWD=700 timeout 300 python - > gpurun_out/trace.log 2>&1 <<'PY'
 import torch, sys

@@ -1,6 +1,6 @@
 #!/bin/bash
 # in-kernel phase timestamps of one CTA of the split-precision forward (pubmed-shaped call, train mode)
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 PN_TRACE_FWD=${1:-700} timeout 300 python - > gpurun_out/trace3.log 2>&1 <<'PY'
 import torch, sys
