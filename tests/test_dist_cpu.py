@@ -66,7 +66,9 @@ def _worker(rank, world, port, q):
     if rank == 0:
         q.put(({k: p.grad.clone() for k, p in params.items()}, loss))
     dist.barrier()
-    dist.destroy_process_group()
+    from pathnet_b200.dist import shutdown
+    shutdown(30.0)        # the teardown every multi-rank entry point of the package uses (destroy under a watchdog)
+    assert not dist.is_initialized()
 
 
 def _run_two_ranks():

@@ -124,3 +124,39 @@ def test_math_mode_resolution(monkeypatch):
     assert pagg.resolve_math_mode("tc3", 128, 4) == "tc3"
     with pytest.raises(ValueError):
         pagg.resolve_math_mode("bf16", 128, 4)
+
+
+def test_math_mode_codes_match_the_header_and_size_the_workspace():
+    """pagg.MATH mirrors `pn_math` of include/pathnet_b200.h; the workspace query is host-only arithmetic, so the per-mode
+    sizing can be checked without a GPU: the split-precision mode carries the gathered table as two fp16 terms (as many bytes
+    as the fp32 table), the fast mode as one (half), plus the fp16 operand copies of its TMA-fed projections."""
+    import ctypes as C
+    import re
+    from pathlib import Path
+    from pathnet_b200 import _lib, pagg
+    hdr = (Path(__file__).resolve().parents[1] / "include" / "pathnet_b200.h").read_text()
+    codes = {m.group(1): int(m.group(2)) for m in re.finditer(r"PN_MATH_(FP32|TC3|TC)\s*=\s*(\d+)", hdr)}
+    assert codes == {"FP32": pagg.MATH["fp32"], "TC": pagg.MATH["tc"], "TC3": pagg.MATH["tc3"]}
+    N, F, H, Cc, S, nw, L = 1000, 40, 128, 4, 300, 5, 4
+
+    def ws(mode, **kw):
+        cfg = _lib.PaggCfg(N=N, F=F, H=H, C=Cc, S=S, nw=nw, L=L, variant=0, math_mode=pagg.MATH[mode], training=1, dropout_p=0.5,
+                           dropout_seed=1, no_backward=0, row_chunk=kw.get("row_chunk", 0), dropout_seed_dev=None, x16=None, cell=0, pool=0)
+        return _lib.lib().pn_pagg_workspace_bytes(C.byref(cfg))
+
+    b32, btc, b3 = ws("fp32"), ws("tc"), ws("tc3")
+    assert b32 > 0 and btc > b32 and b3 > b32
+    table = N * L * H * 4
+    assert b3 - b32 >= table and btc - b32 >= table // 2      # two fp16 terms vs one (+ mask words, + the fast mode's fp16 copies)
+    assert ws("tc3", row_chunk=50) < b3                        # row chunking bounds the per-sequence part in this mode too
+    bad = _lib.PaggCfg(N=N, F=F, H=H, C=Cc, S=S, nw=nw, L=L, variant=0, math_mode=7, training=0, dropout_p=0.0, dropout_seed=0,
+                       no_backward=0, row_chunk=0, dropout_seed_dev=None, x16=None, cell=0, pool=0)
+    assert _lib.lib().pn_pagg_workspace_bytes(C.byref(bad)) == 0      # unknown math mode: rejected by the config check
+    gru = _lib.PaggCfg(N=N, F=F, H=H, C=Cc, S=S, nw=nw, L=L, variant=0, math_mode=pagg.MATH["tc3"], training=0, dropout_p=0.0,
+                       dropout_seed=0, no_backward=0, row_chunk=0, dropout_seed_dev=None, x16=None, cell=2, pool=0)
+    assert _lib.lib().pn_pagg_workspace_bytes(C.byref(gru)) == 0      # the tensor-core modes implement the LSTM cell only
+
+
+def test_dist_shutdown_is_a_no_op_without_a_process_group():
+    from pathnet_b200.dist import shutdown
+    shutdown(1.0)   # nothing initialised: returns at once
