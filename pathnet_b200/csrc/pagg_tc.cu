@@ -1,20 +1,23 @@
-// Tensor-core (tcgen05 / TMEM) math mode of PAGG: fp16 operands, fp32
-// accumulation in TMEM, fp32 gate math.  See tc_util.cuh for the operand layout.
+// Tensor-core (tcgen05 / TMEM) math modes of PAGG: fp16 operands, fp32 accumulation in TMEM, fp32 gate math.
+// See tc_util.cuh for the operand layout, pagg_tc.cuh for the shared declarations and pagg_tc3.cu for the
+// split-precision ("tc3") LSTM kernels.
 //
-//   k_gemm_tc      C = act(A B^T + bias), A/B fp32 in global, converted to fp16
-//                  while staged into the canonical UMMA layout (fc0, table
-//                  projection; also the stand-alone tcgen05 unit test).
-//   k_lstm_fwd_tc  fused gather + dropout + LSTM forward.  One CTA = 128
-//                  sequences (one TMEM lane each), all L steps:
-//                    warps 0-3  gather x_t into the A tile (fp16), then per step
-//                               read the 128x512 fp32 gate pre-activations from
-//                               TMEM, do the gate math (c in registers), write
-//                               h_t back into the A tile as the next step's
-//                               operand, save activations for backward;
-//                    warp 4     one thread issues tcgen05.mma (M128 N256 K16);
-//                    warp 5     one thread streams the packed fp16 weights
-//                               (256 KB, L2-resident) through a 9-stage smem
-//                               ring with cp.async.bulk + mbarriers.
+//   k_gemm_tc      C (+)= act(op(A) op(B)^T + bias), fp32 operands in global memory converted to fp16 while staged into
+//                  the canonical UMMA layout (K- or MN-major, split-K, scaled gradients): the backward projection
+//                  GEMMs and the stand-alone tcgen05 unit test.  <..., BK = 32, SPLIT>: both operands as two fp16
+//                  terms, three MMAs per K step (fp32-grade products; the projections of the tc3 mode).
+//   k_lstm_fwd_tc  fused gather + dropout + LSTM forward.  One CTA = 128 sequences (one TMEM lane each), all L steps:
+//                    16 compute warps (4 TMEM lane quarters x 4 column quarters): gather x_{t+1} (fp16 table rows,
+//                               dropout as a bit mask) into the other x buffer while the tensor core works, read the
+//                               128 x 512 fp32 gate pre-activations from TMEM, gate math (c in registers), write h_t
+//                               back as the next step's operand, save activations and the wgrad operand image;
+//                    MMA warp   converged warp, one elected lane issues tcgen05.mma (M128 N256 K16, 32 per step);
+//                    producer   one thread streams the packed fp16 weights (256 KB per step, L2-resident) through a
+//                               7-stage shared-memory ring with cp.async.bulk + mbarriers.
+//   k_lstm_bwd_tc  BPTT: gate gradients -> da (dgrad operand in smem + wgrad image), [dx | dh] = da W' pipelined in
+//                  K-quarters, dx scattered into dT with vector REDs, dc / dh carried in TMEM.
+//   k_wgrad_tc     dW = sum over blocks [x|h]^T da: 4-CTA clusters, multicast operand quarters.
+//   pagg_tc_project / _backward: the projections around the LSTM (TMA-fed k_gemm_tma forward, k_gemm_tc backward).
 #include "pagg_common.cuh"
 #include <cuda_bf16.h>
 
@@ -1247,7 +1250,9 @@ int pagg_tc_backward_lstm(const pn_pagg_cfg &c, const PaggWs &w, const pn_pagg_p
         // 6 clusters = 24 more SMs: its GEMM CTAs (64 KB of shared memory) cannot share an SM with a 230 KB wgrad CTA.  Same-box
         // sweep on the pubmed step, clusters -> ms/step: 33 2.689, 31 2.698, 29 2.675, 27 2.647, 25 2.674 (this kernel alone slows
         // from 0.465 to 0.534 ms at 27, the step gains).  PN_WGRAD_CLUSTERS overrides.
-        int cap = after_bptt ? std::max(1, max_clusters - 6) : max_clusters;
+        // (Split-precision mode: its three passes are the longer branch by far -- same-box sweep 33 / 30 / 27 / 24 clusters -> 5.17 / 5.20 /
+        // 5.29 / 5.39 ms per step -- so it keeps every cluster.)
+        int cap = (after_bptt && !split) ? std::max(1, max_clusters - 6) : max_clusters;
         if (const char *e = getenv("PN_WGRAD_CLUSTERS")) { const int v = atoi(e); if (v >= 1) cap = std::min(max_clusters, v); }
         const unsigned nsplit = (unsigned)std::max<int64_t>(1, std::min<int64_t>(cap, nblocks));
         lc.gridDim = dim3(nsplit, 4);
