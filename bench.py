@@ -2,7 +2,7 @@
 """Benchmark of the PathNet hot path (MERW sampler -> PAGG fwd+bwd) on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
-                    [--workload pubmed|cora|bgp] [--scaling weak|strong] [--math tc|fp32]
+                    [--workload pubmed|cora|bgp] [--scaling weak|strong] [--math tc|tc3|fp32]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
 Headline (`value`): PAGG paths aggregated per second, forward+backward of one
@@ -17,6 +17,11 @@ A "step" = one pass over one batch through pathnet_b200.train.TrainStep (the
 whole step captured as one CUDA graph): inputs resident in HBM for `value`;
 pinned HOST index tensors copied in and the loss read back every step for
 `e2e`.  Prints ONE JSON line (rank 0).
+
+Math modes: the headline runs the fast tensor-core mode ("tc": single fp16 pass, logits within ~1e-3 of fp32 math); the
+same step is timed in the split-precision tensor-core mode ("tc3": the fp32 mode's 1e-4 parity bar, what the modules'
+"auto" selects) under `e2e.strict_tc3` and in the CUDA-core fp32 mode under `e2e.strict`.  `gpu_status_quo` = the
+reference's own classes on the same GPU through stock PyTorch; `cpu_baseline` / `--impl reference` = on the host CPU.
 """
 from __future__ import annotations
 
